@@ -1,0 +1,149 @@
+/* CPU oracle for the bit-exact part of the dro-sfm warping path (TEST INFRASTRUCTURE ONLY).
+ *
+ * Plain-C restatement of the coordinate chain
+ *   Camera.scaled      dro_sfm/geometry/camera.py:83-107, camera_utils.py:13-19
+ *   Camera.Kinv        dro_sfm/geometry/camera.py:70-79
+ *   image_grid         dro_sfm/utils/image.py:267-332
+ *   Camera.reconstruct dro_sfm/geometry/camera.py:111-147
+ *   Pose @ points      dro_sfm/geometry/pose.py:79-85
+ *   Camera.project     dro_sfm/geometry/camera.py:149-194
+ *   inv2depth          dro_sfm/utils/depth.py:102-121
+ *   valid mask         dro_sfm/losses/supervised_loss.py:290
+ * in IEEE binary32 with the rounding sequence of the reference's CPU path: every 3-term row
+ * product of the three bmm calls is the FMA chain fma(a2,b2, fma(a1,b1, a0*b0)) (what the
+ * sgemm micro-kernel does for K=3), the rigid transform adds t as a SEPARATE rounding
+ * (pose.py:83-84 is bmm(...) + t), depth scaling is a plain multiply, and the normalisation
+ * is 2*(X/Z), then a true division by (W-1), then -1.
+ * Must be compiled with -ffp-contract=off (see oracle/Makefile) so nothing else is fused.
+ *
+ * Parity status: pinned against tests/golden/coords.npz and supervised.npz (outputs of the
+ * unmodified reference, torch 2.11 CPU).
+ */
+#include <math.h>
+#include <stddef.h>
+
+static inline float dot3(const float* a, float b0, float b1, float b2) {
+    return fmaf(a[2], b2, fmaf(a[1], b1, a[0] * b0));
+}
+
+/* K (row-major 3x3) -> scaled copy; scale==1 on both axes returns K unchanged. */
+void drosfm_oracle_scale_K(const float* K, float sx, float sy, float* out) {
+    for (int i = 0; i < 9; ++i) out[i] = K[i];
+    if (sx == 1.0f && sy == 1.0f) return;
+    out[0] = K[0] * sx;
+    out[4] = K[4] * sy;
+    out[2] = (K[2] + 0.5f) * sx - 0.5f;
+    out[5] = (K[5] + 0.5f) * sy - 0.5f;
+}
+
+void drosfm_oracle_K_inverse(const float* K, float* out) {
+    for (int i = 0; i < 9; ++i) out[i] = K[i];
+    out[0] = 1.0f / K[0];
+    out[4] = 1.0f / K[4];
+    out[2] = (-1.0f * K[2]) / K[0];
+    out[5] = (-1.0f * K[5]) / K[4];
+}
+
+void drosfm_oracle_inv2depth(const float* inv, float* depth, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        float x = inv[i];
+        float c = x < 1e-6f ? 1e-6f : x;           /* clamp(min=1e-6); NaN passes through */
+        depth[i] = (x <= 0.0f) ? 0.0f : 1.0f / c;
+    }
+}
+
+/* reconstruct: depth [B,H,W] -> points [B,3,H,W].  Twc == NULL means frame 'c'; otherwise the
+ * 4x4 row-major world<-camera matrices [B,16] are applied (frame 'w'). */
+void drosfm_oracle_reconstruct(const float* depth, const float* K, const float* Twc, float* points,
+                               int B, int H, int W) {
+    const size_t P = (size_t)H * W;
+    for (int b = 0; b < B; ++b) {
+        float Ki[9];
+        drosfm_oracle_K_inverse(K + 9 * b, Ki);
+        const float* T = Twc ? Twc + 16 * b : NULL;
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                size_t p = (size_t)y * W + x;
+                float d = depth[b * P + p];
+                float fx = (float)x, fy = (float)y;
+                float X[3];
+                for (int r = 0; r < 3; ++r) X[r] = dot3(Ki + 3 * r, fx, fy, 1.0f) * d;
+                for (int r = 0; r < 3; ++r) {
+                    float v = X[r];
+                    if (T) v = dot3(T + 4 * r, X[0], X[1], X[2]) + T[4 * r + 3];
+                    points[(b * 3 + r) * P + p] = v;
+                }
+            }
+    }
+}
+
+/* project: points [B,3,H,W] -> uv [B,H,W,2].  Tcw == NULL means frame 'c'. */
+void drosfm_oracle_project(const float* points, const float* K, const float* Tcw, float* uv,
+                           int B, int H, int W, int normalize) {
+    const size_t P = (size_t)H * W;
+    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    for (int b = 0; b < B; ++b) {
+        const float* Kb = K + 9 * b;
+        const float* T = Tcw ? Tcw + 16 * b : NULL;
+        for (size_t p = 0; p < P; ++p) {
+            float X[3], Y[3];
+            for (int r = 0; r < 3; ++r) X[r] = points[(b * 3 + r) * P + p];
+            for (int r = 0; r < 3; ++r) Y[r] = T ? dot3(T + 4 * r, X[0], X[1], X[2]) + T[4 * r + 3] : X[r];
+            float xc = dot3(Kb, Y[0], Y[1], Y[2]);
+            float yc = dot3(Kb + 3, Y[0], Y[1], Y[2]);
+            float zc = dot3(Kb + 6, Y[0], Y[1], Y[2]);
+            zc = zc < 1e-5f ? 1e-5f : zc;
+            float u = xc / zc, v = yc / zc;
+            if (normalize) {
+                u = (2.0f * u) / wm1 - 1.0f;
+                v = (2.0f * v) / hm1 - 1.0f;
+            }
+            uv[(b * P + p) * 2 + 0] = u;
+            uv[(b * P + p) * 2 + 1] = v;
+        }
+    }
+}
+
+/* The fused composition every hot-path caller uses: target camera at the identity
+ * (Twc = inverse(identity) = identity with t = +0), source camera with pose T [B,16].
+ * K / Kref are the UNSCALED float32 intrinsics; sx, sy the Camera.scaled factors.
+ * mask (optional, may be NULL) receives (uv >= -1) & (uv <= 1) per component. */
+void drosfm_oracle_warp_coords(const float* depth, const float* K, const float* Kref, const float* T,
+                               float sx, float sy, float* uv, unsigned char* mask,
+                               int B, int H, int W, int normalize) {
+    const size_t P = (size_t)H * W;
+    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    static const float I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    for (int b = 0; b < B; ++b) {
+        float Kt[9], Ki[9], Kr[9];
+        drosfm_oracle_scale_K(K + 9 * b, sx, sy, Kt);
+        drosfm_oracle_K_inverse(Kt, Ki);
+        drosfm_oracle_scale_K(Kref + 9 * b, sx, sy, Kr);
+        const float* Tb = T + 16 * b;
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                size_t p = (size_t)y * W + x;
+                float d = depth[b * P + p];
+                float fx = (float)x, fy = (float)y;
+                float Xc[3], Xw[3], Y[3];
+                for (int r = 0; r < 3; ++r) Xc[r] = dot3(Ki + 3 * r, fx, fy, 1.0f) * d;
+                for (int r = 0; r < 3; ++r) Xw[r] = dot3(I4 + 4 * r, Xc[0], Xc[1], Xc[2]) + I4[4 * r + 3];
+                for (int r = 0; r < 3; ++r) Y[r] = dot3(Tb + 4 * r, Xw[0], Xw[1], Xw[2]) + Tb[4 * r + 3];
+                float xc = dot3(Kr, Y[0], Y[1], Y[2]);
+                float yc = dot3(Kr + 3, Y[0], Y[1], Y[2]);
+                float zc = dot3(Kr + 6, Y[0], Y[1], Y[2]);
+                zc = zc < 1e-5f ? 1e-5f : zc;
+                float u = xc / zc, v = yc / zc;
+                if (normalize) {
+                    u = (2.0f * u) / wm1 - 1.0f;
+                    v = (2.0f * v) / hm1 - 1.0f;
+                }
+                uv[(b * P + p) * 2 + 0] = u;
+                uv[(b * P + p) * 2 + 1] = v;
+                if (mask) {
+                    mask[(b * P + p) * 2 + 0] = (u >= -1.0f) && (u <= 1.0f);
+                    mask[(b * P + p) * 2 + 1] = (v >= -1.0f) && (v <= 1.0f);
+                }
+            }
+    }
+}
