@@ -1,0 +1,188 @@
+"""ctypes binding of libdrosfm_b200.so (the C ABI declared in include/drosfm_b200.h).
+
+There is no CPU fallback: every operator of this package goes through this module, and loading
+fails loudly when the CUDA library has not been built (``python -m dro_sfm_b200.build``).
+PyTorch is used for device memory and streams only.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libdrosfm_b200.so")
+
+ABI_VERSION = 1
+MAX_VIEWS = 8
+MAX_PREDS = 16
+
+POSE_IDENTITY, POSE_MAT4, POSE_EULER6 = 0, 1, 2
+PAD_ZEROS, PAD_BORDER = 0, 1
+F32, F64 = 0, 1
+DEPTH, INV_DEPTH = 0, 1
+REDUCE_MIN, REDUCE_MEAN = 0, 1
+NCHW, NHWC = 0, 1
+SLOT_BYTES = 128
+
+_vp = ctypes.c_void_p
+_int = ctypes.c_int
+_f32 = ctypes.c_float
+_pp = ctypes.POINTER(ctypes.c_void_p)
+
+
+class Cams(ctypes.Structure):
+    """drosfm_cams_t"""
+    _fields_ = [("K", _vp), ("Kref", _vp), ("k_dtype", ctypes.c_int32), ("sx", _f32), ("sy", _f32),
+                ("Twc", _vp), ("pose", _vp), ("pose_kind", ctypes.c_int32)]
+
+
+class PhotoOpts(ctypes.Structure):
+    """drosfm_photo_opts_t"""
+    _fields_ = [("ssim_w", _f32), ("C1", _f32), ("C2", _f32), ("padding", ctypes.c_int32),
+                ("reduce_op", ctypes.c_int32), ("automask", ctypes.c_int32), ("gamma", _f32)]
+
+
+_cp = ctypes.POINTER(Cams)
+_op = ctypes.POINTER(PhotoOpts)
+
+# name -> argtypes; every symbol include/drosfm_b200.h declares (tests check the export list)
+SIGNATURES = {
+    "drosfm_version": ([], _int),
+    "drosfm_last_error": ([], ctypes.c_char_p),
+    "drosfm_ws_bytes": ([_int], ctypes.c_size_t),
+    "drosfm_reconstruct_fwd": ([_vp, _vp, _int, _vp, _vp, _int, _int, _int, _vp], _int),
+    "drosfm_reconstruct_bwd": ([_vp, _vp, _int, _vp, _vp, _int, _int, _int, _vp], _int),
+    "drosfm_project_fwd": ([_vp, _vp, _int, _vp, _vp, _int, _int, _int, _int, _vp], _int),
+    "drosfm_project_bwd": ([_vp, _vp, _vp, _int, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp], _int),
+    "drosfm_warp_coords_fwd": ([_vp, _int, _cp, _vp, _vp, _int, _int, _int, _int, _vp], _int),
+    "drosfm_warp_coords_bwd": ([_vp, _vp, _int, _cp, _vp, _vp, _vp, _int, _int, _int, _int, _vp], _int),
+    "drosfm_grid_gather_fwd": ([_vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp], _int),
+    "drosfm_grid_gather_bwd": ([_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp], _int),
+    "drosfm_view_synthesis_fwd": ([_vp, _vp, _int, _cp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp], _int),
+    "drosfm_view_synthesis_bwd": ([_vp, _vp, _vp, _int, _cp, _vp, _vp, _vp, _vp,
+                                   _int, _int, _int, _int, _int, _int, _int, _vp], _int),
+    "drosfm_feat_cost_fwd": ([_vp, _pp, _vp, _int, _cp, _pp, _int, _vp, _int, _int, _int, _int, _int, _vp], _int),
+    "drosfm_feat_cost_bwd": ([_vp, _vp, _pp, _vp, _int, _cp, _pp, _int, _vp, _pp, _vp, _pp, _vp,
+                              _int, _int, _int, _int, _int, _vp], _int),
+    "drosfm_automask_fwd": ([_vp, _pp, _int, _op, _vp, _int, _int, _int, _vp], _int),
+    "drosfm_photometric_fwd": ([_vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _vp, _vp, _vp,
+                                _int, _int, _int, _vp], _int),
+    "drosfm_photometric_bwd": ([_vp, _vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _pp, _pp, _vp,
+                                _int, _int, _int, _vp], _int),
+    "drosfm_smoothness_fwd": ([_vp, _pp, _int, _f32, _vp, _vp, _vp, _int, _int, _int, _vp], _int),
+    "drosfm_smoothness_bwd": ([_vp, _vp, _pp, _int, _f32, _vp, _pp, _vp, _int, _int, _int, _vp], _int),
+    "drosfm_reproj_loss_fwd": ([_vp, _int, _cp, _pp, _pp, _int, _int, _f32, _f32, _f32, _vp, _vp,
+                                _int, _int, _int, _vp], _int),
+    "drosfm_reproj_loss_bwd": ([_vp, _vp, _int, _cp, _pp, _pp, _int, _int, _f32, _f32, _f32, _pp, _vp,
+                                _int, _int, _int, _vp], _int),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """The loaded library; raises RuntimeError if it is missing (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(SO_PATH):
+                    raise RuntimeError(
+                        "dro_sfm_b200: %s not found. Build it with `python -m dro_sfm_b200.build` "
+                        "(nvcc, sm_100a). There is no CPU or PyTorch fallback." % SO_PATH)
+                handle = ctypes.CDLL(SO_PATH)
+                missing = [n for n in SIGNATURES if not hasattr(handle, n)]
+                if missing:
+                    raise RuntimeError("dro_sfm_b200: %s does not export %s (stale build?)" % (SO_PATH, missing))
+                for name, (argtypes, restype) in SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.argtypes = argtypes
+                    fn.restype = restype
+                if handle.drosfm_version() != ABI_VERSION:
+                    raise RuntimeError("dro_sfm_b200: ABI version mismatch (library %d, binding %d)"
+                                       % (handle.drosfm_version(), ABI_VERSION))
+                _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().drosfm_last_error().decode("utf-8", "replace")
+        kind = ValueError if rc < 0 else RuntimeError
+        raise kind("drosfm %s failed (%d): %s" % (what, rc, msg))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def ptr_array(tensors):
+    """Host array of device pointers (const float* const*); entries may be None."""
+    arr = (ctypes.c_void_p * max(1, len(tensors)))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return ctypes.cast(arr, _pp)
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dro_sfm_b200 operators run on CUDA tensors only (got a %s tensor); "
+                               "there is no CPU fallback" % t.device)
+
+
+def f32c(t):
+    """float32 contiguous view/copy of t."""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def k_arg(K):
+    """Intrinsics for the kernels: float64 is consumed directly (rounded in-kernel == K.float())."""
+    if K.dtype not in (torch.float32, torch.float64):
+        K = K.float()
+    K = K.contiguous()
+    return K, (F64 if K.dtype == torch.float64 else F32)
+
+
+def make_cams(K, Kref, sx=1.0, sy=None, Twc=None, pose=None, pose_kind=POSE_IDENTITY):
+    """Builds a drosfm_cams_t; returns (struct, keepalive tuple)."""
+    K, kd = k_arg(K)
+    if Kref is K:
+        Kref_c, kd2 = K, kd
+    else:
+        Kref_c, kd2 = k_arg(Kref)
+        if kd2 != kd:
+            K, Kref_c, kd = K.float().contiguous(), Kref_c.float().contiguous(), F32
+    c = Cams()
+    c.K, c.Kref, c.k_dtype = K.data_ptr(), Kref_c.data_ptr(), kd
+    c.sx = float(sx)
+    c.sy = float(sx if sy is None else sy)
+    c.Twc = None if Twc is None else Twc.data_ptr()
+    c.pose = None if pose is None else pose.data_ptr()
+    c.pose_kind = int(pose_kind)
+    return c, (K, Kref_c, Twc, pose)
+
+
+_workspaces = {}
+
+
+def workspace(device, slots):
+    """Zero-initialised, self-cleaning reduction workspace, one per (device, stream)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    need = max(64, int(slots)) * SLOT_BYTES
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(need * 2, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws

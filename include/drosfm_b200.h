@@ -1,0 +1,183 @@
+/* drosfm_b200 -- C ABI of the B200-native dense depth-pose warping path of dro-sfm.
+ *
+ * One shared library (dro_sfm_b200/libdrosfm_b200.so, sm_100a) exports exactly the entry points a
+ * binding of the reference's hot path needs.  The reference (xyang9527/dro-sfm) is pure Python on
+ * top of ATen, so it has no FFI of its own; each function below names the reference operator it
+ * replaces (paths relative to the upstream repo root) and INTEGRATION.md shows the ctypes stub a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - All tensors are contiguous float32 device memory unless stated; images/features are NCHW.
+ *  - The library never allocates, frees or synchronises: outputs and workspaces are caller
+ *    owned, every call only enqueues kernels on `stream` (CUDA-graph capturable).
+ *  - Return value: 0 = ok, <0 = argument error (DROSFM_E*), >0 = cudaError_t of the launch.
+ *    drosfm_last_error() returns a thread-local message for the last non-zero return.
+ *  - "ws" workspaces must be zero-filled once by the caller (drosfm_ws_bytes gives the size);
+ *    kernels leave them zeroed again, so one allocation per (device, stream) can be reused.
+ *  - Buffers marked "accumulated" must be zero-filled by the caller on the same stream before the
+ *    call (they are scatter targets of red.global.add).
+ *  - Gradient outputs may be NULL when not wanted.
+ */
+#ifndef DROSFM_B200_H_
+#define DROSFM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DROSFM_ABI_VERSION 1
+#define DROSFM_MAX_VIEWS 8      /* source views per call (forward_context + back_context) */
+#define DROSFM_MAX_PREDS 16     /* depth predictions per loss call (GRU iterations seen by the loss) */
+
+enum { DROSFM_OK = 0, DROSFM_EINVAL = -1, DROSFM_ERANGE = -2, DROSFM_EALIGN = -3, DROSFM_ENOTSUP = -4 };
+enum { DROSFM_POSE_IDENTITY = 0, DROSFM_POSE_MAT4 = 1, DROSFM_POSE_EULER6 = 2 };
+enum { DROSFM_PAD_ZEROS = 0, DROSFM_PAD_BORDER = 1 };
+enum { DROSFM_F32 = 0, DROSFM_F64 = 1 };
+enum { DROSFM_DEPTH = 0, DROSFM_INV_DEPTH = 1 };
+enum { DROSFM_REDUCE_MIN = 0, DROSFM_REDUCE_MEAN = 1 };
+enum { DROSFM_NCHW = 0, DROSFM_NHWC = 1 };
+
+typedef void* drosfm_stream_t;  /* cudaStream_t */
+
+/* The camera pair of one warp: target camera (pose = identity unless Twc given) and source camera.
+ * Replaces the per-call host work of the reference: K.float(), Camera.scaled (camera.py:83-107),
+ * Camera.Kinv (camera.py:70-79), Pose.from_vec / euler2mat (pose.py:38-45, pose_utils.py:40-85). */
+typedef struct {
+    const void* K;        /* [B,3,3] target intrinsics, float32 or float64 (k_dtype)            */
+    const void* Kref;     /* [B,3,3] source intrinsics, same dtype                              */
+    int32_t k_dtype;      /* DROSFM_F32 | DROSFM_F64 (float64 is rounded to float32 = K.float()) */
+    float sx, sy;         /* Camera.scaled factors; 1,1 = untouched intrinsics                  */
+    const float* Twc;     /* [B,4,4] world<-target-camera, NULL = identity (Camera(K) default)  */
+    const float* pose;    /* source camera Tcw: [B,4,4] (MAT4) or [B,6] (EULER6) or NULL        */
+    int32_t pose_kind;    /* DROSFM_POSE_*                                                      */
+} drosfm_cams_t;
+
+int drosfm_version(void);
+const char* drosfm_last_error(void);
+/* Bytes of zero-initialised workspace for calls that reduce pose gradients or scalar losses over
+ * `slots` independent accumulators (one slot = one (sample, view, prediction) pose or one scalar). */
+size_t drosfm_ws_bytes(int slots);
+
+/* ---- Camera.reconstruct (camera.py:111-147) -------------------------------------------------
+ * depth [B,1,H,W] -> points [B,3,H,W].  K: [B,3,3] (k_dtype).  Twc: [B,4,4] or NULL (frame 'c'). */
+int drosfm_reconstruct_fwd(const float* depth, const void* K, int k_dtype, const float* Twc,
+                           float* points, int B, int H, int W, drosfm_stream_t stream);
+int drosfm_reconstruct_bwd(const float* g_points, const void* K, int k_dtype, const float* Twc,
+                           float* g_depth, int B, int H, int W, drosfm_stream_t stream);
+
+/* ---- Camera.project (camera.py:149-194) -----------------------------------------------------
+ * points [B,3,H,W] -> uv [B,H,W,2].  Tcw: [B,4,4] or NULL (frame 'c').
+ * bwd: g_points [B,3,H,W] and/or g_Tcw [B,4,4] (needs ws of drosfm_ws_bytes(B)). */
+int drosfm_project_fwd(const float* points, const void* K, int k_dtype, const float* Tcw, float* uv,
+                       int B, int H, int W, int normalize, drosfm_stream_t stream);
+int drosfm_project_bwd(const float* g_uv, const float* points, const void* K, int k_dtype,
+                       const float* Tcw, float* g_points, float* g_Tcw, void* ws,
+                       int B, int H, int W, int normalize, drosfm_stream_t stream);
+
+/* ---- fused reconstruct -> project (camera_utils.py:50-52, DepthPoseNet.py:83-90,
+ *      supervised_loss.py:279-291) ------------------------------------------------------------
+ * depth (or inverse depth, depth_kind) [B,1,H,W] -> uv [B,H,W,2]; optional mask [B,H,W,2] u8 =
+ * (uv >= -1) & (uv <= 1).  bwd: g_depth [B,1,H,W]; g_pose [B,4,4] (MAT4) or [B,6] (EULER6). */
+int drosfm_warp_coords_fwd(const float* depth, int depth_kind, const drosfm_cams_t* cams, float* uv,
+                           uint8_t* mask, int B, int H, int W, int normalize, drosfm_stream_t stream);
+int drosfm_warp_coords_bwd(const float* g_uv, const float* depth, int depth_kind, const drosfm_cams_t* cams,
+                           float* g_depth, float* g_pose, void* ws, int B, int H, int W, int normalize,
+                           drosfm_stream_t stream);
+
+/* ---- F.grid_sample(bilinear, align_corners=True) (camera_utils.py:55, DepthPoseNet.py:92) ---
+ * src [B,C,Hs,Ws], uv [B,H,W,2] -> out [B,C,H,W].  bwd: g_src accumulated; g_uv written. */
+int drosfm_grid_gather_fwd(const float* src, const float* uv, float* out, int B, int C, int Hs, int Ws,
+                           int H, int W, int padding, drosfm_stream_t stream);
+int drosfm_grid_gather_bwd(const float* g_out, const float* src, const float* uv, float* g_src, float* g_uv,
+                           int B, int C, int Hs, int Ws, int H, int W, int padding, drosfm_stream_t stream);
+
+/* ---- view_synthesis (camera_utils.py:23-56), coordinates never materialised -----------------
+ * src [B,C,Hs,Ws], depth [B,1,H,W] -> out [B,C,H,W].
+ * bwd: g_src accumulated (may be NULL), g_depth written, g_pose written (ws of drosfm_ws_bytes(B)). */
+int drosfm_view_synthesis_fwd(const float* src, const float* depth, int depth_kind, const drosfm_cams_t* cams,
+                              float* out, int B, int C, int Hs, int Ws, int H, int W, int padding,
+                              drosfm_stream_t stream);
+int drosfm_view_synthesis_bwd(const float* g_out, const float* src, const float* depth, int depth_kind,
+                              const drosfm_cams_t* cams, float* g_src, float* g_depth, float* g_pose, void* ws,
+                              int B, int C, int Hs, int Ws, int H, int W, int padding, drosfm_stream_t stream);
+
+/* ---- feature-metric cost (DepthPoseNet.get_cost_each :76-96, depth_cost_calc :98-105) --------
+ * cost[b,c,y,x] = (1/V) * sum_v (fmap - warp_v(fmap_ref_v))^2, zeros padding, V = n_views
+ * (V = 1 is get_cost_each).  fmap, fmap_ref[v], cost: [B,C,h,w] in `layout` (NCHW, or NHWC =
+ * torch channels_last storage of the same logical tensor).  poses[v]: per-view source pose in
+ * cams->pose_kind encoding ([B,4,4] or [B,6]); cams->pose is ignored.
+ * bwd: g_fmap written; g_fmap_ref[v] and g_depth accumulated (entries may be NULL);
+ * g_poses[v] written ([B,4,4] or [B,6]; entries may be NULL; ws of drosfm_ws_bytes(V*B)). */
+int drosfm_feat_cost_fwd(const float* fmap, const float* const* fmap_ref, const float* depth, int depth_kind,
+                         const drosfm_cams_t* cams, const float* const* poses, int n_views, float* cost,
+                         int B, int C, int h, int w, int layout, drosfm_stream_t stream);
+int drosfm_feat_cost_bwd(const float* g_cost, const float* fmap, const float* const* fmap_ref,
+                         const float* depth, int depth_kind, const drosfm_cams_t* cams,
+                         const float* const* poses, int n_views, float* g_fmap, float* const* g_fmap_ref,
+                         float* g_depth, float* const* g_poses, void* ws,
+                         int B, int C, int h, int w, int layout, drosfm_stream_t stream);
+
+/* ---- photometric loss (multiview_photometric_loss_mf.py:15-54,132-269,333-353) ---------------
+ * Options shared by the photometric entry points. */
+typedef struct {
+    float ssim_w;        /* ssim_loss_weight (0.85) */
+    float C1, C2;        /* SSIM constants (1e-4, 9e-4) */
+    int32_t padding;     /* DROSFM_PAD_* for the warp */
+    int32_t reduce_op;   /* DROSFM_REDUCE_MIN | DROSFM_REDUCE_MEAN */
+    int32_t automask;    /* 1: un-warped source maps compete in the per-pixel min (min only) */
+    float gamma;         /* decay over predictions: weight_i = gamma^(n-1-i) (0.85) */
+} drosfm_photo_opts_t;
+
+/* Un-warped (auto-mask) pass: automask[b,y,x] = min_v photometric(context_v, image), computed once
+ * per step instead of once per prediction (lines 346-351 recompute it n times). */
+int drosfm_automask_fwd(const float* image, const float* const* context, int n_views,
+                        const drosfm_photo_opts_t* opts, float* automask, int B, int H, int W,
+                        drosfm_stream_t stream);
+/* loss = sum_i gamma^(n-1-i) * reduce_v,pixels(photometric(warp(context_v; inv_depth_i, pose_{v,i}), image)).
+ * inv_depths[i]: [B,1,H,W]; poses[v*n_preds+i]: [B,4,4] or [B,6] per cams->pose_kind.
+ * sel [n_preds,B,H,W] u8 receives the arg-min view per pixel (255 = auto-mask won); loss: 1 float.
+ * ws of drosfm_ws_bytes(n_preds). */
+int drosfm_photometric_fwd(const float* image, const float* const* context, int n_views,
+                           const float* const* inv_depths, int depth_kind, int n_preds,
+                           const drosfm_cams_t* cams, const float* const* poses, const float* automask,
+                           const drosfm_photo_opts_t* opts, uint8_t* sel, float* loss, void* ws,
+                           int B, int H, int W, drosfm_stream_t stream);
+/* g_loss: 1 float on the device (upstream gradient).  g_inv_depths[i] [B,1,H,W] written;
+ * g_poses[v*n_preds+i] written ([B,4,4] or [B,6]); ws of drosfm_ws_bytes(n_views*n_preds*B). */
+int drosfm_photometric_bwd(const float* g_loss, const float* image, const float* const* context, int n_views,
+                           const float* const* inv_depths, int depth_kind, int n_preds,
+                           const drosfm_cams_t* cams, const float* const* poses, const uint8_t* sel,
+                           const drosfm_photo_opts_t* opts, float* const* g_inv_depths, float* const* g_poses,
+                           void* ws, int B, int H, int W, drosfm_stream_t stream);
+
+/* ---- smoothness loss (multiview_photometric_loss_mf.py:273-299, utils/depth.py:147-199) -------
+ * loss = weight/n * sum_i (mean|dx(d_i/mean(d_i)) * wx| + mean|dy(..) * wy|) / 2^i.
+ * means [n_preds,B] float scratch (per-sample mean inverse depth, kept for bwd); ws of
+ * drosfm_ws_bytes(n_preds*B + 1). */
+int drosfm_smoothness_fwd(const float* image, const float* const* inv_depths, int n_preds, float weight,
+                          float* means, float* loss, void* ws, int B, int H, int W, drosfm_stream_t stream);
+int drosfm_smoothness_bwd(const float* g_loss, const float* image, const float* const* inv_depths, int n_preds,
+                          float weight, const float* means, float* const* g_inv_depths, void* ws,
+                          int B, int H, int W, drosfm_stream_t stream);
+
+/* ---- reprojection pose loss (supervised_loss.py:279-325) ------------------------------------
+ * loss = sum_i w_i/V * sum_v mean(valid * clamp(|uv(pred_{v,i}) - uv(gt_v)|, -1, 1)) / sum_i w_i,
+ * valid = in-range(gt) & in-range(pred) & (min_depth < depth < max_depth/4), depth = GT depth
+ * [B,1,H,W] (depth_kind may be DROSFM_INV_DEPTH: inv2depth is fused).  gt_poses[v], pred_poses[v*n+i]
+ * in cams->pose_kind encoding.  bwd: g_pred_poses[v*n+i] written; ws of drosfm_ws_bytes(V*n*B + 1). */
+int drosfm_reproj_loss_fwd(const float* depth, int depth_kind, const drosfm_cams_t* cams,
+                           const float* const* gt_poses, const float* const* pred_poses, int n_views, int n_preds,
+                           float min_depth, float max_depth, float gamma, float* loss, void* ws,
+                           int B, int H, int W, drosfm_stream_t stream);
+int drosfm_reproj_loss_bwd(const float* g_loss, const float* depth, int depth_kind, const drosfm_cams_t* cams,
+                           const float* const* gt_poses, const float* const* pred_poses, int n_views, int n_preds,
+                           float min_depth, float max_depth, float gamma, float* const* g_pred_poses, void* ws,
+                           int B, int H, int W, drosfm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DROSFM_B200_H_ */

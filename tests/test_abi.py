@@ -1,0 +1,59 @@
+"""CPU checks of the C-ABI boundary: the library builds/loads and exports every declared symbol."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "drosfm_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(drosfm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_hot_path():
+    names = declared_symbols()
+    for need in ("drosfm_warp_coords_fwd", "drosfm_warp_coords_bwd", "drosfm_view_synthesis_fwd", "drosfm_view_synthesis_bwd",
+                 "drosfm_feat_cost_fwd", "drosfm_feat_cost_bwd", "drosfm_photometric_fwd", "drosfm_photometric_bwd"):
+        assert need in names
+
+
+def test_library_exports_every_declared_symbol():
+    from dro_sfm_b200 import _lib
+    from dro_sfm_b200.build import build
+    build()
+    handle = ctypes.CDLL(_lib.SO_PATH)
+    missing = [n for n in declared_symbols() if not hasattr(handle, n)]
+    assert not missing, missing
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    assert _lib.lib().drosfm_version() == _lib.ABI_VERSION
+    assert _lib.lib().drosfm_ws_bytes(4) == 4 * _lib.SLOT_BYTES
+
+
+def test_structs_match_header_layout():
+    from dro_sfm_b200 import _lib
+    # drosfm_cams_t: 2 pointers, int32, 2 floats, (pad), 2 pointers, int32 (+pad) on LP64
+    assert ctypes.sizeof(_lib.Cams) == 56
+    assert _lib.Cams.Twc.offset == 32 and _lib.Cams.pose_kind.offset == 48
+    assert ctypes.sizeof(_lib.PhotoOpts) == 28
+
+
+def test_no_cpu_fallback():
+    import torch
+    from dro_sfm_b200 import ops
+    K = torch.eye(3).repeat(1, 1, 1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.warp_coords(torch.ones(1, 1, 4, 4), torch.eye(4).repeat(1, 1, 1), K)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "dro_sfm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
