@@ -51,6 +51,8 @@ SIGNATURES = {
     "drosfm_version": ([], _int),
     "drosfm_last_error": ([], ctypes.c_char_p),
     "drosfm_ws_bytes": ([_int], ctypes.c_size_t),
+    "drosfm_pose_vec2mat_fwd": ([_vp, _vp, _int, _vp], _int),
+    "drosfm_pose_vec2mat_bwd": ([_vp, _vp, _vp, _int, _vp], _int),
     "drosfm_reconstruct_fwd": ([_vp, _vp, _int, _vp, _vp, _int, _int, _int, _vp], _int),
     "drosfm_reconstruct_bwd": ([_vp, _vp, _int, _vp, _vp, _int, _int, _int, _vp], _int),
     "drosfm_project_fwd": ([_vp, _vp, _int, _vp, _vp, _int, _int, _int, _int, _vp], _int),
@@ -71,7 +73,7 @@ SIGNATURES = {
     "drosfm_photometric_bwd": ([_vp, _vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _pp, _pp, _vp,
                                 _int, _int, _int, _vp], _int),
     "drosfm_smoothness_fwd": ([_vp, _pp, _int, _f32, _vp, _vp, _vp, _int, _int, _int, _vp], _int),
-    "drosfm_smoothness_bwd": ([_vp, _vp, _pp, _int, _f32, _vp, _pp, _vp, _int, _int, _int, _vp], _int),
+    "drosfm_smoothness_bwd": ([_vp, _vp, _pp, _int, _f32, _vp, _pp, _int, _int, _int, _int, _vp], _int),
     "drosfm_reproj_loss_fwd": ([_vp, _int, _cp, _pp, _pp, _int, _int, _f32, _f32, _f32, _vp, _vp,
                                 _int, _int, _int, _vp], _int),
     "drosfm_reproj_loss_bwd": ([_vp, _vp, _int, _cp, _pp, _pp, _int, _int, _f32, _f32, _f32, _pp, _vp,

@@ -110,7 +110,7 @@ warp_coords_bwd_kernel(const float* __restrict__ g_uv, const float* __restrict__
             pix_xy(p0 + k, W, x, y);
             Warp w;
             warp_pixel(cam, x, y, to_depth(d[k], depth_kind), wm1, hm1, normalize != 0, w);
-            const float gdk = warp_pixel_adjoint(cam, w, wm1, hm1, normalize != 0, g[2 * k], g[2 * k + 1], gT);
+            const float gdk = warp_pixel_adjoint(cam, w, to_depth(d[k], depth_kind), wm1, hm1, normalize != 0, g[2 * k], g[2 * k + 1], gT);
             gd[k] = depth_kind == DROSFM_INV_DEPTH ? inv2depth_grad(d[k], gdk) : gdk;
         }
         if (g_depth != nullptr) {
@@ -243,7 +243,7 @@ project_bwd_kernel(const float* __restrict__ g_uv, const float* __restrict__ poi
         Proj pr;
         project_cam(c.Kr, Y, wm1, hm1, normalize != 0, pr);
         const float2 g = __ldg(reinterpret_cast<const float2*>(g_uv) + static_cast<size_t>(b) * P + p);
-        project_cam_adjoint(c.Kr, pr, wm1, hm1, normalize != 0, g.x, g.y, gY);
+        project_cam_adjoint(c.Kr, pr, Y, wm1, hm1, normalize != 0, g.x, g.y, gY);
         if (Tcw != nullptr) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -266,6 +266,37 @@ project_bwd_kernel(const float* __restrict__ g_uv, const float* __restrict__ poi
     block_accumulate<12>(gT, red, slot->acc);
     if (last_block(slot, gridDim.x, &flag) && threadIdx.x == 0)
         finish_pose_grad(slot, DROSFM_POSE_MAT4, nullptr, g_Tcw + b * 16);
+}
+
+// ------------------------------------------------------------------------------------------
+// Pose.from_vec(vec, 'euler')
+// ------------------------------------------------------------------------------------------
+__global__ void pose_vec2mat_fwd_kernel(const float* __restrict__ vec, float* __restrict__ mat, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float v[6], T[12], trig[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = vec[i * 6 + k];
+    euler_to_mat34(v, T, trig);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) mat[i * 16 + k] = T[k];
+    mat[i * 16 + 12] = 0.0f; mat[i * 16 + 13] = 0.0f; mat[i * 16 + 14] = 0.0f; mat[i * 16 + 15] = 1.0f;
+}
+
+__global__ void pose_vec2mat_bwd_kernel(const float* __restrict__ g_mat, const float* __restrict__ vec,
+                                        float* __restrict__ g_vec, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float v[6], T[12], trig[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = vec[i * 6 + k];
+    euler_to_mat34(v, T, trig);
+    double g[12], gv[6];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) g[k] = g_mat[i * 16 + k];
+    euler_adjoint(g, trig, gv);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g_vec[i * 6 + k] = static_cast<float>(gv[k]);
 }
 
 static int check_dims(int B, int H, int W) {
@@ -297,11 +328,27 @@ using namespace drosfm;
 
 extern "C" {
 
+int drosfm_pose_vec2mat_fwd(const float* vec, float* mat, int N, drosfm_stream_t stream) {
+    DROSFM_REQUIRE(N >= 0, DROSFM_EINVAL, "pose_vec2mat_fwd: negative N");
+    if (N == 0) return DROSFM_OK;
+    DROSFM_REQUIRE(vec && mat, DROSFM_EINVAL, "pose_vec2mat_fwd: NULL argument");
+    pose_vec2mat_fwd_kernel<<<(N + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(vec, mat, N);
+    return launch_status("pose_vec2mat_fwd");
+}
+
+int drosfm_pose_vec2mat_bwd(const float* g_mat, const float* vec, float* g_vec, int N, drosfm_stream_t stream) {
+    DROSFM_REQUIRE(N >= 0, DROSFM_EINVAL, "pose_vec2mat_bwd: negative N");
+    if (N == 0) return DROSFM_OK;
+    DROSFM_REQUIRE(g_mat && vec && g_vec, DROSFM_EINVAL, "pose_vec2mat_bwd: NULL argument");
+    pose_vec2mat_bwd_kernel<<<(N + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(g_mat, vec, g_vec, N);
+    return launch_status("pose_vec2mat_bwd");
+}
+
 int drosfm_warp_coords_fwd(const float* depth, int depth_kind, const drosfm_cams_t* cams, float* uv, uint8_t* mask,
                            int B, int H, int W, int normalize, drosfm_stream_t stream) {
     if (int e = check_dims(B, H, W)) return e;
-    if (int e = check_cams(cams)) return e;
     if (B == 0 || H * W == 0) return DROSFM_OK;
+    if (int e = check_cams(cams)) return e;
     DROSFM_REQUIRE(depth && uv, DROSFM_EINVAL, "warp_coords_fwd: NULL depth/uv");
     DROSFM_REQUIRE(cams->pose_kind == DROSFM_POSE_IDENTITY || cams->pose != nullptr, DROSFM_EINVAL,
                    "warp_coords_fwd: pose_kind %d needs cams->pose", cams->pose_kind);
@@ -319,9 +366,9 @@ int drosfm_warp_coords_bwd(const float* g_uv, const float* depth, int depth_kind
                            float* g_depth, float* g_pose, void* ws, int B, int H, int W, int normalize,
                            drosfm_stream_t stream) {
     if (int e = check_dims(B, H, W)) return e;
-    if (int e = check_cams(cams)) return e;
     if (B == 0) return DROSFM_OK;
-    DROSFM_REQUIRE(g_uv && depth, DROSFM_EINVAL, "warp_coords_bwd: NULL g_uv/depth");
+    if (int e = check_cams(cams)) return e;
+    DROSFM_REQUIRE((g_uv && depth) || H * W == 0, DROSFM_EINVAL, "warp_coords_bwd: NULL g_uv/depth");
     DROSFM_REQUIRE(g_pose == nullptr || (ws != nullptr && cams->pose != nullptr), DROSFM_EINVAL,
                    "warp_coords_bwd: g_pose needs ws and cams->pose");
     const int P = H * W;

@@ -210,7 +210,7 @@ feat_cost_bwd_nchw(const float* __restrict__ g_cost, const float* __restrict__ f
             if (active) {
                 Warp wp;
                 warp_pixel(cam[v], x, y, d, wm1, hm1, true, wp);
-                gd += warp_pixel_adjoint(cam[v], wp, wm1, hm1, true, gx[v] * t[v].mx, gy[v] * t[v].my, gT);
+                gd += warp_pixel_adjoint(cam[v], wp, d, wm1, hm1, true, gx[v] * t[v].mx, gy[v] * t[v].my, gT);
             }
             if (vg.g_pose[v] != nullptr) {
                 Slot* slot = ws + (v * B + b);
@@ -424,7 +424,7 @@ feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ f
             if (active) {
                 Warp wp;
                 warp_pixel(cam[v], x, y, d, wm1, hm1, true, wp);
-                gd += warp_pixel_adjoint(cam[v], wp, wm1, hm1, true, gx[v] * t[v].mx, gy[v] * t[v].my, gT);
+                gd += warp_pixel_adjoint(cam[v], wp, d, wm1, hm1, true, gx[v] * t[v].mx, gy[v] * t[v].my, gT);
             }
             if (vg.g_pose[v] != nullptr) {
                 Slot* slot = ws + (v * B + b);
@@ -486,8 +486,8 @@ extern "C" {
 int drosfm_feat_cost_fwd(const float* fmap, const float* const* fmap_ref, const float* depth, int depth_kind,
                          const drosfm_cams_t* cams, const float* const* poses, int n_views, float* cost,
                          int B, int C, int h, int w, int layout, drosfm_stream_t stream) {
-    if (int e = check_cost_args(cams, fmap_ref, poses, n_views, B, C, h, w, layout)) return e;
     if (B == 0 || C == 0 || h * w == 0) return DROSFM_OK;
+    if (int e = check_cost_args(cams, fmap_ref, poses, n_views, B, C, h, w, layout)) return e;
     DROSFM_REQUIRE(fmap && depth && cost, DROSFM_EINVAL, "feat_cost_fwd: NULL argument");
     ViewPtrs vp{};
     for (int v = 0; v < n_views; ++v) { vp.ref[v] = fmap_ref[v]; vp.pose[v] = poses[v]; }
@@ -515,8 +515,8 @@ int drosfm_feat_cost_bwd(const float* g_cost, const float* fmap, const float* co
                          int depth_kind, const drosfm_cams_t* cams, const float* const* poses, int n_views,
                          float* g_fmap, float* const* g_fmap_ref, float* g_depth, float* const* g_poses, void* ws,
                          int B, int C, int h, int w, int layout, drosfm_stream_t stream) {
+    if (B == 0 || h * w == 0 || C == 0) return DROSFM_OK;
     if (int e = check_cost_args(cams, fmap_ref, poses, n_views, B, C, h, w, layout)) return e;
-    if (B == 0 || h * w == 0) return DROSFM_OK;
     DROSFM_REQUIRE(g_cost && fmap && depth, DROSFM_EINVAL, "feat_cost_bwd: NULL argument");
     ViewPtrs vp{};
     ViewGrads vg{};

@@ -237,7 +237,7 @@ view_synthesis_bwd_kernel(const float* __restrict__ g_out, const float* __restri
             if (g_src != nullptr) scatter_taps(g_src + (static_cast<size_t>(b) * C + ch) * sp, Ws, t, w, m, g);
         }
         if (active) {
-            const float gd = warp_pixel_adjoint(cam, wp, wm1, hm1, true, gx * t.mx, gy * t.my, gT);
+            const float gd = warp_pixel_adjoint(cam, wp, to_depth(dv, depth_kind), wm1, hm1, true, gx * t.mx, gy * t.my, gT);
             if (g_depth != nullptr)
                 g_depth[static_cast<size_t>(b) * P + p] = depth_kind == DROSFM_INV_DEPTH ? inv2depth_grad(dv, gd) : gd;
         }
@@ -294,8 +294,8 @@ int drosfm_view_synthesis_fwd(const float* src, const float* depth, int depth_ki
                               float* out, int B, int C, int Hs, int Ws, int H, int W, int padding,
                               drosfm_stream_t stream) {
     if (int e = check_gather(B, C, Hs, Ws, H, W, padding)) return e;
-    DROSFM_REQUIRE(cams && cams->K && cams->Kref, DROSFM_EINVAL, "view_synthesis_fwd: NULL cams");
     if (B == 0 || C == 0 || H * W == 0) return DROSFM_OK;
+    DROSFM_REQUIRE(cams && cams->K && cams->Kref, DROSFM_EINVAL, "view_synthesis_fwd: NULL cams");
     DROSFM_REQUIRE(src && depth && out, DROSFM_EINVAL, "view_synthesis_fwd: NULL argument");
     DROSFM_REQUIRE(Hs > 0 && Ws > 0, DROSFM_EINVAL, "view_synthesis_fwd: empty source");
     const int P = H * W;
@@ -312,8 +312,8 @@ int drosfm_view_synthesis_bwd(const float* g_out, const float* src, const float*
                               const drosfm_cams_t* cams, float* g_src, float* g_depth, float* g_pose, void* ws,
                               int B, int C, int Hs, int Ws, int H, int W, int padding, drosfm_stream_t stream) {
     if (int e = check_gather(B, C, Hs, Ws, H, W, padding)) return e;
-    DROSFM_REQUIRE(cams && cams->K && cams->Kref, DROSFM_EINVAL, "view_synthesis_bwd: NULL cams");
     if (B == 0) return DROSFM_OK;
+    DROSFM_REQUIRE(cams && cams->K && cams->Kref, DROSFM_EINVAL, "view_synthesis_bwd: NULL cams");
     DROSFM_REQUIRE(g_out && src && depth, DROSFM_EINVAL, "view_synthesis_bwd: NULL argument");
     DROSFM_REQUIRE(g_pose == nullptr || (ws != nullptr && cams->pose != nullptr), DROSFM_EINVAL,
                    "view_synthesis_bwd: g_pose needs ws and cams->pose");

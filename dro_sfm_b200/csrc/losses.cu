@@ -1,0 +1,384 @@
+// Scalar-loss kernels next to the photometric term.
+//
+//   drosfm_smoothness_*   calc_smoothness_loss (dro_sfm/losses/multiview_photometric_loss_mf.py:273-299),
+//                         calc_smoothness / inv_depths_normalize (dro_sfm/utils/depth.py:147-199),
+//                         gradient_x / gradient_y (dro_sfm/utils/image.py:134-162)
+//   drosfm_reproj_loss_*  SupervisedDepthPoseLoss.get_ref_coords / calc_pose_loss
+//                         (dro_sfm/losses/supervised_loss.py:279-325)
+//
+// Smoothness: the edge weights exp(-mean_c |dI|) do not depend on the prediction, so one pass over the
+// image serves all n predictions (12 + 4n bytes per pixel instead of n * 16).  The loss is homogeneous
+// of degree one in the mean-normalised inverse depth, which turns the gradient through the per-sample
+// mean into  -L_{i,b} / (mean * P)  (Euler's theorem) and makes the backward a single streaming pass.
+//
+// Reprojection loss: the GT-pose coordinates are identical for every prediction; one pass over the GT
+// depth evaluates all V + V*n projections per pixel (4 bytes per pixel of HBM traffic).
+#include "common.cuh"
+
+namespace drosfm {
+
+constexpr int kLossThreads = 256;
+
+struct DepthList {
+    const float* d[DROSFM_MAX_PREDS];
+};
+struct DepthGrads {
+    float* g[DROSFM_MAX_PREDS];
+};
+
+// ------------------------------------------------------------------------------------------
+// smoothness
+// ------------------------------------------------------------------------------------------
+// pass 1: per (prediction, sample) mean of the inverse depth -> stats[(i*B+b)*4 + 0]
+__global__ void __launch_bounds__(kLossThreads)
+smooth_mean_kernel(const __grid_constant__ DepthList dl, float* __restrict__ stats, Slot* ws, int B, int P) {
+    __shared__ double red[kLossThreads / 32];
+    __shared__ int flag;
+    const int ib = blockIdx.y;                 // i * B + b
+    const int i = ib / B, b = ib - i * B;
+    const float* d = dl.d[i] + static_cast<size_t>(b) * P;
+    double s = 0.0;
+    for (int p = blockIdx.x * kLossThreads + threadIdx.x; p < P; p += gridDim.x * kLossThreads) s += __ldg(d + p);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    Slot* slot = ws + ib;
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < kLossThreads / 32; ++k) t += red[k];
+        atomicAdd(&slot->acc[0], t);
+    }
+    if (last_block(slot, gridDim.x, &flag) && threadIdx.x == 0) {
+        stats[ib * 4 + 0] = static_cast<float>(__ldcg(&slot->acc[0]) / static_cast<double>(P));
+        slot->acc[0] = 0.0;
+        slot->ticket = 0ull;
+    }
+}
+
+__device__ __forceinline__ float edge_weight(const float* __restrict__ img, int P, int p, int q) {
+    const float a = fabsf(__ldg(img + p) - __ldg(img + q)) + fabsf(__ldg(img + P + p) - __ldg(img + P + q)) +
+                    fabsf(__ldg(img + 2 * P + p) - __ldg(img + 2 * P + q));
+    return expf(-(a / 3.0f));
+}
+
+// pass 2: sums of |dx|*wx and |dy|*wy per (prediction, sample); the last block folds them into the loss
+__global__ void __launch_bounds__(kLossThreads)
+smooth_fwd_kernel(const float* __restrict__ image, const __grid_constant__ DepthList dl, int n_preds, float weight,
+                  float* __restrict__ stats, float* __restrict__ loss, Slot* ws, int B, int H, int W) {
+    __shared__ double red[2 * (kLossThreads / 32)];
+    __shared__ int flag;
+    const int b = blockIdx.y, P = H * W;
+    const float* img = image + static_cast<size_t>(b) * 3 * P;
+    float sx[DROSFM_MAX_PREDS], sy[DROSFM_MAX_PREDS];
+#pragma unroll
+    for (int i = 0; i < DROSFM_MAX_PREDS; ++i) sx[i] = sy[i] = 0.0f;
+    for (int p = blockIdx.x * kLossThreads + threadIdx.x; p < P; p += gridDim.x * kLossThreads) {
+        const int y = p / W, x = p - y * W;
+        const bool hx = x + 1 < W, hy = y + 1 < H;
+        const float wx = hx ? edge_weight(img, P, p, p + 1) : 0.0f;
+        const float wy = hy ? edge_weight(img, P, p, p + W) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < DROSFM_MAX_PREDS; ++i) {
+            if (i < n_preds) {
+                const float* d = dl.d[i] + static_cast<size_t>(b) * P;
+                const float m = fmaxf(stats[(i * B + b) * 4], 1e-6f);
+                const float dc = __ldg(d + p) / m;
+                if (hx) sx[i] += fabsf((dc - __ldg(d + p + 1) / m) * wx);
+                if (hy) sy[i] += fabsf((dc - __ldg(d + p + W) / m) * wy);
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < DROSFM_MAX_PREDS; ++i) {
+        if (i >= n_preds) break;
+        const double a = warp_sum(static_cast<double>(sx[i])), c = warp_sum(static_cast<double>(sy[i]));
+        if (lane == 0) { red[2 * wid] = a; red[2 * wid + 1] = c; }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            double t = 0.0;
+            for (int k = 0; k < kLossThreads / 32; ++k) t += red[2 * k + threadIdx.x];
+            if (t != 0.0) atomicAdd(&ws[i * B + b].acc[threadIdx.x], t);
+        }
+        __syncthreads();
+    }
+    Slot* ticket = ws + n_preds * B;
+    if (last_block(ticket, gridDim.x * gridDim.y, &flag) && threadIdx.x == 0) {
+        const double nx = static_cast<double>(B) * H * (W - 1), ny = static_cast<double>(B) * (H - 1) * W;
+        double total = 0.0, pw = 1.0;
+        for (int i = 0; i < n_preds; ++i) {
+            double tx = 0.0, ty = 0.0;
+            for (int bb = 0; bb < B; ++bb) {
+                Slot* s = ws + i * B + bb;
+                const double ax = __ldcg(&s->acc[0]), ay = __ldcg(&s->acc[1]);
+                s->acc[0] = 0.0;
+                s->acc[1] = 0.0;
+                stats[(i * B + bb) * 4 + 1] = static_cast<float>(ax);
+                stats[(i * B + bb) * 4 + 2] = static_cast<float>(ay);
+                tx += ax;
+                ty += ay;
+            }
+            total += ((nx > 0 ? tx / nx : 0.0) + (ny > 0 ? ty / ny : 0.0)) / pw;
+            pw *= 2.0;
+        }
+        ticket->ticket = 0ull;
+        *loss = static_cast<float>(static_cast<double>(weight) * (total / n_preds));
+    }
+}
+
+__device__ __forceinline__ float sgn(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
+
+__global__ void __launch_bounds__(kLossThreads)
+smooth_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict__ image, const __grid_constant__ DepthList dl,
+                  int n_preds, float weight, const float* __restrict__ stats, const __grid_constant__ DepthGrads dg,
+                  int accumulate, int B, int H, int W) {
+    const int b = blockIdx.y, P = H * W;
+    const int p = blockIdx.x * kLossThreads + threadIdx.x;
+    if (p >= P) return;
+    const float* img = image + static_cast<size_t>(b) * 3 * P;
+    const int y = p / W, x = p - y * W;
+    const bool xr = x + 1 < W, xl = x > 0, yd = y + 1 < H, yu = y > 0;
+    const float w_r = xr ? edge_weight(img, P, p, p + 1) : 0.0f;
+    const float w_l = xl ? edge_weight(img, P, p - 1, p) : 0.0f;
+    const float w_d = yd ? edge_weight(img, P, p, p + W) : 0.0f;
+    const float w_u = yu ? edge_weight(img, P, p - W, p) : 0.0f;
+    const float g0 = __ldg(g_loss) * weight / static_cast<float>(n_preds);
+    const float nx = static_cast<float>(B) * H * (W - 1), ny = static_cast<float>(B) * (H - 1) * W;
+    float pw = 1.0f;
+    for (int i = 0; i < n_preds; ++i, pw *= 2.0f) {
+        float* go = dg.g[i];
+        if (go == nullptr) continue;
+        const float* d = dl.d[i] + static_cast<size_t>(b) * P;
+        const float* st = stats + (i * B + b) * 4;
+        const float mean = st[0], m = fmaxf(mean, 1e-6f);
+        const float kx = nx > 0.0f ? g0 / (pw * nx) : 0.0f, ky = ny > 0.0f ? g0 / (pw * ny) : 0.0f;
+        const float dc = __ldg(d + p) / m;
+        // d L / d dn[p], dn = d / m (the normalised values are formed exactly as in the forward pass)
+        float h = 0.0f;
+        if (xr) h += kx * w_r * sgn(dc - __ldg(d + p + 1) / m);
+        if (xl) h -= kx * w_l * sgn(__ldg(d + p - 1) / m - dc);
+        if (yd) h += ky * w_d * sgn(dc - __ldg(d + p + W) / m);
+        if (yu) h -= ky * w_u * sgn(__ldg(d + p - W) / m - dc);
+        float g = h / m;
+        if (mean >= 1e-6f) g -= (kx * st[1] + ky * st[2]) / (m * static_cast<float>(P));
+        const size_t o = static_cast<size_t>(b) * P + p;
+        go[o] = accumulate ? go[o] + g : g;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// reprojection pose loss
+// ------------------------------------------------------------------------------------------
+struct ReprojPtrs {
+    const float* gt[DROSFM_MAX_VIEWS];
+    const float* pred[DROSFM_MAX_VIEWS * DROSFM_MAX_PREDS];
+    float* g_pred[DROSFM_MAX_VIEWS * DROSFM_MAX_PREDS];
+    float weight[DROSFM_MAX_PREDS];
+};
+
+// source-camera part of the setup only (the target side is shared by all poses of a sample)
+__device__ __forceinline__ void setup_src(const drosfm_cams_t& c, const float* pose, int b, Cam& base, Cam& out) {
+    out = base;
+    load_pose(pose, c.pose_kind, b, out.T, out.trig);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        out.c[k] = out.T[4 * k] * out.Rt[3] + out.T[4 * k + 1] * out.Rt[7] + out.T[4 * k + 2] * out.Rt[11] + out.T[4 * k + 3];
+}
+
+// One block = a strip of pixels of one sample; loops over all (view, prediction) pairs.
+// MODE 0: forward sums per prediction.  MODE 1: backward, pose gradients per (view, prediction).
+template <int MODE>
+__global__ void __launch_bounds__(kLossThreads)
+reproj_kernel(const float* __restrict__ g_loss, const float* __restrict__ depth, int depth_kind, drosfm_cams_t cams,
+              const __grid_constant__ ReprojPtrs rp, int V, int n_preds, float min_depth, float max_depth, float wsum,
+              float* __restrict__ loss, Slot* ws, int B, int H, int W) {
+    __shared__ Cam base, cgt, cpr;
+    __shared__ double red[12 * (kLossThreads / 32)];
+    __shared__ int flag;
+    const int b = blockIdx.y, P = H * W;
+    const float wm1 = static_cast<float>(W - 1), hm1 = static_cast<float>(H - 1);
+    if (threadIdx.x == 0) setup_cam(cams, nullptr, b, base);
+    __syncthreads();
+    const float dmax = max_depth / 4.0f;
+    const int stride = gridDim.x * kLossThreads;
+    for (int v = 0; v < V; ++v) {
+        if (threadIdx.x == 0) setup_src(cams, rp.gt[v], b, base, cgt);
+        for (int i = 0; i < n_preds; ++i) {
+            __syncthreads();
+            if (threadIdx.x == 0) setup_src(cams, rp.pred[v * n_preds + i], b, base, cpr);
+            __syncthreads();
+            float acc = 0.0f;
+            float gT[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) gT[k] = 0.0f;
+            // d loss / d |diff| for this (view, prediction): w_i / (V * wsum * numel)
+            const float kscale = MODE == 1 ? __ldg(g_loss) * rp.weight[i] /
+                                                 (static_cast<float>(V) * wsum * 2.0f * static_cast<float>(B) * static_cast<float>(P))
+                                           : 0.0f;
+            for (int p = blockIdx.x * kLossThreads + threadIdx.x; p < P; p += stride) {
+                const int y = p / W, x = p - y * W;
+                const float d = to_depth(__ldg(depth + static_cast<size_t>(b) * P + p), depth_kind);
+                if (!(d > min_depth && d < dmax)) continue;
+                Warp wg, wp;
+                warp_pixel(cgt, x, y, d, wm1, hm1, true, wg);
+                warp_pixel(cpr, x, y, d, wm1, hm1, true, wp);
+                const bool vu = wg.p.u >= -1.0f && wg.p.u <= 1.0f && wp.p.u >= -1.0f && wp.p.u <= 1.0f;
+                const bool vv = wg.p.v >= -1.0f && wg.p.v <= 1.0f && wp.p.v >= -1.0f && wp.p.v <= 1.0f;
+                const float du = wp.p.u - wg.p.u, dv = wp.p.v - wg.p.v;
+                if (MODE == 0) {
+                    if (vu) acc += fminf(fabsf(du), 1.0f);
+                    if (vv) acc += fminf(fabsf(dv), 1.0f);
+                } else {
+                    const float gu = (vu && fabsf(du) <= 1.0f) ? kscale * sgn(du) : 0.0f;
+                    const float gv = (vv && fabsf(dv) <= 1.0f) ? kscale * sgn(dv) : 0.0f;
+                    if (gu != 0.0f || gv != 0.0f) warp_pixel_adjoint(cpr, wp, d, wm1, hm1, true, gu, gv, gT);
+                }
+            }
+            if (MODE == 0) {
+                block_accumulate<1>(&acc, red, ws[i].acc);
+            } else if (rp.g_pred[v * n_preds + i] != nullptr) {
+                Slot* slot = ws + ((v * n_preds + i) * B + b);
+                block_accumulate<12>(gT, red, slot->acc);
+                if (last_block(slot, gridDim.x, &flag) && threadIdx.x == 0) {
+                    const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
+                    finish_pose_grad(slot, cams.pose_kind, eul ? rp.pred[v * n_preds + i] + b * 6 : nullptr,
+                                     rp.g_pred[v * n_preds + i] + b * (eul ? 6 : 16));
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (MODE == 0) {
+        Slot* ticket = ws + n_preds;
+        if (last_block(ticket, gridDim.x * gridDim.y, &flag) && threadIdx.x == 0) {
+            const double numel = 2.0 * static_cast<double>(B) * P;
+            double total = 0.0;
+            for (int i = 0; i < n_preds; ++i) {
+                total += static_cast<double>(rp.weight[i]) * (__ldcg(&ws[i].acc[0]) / numel / V);
+                ws[i].acc[0] = 0.0;
+            }
+            ticket->ticket = 0ull;
+            *loss = static_cast<float>(total / static_cast<double>(wsum));
+        }
+    }
+}
+
+static int strip_blocks(int P, int B) {
+    int need = (P + kLossThreads - 1) / kLossThreads;
+    int cap = (kNumSMs * 4 + B - 1) / (B > 0 ? B : 1);
+    if (cap < 1) cap = 1;
+    if (need < 1) need = 1;
+    return need < cap ? need : cap;
+}
+
+static int fill_reproj(ReprojPtrs& rp, float& wsum, const float* const* gt_poses, const float* const* pred_poses,
+                       int n_views, int n_preds, float gamma) {
+    DROSFM_REQUIRE(n_views >= 1 && n_views <= DROSFM_MAX_VIEWS, DROSFM_ERANGE, "reproj_loss: n_views=%d outside [1,%d]", n_views,
+                   DROSFM_MAX_VIEWS);
+    DROSFM_REQUIRE(n_preds >= 1 && n_preds <= DROSFM_MAX_PREDS, DROSFM_ERANGE, "reproj_loss: n_preds=%d outside [1,%d]", n_preds,
+                   DROSFM_MAX_PREDS);
+    DROSFM_REQUIRE(gt_poses && pred_poses, DROSFM_EINVAL, "reproj_loss: NULL pose arrays");
+    for (int v = 0; v < n_views; ++v) {
+        DROSFM_REQUIRE(gt_poses[v] != nullptr, DROSFM_EINVAL, "reproj_loss: gt_poses[%d] is NULL", v);
+        rp.gt[v] = gt_poses[v];
+    }
+    for (int k = 0; k < n_views * n_preds; ++k) {
+        DROSFM_REQUIRE(pred_poses[k] != nullptr, DROSFM_EINVAL, "reproj_loss: pred_poses[%d] is NULL", k);
+        rp.pred[k] = pred_poses[k];
+    }
+    double sum = 0.0;
+    for (int i = 0; i < n_preds; ++i) {
+        double wgt = 1.0;
+        for (int k = 0; k < n_preds - 1 - i; ++k) wgt *= static_cast<double>(gamma);
+        rp.weight[i] = static_cast<float>(wgt);
+        sum += wgt;
+    }
+    wsum = static_cast<float>(sum);
+    return DROSFM_OK;
+}
+
+}  // namespace drosfm
+
+using namespace drosfm;
+
+extern "C" {
+
+int drosfm_smoothness_fwd(const float* image, const float* const* inv_depths, int n_preds, float weight, float* stats,
+                          float* loss, void* ws, int B, int H, int W, drosfm_stream_t stream) {
+    DROSFM_REQUIRE(n_preds >= 1 && n_preds <= DROSFM_MAX_PREDS, DROSFM_ERANGE, "smoothness_fwd: n_preds=%d outside [1,%d]",
+                   n_preds, DROSFM_MAX_PREDS);
+    DROSFM_REQUIRE(B > 0 && H > 0 && W > 0, DROSFM_EINVAL, "smoothness_fwd: empty input");
+    DROSFM_REQUIRE(B * n_preds <= 65535 && static_cast<long long>(H) * W < (1ll << 30), DROSFM_ERANGE, "smoothness_fwd: too large");
+    DROSFM_REQUIRE(image && inv_depths && stats && loss && ws, DROSFM_EINVAL, "smoothness_fwd: NULL argument");
+    DepthList dl{};
+    for (int i = 0; i < n_preds; ++i) {
+        DROSFM_REQUIRE(inv_depths[i] != nullptr, DROSFM_EINVAL, "smoothness_fwd: inv_depths[%d] is NULL", i);
+        dl.d[i] = inv_depths[i];
+    }
+    const int P = H * W;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int mb = (P + kLossThreads * 8 - 1) / (kLossThreads * 8);
+    if (mb > 64) mb = 64;
+    smooth_mean_kernel<<<dim3(mb, n_preds * B), kLossThreads, 0, s>>>(dl, stats, static_cast<Slot*>(ws), B, P);
+    if (int e = launch_status("smoothness_fwd (mean)")) return e;
+    smooth_fwd_kernel<<<dim3(strip_blocks(P, B), B), kLossThreads, 0, s>>>(image, dl, n_preds, weight, stats, loss,
+                                                                           static_cast<Slot*>(ws), B, H, W);
+    return launch_status("smoothness_fwd");
+}
+
+int drosfm_smoothness_bwd(const float* g_loss, const float* image, const float* const* inv_depths, int n_preds, float weight,
+                          const float* stats, float* const* g_inv_depths, int accumulate, int B, int H, int W,
+                          drosfm_stream_t stream) {
+    DROSFM_REQUIRE(n_preds >= 1 && n_preds <= DROSFM_MAX_PREDS, DROSFM_ERANGE, "smoothness_bwd: n_preds=%d outside [1,%d]",
+                   n_preds, DROSFM_MAX_PREDS);
+    DROSFM_REQUIRE(B > 0 && H > 0 && W > 0, DROSFM_EINVAL, "smoothness_bwd: empty input");
+    DROSFM_REQUIRE(g_loss && image && inv_depths && stats && g_inv_depths, DROSFM_EINVAL, "smoothness_bwd: NULL argument");
+    DepthList dl{};
+    DepthGrads dg{};
+    for (int i = 0; i < n_preds; ++i) {
+        DROSFM_REQUIRE(inv_depths[i] != nullptr, DROSFM_EINVAL, "smoothness_bwd: inv_depths[%d] is NULL", i);
+        dl.d[i] = inv_depths[i];
+        dg.g[i] = g_inv_depths[i];
+    }
+    const int P = H * W;
+    smooth_bwd_kernel<<<dim3((P + kLossThreads - 1) / kLossThreads, B), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        g_loss, image, dl, n_preds, weight, stats, dg, accumulate, B, H, W);
+    return launch_status("smoothness_bwd");
+}
+
+int drosfm_reproj_loss_fwd(const float* depth, int depth_kind, const drosfm_cams_t* cams, const float* const* gt_poses,
+                           const float* const* pred_poses, int n_views, int n_preds, float min_depth, float max_depth,
+                           float gamma, float* loss, void* ws, int B, int H, int W, drosfm_stream_t stream) {
+    DROSFM_REQUIRE(B > 0 && H > 0 && W > 0, DROSFM_EINVAL, "reproj_loss_fwd: empty input");
+    DROSFM_REQUIRE(B <= 65535 && static_cast<long long>(H) * W < (1ll << 30), DROSFM_ERANGE, "reproj_loss_fwd: too large");
+    DROSFM_REQUIRE(cams && cams->K && cams->Kref && depth && loss && ws, DROSFM_EINVAL, "reproj_loss_fwd: NULL argument");
+    DROSFM_REQUIRE(cams->pose_kind == DROSFM_POSE_MAT4 || cams->pose_kind == DROSFM_POSE_EULER6, DROSFM_EINVAL,
+                   "reproj_loss_fwd: pose_kind must be MAT4 or EULER6");
+    ReprojPtrs rp{};
+    float wsum = 1.0f;
+    if (int e = fill_reproj(rp, wsum, gt_poses, pred_poses, n_views, n_preds, gamma)) return e;
+    reproj_kernel<0><<<dim3(strip_blocks(H * W, B), B), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        nullptr, depth, depth_kind, *cams, rp, n_views, n_preds, min_depth, max_depth, wsum, loss, static_cast<Slot*>(ws), B, H, W);
+    return launch_status("reproj_loss_fwd");
+}
+
+int drosfm_reproj_loss_bwd(const float* g_loss, const float* depth, int depth_kind, const drosfm_cams_t* cams,
+                           const float* const* gt_poses, const float* const* pred_poses, int n_views, int n_preds,
+                           float min_depth, float max_depth, float gamma, float* const* g_pred_poses, void* ws,
+                           int B, int H, int W, drosfm_stream_t stream) {
+    DROSFM_REQUIRE(B > 0 && H > 0 && W > 0, DROSFM_EINVAL, "reproj_loss_bwd: empty input");
+    DROSFM_REQUIRE(B <= 65535 && static_cast<long long>(H) * W < (1ll << 30), DROSFM_ERANGE, "reproj_loss_bwd: too large");
+    DROSFM_REQUIRE(cams && cams->K && cams->Kref && depth && g_loss && ws && g_pred_poses, DROSFM_EINVAL,
+                   "reproj_loss_bwd: NULL argument");
+    DROSFM_REQUIRE(cams->pose_kind == DROSFM_POSE_MAT4 || cams->pose_kind == DROSFM_POSE_EULER6, DROSFM_EINVAL,
+                   "reproj_loss_bwd: pose_kind must be MAT4 or EULER6");
+    ReprojPtrs rp{};
+    float wsum = 1.0f;
+    if (int e = fill_reproj(rp, wsum, gt_poses, pred_poses, n_views, n_preds, gamma)) return e;
+    for (int k = 0; k < n_views * n_preds; ++k) rp.g_pred[k] = g_pred_poses[k];
+    reproj_kernel<1><<<dim3(strip_blocks(H * W, B), B), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        g_loss, depth, depth_kind, *cams, rp, n_views, n_preds, min_depth, max_depth, wsum, nullptr, static_cast<Slot*>(ws), B, H, W);
+    return launch_status("reproj_loss_bwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,604 @@
+// Kernel family 4: single-pass multi-view photometric loss (SSIM + L1, auto-mask, per-pixel min).
+//
+//   SSIM                      dro_sfm/losses/multiview_photometric_loss_mf.py:15-54
+//   warp_ref_image            :132-171   (view_synthesis of every source view for every prediction)
+//   calc_photometric_loss     :194-229   (clamp((1-SSIM)/2,0,1), 0.85*mean_c ssim + 0.15*mean_c |a-b|)
+//   auto-mask                 :346-351   (un-warped source maps join the per-pixel min)
+//   reduce_photometric_loss   :231-269   (cat(2V maps).min(1).mean(), gamma-decay over predictions)
+//
+// One block owns a 2-D tile of one (sample, prediction).  For every source view it warps the source
+// into shared memory (tile + halo; the coordinate chain of common.cuh is fused in, nothing is
+// materialised in HBM), evaluates the 3x3 SSIM statistics with a sliding window over shared memory,
+// and keeps the running per-pixel minimum in registers.  Reflection padding of the SSIM window
+// (ReflectionPad2d(1)) is an index remap into the same tile.  The un-warped (auto-mask) minimum does
+// not depend on the prediction and is computed once per step by drosfm_automask_fwd instead of once per
+// prediction.  The loss scalar is reduced in fp64; sel records the arg-min view for the backward pass.
+//
+// Backward: dSSIM_p/dx_q = A_p + B_p x_q + C_p y_q for every tap q of the window of p, so the gradient
+// w.r.t. a warped pixel is a 3x3 box sum (with reflection multiplicities) of three coefficient maps,
+// evaluated on tile + halo 1 from warped values on tile + halo 2, then pushed through the bilinear
+// taps and the projection adjoint to d/d(inv_depth) and the fp64-reduced pose gradients.
+//
+// Algorithmic bytes per pixel and prediction: fwd 16 + 12 V (target 12 + depth 4 + V sources 12),
+// bwd 20 + 12 V.
+#include "common.cuh"
+
+namespace drosfm {
+
+constexpr int kPhotoThreads = 128;   // 32 columns x 4 row groups
+constexpr int kGroups = 4;
+
+struct PhotoPtrs {
+    const float* context[DROSFM_MAX_VIEWS];
+    const float* inv_depth[DROSFM_MAX_PREDS];
+    const float* pose[DROSFM_MAX_VIEWS * DROSFM_MAX_PREDS];
+    float weight[DROSFM_MAX_PREDS];   // gamma^(n-1-i)
+};
+struct PhotoGrads {
+    float* g_inv_depth[DROSFM_MAX_PREDS];
+    float* g_pose[DROSFM_MAX_VIEWS * DROSFM_MAX_PREDS];
+};
+
+__device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __forceinline__ float tap3(const float* __restrict__ plane, int Ws, const Taps& t, const Weights& w) {
+    float acc = 0.0f;
+    const float* r0 = plane + t.y0 * Ws + t.x0;
+    if (t.valid & 1u) acc += __ldg(r0) * w.nw;
+    if (t.valid & 2u) acc += __ldg(r0 + 1) * w.ne;
+    if (t.valid & 4u) acc += __ldg(r0 + Ws) * w.sw;
+    if (t.valid & 8u) acc += __ldg(r0 + Ws + 1) * w.se;
+    return acc;
+}
+
+// SSIM statistics of one window: sums over the 9 taps
+struct Win {
+    float sx, sy, sxx, syy, sxy;
+};
+
+struct Ssim {
+    float mu_x, mu_y, A1, A2, B1, B2, s;
+};
+
+__device__ __forceinline__ Ssim ssim_from(const Win& w, float C1, float C2) {
+    const float inv9 = 1.0f / 9.0f;
+    Ssim r;
+    r.mu_x = __fmul_rn(w.sx, inv9);
+    r.mu_y = __fmul_rn(w.sy, inv9);
+    const float mu_xy = __fmul_rn(r.mu_x, r.mu_y), mu_xx = __fmul_rn(r.mu_x, r.mu_x), mu_yy = __fmul_rn(r.mu_y, r.mu_y);
+    const float sig_x = __fsub_rn(__fmul_rn(w.sxx, inv9), mu_xx);
+    const float sig_y = __fsub_rn(__fmul_rn(w.syy, inv9), mu_yy);
+    const float sig_xy = __fsub_rn(__fmul_rn(w.sxy, inv9), mu_xy);
+    r.A1 = __fadd_rn(__fmul_rn(2.0f, mu_xy), C1);
+    r.A2 = __fadd_rn(__fmul_rn(2.0f, sig_xy), C2);
+    r.B1 = __fadd_rn(__fadd_rn(mu_xx, mu_yy), C1);
+    r.B2 = __fadd_rn(__fadd_rn(sig_x, sig_y), C2);
+    r.s = __fdiv_rn(__fmul_rn(r.A1, r.A2), __fmul_rn(r.B1, r.B2));
+    return r;
+}
+
+// horizontal 3-tap sums of one shared-memory row
+__device__ __forceinline__ Win row_sums(const float* __restrict__ xr, const float* __restrict__ yr, int cm, int c0, int cp,
+                                        float& xc, float& yc) {
+    const float x0 = xr[cm], x1 = xr[c0], x2 = xr[cp];
+    const float y0 = yr[cm], y1 = yr[c0], y2 = yr[cp];
+    xc = x1;
+    yc = y1;
+    Win w;
+    w.sx = x0 + x1 + x2;
+    w.sy = y0 + y1 + y2;
+    w.sxx = x0 * x0 + x1 * x1 + x2 * x2;
+    w.syy = y0 * y0 + y1 * y1 + y2 * y2;
+    w.sxy = x0 * y0 + x1 * y1 + x2 * y2;
+    return w;
+}
+
+__device__ __forceinline__ Win add3(const Win& a, const Win& b, const Win& c) {
+    Win w;
+    w.sx = a.sx + b.sx + c.sx;
+    w.sy = a.sy + b.sy + c.sy;
+    w.sxx = a.sxx + b.sxx + c.sxx;
+    w.syy = a.syy + b.syy + c.syy;
+    w.sxy = a.sxy + b.sxy + c.sxy;
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward (MODE 0) and auto-mask pre-pass (MODE 1)
+// ------------------------------------------------------------------------------------------
+constexpr int FW = 32, FH = 32, FSW = FW + 2, FSH = FH + 2, FRPT = FH / kGroups;
+
+template <int MODE>
+__global__ void __launch_bounds__(kPhotoThreads)
+photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ PhotoPtrs pp, int V, int depth_kind, int n_preds,
+                       drosfm_cams_t cams, const float* __restrict__ automask_in, drosfm_photo_opts_t opts,
+                       float l1_w, uint8_t* __restrict__ sel_out, float* __restrict__ automask_out,
+                       float* __restrict__ loss, Slot* ws, int B, int H, int W) {
+    __shared__ float ys[3][FSH][FSW];
+    __shared__ float xs[3][FSH][FSW];
+    __shared__ Cam cam[MODE == 0 ? DROSFM_MAX_VIEWS : 1];
+    __shared__ double red[kGroups];
+    __shared__ int flag;
+    const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
+    const int tx0 = blockIdx.x * FW, ty0 = blockIdx.y * FH;
+    const int b = MODE == 0 ? static_cast<int>(blockIdx.z) % B : static_cast<int>(blockIdx.z);
+    const int ip = MODE == 0 ? static_cast<int>(blockIdx.z) / B : 0;
+    const int P = H * W;
+    const float wm1 = static_cast<float>(W - 1), hm1 = static_cast<float>(H - 1);
+
+    for (int idx = tid; idx < 3 * FSH * FSW; idx += kPhotoThreads) {
+        const int c = idx / (FSH * FSW), rem = idx - c * (FSH * FSW);
+        const int ry = rem / FSW, rx = rem - ry * FSW;
+        const int gy = ty0 - 1 + ry, gx = tx0 - 1 + rx;
+        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        ys[c][ry][rx] = in ? __ldg(image + (static_cast<size_t>(b) * 3 + c) * P + gy * W + gx) : 0.0f;
+    }
+    if (MODE == 0 && tid < V) setup_cam(cams, pp.pose[tid * n_preds + ip], b, cam[tid]);
+    __syncthreads();
+
+    // per-thread stat rows: column gx = tx0 + lane, rows ty0 + grp*FRPT + k
+    const int gx = tx0 + lane;
+    const int gy0 = ty0 + grp * FRPT;
+    const int cm = clampi(reflect_idx(gx - 1, W) - tx0 + 1, 0, FSW - 1);
+    const int c0 = lane + 1;
+    const int cp = clampi(reflect_idx(gx + 1, W) - tx0 + 1, 0, FSW - 1);
+
+    float best[FRPT];
+    int sel[FRPT];
+    const bool use_min = opts.reduce_op == DROSFM_REDUCE_MIN;
+#pragma unroll
+    for (int k = 0; k < FRPT; ++k) {
+        best[k] = use_min ? __int_as_float(0x7f800000) : 0.0f;
+        sel[k] = 254;
+    }
+
+    for (int v = 0; v < V; ++v) {
+        // phase A: source view v on tile + halo 1
+        const float* src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
+        for (int idx = tid; idx < FSH * FSW; idx += kPhotoThreads) {
+            const int ry = idx / FSW, rx = idx - ry * FSW;
+            const int sy = ty0 - 1 + ry, sx = tx0 - 1 + rx;
+            float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+            if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+                if (MODE == 0) {
+                    const float d = to_depth(__ldg(pp.inv_depth[ip] + static_cast<size_t>(b) * P + sy * W + sx), depth_kind);
+                    Warp wp;
+                    warp_pixel(cam[v], sx, sy, d, wm1, hm1, true, wp);
+                    Taps t;
+                    make_taps(wp.p.u, wp.p.v, H, W, opts.padding, t);
+                    if (t.valid) {
+                        const Weights wt = tap_weights(t);
+                        o0 = tap3(src, W, t, wt);
+                        o1 = tap3(src + P, W, t, wt);
+                        o2 = tap3(src + 2 * P, W, t, wt);
+                    }
+                } else {
+                    o0 = __ldg(src + sy * W + sx);
+                    o1 = __ldg(src + P + sy * W + sx);
+                    o2 = __ldg(src + 2 * P + sy * W + sx);
+                }
+            }
+            xs[0][ry][rx] = o0;
+            xs[1][ry][rx] = o1;
+            xs[2][ry][rx] = o2;
+        }
+        __syncthreads();
+
+        // phase B: SSIM + L1 with a vertical sliding window
+        float ssim_acc[FRPT], l1_acc[FRPT];
+#pragma unroll
+        for (int k = 0; k < FRPT; ++k) ssim_acc[k] = l1_acc[k] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Win ra, rb;
+            float xca = 0.0f, yca = 0.0f, xcb = 0.0f, ycb = 0.0f;
+#pragma unroll
+            for (int j = 0; j < FRPT + 2; ++j) {
+                const int sr = clampi(reflect_idx(gy0 - 1 + j, H) - ty0 + 1, 0, FSH - 1);
+                float xc, yc;
+                const Win rc = row_sums(xs[c][sr], ys[c][sr], cm, c0, cp, xc, yc);
+                if (j >= 2) {
+                    const Ssim s = ssim_from(add3(ra, rb, rc), opts.C1, opts.C2);
+                    const float l = __fmul_rn(__fsub_rn(1.0f, s.s), 0.5f);
+                    ssim_acc[j - 2] += fminf(fmaxf(l, 0.0f), 1.0f);
+                    l1_acc[j - 2] += fabsf(xcb - ycb);
+                }
+                ra = rb; rb = rc;
+                xca = xcb; yca = ycb; xcb = xc; ycb = yc;
+            }
+            (void)xca; (void)yca;
+        }
+#pragma unroll
+        for (int k = 0; k < FRPT; ++k) {
+            const float pm = __fadd_rn(__fmul_rn(opts.ssim_w, __fdiv_rn(ssim_acc[k], 3.0f)),
+                                       __fmul_rn(l1_w, __fdiv_rn(l1_acc[k], 3.0f)));
+            if (use_min) {
+                if (pm < best[k]) { best[k] = pm; sel[k] = v; }
+            } else {
+                best[k] += pm;
+            }
+        }
+        __syncthreads();
+    }
+
+    // epilogue
+    float local = 0.0f;
+#pragma unroll
+    for (int k = 0; k < FRPT; ++k) {
+        const int gy = gy0 + k;
+        if (gy < H && gx < W) {
+            const size_t o = static_cast<size_t>(b) * P + gy * W + gx;
+            if (MODE == 1) {
+                automask_out[o] = best[k];
+            } else {
+                float val = best[k];
+                int s = sel[k];
+                if (automask_in != nullptr) {
+                    const float a = __ldg(automask_in + o);
+                    if (a < val) { val = a; s = 255; }
+                }
+                if (sel_out != nullptr) sel_out[static_cast<size_t>(ip) * B * P + o] = static_cast<uint8_t>(s);
+                local += val;
+            }
+        }
+    }
+    if (MODE == 1) return;
+    double part = warp_sum(static_cast<double>(local));
+    if (lane == 0) red[grp] = part;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int k = 0; k < kGroups; ++k) s += red[k];
+        atomicAdd(&ws[ip].acc[0], s);
+    }
+    Slot* ticket = ws + n_preds;
+    if (last_block(ticket, gridDim.x * gridDim.y * gridDim.z, &flag) && tid == 0) {
+        double total = 0.0;
+        const double denom = static_cast<double>(B) * P * (use_min ? 1.0 : static_cast<double>(V));
+        for (int i = 0; i < n_preds; ++i) {
+            const double mean_i = __ldcg(&ws[i].acc[0]) / denom;
+            // the reference rounds every per-prediction mean to fp32 before the weighted sum
+            total += static_cast<double>(pp.weight[i]) * static_cast<double>(static_cast<float>(mean_i));
+            ws[i].acc[0] = 0.0;
+        }
+        ticket->ticket = 0ull;
+        *loss = static_cast<float>(total);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+constexpr int CW = 32, CH = 20;                 // coefficient region (tile + halo 1)
+constexpr int IW = CW - 2, IH = CH - 2;         // interior pixels owned by the block
+constexpr int BSW = CW + 2, BSH = CH + 2;       // sample region (tile + halo 2)
+constexpr int BRPT = CH / kGroups;              // coefficient rows per thread
+
+__global__ void __launch_bounds__(kPhotoThreads)
+photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict__ image,
+                       const __grid_constant__ PhotoPtrs pp, int V,
+                       int depth_kind, int n_preds, drosfm_cams_t cams, const uint8_t* __restrict__ sel_in,
+                       drosfm_photo_opts_t opts, float l1_w, const __grid_constant__ PhotoGrads pg, Slot* ws,
+                       int B, int H, int W) {
+    __shared__ float ys[3][BSH][BSW];
+    __shared__ float xs[3][BSH][BSW];
+    __shared__ float ca[CH][CW], cb[CH][CW], cc[CH][CW];
+    __shared__ float gxs[3][IH][CW];
+    __shared__ uint8_t selt[CH][CW];
+    __shared__ Cam cam[DROSFM_MAX_VIEWS];
+    __shared__ double red[12 * kGroups];
+    __shared__ int flag;
+    const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
+    const int tx0 = blockIdx.x * IW, ty0 = blockIdx.y * IH;          // interior origin
+    const int cx0 = tx0 - 1, cy0 = ty0 - 1;                            // coefficient-region origin
+    const int sx0 = tx0 - 2, sy0 = ty0 - 2;                            // sample-region origin
+    const int b = static_cast<int>(blockIdx.z) % B, ip = static_cast<int>(blockIdx.z) / B;
+    const int P = H * W;
+    const float wm1 = static_cast<float>(W - 1), hm1 = static_cast<float>(H - 1);
+    const bool use_min = opts.reduce_op == DROSFM_REDUCE_MIN;
+    const float G = __ldg(g_loss) * pp.weight[ip] /
+                    (static_cast<float>(B) * static_cast<float>(P) * (use_min ? 1.0f : static_cast<float>(V)));
+
+    for (int idx = tid; idx < 3 * BSH * BSW; idx += kPhotoThreads) {
+        const int c = idx / (BSH * BSW), rem = idx - c * (BSH * BSW);
+        const int ry = rem / BSW, rx = rem - ry * BSW;
+        const int gy = sy0 + ry, gx = sx0 + rx;
+        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        ys[c][ry][rx] = in ? __ldg(image + (static_cast<size_t>(b) * 3 + c) * P + gy * W + gx) : 0.0f;
+    }
+    for (int idx = tid; idx < CH * CW; idx += kPhotoThreads) {
+        const int ry = idx / CW, rx = idx - ry * CW;
+        const int gy = cy0 + ry, gx = cx0 + rx;
+        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        selt[ry][rx] = in ? (use_min ? sel_in[(static_cast<size_t>(ip) * B + b) * P + gy * W + gx] : 253) : 254;
+    }
+    if (tid < V) setup_cam(cams, pp.pose[tid * n_preds + ip], b, cam[tid]);
+    __syncthreads();
+
+    // coefficient column / rows of this thread
+    const int pgx = cx0 + lane;
+    const int prow0 = grp * BRPT;                                    // first coefficient row (region coords)
+    const int cm = clampi(reflect_idx(pgx - 1, W) - sx0, 0, BSW - 1);
+    const int c0 = lane + 1;
+    const int cp = clampi(reflect_idx(pgx + 1, W) - sx0, 0, BSW - 1);
+    // interior pixels of this thread: column lane (1..IW), rows prow0+k with 1 <= row <= IH
+    const bool col_ok = lane >= 1 && lane <= IW && pgx < W;
+    float gd[BRPT];
+#pragma unroll
+    for (int k = 0; k < BRPT; ++k) gd[k] = 0.0f;
+
+    for (int v = 0; v < V; ++v) {
+        const float* src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
+        // phase A: warped source on tile + halo 2
+        for (int idx = tid; idx < BSH * BSW; idx += kPhotoThreads) {
+            const int ry = idx / BSW, rx = idx - ry * BSW;
+            const int sy = sy0 + ry, sx = sx0 + rx;
+            float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+            if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+                const float d = to_depth(__ldg(pp.inv_depth[ip] + static_cast<size_t>(b) * P + sy * W + sx), depth_kind);
+                Warp wp;
+                warp_pixel(cam[v], sx, sy, d, wm1, hm1, true, wp);
+                Taps t;
+                make_taps(wp.p.u, wp.p.v, H, W, opts.padding, t);
+                if (t.valid) {
+                    const Weights wt = tap_weights(t);
+                    o0 = tap3(src, W, t, wt);
+                    o1 = tap3(src + P, W, t, wt);
+                    o2 = tap3(src + 2 * P, W, t, wt);
+                }
+            }
+            xs[0][ry][rx] = o0;
+            xs[1][ry][rx] = o1;
+            xs[2][ry][rx] = o2;
+        }
+        __syncthreads();
+
+        for (int c = 0; c < 3; ++c) {
+            // phase B: coefficient maps of channel c on tile + halo 1
+            {
+                Win ra, rb;
+#pragma unroll
+                for (int j = 0; j < BRPT + 2; ++j) {
+                    const int sr = clampi(reflect_idx(cy0 + prow0 - 1 + j, H) - sy0, 0, BSH - 1);
+                    float xc, yc;
+                    const Win rc = row_sums(xs[c][sr], ys[c][sr], cm, c0, cp, xc, yc);
+                    if (j >= 2) {
+                        const int r = prow0 + j - 2;
+                        float a = 0.0f, bb = 0.0f, cq = 0.0f;
+                        const int sv = selt[r][lane];
+                        if (sv == v || sv == 253) {
+                            const Ssim s = ssim_from(add3(ra, rb, rc), opts.C1, opts.C2);
+                            const float l = (1.0f - s.s) * 0.5f;
+                            if (l >= 0.0f && l <= 1.0f) {
+                                const float kp = G * opts.ssim_w * (-1.0f / 6.0f);
+                                const float q = kp * (2.0f / 9.0f) / (s.B1 * s.B2);
+                                a = q * (s.mu_y * (s.A2 - s.A1) - s.s * s.mu_x * (s.B2 - s.B1));
+                                bb = -q * s.s * s.B1;
+                                cq = q * s.A1;
+                            }
+                        }
+                        ca[r][lane] = a;
+                        cb[r][lane] = bb;
+                        cc[r][lane] = cq;
+                    }
+                    ra = rb; rb = rc;
+                }
+            }
+            __syncthreads();
+            // phase C: gradient w.r.t. the warped pixel, channel c
+#pragma unroll
+            for (int k = 0; k < BRPT; ++k) {
+                const int r = prow0 + k;                 // coefficient-region row of q
+                const int qy = cy0 + r;
+                if (col_ok && r >= 1 && r <= IH && qy < H) {
+                    float ga = 0.0f, gb = 0.0f, gc = 0.0f;
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        const int py = qy + dy;
+                        if (py < 0 || py >= H) continue;
+                        const float my = 1.0f + ((py == 0 && qy == 1) ? 1.0f : 0.0f) + ((py == H - 1 && qy == H - 2) ? 1.0f : 0.0f);
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int px = pgx + dx;
+                            if (px < 0 || px >= W) continue;
+                            const float m = my * (1.0f + ((px == 0 && pgx == 1) ? 1.0f : 0.0f) +
+                                                  ((px == W - 1 && pgx == W - 2) ? 1.0f : 0.0f));
+                            ga += m * ca[r + dy][lane + dx];
+                            gb += m * cb[r + dy][lane + dx];
+                            gc += m * cc[r + dy][lane + dx];
+                        }
+                    }
+                    const float xq = xs[c][r + 1][lane + 1], yq = ys[c][r + 1][lane + 1];
+                    float gxv = ga + gb * xq + gc * yq;
+                    const int sv = selt[r][lane];
+                    if (sv == v || sv == 253) {
+                        const float df = xq - yq;
+                        gxv += G * l1_w * (1.0f / 3.0f) * (df > 0.0f ? 1.0f : (df < 0.0f ? -1.0f : 0.0f));
+                    }
+                    gxs[c][r - 1][lane] = gxv;
+                }
+            }
+            __syncthreads();
+        }
+
+        // phase D: through the bilinear taps and the projection adjoint
+        float gT[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) gT[i] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < BRPT; ++k) {
+            const int r = prow0 + k;
+            const int qy = cy0 + r;
+            if (col_ok && r >= 1 && r <= IH && qy < H) {
+                const float d = to_depth(__ldg(pp.inv_depth[ip] + static_cast<size_t>(b) * P + qy * W + pgx), depth_kind);
+                Warp wp;
+                warp_pixel(cam[v], pgx, qy, d, wm1, hm1, true, wp);
+                Taps t;
+                make_taps(wp.p.u, wp.p.v, H, W, opts.padding, t);
+                if (t.valid) {
+                    float gix = 0.0f, giy = 0.0f;
+                    const float bx = 1.0f - t.ax, by = 1.0f - t.ay;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float* r0 = src + c * P + t.y0 * W + t.x0;
+                        const float v0 = (t.valid & 1u) ? __ldg(r0) : 0.0f, v1 = (t.valid & 2u) ? __ldg(r0 + 1) : 0.0f;
+                        const float v2 = (t.valid & 4u) ? __ldg(r0 + W) : 0.0f, v3 = (t.valid & 8u) ? __ldg(r0 + W + 1) : 0.0f;
+                        const float g = gxs[c][r - 1][lane];
+                        gix += g * ((v1 - v0) * by + (v3 - v2) * t.ay);
+                        giy += g * ((v2 - v0) * bx + (v3 - v1) * t.ax);
+                    }
+                    gd[k] += warp_pixel_adjoint(cam[v], wp, d, wm1, hm1, true, gix * t.mx, giy * t.my, gT);
+                }
+            }
+        }
+        float* gp = pg.g_pose[v * n_preds + ip];
+        if (gp != nullptr) {
+            Slot* slot = ws + ((v * n_preds + ip) * B + b);
+            block_accumulate<12>(gT, red, slot->acc);
+            if (last_block(slot, gridDim.x * gridDim.y, &flag) && tid == 0) {
+                const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
+                finish_pose_grad(slot, cams.pose_kind, eul ? pp.pose[v * n_preds + ip] + b * 6 : nullptr,
+                                 gp + b * (eul ? 6 : 16));
+            }
+        }
+        __syncthreads();
+    }
+
+    float* gout = pg.g_inv_depth[ip];
+    if (gout != nullptr) {
+#pragma unroll
+        for (int k = 0; k < BRPT; ++k) {
+            const int r = prow0 + k;
+            const int qy = cy0 + r;
+            if (col_ok && r >= 1 && r <= IH && qy < H) {
+                const size_t o = static_cast<size_t>(b) * P + qy * W + pgx;
+                float g = gd[k];
+                if (depth_kind == DROSFM_INV_DEPTH) g = inv2depth_grad(__ldg(pp.inv_depth[ip] + o), g);
+                gout[o] = g;
+            }
+        }
+    }
+}
+
+static int check_photo(const float* image, const float* const* context, int n_views, const drosfm_photo_opts_t* opts,
+                       int B, int H, int W) {
+    DROSFM_REQUIRE(B >= 0 && H >= 0 && W >= 0, DROSFM_EINVAL, "photometric: negative dimension");
+    DROSFM_REQUIRE(n_views >= 1 && n_views <= DROSFM_MAX_VIEWS, DROSFM_ERANGE, "photometric: n_views=%d outside [1,%d]",
+                   n_views, DROSFM_MAX_VIEWS);
+    DROSFM_REQUIRE(opts != nullptr, DROSFM_EINVAL, "photometric: NULL opts");
+    DROSFM_REQUIRE(opts->padding == DROSFM_PAD_ZEROS || opts->padding == DROSFM_PAD_BORDER, DROSFM_EINVAL, "photometric: bad padding");
+    DROSFM_REQUIRE(opts->reduce_op == DROSFM_REDUCE_MIN || opts->reduce_op == DROSFM_REDUCE_MEAN, DROSFM_EINVAL,
+                   "photometric: bad reduce_op");
+    DROSFM_REQUIRE(opts->ssim_w > 0.0f, DROSFM_ENOTSUP,
+                   "photometric: ssim_loss_weight == 0 (per-channel L1 maps) is not supported by the fused kernel");
+    if (B == 0 || H * W == 0) return DROSFM_OK;
+    DROSFM_REQUIRE(H >= 2 && W >= 2, DROSFM_ENOTSUP, "photometric: reflection padding needs H, W >= 2");
+    DROSFM_REQUIRE(static_cast<long long>(H) * W < (1ll << 28) && B <= 4096, DROSFM_ERANGE, "photometric: dimension out of range");
+    DROSFM_REQUIRE(image != nullptr && context != nullptr, DROSFM_EINVAL, "photometric: NULL image/context");
+    for (int v = 0; v < n_views; ++v) DROSFM_REQUIRE(context[v] != nullptr, DROSFM_EINVAL, "photometric: context[%d] is NULL", v);
+    return DROSFM_OK;
+}
+
+static float l1_weight(const drosfm_photo_opts_t* opts) {
+    // (1 - ssim_loss_weight) is evaluated in double by the reference and rounded when it meets the fp32 tensor
+    return static_cast<float>(1.0 - static_cast<double>(opts->ssim_w));
+}
+
+}  // namespace drosfm
+
+using namespace drosfm;
+
+extern "C" {
+
+int drosfm_automask_fwd(const float* image, const float* const* context, int n_views, const drosfm_photo_opts_t* opts,
+                        float* automask, int B, int H, int W, drosfm_stream_t stream) {
+    if (int e = check_photo(image, context, n_views, opts, B, H, W)) return e;
+    if (B == 0 || H * W == 0) return DROSFM_OK;
+    DROSFM_REQUIRE(automask != nullptr, DROSFM_EINVAL, "automask_fwd: NULL output");
+    PhotoPtrs pp{};
+    for (int v = 0; v < n_views; ++v) pp.context[v] = context[v];
+    drosfm_photo_opts_t o = *opts;
+    o.reduce_op = DROSFM_REDUCE_MIN;
+    drosfm_cams_t none{};
+    dim3 grid((W + FW - 1) / FW, (H + FH - 1) / FH, B);
+    photometric_fwd_kernel<1><<<grid, kPhotoThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        image, pp, n_views, DROSFM_DEPTH, 1, none, nullptr, o, l1_weight(opts), nullptr, automask, nullptr, nullptr, B, H, W);
+    return launch_status("automask_fwd");
+}
+
+static int fill_ptrs(PhotoPtrs& pp, const float* const* context, int n_views, const float* const* inv_depths, int n_preds,
+                     const float* const* poses, float gamma) {
+    DROSFM_REQUIRE(n_preds >= 1 && n_preds <= DROSFM_MAX_PREDS, DROSFM_ERANGE, "photometric: n_preds=%d outside [1,%d]",
+                   n_preds, DROSFM_MAX_PREDS);
+    DROSFM_REQUIRE(inv_depths != nullptr && poses != nullptr, DROSFM_EINVAL, "photometric: NULL depth/pose arrays");
+    for (int v = 0; v < n_views; ++v) pp.context[v] = context[v];
+    for (int i = 0; i < n_preds; ++i) {
+        DROSFM_REQUIRE(inv_depths[i] != nullptr, DROSFM_EINVAL, "photometric: inv_depths[%d] is NULL", i);
+        pp.inv_depth[i] = inv_depths[i];
+        // gamma ** (n - i - 1) is a Python double that is rounded when it multiplies the fp32 loss
+        double wgt = 1.0;
+        for (int k = 0; k < n_preds - 1 - i; ++k) wgt *= static_cast<double>(gamma);
+        pp.weight[i] = static_cast<float>(wgt);
+    }
+    for (int k = 0; k < n_views * n_preds; ++k) {
+        DROSFM_REQUIRE(poses[k] != nullptr, DROSFM_EINVAL, "photometric: poses[%d] is NULL", k);
+        pp.pose[k] = poses[k];
+    }
+    return DROSFM_OK;
+}
+
+int drosfm_photometric_fwd(const float* image, const float* const* context, int n_views, const float* const* inv_depths,
+                           int depth_kind, int n_preds, const drosfm_cams_t* cams, const float* const* poses,
+                           const float* automask, const drosfm_photo_opts_t* opts, uint8_t* sel, float* loss, void* ws,
+                           int B, int H, int W, drosfm_stream_t stream) {
+    if (int e = check_photo(image, context, n_views, opts, B, H, W)) return e;
+    DROSFM_REQUIRE(B > 0 && H * W > 0, DROSFM_EINVAL, "photometric_fwd: empty batch (the mean over zero pixels is undefined)");
+    DROSFM_REQUIRE(cams && cams->K && cams->Kref, DROSFM_EINVAL, "photometric_fwd: NULL cams");
+    DROSFM_REQUIRE(cams->pose_kind == DROSFM_POSE_MAT4 || cams->pose_kind == DROSFM_POSE_EULER6, DROSFM_EINVAL,
+                   "photometric_fwd: pose_kind must be MAT4 or EULER6");
+    DROSFM_REQUIRE(loss != nullptr && ws != nullptr, DROSFM_EINVAL, "photometric_fwd: NULL loss/ws");
+    DROSFM_REQUIRE(opts->reduce_op == DROSFM_REDUCE_MEAN || sel != nullptr, DROSFM_EINVAL, "photometric_fwd: min needs sel");
+    DROSFM_REQUIRE(!(opts->automask && opts->reduce_op != DROSFM_REDUCE_MIN), DROSFM_EINVAL,
+                   "photometric_fwd: auto-masking needs the min reduce op");
+    DROSFM_REQUIRE(!opts->automask || automask != nullptr, DROSFM_EINVAL, "photometric_fwd: automask map is NULL");
+    PhotoPtrs pp{};
+    if (int e = fill_ptrs(pp, context, n_views, inv_depths, n_preds, poses, opts->gamma)) return e;
+    DROSFM_REQUIRE(static_cast<long long>(B) * n_preds <= 65535, DROSFM_ERANGE, "photometric_fwd: B * n_preds too large");
+    dim3 grid((W + FW - 1) / FW, (H + FH - 1) / FH, B * n_preds);
+    photometric_fwd_kernel<0><<<grid, kPhotoThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        image, pp, n_views, depth_kind, n_preds, *cams, opts->automask ? automask : nullptr, *opts, l1_weight(opts), sel,
+        nullptr, loss, static_cast<Slot*>(ws), B, H, W);
+    return launch_status("photometric_fwd");
+}
+
+int drosfm_photometric_bwd(const float* g_loss, const float* image, const float* const* context, int n_views,
+                           const float* const* inv_depths, int depth_kind, int n_preds, const drosfm_cams_t* cams,
+                           const float* const* poses, const uint8_t* sel, const drosfm_photo_opts_t* opts,
+                           float* const* g_inv_depths, float* const* g_poses, void* ws, int B, int H, int W,
+                           drosfm_stream_t stream) {
+    if (int e = check_photo(image, context, n_views, opts, B, H, W)) return e;
+    if (B == 0 || H * W == 0) return DROSFM_OK;
+    DROSFM_REQUIRE(cams && cams->K && cams->Kref, DROSFM_EINVAL, "photometric_bwd: NULL cams");
+    DROSFM_REQUIRE(cams->pose_kind == DROSFM_POSE_MAT4 || cams->pose_kind == DROSFM_POSE_EULER6, DROSFM_EINVAL,
+                   "photometric_bwd: pose_kind must be MAT4 or EULER6");
+    DROSFM_REQUIRE(g_loss != nullptr, DROSFM_EINVAL, "photometric_bwd: NULL g_loss");
+    DROSFM_REQUIRE(opts->reduce_op == DROSFM_REDUCE_MEAN || sel != nullptr, DROSFM_EINVAL, "photometric_bwd: min needs sel");
+    PhotoPtrs pp{};
+    if (int e = fill_ptrs(pp, context, n_views, inv_depths, n_preds, poses, opts->gamma)) return e;
+    PhotoGrads pg{};
+    bool want_pose = false;
+    for (int i = 0; i < n_preds; ++i) pg.g_inv_depth[i] = g_inv_depths ? g_inv_depths[i] : nullptr;
+    for (int k = 0; k < n_views * n_preds; ++k) {
+        pg.g_pose[k] = g_poses ? g_poses[k] : nullptr;
+        want_pose |= pg.g_pose[k] != nullptr;
+    }
+    DROSFM_REQUIRE(!want_pose || ws != nullptr, DROSFM_EINVAL, "photometric_bwd: pose gradients need ws");
+    DROSFM_REQUIRE(static_cast<long long>(B) * n_preds <= 65535, DROSFM_ERANGE, "photometric_bwd: B * n_preds too large");
+    dim3 grid((W + IW - 1) / IW, (H + IH - 1) / IH, B * n_preds);
+    photometric_bwd_kernel<<<grid, kPhotoThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        g_loss, image, pp, n_views, depth_kind, n_preds, *cams, sel, *opts, l1_weight(opts), pg, static_cast<Slot*>(ws), B, H, W);
+    return launch_status("photometric_bwd");
+}
+
+}  // extern "C"

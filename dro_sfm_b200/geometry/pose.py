@@ -1,0 +1,87 @@
+"""Drop-in for dro_sfm.geometry.pose.Pose (reference: dro_sfm/geometry/pose.py:7-98).
+
+Same constructor, class methods and operators.  ``from_vec(vec, 'euler')`` is one kernel launch
+(drosfm_pose_vec2mat) instead of ~40 ATen ops; the 4x4 bookkeeping (inverse, composition) stays in
+PyTorch -- it is B x 16 numbers and provides autograd for free.
+"""
+import torch
+
+from .. import ops
+
+
+class Pose:
+    """Encapsulates a [B,4,4] rigid transformation."""
+
+    def __init__(self, mat):
+        assert tuple(mat.shape[-2:]) == (4, 4)
+        if mat.dim() == 2:
+            mat = mat.unsqueeze(0)
+        assert mat.dim() == 3
+        self.mat = mat
+        self._is_identity = False
+
+    def __len__(self):
+        return len(self.mat)
+
+    @classmethod
+    def identity(cls, N=1, device=None, dtype=torch.float):
+        pose = cls(torch.eye(4, device=device, dtype=dtype).repeat([N, 1, 1]))
+        pose._is_identity = True
+        return pose
+
+    @classmethod
+    def from_vec(cls, vec, mode):
+        """[B,6] = (tx,ty,tz,rx,ry,rz) -> Pose; reference pose.py:38-45 + pose_utils.py:73-85."""
+        if mode is None:
+            return cls(vec)
+        if mode != "euler":
+            raise NotImplementedError("dro_sfm_b200: rotation mode {!r} is not supported (configs use 'euler', "
+                                      "configs/default_config.py:93)".format(mode))
+        return cls(ops.pose_vec2mat(vec))
+
+    @property
+    def shape(self):
+        return self.mat.shape
+
+    def item(self):
+        return self.mat
+
+    def repeat(self, *args, **kwargs):
+        self.mat = self.mat.repeat(*args, **kwargs)
+        return self
+
+    def inverse(self):
+        """[R|t]^-1 = [R^T | -R^T t] (reference pose_utils.py:89-94)."""
+        T = self.mat
+        Tinv = torch.eye(4, device=T.device, dtype=T.dtype).repeat([len(T), 1, 1])
+        Tinv[:, :3, :3] = torch.transpose(T[:, :3, :3], -2, -1)
+        Tinv[:, :3, -1] = torch.bmm(-1. * Tinv[:, :3, :3], T[:, :3, -1].unsqueeze(-1)).squeeze(-1)
+        out = Pose(Tinv)
+        out._is_identity = self._is_identity
+        return out
+
+    def to(self, *args, **kwargs):
+        self.mat = self.mat.to(*args, **kwargs)
+        return self
+
+    def transform_pose(self, pose):
+        assert tuple(pose.shape[-2:]) == (4, 4)
+        return Pose(self.mat.bmm(pose.item()))
+
+    def transform_points(self, points):
+        """R X + t for [B,3,H,W] (or [B,3,N]) points.  Inside view synthesis / cost / loss this
+        step is fused into the kernels; the stand-alone operator is kept for API parity."""
+        assert points.shape[1] == 3
+        shape = points.shape
+        out = self.mat[:, :3, :3].bmm(points.reshape(shape[0], 3, -1)) + self.mat[:, :3, -1].unsqueeze(-1)
+        return out.view(shape)
+
+    def __matmul__(self, other):
+        if isinstance(other, Pose):
+            return self.transform_pose(other)
+        if isinstance(other, torch.Tensor):
+            if other.shape[1] == 3 and other.dim() > 2:
+                assert other.dim() == 3 or other.dim() == 4
+                return self.transform_points(other)
+            raise ValueError("Unknown tensor dimensions {}".format(other.shape))
+        raise NotImplementedError()

@@ -9,8 +9,8 @@ import torch
 
 from . import _lib as L
 
-__all__ = ["reconstruct", "project", "warp_coords", "grid_gather", "view_synthesis", "feat_cost",
-           "photometric_loss", "smoothness_loss", "reproj_pose_loss"]
+__all__ = ["pose_vec2mat", "reconstruct", "project", "warp_coords", "grid_gather", "view_synthesis", "feat_cost",
+           "photometric_loss", "reproj_pose_loss"]
 
 
 def _pose_kind(pose):
@@ -34,6 +34,39 @@ def _padding(mode):
 def _no_grad_for(name, t):
     if t is not None and torch.is_tensor(t) and t.requires_grad and torch.is_grad_enabled():
         raise NotImplementedError("dro_sfm_b200: gradient w.r.t. {} is not implemented".format(name))
+
+
+# ------------------------------------------------------------------------------------------------
+# Pose.from_vec
+# ------------------------------------------------------------------------------------------------
+class _PoseVec2Mat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vec):
+        L.require_cuda(vec)
+        vec = L.f32c(vec)
+        N = vec.shape[0]
+        mat = torch.empty(N, 4, 4, device=vec.device, dtype=torch.float32)
+        with torch.cuda.device(vec.device):
+            L.check(L.lib().drosfm_pose_vec2mat_fwd(L.ptr(vec), L.ptr(mat), N, L.stream()), "pose_vec2mat_fwd")
+        ctx.save_for_backward(vec)
+        return mat
+
+    @staticmethod
+    def backward(ctx, g):
+        (vec,) = ctx.saved_tensors
+        g = L.f32c(g)
+        gv = torch.empty_like(vec)
+        with torch.cuda.device(vec.device):
+            L.check(L.lib().drosfm_pose_vec2mat_bwd(L.ptr(g), L.ptr(vec), L.ptr(gv), vec.shape[0], L.stream()),
+                    "pose_vec2mat_bwd")
+        return gv
+
+
+def pose_vec2mat(vec):
+    """Pose.from_vec(vec, 'euler').mat (pose.py:38-45): [N,6] -> [N,4,4], R = Rx Ry Rz."""
+    if vec.dim() != 2 or vec.shape[1] != 6:
+        raise ValueError("pose vector must be [N,6]")
+    return _PoseVec2Mat.apply(vec)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -339,13 +372,177 @@ def feat_cost(depth, fmap, fmaps_ref, poses, K, Kref=None, scale=1.0, inverse_de
                            *fmaps_ref, *poses)
 
 
-def photometric_loss(*args, **kwargs):
-    raise NotImplementedError
+# ------------------------------------------------------------------------------------------------
+# photometric + smoothness loss
+# ------------------------------------------------------------------------------------------------
+def _reduce_op(name):
+    if name == "min":
+        return L.REDUCE_MIN
+    if name == "mean":
+        return L.REDUCE_MEAN
+    raise NotImplementedError("Unknown photometric_reduce_op: {}".format(name))
 
 
-def smoothness_loss(*args, **kwargs):
-    raise NotImplementedError
+class _PhotoLoss(torch.autograd.Function):
+    """inputs: image, K, Kref, cfg, V, n, context_0..V-1, inv_depth_0..n-1, pose_{v,i} (v-major).
+    outputs: total loss [1]; [photometric term, smoothness term] (non-differentiable metrics)."""
+
+    @staticmethod
+    def forward(ctx, image, K, Kref, cfg, V, n, *tensors):
+        ssim_w, C1, C2, padding, reduce_op, automask, gamma, smooth_w, depth_kind = cfg
+        context = [L.f32c(x) for x in tensors[:V]]
+        invs = [L.f32c(x) for x in tensors[V:V + n]]
+        poses = [L.f32c(x) for x in tensors[V + n:]]
+        L.require_cuda(image, K, Kref, *tensors)
+        image = L.f32c(image)
+        B, _, H, W = image.shape
+        dev = image.device
+        kind = _pose_kind(poses[0])
+        cams, keep = L.make_cams(K, Kref, 1.0, None, None, None, kind)
+        opts = L.PhotoOpts(ssim_w, C1, C2, padding, reduce_op, int(automask), gamma)
+        losses = torch.zeros(2, device=dev, dtype=torch.float32)
+        sel = torch.empty(n, B, H, W, device=dev, dtype=torch.uint8) if reduce_op == L.REDUCE_MIN else None
+        stats = torch.empty(n, B, 4, device=dev, dtype=torch.float32) if smooth_w > 0.0 else None
+        lib = L.lib()
+        with torch.cuda.device(dev):
+            ws = L.workspace(dev, max(n * B + 1, V * n * B))
+            st = L.stream()
+            amask = None
+            if automask:
+                amask = torch.empty(B, H, W, device=dev, dtype=torch.float32)
+                L.check(lib.drosfm_automask_fwd(L.ptr(image), L.ptr_array(context), V, opts, L.ptr(amask), B, H, W, st),
+                        "automask_fwd")
+            L.check(lib.drosfm_photometric_fwd(L.ptr(image), L.ptr_array(context), V, L.ptr_array(invs), depth_kind, n, cams,
+                                               L.ptr_array(poses), L.ptr(amask), opts, L.ptr(sel), L.ptr(losses), L.ptr(ws),
+                                               B, H, W, st), "photometric_fwd")
+            if smooth_w > 0.0:
+                L.check(lib.drosfm_smoothness_fwd(L.ptr(image), L.ptr_array(invs), n, smooth_w, L.ptr(stats),
+                                                  L.ptr(losses[1:]), L.ptr(ws), B, H, W, st), "smoothness_fwd")
+        total = losses.sum().reshape(1)
+        ctx.save_for_backward(image, keep[0], keep[1], sel, stats, *context, *invs, *poses)
+        ctx.cfg, ctx.V, ctx.n, ctx.kind = cfg, V, n, kind
+        ctx.mark_non_differentiable(losses)
+        return total, losses
+
+    @staticmethod
+    def backward(ctx, g_total, *unused):
+        ssim_w, C1, C2, padding, reduce_op, automask, gamma, smooth_w, depth_kind = ctx.cfg
+        V, n, kind = ctx.V, ctx.n, ctx.kind
+        image, K, Kref, sel, stats = ctx.saved_tensors[:5]
+        rest = ctx.saved_tensors[5:]
+        context, invs, poses = rest[:V], rest[V:V + n], rest[V + n:]
+        B, _, H, W = image.shape
+        dev = image.device
+        need = ctx.needs_input_grad
+        if any(need[6 + v] for v in range(V)) or need[0]:
+            raise NotImplementedError("dro_sfm_b200: the fused photometric loss has no gradient w.r.t. the images")
+        need_inv = [need[6 + V + i] for i in range(n)]
+        need_pose = [need[6 + V + n + k] for k in range(V * n)]
+        g = L.f32c(g_total.reshape(1))
+        cams, _ = L.make_cams(K, Kref, 1.0, None, None, None, kind)
+        opts = L.PhotoOpts(ssim_w, C1, C2, padding, reduce_op, int(automask), gamma)
+        g_inv_slab = torch.empty(n, *invs[0].shape, device=dev, dtype=torch.float32) if any(need_inv) else None
+        g_invs = [g_inv_slab[i] if need_inv[i] else None for i in range(n)]
+        g_pose_slab = torch.empty(V * n, *poses[0].shape, device=dev, dtype=torch.float32) if any(need_pose) else None
+        g_poses = [g_pose_slab[k] if need_pose[k] else None for k in range(V * n)]
+        lib = L.lib()
+        with torch.cuda.device(dev):
+            ws = L.workspace(dev, max(n * B + 1, V * n * B))
+            st = L.stream()
+            L.check(lib.drosfm_photometric_bwd(L.ptr(g), L.ptr(image), L.ptr_array(context), V, L.ptr_array(invs), depth_kind, n,
+                                               cams, L.ptr_array(poses), L.ptr(sel), opts, L.ptr_array(g_invs),
+                                               L.ptr_array(g_poses), L.ptr(ws), B, H, W, st), "photometric_bwd")
+            if smooth_w > 0.0 and any(need_inv):
+                L.check(lib.drosfm_smoothness_bwd(L.ptr(g), L.ptr(image), L.ptr_array(invs), n, smooth_w, L.ptr(stats),
+                                                  L.ptr_array(g_invs), 1, B, H, W, st), "smoothness_bwd")
+        return (None, None, None, None, None, None, *([None] * V), *g_invs, *g_poses)
 
 
-def reproj_pose_loss(*args, **kwargs):
-    raise NotImplementedError
+def photometric_loss(image, context, inv_depths, K, ref_K, poses, ssim_w=0.85, C1=1e-4, C2=9e-4, reduce_op="min",
+                     padding_mode="zeros", automask=True, smooth_w=0.001, gamma=0.85, inverse_depth=True):
+    """MultiViewPhotometricDecayLoss.forward (multiview_photometric_loss_mf.py:303-361), fused.
+
+    context: V source images; inv_depths: n predictions [B,1,H,W]; poses[v][i]: [B,4,4] or [B,6].
+    Returns (total [1], terms [2]) with terms = detached [photometric, smoothness] values."""
+    V, n = len(context), len(inv_depths)
+    if not (1 <= V <= L.MAX_VIEWS and 1 <= n <= L.MAX_PREDS):
+        raise ValueError("photometric_loss supports 1..{} views and 1..{} predictions".format(L.MAX_VIEWS, L.MAX_PREDS))
+    if len(poses) != V or any(len(p) != n for p in poses):
+        raise ValueError("poses must be a list of V lists of n transforms")
+    if automask and reduce_op != "min":
+        raise AssertionError("For automasking only the min photometric_reduce_op is supported.")
+    if ssim_w <= 0.0:
+        raise NotImplementedError("dro_sfm_b200: ssim_loss_weight == 0 is not supported by the fused photometric kernel")
+    for d in inv_depths:
+        if tuple(d.shape[-2:]) != tuple(image.shape[-2:]):
+            raise NotImplementedError("dro_sfm_b200: predictions must be at the image resolution")
+    _no_grad_for("K", K)
+    cfg = (float(ssim_w), float(C1), float(C2), _padding(padding_mode), _reduce_op(reduce_op), bool(automask), float(gamma),
+           float(smooth_w), L.INV_DEPTH if inverse_depth else L.DEPTH)
+    flat = [p for pv in poses for p in pv]
+    return _PhotoLoss.apply(image, K, ref_K, cfg, V, n, *context, *inv_depths, *flat)
+
+
+# ------------------------------------------------------------------------------------------------
+# reprojection pose loss
+# ------------------------------------------------------------------------------------------------
+class _ReprojLoss(torch.autograd.Function):
+    """inputs: depth, K, Kref, cfg, V, n, gt_0..V-1, pred_{v,i} (v-major)"""
+
+    @staticmethod
+    def forward(ctx, depth, K, Kref, cfg, V, n, *tensors):
+        min_depth, max_depth, gamma, depth_kind = cfg
+        L.require_cuda(depth, K, Kref, *tensors)
+        depth = L.f32c(depth)
+        gts = [L.f32c(x) for x in tensors[:V]]
+        preds = [L.f32c(x) for x in tensors[V:]]
+        B, _, H, W = depth.shape
+        kind = _pose_kind(preds[0])
+        if _pose_kind(gts[0]) != kind:
+            raise ValueError("GT and predicted poses must use the same encoding ([B,4,4] or [B,6])")
+        cams, keep = L.make_cams(K, Kref, 1.0, None, None, None, kind)
+        loss = torch.empty(1, device=depth.device, dtype=torch.float32)
+        with torch.cuda.device(depth.device):
+            ws = L.workspace(depth.device, max(n + 1, V * n * B))
+            L.check(L.lib().drosfm_reproj_loss_fwd(L.ptr(depth), depth_kind, cams, L.ptr_array(gts), L.ptr_array(preds), V, n,
+                                                   min_depth, max_depth, gamma, L.ptr(loss), L.ptr(ws), B, H, W, L.stream()),
+                    "reproj_loss_fwd")
+        ctx.save_for_backward(depth, keep[0], keep[1], *gts, *preds)
+        ctx.cfg, ctx.V, ctx.n, ctx.kind = cfg, V, n, kind
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        min_depth, max_depth, gamma, depth_kind = ctx.cfg
+        V, n, kind = ctx.V, ctx.n, ctx.kind
+        depth, K, Kref = ctx.saved_tensors[:3]
+        gts, preds = ctx.saved_tensors[3:3 + V], ctx.saved_tensors[3 + V:]
+        B, _, H, W = depth.shape
+        need = ctx.needs_input_grad
+        if need[0] or any(need[6 + v] for v in range(V)):
+            raise NotImplementedError("dro_sfm_b200: the reprojection loss has gradients w.r.t. the predicted poses only")
+        need_pose = [need[6 + V + k] for k in range(V * n)]
+        g = L.f32c(g.reshape(1))
+        cams, _ = L.make_cams(K, Kref, 1.0, None, None, None, kind)
+        slab = torch.empty(V * n, *preds[0].shape, device=depth.device, dtype=torch.float32)
+        g_preds = [slab[k] if need_pose[k] else None for k in range(V * n)]
+        with torch.cuda.device(depth.device):
+            ws = L.workspace(depth.device, max(n + 1, V * n * B))
+            L.check(L.lib().drosfm_reproj_loss_bwd(L.ptr(g), L.ptr(depth), depth_kind, cams, L.ptr_array(gts), L.ptr_array(preds),
+                                                   V, n, min_depth, max_depth, gamma, L.ptr_array(g_preds), L.ptr(ws), B, H, W,
+                                                   L.stream()), "reproj_loss_bwd")
+        return (None, None, None, None, None, None, *([None] * V), *g_preds)
+
+
+def reproj_pose_loss(pred_poses, gt_poses, gt_depth, K, ref_K, min_depth, max_depth, gamma=0.85, inverse_depth=False):
+    """SupervisedDepthPoseLoss.calc_pose_loss (supervised_loss.py:293-325), fused.
+
+    pred_poses[v][i], gt_poses[v]: [B,4,4] (or [B,6]); gt_depth [B,1,H,W] (GT inverse depth when
+    inverse_depth=True: inv2depth is applied inside the kernel)."""
+    V, n = len(gt_poses), len(pred_poses[0])
+    if not (1 <= V <= L.MAX_VIEWS and 1 <= n <= L.MAX_PREDS) or len(pred_poses) != V:
+        raise ValueError("reproj_pose_loss supports 1..{} views and 1..{} predictions".format(L.MAX_VIEWS, L.MAX_PREDS))
+    _no_grad_for("K", K)
+    cfg = (float(min_depth), float(max_depth), float(gamma), L.INV_DEPTH if inverse_depth else L.DEPTH)
+    flat = [p for pv in pred_poses for p in pv]
+    return _ReprojLoss.apply(gt_depth, K, ref_K, cfg, V, n, *gt_poses, *flat)

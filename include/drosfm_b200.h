@@ -61,6 +61,13 @@ const char* drosfm_last_error(void);
  * `slots` independent accumulators (one slot = one (sample, view, prediction) pose or one scalar). */
 size_t drosfm_ws_bytes(int slots);
 
+/* ---- Pose.from_vec(vec, 'euler') (pose.py:38-45, pose_utils.py:40-85) -----------------------
+ * vec [N,6] = (tx,ty,tz,rx,ry,rz) -> mat [N,4,4] with R = Rx Ry Rz; one launch instead of ~40
+ * ATen ops.  bwd: g_mat [N,4,4] -> g_vec [N,6].  The kernels that take DROSFM_POSE_EULER6 poses
+ * evaluate exactly this conversion in their prologue. */
+int drosfm_pose_vec2mat_fwd(const float* vec, float* mat, int N, drosfm_stream_t stream);
+int drosfm_pose_vec2mat_bwd(const float* g_mat, const float* vec, float* g_vec, int N, drosfm_stream_t stream);
+
 /* ---- Camera.reconstruct (camera.py:111-147) -------------------------------------------------
  * depth [B,1,H,W] -> points [B,3,H,W].  K: [B,3,3] (k_dtype).  Twc: [B,4,4] or NULL (frame 'c'). */
 int drosfm_reconstruct_fwd(const float* depth, const void* K, int k_dtype, const float* Twc,
@@ -139,7 +146,7 @@ int drosfm_automask_fwd(const float* image, const float* const* context, int n_v
 /* loss = sum_i gamma^(n-1-i) * reduce_v,pixels(photometric(warp(context_v; inv_depth_i, pose_{v,i}), image)).
  * inv_depths[i]: [B,1,H,W]; poses[v*n_preds+i]: [B,4,4] or [B,6] per cams->pose_kind.
  * sel [n_preds,B,H,W] u8 receives the arg-min view per pixel (255 = auto-mask won); loss: 1 float.
- * ws of drosfm_ws_bytes(n_preds). */
+ * ws of drosfm_ws_bytes(n_preds + 1). */
 int drosfm_photometric_fwd(const float* image, const float* const* context, int n_views,
                            const float* const* inv_depths, int depth_kind, int n_preds,
                            const drosfm_cams_t* cams, const float* const* poses, const float* automask,
@@ -155,19 +162,21 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
 
 /* ---- smoothness loss (multiview_photometric_loss_mf.py:273-299, utils/depth.py:147-199) -------
  * loss = weight/n * sum_i (mean|dx(d_i/mean(d_i)) * wx| + mean|dy(..) * wy|) / 2^i.
- * means [n_preds,B] float scratch (per-sample mean inverse depth, kept for bwd); ws of
- * drosfm_ws_bytes(n_preds*B + 1). */
+ * stats [n_preds,B,4] float scratch written by fwd and read by bwd (per-sample mean inverse depth
+ * and the two per-sample edge sums); ws of drosfm_ws_bytes(n_preds*B + 1).
+ * bwd: g_inv_depths[i] [B,1,H,W] written, or added to when accumulate != 0 (entries may be NULL). */
 int drosfm_smoothness_fwd(const float* image, const float* const* inv_depths, int n_preds, float weight,
-                          float* means, float* loss, void* ws, int B, int H, int W, drosfm_stream_t stream);
+                          float* stats, float* loss, void* ws, int B, int H, int W, drosfm_stream_t stream);
 int drosfm_smoothness_bwd(const float* g_loss, const float* image, const float* const* inv_depths, int n_preds,
-                          float weight, const float* means, float* const* g_inv_depths, void* ws,
+                          float weight, const float* stats, float* const* g_inv_depths, int accumulate,
                           int B, int H, int W, drosfm_stream_t stream);
 
 /* ---- reprojection pose loss (supervised_loss.py:279-325) ------------------------------------
  * loss = sum_i w_i/V * sum_v mean(valid * clamp(|uv(pred_{v,i}) - uv(gt_v)|, -1, 1)) / sum_i w_i,
  * valid = in-range(gt) & in-range(pred) & (min_depth < depth < max_depth/4), depth = GT depth
  * [B,1,H,W] (depth_kind may be DROSFM_INV_DEPTH: inv2depth is fused).  gt_poses[v], pred_poses[v*n+i]
- * in cams->pose_kind encoding.  bwd: g_pred_poses[v*n+i] written; ws of drosfm_ws_bytes(V*n*B + 1). */
+ * in cams->pose_kind encoding.  fwd: ws of drosfm_ws_bytes(n + 1).  bwd: g_pred_poses[v*n+i] written
+ * (entries may be NULL); ws of drosfm_ws_bytes(V*n*B). */
 int drosfm_reproj_loss_fwd(const float* depth, int depth_kind, const drosfm_cams_t* cams,
                            const float* const* gt_poses, const float* const* pred_poses, int n_views, int n_preds,
                            float min_depth, float max_depth, float gamma, float* loss, void* ws,

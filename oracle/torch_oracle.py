@@ -184,9 +184,14 @@ def view_synthesis(src, depth, K, ref_K, T, scale=1.0, padding_mode="zeros"):
 # ----------------------------------------------------------------------------------------------
 # feature-metric cost (recurrent optimiser)
 # ----------------------------------------------------------------------------------------------
+def _as_T(pose):
+    """[B,6] euler vector -> [B,4,4] (Pose.from_vec); a [B,4,4] matrix passes through."""
+    return pose if pose.dim() == 3 else pose_vec_to_T(pose)
+
+
 def feat_cost_each(pose_vec, fmap, fmap_ref, depth, K, ref_K, scale):
     """dro_sfm/networks/depth_pose/DepthPoseNet.py:76-96 -- per-channel squared difference."""
-    coords = warp_coords(depth, K, ref_K, pose_vec_to_T(pose_vec), scale)
+    coords = warp_coords(depth, K, ref_K, _as_T(pose_vec), scale)
     return (fmap - grid_gather(fmap_ref, coords, "zeros")) ** 2
 
 

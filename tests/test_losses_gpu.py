@@ -1,0 +1,236 @@
+"""GPU parity tests of the fused loss kernels and of the drop-in modules (same operator surface as
+the reference) against the golden fixtures and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import t, assert_close, assert_close_or_better
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cu(a, dtype=torch.float32):
+    return t(a, dtype, DEV)
+
+
+PHOTO_VARIANTS = {
+    "default": dict(automask_loss=True, photometric_reduce_op="min", clip_loss=0.0, smooth_loss_weight=0.001,
+                    padding_mode="zeros", ssim_loss_weight=0.85),
+    "nomask_mean_border": dict(automask_loss=False, photometric_reduce_op="mean", clip_loss=0.0, smooth_loss_weight=0.1,
+                               padding_mode="border", ssim_loss_weight=0.85),
+}
+
+
+@pytest.mark.parametrize("name", list(PHOTO_VARIANTS))
+def test_photometric_loss_module_golden(golden, name):
+    """MultiViewPhotometricDecayLoss.forward against the reference's fixtures (loss, metrics, gradients)."""
+    from dro_sfm_b200.losses import MultiViewPhotometricDecayLoss
+    from dro_sfm_b200.geometry import Pose
+    g = golden("photometric")
+    V, n = 2, 3
+    K = cu(g["K"], torch.float64)
+    image = cu(g["image"])
+    context = [cu(g[f"context{v}"]) for v in range(V)]
+    invs = [cu(g[f"inv{i}"]).requires_grad_(True) for i in range(n)]
+    Ts = [[cu(g[f"T{v}_{i}"]).requires_grad_(True) for i in range(n)] for v in range(V)]
+    mod = MultiViewPhotometricDecayLoss(**PHOTO_VARIANTS[name])
+    out = mod(image, context, invs, K, K, [[Pose(x) for x in tv] for tv in Ts])
+    assert set(out) == {"loss", "metrics"} and out["loss"].shape == (1,)
+    flat = invs + [x for tv in Ts for x in tv]
+    grads = torch.autograd.grad(out["loss"].sum(), flat)
+    assert_close(out["loss"].detach().cpu(), g[f"{name}_f32_loss"], what="loss")
+    for k in ("photometric_loss", "smoothness_loss"):
+        assert_close(out["metrics"][k].cpu(), g[f"{name}_f32_{k}"], what=k)
+    for i in range(n):
+        assert_close_or_better(grads[i].cpu(), g[f"{name}_f32_g_inv{i}"], g[f"{name}_f64_g_inv{i}"], what=f"g_inv{i}")
+    k = n
+    for v in range(V):
+        for i in range(n):
+            assert_close_or_better(grads[k].cpu(), g[f"{name}_f32_g_T{v}_{i}"], g[f"{name}_f64_g_T{v}_{i}"], what=f"g_T{v}_{i}")
+            k += 1
+
+
+def test_unsupported_options_fail_loudly():
+    from dro_sfm_b200.losses import MultiViewPhotometricDecayLoss
+    with pytest.raises(NotImplementedError):
+        MultiViewPhotometricDecayLoss(clip_loss=0.5)
+    with pytest.raises(AssertionError):
+        MultiViewPhotometricDecayLoss(clip_loss=0.0, automask_loss=True, photometric_reduce_op="mean")
+
+
+@pytest.mark.parametrize("wl_name,B,n", [("train_kitti_mf_selfsup_192x640", 1, 3), ("train_scannet_mf_selfsup_view5", 2, 2)])
+def test_photometric_loss_vs_oracle_full_size(wl_name, B, n):
+    """BASELINE shapes (192x640 V=2, 240x320 V=4) straight through the C ABI.
+
+    The per-pixel min over 2V maps is discontinuous: where two candidates differ by less than fp32
+    noise of the SSIM statistics (relative margin < 1e-3 -- a handful of pixels per 10^5) the winner may
+    differ between any two fp32 implementations, and one flipped pixel moves a pose gradient by more than
+    the tolerance.  The test therefore checks (1) the loss, (2) that the recorded arg-min equals the
+    oracle's except at such near-ties, and (3) the gradients for the oracle's selection."""
+    from dro_sfm_b200 import synthetic as syn, _lib as L
+    wl = syn.WORKLOADS[wl_name]
+    g = syn.gen(77)
+    H, W, V = wl.H, wl.W, wl.V
+    K = syn.intrinsics(wl.dataset, B, H, W)
+    image = syn.images(g, B, H, W)
+    context = [0.8 * torch.roll(image, (v + 1) * (1 if v % 2 == 0 else -1), 3) + 0.2 * syn.images(g, B, H, W) for v in range(V)]
+    invs = [syn.inv_depth(g, B, H, W, wl.min_depth, wl.max_depth, frac_nonpos=0.01) for _ in range(n)]
+    vecs = [[syn.pose_vec(g, B, wl.dataset, 1.0 if v % 2 == 0 else -1.0) * 0.3 for _ in range(n)] for v in range(V)]
+    Ts = [[oracle.pose_vec_to_T(x) for x in tv] for tv in vecs]
+    gamma = 0.85
+
+    def oracle_run(dt, forced_sel=None):
+        """loss and gradients; with forced_sel the per-pixel winner is taken from it (index into 2V maps)."""
+        d = [x.to(dt).requires_grad_(True) for x in invs]
+        P = [[x.to(dt).requires_grad_(True) for x in tv] for tv in Ts]
+        Kd = K.float().to(dt)
+        total, stacks = 0.0, []
+        for i in range(n):
+            ms = []
+            for v in range(V):
+                warped = oracle.view_synthesis(context[v].to(dt), oracle.inv2depth(d[i]), Kd, Kd, P[v][i], 1.0, "zeros")
+                ms += [oracle.photometric_map(warped, image.to(dt)), oracle.photometric_map(context[v].to(dt), image.to(dt))]
+            st = torch.cat(ms, 1)
+            stacks.append(st.detach())
+            li = st.min(1, True)[0].mean() if forced_sel is None else st.gather(1, forced_sel[i].unsqueeze(1)).mean()
+            total = total + gamma ** (n - i - 1) * li
+        grads = torch.autograd.grad(total, d + [x for tv in P for x in tv])
+        return total.detach(), stacks, grads
+
+    loss32, stacks32, _ = oracle_run(torch.float32)
+    sel_ref = [st.argmin(1) for st in stacks32]                           # [B,H,W] index into the 2V maps
+    _, _, g32 = oracle_run(torch.float32, sel_ref)
+    _, _, g64 = oracle_run(torch.float64, sel_ref)
+
+    dev = torch.device(DEV)
+    img, ctx = image.to(dev), [c.to(dev) for c in context]
+    inv, P = [x.to(dev) for x in invs], [x.to(dev) for tv in Ts for x in tv]
+    cams, _keep = L.make_cams(K.to(dev), K.to(dev), 1.0, None, None, None, L.POSE_MAT4)
+    opts = L.PhotoOpts(0.85, 1e-4, 9e-4, L.PAD_ZEROS, L.REDUCE_MIN, 1, gamma)
+    amask = torch.empty(B, H, W, device=dev)
+    sel = torch.empty(n, B, H, W, device=dev, dtype=torch.uint8)
+    loss = torch.zeros(1, device=dev)
+    ws = L.workspace(dev, V * n * B + n + 1)
+    lib = L.lib()
+    L.check(lib.drosfm_automask_fwd(L.ptr(img), L.ptr_array(ctx), V, opts, L.ptr(amask), B, H, W, L.stream()))
+    L.check(lib.drosfm_photometric_fwd(L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
+                                       L.ptr(amask), opts, L.ptr(sel), L.ptr(loss), L.ptr(ws), B, H, W, L.stream()))
+    assert_close(loss.cpu()[0], loss32, what="loss")
+    # (2) selection: identical except at near-ties
+    flips = 0
+    for i in range(n):
+        ours = sel[i].cpu().long()
+        ref = sel_ref[i]
+        same = torch.where(ours == 255, ref % 2 == 1, ours * 2 == ref)
+        srt = torch.sort(stacks32[i], 1)[0]
+        margin = (srt[:, 1] - srt[:, 0]) / srt[:, 0].clamp(min=1e-6)
+        assert (margin[~same] < 1e-3).all(), "arg-min differs from the oracle away from a tie"
+        flips += int((~same).sum())
+    assert flips <= 1e-4 * n * B * H * W
+    # (3) gradients for the oracle's selection
+    sel_forced = torch.stack([torch.where(r % 2 == 1, torch.full_like(r, 255), r // 2) for r in sel_ref]).to(torch.uint8).to(dev)
+    g_inv = torch.empty(n, B, 1, H, W, device=dev)
+    g_pose = torch.empty(V * n, B, 4, 4, device=dev)
+    one = torch.ones(1, device=dev)
+    L.check(lib.drosfm_photometric_bwd(L.ptr(one), L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams,
+                                       L.ptr_array(P), L.ptr(sel_forced), opts, L.ptr_array(list(g_inv)), L.ptr_array(list(g_pose)),
+                                       L.ptr(ws), B, H, W, L.stream()))
+    for i in range(n):
+        assert_close_or_better(g_inv[i].cpu(), g32[i], g64[i], what=f"g_inv{i}")
+    for k in range(V * n):
+        assert_close_or_better(g_pose[k].cpu(), g32[n + k], g64[n + k], what=f"g_pose{k}")
+
+
+def test_photometric_euler_poses_match_matrix_poses():
+    from dro_sfm_b200 import ops, synthetic as syn
+    g = syn.gen(5)
+    B, H, W, V, n = 2, 64, 96, 2, 2
+    K = syn.intrinsics("kitti", B, H, W).to(DEV)
+    image = syn.images(g, B, H, W).to(DEV)
+    context = [syn.images(g, B, H, W).to(DEV) for _ in range(V)]
+    invs = [syn.inv_depth(g, B, H, W, 0.5, 80.0).to(DEV) for _ in range(n)]
+    vecs = [[(syn.pose_vec(g, B, "kitti") * 0.2).to(DEV).requires_grad_(True) for _ in range(n)] for _ in range(V)]
+    total_v, _ = ops.photometric_loss(image, context, invs, K, K, vecs)
+    gv = torch.autograd.grad(total_v.sum(), [x for tv in vecs for x in tv])
+    vecs2 = [[x.detach().clone().requires_grad_(True) for x in tv] for tv in vecs]
+    total_m, _ = ops.photometric_loss(image, context, invs, K, K, [[ops.pose_vec2mat(x) for x in tv] for tv in vecs2])
+    gm = torch.autograd.grad(total_m.sum(), [x for tv in vecs2 for x in tv])
+    assert torch.equal(total_v, total_m)
+    for a, b in zip(gv, gm):
+        assert_close(a.cpu(), b.cpu(), what="g_vec fused vs chained")
+
+
+def test_supervised_loss_module_golden(golden):
+    from dro_sfm_b200.losses import SupervisedDepthPoseLoss
+    from dro_sfm_b200.geometry import Pose
+    g = golden("supervised")
+    V, n = 2, 3
+    K = cu(g["K"], torch.float64)
+    gt_inv = cu(g["gt_inv_depth"])
+    invs = [cu(g[f"inv{i}"]).requires_grad_(True) for i in range(n)]
+    pred = [[cu(g[f"pred_T{v}_{i}"]).requires_grad_(True) for i in range(n)] for v in range(V)]
+    gtT = [cu(g[f"gt_T{v}"]) for v in range(V)]
+    mod = SupervisedDepthPoseLoss(min_depth=0.2, max_depth=80.0)
+    image = torch.zeros(2, 3, 24, 40, device=DEV)
+    out = mod(image, [image, image], invs, gt_inv, gtT, K, K, [[Pose(x) for x in tv] for tv in pred])
+    flat = invs + [x for tv in pred for x in tv]
+    grads = torch.autograd.grad(out["loss"].sum(), flat)
+    assert_close(out["metrics"]["pose_loss"].cpu(), g["f32_pose_loss"], what="pose_loss")
+    assert_close(out["metrics"]["depth_loss"].cpu(), g["f32_depth_loss"], what="depth_loss")
+    assert_close(out["loss"].detach().cpu()[0], g["f32_pose_loss"] + g["f32_depth_loss"], what="loss")
+    for i in range(n):
+        assert_close_or_better(grads[i].cpu(), g[f"f32_g_inv{i}"], g[f"f64_g_inv{i}"], what=f"g_inv{i}", reduction=False)
+    k = n
+    for v in range(V):
+        for i in range(n):
+            assert_close_or_better(grads[k].cpu(), g[f"f32_g_T{v}_{i}"], g[f"f64_g_T{v}_{i}"], what=f"g_T{v}_{i}")
+            k += 1
+    # the reference's stand-alone helper keeps working: coordinates and mask are bit-exact
+    coords, mask = mod.get_ref_coords(gtT[0], K, K, cu(oracle.inv2depth(t(g["gt_inv_depth"])).numpy()), 1, DEV)
+    assert np.array_equal(coords.cpu().numpy(), g["coords_gt0"]) and np.array_equal(mask.cpu().numpy(), g["mask_gt0"])
+
+
+def test_camera_and_view_synthesis_dropins(golden):
+    """Reference-style calls: Camera(K).scaled(s), reconstruct/project, view_synthesis(ref_image, depth, ref_cam, cam)."""
+    from dro_sfm_b200.geometry import Camera, Pose, view_synthesis
+    g = golden("coords")
+    for tag in ("kitti", "scan8"):
+        K, s = cu(g[f"{tag}_K"], torch.float64), float(g[f"{tag}_scale"])
+        depth, T = cu(g[f"{tag}_depth"]), cu(g[f"{tag}_T"])
+        cam = Camera(K=K.float()).scaled(s).to(DEV)
+        ref_cam = Camera(K=K.float(), Tcw=Pose(T)).scaled(s).to(DEV)
+        assert np.array_equal(cam.K.cpu().numpy(), g[f"{tag}_Ks"]) and np.array_equal(cam.Kinv.cpu().numpy(), g[f"{tag}_Kinv"])
+        Pw = cam.reconstruct(depth, frame="w")
+        assert np.array_equal(Pw.cpu().numpy(), g[f"{tag}_Pw"])
+        assert np.array_equal(cam.reconstruct(depth, frame="c").cpu().numpy(), g[f"{tag}_Pc"])
+        assert np.array_equal(ref_cam.project(Pw, frame="w").cpu().numpy(), g[f"{tag}_uv"])
+        assert np.array_equal(ref_cam.project(Pw, frame="w", normalize=False).cpu().numpy(), g[f"{tag}_uv_raw"])
+        with pytest.raises(ValueError):
+            cam.reconstruct(depth, frame="x")
+        with pytest.raises(AssertionError):
+            cam.reconstruct(torch.cat([depth, depth], 1))
+    g = golden("view_synthesis")
+    K = cu(g["K"]).float()
+    depth = cu(oracle.inv2depth(t(g["inv_depth"])).numpy())
+    for pad in ("zeros", "border"):
+        out = view_synthesis(cu(g["src"]), depth, Camera(K=K, Tcw=Pose(cu(g["T"]))), Camera(K=K), padding_mode=pad)
+        assert_close(out.cpu(), g[f"{pad}_f32_out"], what=f"view_synthesis {pad}")
+        # non-identity target camera: falls back to the three individual kernels
+        eye = Pose(torch.eye(4, device=DEV).repeat(2, 1, 1))
+        out2 = view_synthesis(cu(g["src"]), depth, Camera(K=K, Tcw=Pose(cu(g["T"]))), Camera(K=K, Tcw=eye), padding_mode=pad)
+        assert_close(out2.cpu(), g[f"{pad}_f32_out"], what=f"view_synthesis (unfused) {pad}")
+
+
+def test_cost_dropins_match_reference_signature(golden):
+    from dro_sfm_b200.networks import get_cost_each, depth_cost_calc
+    g = golden("feat_cost")
+    K = cu(g["K"], torch.float64)
+    depth = cu(oracle.inv2depth(t(g["inv_depth"])).numpy())
+    c = get_cost_each(cu(g["pose0"]), cu(g["fmap"]), cu(g["fref0"]), depth, K, K, 1.0 / 8)
+    assert c.shape == g["each_f32_cost"].shape
+    assert_close(c.cpu(), g["each_f32_cost"], rtol=1e-4, atol=1e-5, what="get_cost_each (euler prologue: 1-ulp trig)")
+    c = depth_cost_calc(cu(g["inv_depth"]), cu(g["fmap"]), (cu(g["fref0"]), cu(g["fref1"])), [cu(g["pose0"]), cu(g["pose1"])],
+                        K, K, 1.0 / 8)
+    assert_close(c.cpu(), g["depth_f32_cost"], rtol=1e-4, atol=1e-5, what="depth_cost_calc (euler prologue: 1-ulp trig)")
