@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Hot-path benchmark of dro_sfm_b200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--layout nchw|nhwc]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # CPU arm: the reference's algorithm on the host cores
+
+A step = one pass of the dense depth-pose warping hot path over one batch (dro_sfm_b200/hotpath.py):
+2*V*T feature-metric cost evaluations fwd+bwd plus the multi-view photometric (or supervised
+reprojection) loss fwd+bwd, issued through the reference's operator surface.  Metric: frames/s
+(frame = one batch sample).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "warp+cost+photometric fwd+bwd frames/sec"
+UNIT = "frames/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle port, PyTorch CPU) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step(wl, batch, threads):
+    """One frame-batch of the same hot-path work with the CPU oracle (test infrastructure used here only
+    as the reported baseline): 2*V*T cost evaluations fwd+bwd + the loss fwd+bwd."""
+    import oracle
+    torch.set_num_threads(threads)
+    K = batch["K"]
+    fmap = batch["fmap"].clone().requires_grad_(True)
+    frefs = [f.clone().requires_grad_(True) for f in batch["fmaps_ref"]]
+    B, C, h, w = fmap.shape
+    g = torch.Generator().manual_seed(99)
+    gout = torch.randn(B, C, h, w, generator=g)
+    outs = []
+    for t in range(wl.T):
+        inv = batch["inv_depth_lr"][t].clone().requires_grad_(True)
+        outs.append(oracle.depth_cost(inv, fmap, frefs, [p for p in batch["pose_lr"][t]], K, K, 0.125))
+        depth = oracle.inv2depth(batch["inv_depth_lr"][(t // wl.seq_len) * wl.seq_len])
+        for v in range(wl.V):
+            pose = batch["pose_lr"][t][v].clone().requires_grad_(True)
+            outs.append(oracle.feat_cost_each(pose, fmap, frefs[v], depth, K, K, 0.125))
+    invs = [x.clone().requires_grad_(True) for x in batch["inv_depths"]]
+    pvec = [[p.clone().requires_grad_(True) for p in row] for row in batch["poses"]]
+    Ts = [[oracle.pose_vec_to_T(p) for p in row] for row in pvec]
+    if wl.supervised:
+        loss = oracle.reproj_pose_loss(Ts, [oracle.pose_vec_to_T(p) for p in batch["gt_poses"]],
+                                       oracle.inv2depth(batch["gt_inv_depth"]), K, K, wl.min_depth, wl.max_depth) \
+            + oracle.supervised_depth_loss(invs, batch["gt_inv_depth"], wl.min_depth, wl.max_depth)
+    else:
+        loss, _ = oracle.multiview_photometric_decay_loss(batch["image"], batch["context"], invs, K, K, Ts, smooth_w=0.001,
+                                                          automask=True, reduce_op="min")
+    torch.autograd.backward([loss.sum()] + outs, [torch.ones(())] + [gout] * len(outs))
+    return float(loss.sum())
+
+
+def time_cpu(wl, B, reps, threads):
+    from dro_sfm_b200 import synthetic as syn
+    batch = syn.hot_path_batch(wl, seed=1234, C=128, B=B)
+    cpu_step(wl, batch, threads)                     # warm-up
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_step(wl, batch, threads)
+        best = min(best, time.perf_counter() - t0)
+    return B / best, best
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    from dro_sfm_b200 import synthetic as syn
+    B = 1
+    batch = syn.hot_path_batch(wl, seed=1234, C=128, B=B)
+    for _ in range(min(args.warmup, 1)):
+        cpu_step(wl, batch, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(wl, batch, threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = B / dt
+    sample = "B=1 frame of %s per step (all %d cost calls + loss, fwd+bwd), PyTorch-CPU oracle port" % (wl.name, 2 * wl.V * wl.T)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl.name, "H": wl.H, "W": wl.W, "views": wl.V, "gru_steps": wl.T, "predictions": wl.n,
+                   "batch_per_step": B, "device": "cpu"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+KERNEL_KEYS = {
+    "drosfm_feat_cost_fwd": lambda a: "feat_cost_fwd_v1" if a[6] == 1 else "feat_cost_fwd_vN",
+    "drosfm_feat_cost_bwd": lambda a: "feat_cost_bwd_v1" if a[7] == 1 else "feat_cost_bwd_vN",
+    "drosfm_photometric_fwd": lambda a: "photometric_fwd", "drosfm_photometric_bwd": lambda a: "photometric_bwd",
+    "drosfm_automask_fwd": lambda a: "automask_fwd", "drosfm_smoothness_fwd": lambda a: "smoothness_fwd",
+    "drosfm_smoothness_bwd": lambda a: "smoothness_bwd", "drosfm_reproj_loss_fwd": lambda a: "reproj_loss_fwd",
+    "drosfm_reproj_loss_bwd": lambda a: "reproj_loss_bwd", "drosfm_pose_vec2mat_fwd": lambda a: "pose_vec2mat_fwd",
+    "drosfm_pose_vec2mat_bwd": lambda a: "pose_vec2mat_bwd",
+}
+
+
+def run_gpu(args, wl):
+    import torch.distributed as dist
+    from dro_sfm_b200 import _lib as L
+    from dro_sfm_b200.hotpath import HotPathStep
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.lib()
+    B = args.batch or wl.B
+    step = HotPathStep(wl, dev, B=B, seed=1234 + 1000 * rank, channels_last=(args.layout == "nhwc"))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB of L2
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if not args.no_graph:
+        step.capture(warmup=3)
+    launches_per_step = getattr(step, "launches_per_step", None)
+    loss_host = torch.empty(1, pin_memory=True)
+
+    def one_step(e2e):
+        if e2e:
+            step.upload()
+        loss = step.step()
+        if world > 1:
+            dist.all_reduce(loss, op=dist.ReduceOp.AVG)        # the only collective on the path: the logged loss
+        if e2e:
+            loss_host.copy_(loss.detach(), non_blocking=True)
+        return loss
+
+    def timed(e2e, steps):
+        evs = []
+        for _ in range(steps):
+            flush.zero_()                                         # evict L2 between timed iterations
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            one_step(e2e)
+            e.record()
+            evs.append((s, e))
+        return evs
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(False)
+        one_step(True)
+    if launches_per_step is None:
+        before = L.lib().drosfm_launch_count()
+        one_step(False)
+        launches_per_step = int(L.lib().drosfm_launch_count() - before)
+
+    clocks = ClockSampler(local)
+    sync_all()
+    if rank == 0:
+        clocks.start()
+    evs = timed(False, args.steps)
+    sync_all()
+    ms = sum(s.elapsed_time(e) for s, e in evs)
+    evs = timed(True, args.steps)
+    sync_all()
+    ms_e2e = sum(s.elapsed_time(e) for s, e in evs)
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    frames = B * world * args.steps
+    value, e2e_value = frames / (ms * 1e-3), frames / (ms_e2e * 1e-3)
+
+    # per-kernel durations: the same K steps issued eagerly with CUDA events around every C-ABI launch
+    roofline = None
+    if rank == 0:
+        graph, step.graph = step.graph, None
+        step.step()
+        torch.cuda.synchronize()
+        L.profile_begin()
+        for _ in range(args.steps):
+            flush.zero_()
+            step.step()
+        recs = L.profile_end()
+        step.graph = graph
+        per = {}
+        for name, a, t_ms in recs:
+            key = KERNEL_KEYS.get(name, lambda _a: name)(a)
+            per.setdefault(key, []).append(t_ms)
+        alg = step.algorithmic_bytes()
+        totals = {k: sum(v) for k, v in per.items()}
+        dom = max((k for k in totals if k in alg), key=lambda k: totals[k])
+        avg_ms = totals[dom] / len(per[dom])
+        peak, peak_src = measured_peaks()
+        achieved = alg[dom] / (avg_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "bytes_per_launch": alg[dom], "avg_launch_ms": avg_ms,
+                    "launches": len(per[dom]) // args.steps,
+                    "share_of_kernel_time": totals[dom] / sum(totals.values()),
+                    "step_algorithmic_GBps": alg["step_total"] / (ms / args.steps * 1e-3) / 1e9,
+                    "kernel_ms_per_step": {k: round(v / args.steps, 4) for k, v in sorted(totals.items())}}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, best = time_cpu(wl, 1, 3, threads)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "B=1 frame of %s (all %d cost calls + loss, fwd+bwd), best of 3 after 1 warm-up, %.2f s each; "
+                             "PyTorch-CPU oracle port of the reference" % (wl.name, 2 * wl.V * wl.T, best)}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl.name, "H": wl.H, "W": wl.W, "views": wl.V, "gru_steps": wl.T, "predictions": wl.n,
+                       "batch_per_gpu": B, "global_batch": B * world, "feature_layout": args.layout,
+                       "cuda_graph": not args.no_graph, "l2": "flushed between timed iterations (256 MiB write)",
+                       "parallelism": "dp%d" % world},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": step.h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="train_kitti_mf_selfsup")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the YAML's batch_size)")
+    ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    from dro_sfm_b200 import synthetic as syn
+    wl = syn.WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_gpu(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,7 @@ _op = ctypes.POINTER(PhotoOpts)
 SIGNATURES = {
     "drosfm_version": ([], _int),
     "drosfm_last_error": ([], ctypes.c_char_p),
+    "drosfm_launch_count": ([], ctypes.c_ulonglong),
     "drosfm_ws_bytes": ([_int], ctypes.c_size_t),
     "drosfm_pose_vec2mat_fwd": ([_vp, _vp, _int, _vp], _int),
     "drosfm_pose_vec2mat_bwd": ([_vp, _vp, _vp, _int, _vp], _int),
@@ -84,9 +85,52 @@ _lib = None
 _lock = threading.Lock()
 
 
+class _TimedLib:
+    """Proxy that brackets every kernel entry point with CUDA events on the launching stream
+    (bench.py uses it for the per-kernel roofline; never active on the product path)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self.records = []      # (name, args, start_event, end_event)
+
+    def __getattr__(self, name):
+        fn = getattr(self._h, name)
+        if not name.endswith(("_fwd", "_bwd")):
+            return fn
+
+        def timed(*args):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = fn(*args)
+            e.record()
+            self.records.append((name, args, s, e))
+            return rc
+        return timed
+
+
+_timed = None
+
+
+def profile_begin():
+    """Start per-call CUDA-event timing of the C-ABI entry points."""
+    global _timed
+    _timed = _TimedLib(lib())
+    return _timed
+
+
+def profile_end():
+    """Stop timing; returns [(name, args, milliseconds)] after synchronising."""
+    global _timed
+    t, _timed = _timed, None
+    torch.cuda.synchronize()
+    return [(name, args, s.elapsed_time(e)) for name, args, s, e in t.records]
+
+
 def lib():
     """The loaded library; raises RuntimeError if it is missing (no fallback path exists)."""
     global _lib
+    if _timed is not None:
+        return _timed
     if _lib is None:
         with _lock:
             if _lib is None:
@@ -182,7 +226,7 @@ _workspaces = {}
 def workspace(device, slots):
     """Zero-initialised, self-cleaning reduction workspace, one per (device, stream)."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    need = max(64, int(slots)) * SLOT_BYTES
+    need = int(lib().drosfm_ws_bytes(max(64, int(slots))))
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.zeros(need * 2, dtype=torch.uint8, device=device)

@@ -119,8 +119,8 @@ warp_coords_bwd_kernel(const float* __restrict__ g_uv, const float* __restrict__
         }
     }
     if (g_pose == nullptr) return;
-    Slot* slot = ws + b;
-    block_accumulate<12>(gT, red, slot->acc);
+    Slot* slot = slot_at(ws, b);
+    block_accumulate<12>(gT, red, spread_acc(slot));
     if (last_block(slot, gridDim.x, &flag) && threadIdx.x == 0) {
         const int stride = cams.pose_kind == DROSFM_POSE_EULER6 ? 6 : 16;
         finish_pose_grad(slot, cams.pose_kind, cams.pose_kind == DROSFM_POSE_EULER6 ? cams.pose + b * 6 : nullptr,
@@ -262,8 +262,8 @@ project_bwd_kernel(const float* __restrict__ g_uv, const float* __restrict__ poi
         }
     }
     if (g_Tcw == nullptr) return;
-    Slot* slot = ws + b;
-    block_accumulate<12>(gT, red, slot->acc);
+    Slot* slot = slot_at(ws, b);
+    block_accumulate<12>(gT, red, spread_acc(slot));
     if (last_block(slot, gridDim.x, &flag) && threadIdx.x == 0)
         finish_pose_grad(slot, DROSFM_POSE_MAT4, nullptr, g_Tcw + b * 16);
 }

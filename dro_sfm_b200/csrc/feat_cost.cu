@@ -47,57 +47,91 @@ __device__ __forceinline__ float blend(const float* v, const Weights& w) {
 }
 
 // ------------------------------------------------------------------------------------------
-// NCHW forward
+// NCHW: lane = pixel, CG channels per thread with every load of a view issued before the first use
 // ------------------------------------------------------------------------------------------
 constexpr int kPixThreads = 128;
 
-template <int VT>
+// Bilinear taps in "clamped" form: the four element offsets are always inside the source plane and an
+// out-of-bounds tap carries weight 0, so the gathers need no predicates.
+struct CTaps {
+    int o00, dx, dy;            // offset of the clamped north-west tap, +dx = east, +dy = south
+    float w00, w01, w10, w11;
+    float ax, ay;
+    unsigned valid;
+    int x0, y0;
+};
+
+__device__ __forceinline__ void make_ctaps(float u, float v, int h, int w, CTaps& c) {
+    Taps t;
+    make_taps(u, v, h, w, DROSFM_PAD_ZEROS, t);
+    const float bx = 1.0f - t.ax, by = 1.0f - t.ay;
+    c.w00 = (t.valid & 1u) ? bx * by : 0.0f;
+    c.w01 = (t.valid & 2u) ? t.ax * by : 0.0f;
+    c.w10 = (t.valid & 4u) ? bx * t.ay : 0.0f;
+    c.w11 = (t.valid & 8u) ? t.ax * t.ay : 0.0f;
+    const int x0 = max(t.x0, 0), y0 = max(t.y0, 0);
+    const int x1 = min(t.x0 + 1, w - 1), y1 = min(t.y0 + 1, h - 1);
+    c.o00 = y0 * w + x0;
+    c.dx = x1 - x0;
+    c.dy = (y1 - y0) * w;
+    c.ax = t.ax; c.ay = t.ay; c.valid = t.valid; c.x0 = t.x0; c.y0 = t.y0;
+}
+
+template <int VT, int CG>
 __global__ void __launch_bounds__(kPixThreads)
 feat_cost_fwd_nchw(const float* __restrict__ fmap, ViewPtrs vp, const float* __restrict__ depth, int depth_kind,
-                   drosfm_cams_t cams, int V, float* __restrict__ cost, int C, int h, int w, int cg) {
+                   drosfm_cams_t cams, int V, float* __restrict__ cost, int C, int h, int w) {
     __shared__ Cam cam[VT];
     const int b = blockIdx.z, P = h * w;
     const int p = blockIdx.x * kPixThreads + threadIdx.x;
     const bool active = p < P;
-    const float d = active ? to_depth(__ldg(depth + static_cast<size_t>(b) * P + p), depth_kind) : 0.0f;
+    const int c0 = blockIdx.y * CG;
+    const size_t base = (static_cast<size_t>(b) * C + c0) * P + p;
+    // loads that do not depend on the coordinates go out first and overlap the camera set-up
+    const float draw = active ? __ldg(depth + static_cast<size_t>(b) * P + p) : 0.0f;
+    float f[CG];
+#pragma unroll
+    for (int k = 0; k < CG; ++k) f[k] = (active && c0 + k < C) ? __ldg(fmap + base + static_cast<size_t>(k) * P) : 0.0f;
 #pragma unroll
     for (int v = 0; v < VT; ++v)
         if (v < V && threadIdx.x == v) setup_cam(cams, vp.pose[v], b, cam[v]);
     __syncthreads();
     if (!active) return;
+    const float d = to_depth(draw, depth_kind);
     const float wm1 = static_cast<float>(w - 1), hm1 = static_cast<float>(h - 1);
     int x, y;
     pix_xy(p, w, x, y);
-    Taps t[VT];
-    Weights wt[VT];
+    float acc[CG];
+#pragma unroll
+    for (int k = 0; k < CG; ++k) acc[k] = 0.0f;
 #pragma unroll
     for (int v = 0; v < VT; ++v) {
         if (v < V) {
             Warp wp;
             warp_pixel(cam[v], x, y, d, wm1, hm1, true, wp);
-            make_taps(wp.p.u, wp.p.v, h, w, DROSFM_PAD_ZEROS, t[v]);
-            wt[v] = tap_weights(t[v]);
-        }
-    }
-    const int c0 = blockIdx.y * cg, c1 = min(C, c0 + cg);
-    const float fV = static_cast<float>(V);
-    const size_t sample = static_cast<size_t>(b) * C * P;
-#pragma unroll 4
-    for (int c = c0; c < c1; ++c) {
-        const size_t plane = sample + static_cast<size_t>(c) * P;
-        const float f = __ldg(fmap + plane + p);
-        float acc = 0.0f;
+            CTaps t;
+            make_ctaps(wp.p.u, wp.p.v, h, w, t);
+            const float* r = vp.ref[v] + (static_cast<size_t>(b) * C + c0) * P + t.o00;
+            float tv[CG][4];
 #pragma unroll
-        for (int v = 0; v < VT; ++v) {
-            if (v < V) {
-                float tv[4];
-                tap_values(vp.ref[v] + plane, w, t[v], tv);
-                const float df = f - blend(tv, wt[v]);
-                acc += df * df;
+            for (int k = 0; k < CG; ++k) {
+                const float* rk = r + static_cast<size_t>(c0 + k < C ? k : 0) * P;
+                tv[k][0] = __ldg(rk);
+                tv[k][1] = __ldg(rk + t.dx);
+                tv[k][2] = __ldg(rk + t.dy);
+                tv[k][3] = __ldg(rk + t.dy + t.dx);
+            }
+#pragma unroll
+            for (int k = 0; k < CG; ++k) {
+                const float df = f[k] - (tv[k][0] * t.w00 + tv[k][1] * t.w01 + tv[k][2] * t.w10 + tv[k][3] * t.w11);
+                acc[k] += df * df;
             }
         }
-        cost[plane + p] = V == 1 ? acc : acc / fV;
     }
+    const float fV = static_cast<float>(V);
+#pragma unroll
+    for (int k = 0; k < CG; ++k)
+        if (c0 + k < C) cost[base + static_cast<size_t>(k) * P] = V == 1 ? acc[k] : acc[k] / fV;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -107,7 +141,8 @@ struct MergePlan {
     bool give, take;
 };
 
-__device__ __forceinline__ MergePlan plan_merge(const Taps& t, bool active) {
+// Lane L hands its east taps to lane L+1 when that lane's west taps are the same source pixels.
+__device__ __forceinline__ MergePlan plan_merge(const CTaps& t, bool active) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const bool on = active && t.valid != 0u;
@@ -119,102 +154,114 @@ __device__ __forceinline__ MergePlan plan_merge(const Taps& t, bool active) {
     return m;
 }
 
-__device__ __forceinline__ void scatter_taps(float* __restrict__ plane, int Ws, const Taps& t, const Weights& w,
-                                             const MergePlan& m, float g) {
+__device__ __forceinline__ void scatter_taps(float* __restrict__ plane, const CTaps& t, const MergePlan& m, float g) {
     const unsigned full = 0xffffffffu;
-    float cnw = g * w.nw, cne = g * w.ne, csw = g * w.sw, cse = g * w.se;
+    float cnw = g * t.w00, cne = g * t.w01, csw = g * t.w10, cse = g * t.w11;
     const float rn = __shfl_up_sync(full, cne, 1), rs = __shfl_up_sync(full, cse, 1);
     if (m.take) { cnw += rn; csw += rs; }
-    float* r0 = plane + t.y0 * Ws + t.x0;
+    float* r0 = plane + t.o00;
     if (t.valid & 1u) atomicAdd(r0, cnw);
-    if (t.valid & 4u) atomicAdd(r0 + Ws, csw);
+    if (t.valid & 4u) atomicAdd(r0 + t.dy, csw);
     if (!m.give) {
-        if (t.valid & 2u) atomicAdd(r0 + 1, cne);
-        if (t.valid & 8u) atomicAdd(r0 + Ws + 1, cse);
+        if (t.valid & 2u) atomicAdd(r0 + t.dx, cne);
+        if (t.valid & 8u) atomicAdd(r0 + t.dy + t.dx, cse);
     }
 }
 
-template <int VT>
+template <int VT, int CG>
 __global__ void __launch_bounds__(kPixThreads)
 feat_cost_bwd_nchw(const float* __restrict__ g_cost, const float* __restrict__ fmap, ViewPtrs vp,
                    const float* __restrict__ depth, int depth_kind, drosfm_cams_t cams, int V,
                    float* __restrict__ g_fmap, ViewGrads vg, float* __restrict__ g_depth, Slot* ws,
-                   int B, int C, int h, int w, int cg, int need_coord_grad) {
+                   int B, int C, int h, int w, int need_coord_grad) {
     __shared__ Cam cam[VT];
-    __shared__ double red[12 * (kPixThreads / 32)];
     __shared__ int flag;
     const int b = blockIdx.z, P = h * w;
     const int p = blockIdx.x * kPixThreads + threadIdx.x;
     const bool active = p < P;
+    const int c0 = blockIdx.y * CG;
+    const size_t base = (static_cast<size_t>(b) * C + c0) * P + p;
     const float draw = active ? __ldg(depth + static_cast<size_t>(b) * P + p) : 0.0f;
-    const float d = to_depth(draw, depth_kind);
+    const float scale = 2.0f / static_cast<float>(V);
+    float g[CG], f[CG], gf[CG];
+#pragma unroll
+    for (int k = 0; k < CG; ++k) {
+        const bool ok = active && c0 + k < C;
+        g[k] = ok ? __ldg(g_cost + base + static_cast<size_t>(k) * P) * scale : 0.0f;
+        f[k] = ok ? __ldg(fmap + base + static_cast<size_t>(k) * P) : 0.0f;
+        gf[k] = 0.0f;
+    }
 #pragma unroll
     for (int v = 0; v < VT; ++v)
         if (v < V && threadIdx.x == v) setup_cam(cams, vp.pose[v], b, cam[v]);
     __syncthreads();
+    const float d = to_depth(draw, depth_kind);
     const float wm1 = static_cast<float>(w - 1), hm1 = static_cast<float>(h - 1);
     int x = 0, y = 0;
     if (active) pix_xy(p, w, x, y);
-    Taps t[VT];
-    Weights wt[VT];
-    MergePlan mp[VT];
-    float gx[VT], gy[VT];
-#pragma unroll
-    for (int v = 0; v < VT; ++v) {
-        t[v].valid = 0u; t[v].x0 = t[v].y0 = 0; t[v].ax = t[v].ay = 0.0f; t[v].mx = t[v].my = 0.0f;
-        gx[v] = gy[v] = 0.0f;
-        mp[v].give = mp[v].take = false;
-        if (v < V) {
-            if (active) {
-                Warp wp;
-                warp_pixel(cam[v], x, y, d, wm1, hm1, true, wp);
-                make_taps(wp.p.u, wp.p.v, h, w, DROSFM_PAD_ZEROS, t[v]);
-            }
-            if (vg.g_ref[v] != nullptr) mp[v] = plan_merge(t[v], active);
-        }
-        wt[v] = tap_weights(t[v]);
-    }
-    const int c0 = blockIdx.y * cg, c1 = min(C, c0 + cg);
-    const float scale = 2.0f / static_cast<float>(V);
-    const size_t sample = static_cast<size_t>(b) * C * P;
-    for (int c = c0; c < c1; ++c) {
-        const size_t plane = sample + static_cast<size_t>(c) * P;
-        const float g = active ? __ldg(g_cost + plane + p) * scale : 0.0f;
-        const float f = active ? __ldg(fmap + plane + p) : 0.0f;
-        float gf = 0.0f;
-#pragma unroll
-        for (int v = 0; v < VT; ++v) {
-            if (v < V) {
-                float tv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                if (t[v].valid) tap_values(vp.ref[v] + plane, w, t[v], tv);
-                const float coef = (f - blend(tv, wt[v])) * g;   // d cost / d fmap  (= -d cost / d warped)
-                gf += coef;
-                if (need_coord_grad) {
-                    const float bx = 1.0f - t[v].ax, by = 1.0f - t[v].ay;
-                    gx[v] -= coef * ((tv[1] - tv[0]) * by + (tv[3] - tv[2]) * t[v].ay);
-                    gy[v] -= coef * ((tv[2] - tv[0]) * bx + (tv[3] - tv[1]) * t[v].ax);
-                }
-                if (vg.g_ref[v] != nullptr) scatter_taps(vg.g_ref[v] + plane, w, t[v], wt[v], mp[v], -coef);
-            }
-        }
-        if (active && g_fmap != nullptr) g_fmap[plane + p] = gf;
-    }
-    if (!need_coord_grad) return;
     float gd = 0.0f;
 #pragma unroll
     for (int v = 0; v < VT; ++v) {
         if (v < V) {
-            float gT[12];
-#pragma unroll
-            for (int i = 0; i < 12; ++i) gT[i] = 0.0f;
+            CTaps t;
+            t.o00 = t.dx = t.dy = 0; t.w00 = t.w01 = t.w10 = t.w11 = 0.0f; t.ax = t.ay = 0.0f; t.valid = 0u; t.x0 = t.y0 = 0;
+            Warp wp;
             if (active) {
-                Warp wp;
                 warp_pixel(cam[v], x, y, d, wm1, hm1, true, wp);
-                gd += warp_pixel_adjoint(cam[v], wp, d, wm1, hm1, true, gx[v] * t[v].mx, gy[v] * t[v].my, gT);
+                make_ctaps(wp.p.u, wp.p.v, h, w, t);
             }
-            if (vg.g_pose[v] != nullptr) {
-                Slot* slot = ws + (v * B + b);
-                block_accumulate<12>(gT, red, slot->acc);
+            const float* r = vp.ref[v] + (static_cast<size_t>(b) * C + c0) * P + t.o00;
+            float tv[CG][4];
+#pragma unroll
+            for (int k = 0; k < CG; ++k) {
+                const float* rk = r + static_cast<size_t>(c0 + k < C ? k : 0) * P;
+                tv[k][0] = __ldg(rk);
+                tv[k][1] = __ldg(rk + t.dx);
+                tv[k][2] = __ldg(rk + t.dy);
+                tv[k][3] = __ldg(rk + t.dy + t.dx);
+            }
+            MergePlan mp;
+            mp.give = mp.take = false;
+            float* gref = vg.g_ref[v];
+            if (gref != nullptr) mp = plan_merge(t, active);
+            float gx = 0.0f, gy = 0.0f;
+            const float bx = 1.0f - t.ax, by = 1.0f - t.ay;
+#pragma unroll
+            for (int k = 0; k < CG; ++k) {
+                // d cost / d fmap  (= -d cost / d warped)
+                const float coef = (f[k] - (tv[k][0] * t.w00 + tv[k][1] * t.w01 + tv[k][2] * t.w10 + tv[k][3] * t.w11)) * g[k];
+                gf[k] += coef;
+                // taps outside the source count as zeros in the coordinate gradient
+                const float a0 = (t.valid & 1u) ? tv[k][0] : 0.0f, a1 = (t.valid & 2u) ? tv[k][1] : 0.0f;
+                const float a2 = (t.valid & 4u) ? tv[k][2] : 0.0f, a3 = (t.valid & 8u) ? tv[k][3] : 0.0f;
+                gx -= coef * ((a1 - a0) * by + (a3 - a2) * t.ay);
+                gy -= coef * ((a2 - a0) * bx + (a3 - a1) * t.ax);
+                if (gref != nullptr && c0 + k < C)
+                    scatter_taps(gref + (static_cast<size_t>(b) * C + c0 + k) * P, t, mp, -coef);
+            }
+            if (need_coord_grad) {
+                float gT[12];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) gT[i] = 0.0f;
+                if (active && t.valid) {
+                    const float mx = 0.5f * static_cast<float>(w - 1), my = 0.5f * static_cast<float>(h - 1);
+                    gd += warp_pixel_adjoint(cam[v], wp, d, wm1, hm1, true, gx * mx, gy * my, gT);
+                }
+                if (vg.g_pose[v] != nullptr) warp_accumulate<12>(gT, spread_acc(slot_at(ws, v * B + b)));
+            }
+        }
+    }
+    if (active && g_fmap != nullptr) {
+#pragma unroll
+        for (int k = 0; k < CG; ++k)
+            if (c0 + k < C) g_fmap[base + static_cast<size_t>(k) * P] = gf[k];
+    }
+    if (need_coord_grad) {
+        // one ticket per block and view: the last block converts the fp64 sums into the caller's encoding
+#pragma unroll
+        for (int v = 0; v < VT; ++v) {
+            if (v < V && vg.g_pose[v] != nullptr) {
+                Slot* slot = slot_at(ws, v * B + b);
                 if (last_block(slot, gridDim.x * gridDim.y, &flag) && threadIdx.x == 0) {
                     const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
                     finish_pose_grad(slot, cams.pose_kind, eul ? vp.pose[v] + b * 6 : nullptr,
@@ -223,37 +270,37 @@ feat_cost_bwd_nchw(const float* __restrict__ g_cost, const float* __restrict__ f
             }
         }
     }
-    if (active && g_depth != nullptr) {
-        if (depth_kind == DROSFM_INV_DEPTH) gd = inv2depth_grad(draw, gd);
-        if (gridDim.y == 1) g_depth[static_cast<size_t>(b) * P + p] = gd;
-        else atomicAdd(g_depth + static_cast<size_t>(b) * P + p, gd);
+    if (active) {
+        if (need_coord_grad && g_depth != nullptr) {
+            if (depth_kind == DROSFM_INV_DEPTH) gd = inv2depth_grad(draw, gd);
+            if (gridDim.y == 1) g_depth[static_cast<size_t>(b) * P + p] = gd;
+            else atomicAdd(g_depth + static_cast<size_t>(b) * P + p, gd);
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// NHWC (channels_last) forward: warp = 32 consecutive pixels, lane = 4 channels of a 128-channel slab
+// NHWC (torch channels_last): warp = `ppw` consecutive pixels, lane = 4 channels of a 128-channel slab.
+// Every tap, load and store is one 128-bit access per lane, i.e. 512 contiguous bytes per warp.
+// Lanes 0..ppw-1 first compute the taps of "their" pixel and park them in shared memory; the warp then
+// walks over the pixels with all lanes on the channel axis.  ppw is chosen by the host: small for small
+// maps (more warps in flight), 32 for large ones (coordinate work amortised over more bytes).
 // ------------------------------------------------------------------------------------------
 constexpr int kWarpsPerBlock = 4;
+constexpr int kMaxPpw = 32;
 
-struct TapB {   // taps of one pixel, broadcast from the lane that computed them
-    int off;        // (y0 * w + x0) element offset of the north-west tap (may be negative)
-    float ax, ay;
+struct alignas(16) STap {      // 32 bytes: two broadcast LDS.128 per pixel and view
+    int o00, dx, dy;           // element offsets (pixel units, to be multiplied by C)
     unsigned valid;
+    float w00, w01, w10, w11;
 };
 
-__device__ __forceinline__ TapB bcast(const Taps& t, int w, int src) {
-    const unsigned full = 0xffffffffu;
-    TapB o;
-    o.off = __shfl_sync(full, t.y0 * w + t.x0, src);
-    o.ax = __shfl_sync(full, t.ax, src);
-    o.ay = __shfl_sync(full, t.ay, src);
-    o.valid = __shfl_sync(full, t.valid, src);
-    return o;
+__device__ __forceinline__ void store_stap(STap* dst, const CTaps& t) {
+    dst->o00 = t.o00; dst->dx = t.dx; dst->dy = t.dy; dst->valid = t.valid;
+    dst->w00 = t.w00; dst->w01 = t.w01; dst->w10 = t.w10; dst->w11 = t.w11;
 }
 
-__device__ __forceinline__ float4 ld4z(const float* p, bool ok) {
-    return ok ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
-}
+__device__ __forceinline__ float4 ldg4f(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 __device__ __forceinline__ float4 blend4(const float4& a, const float4& b, const float4& c, const float4& d,
                                          float wa, float wb, float wc, float wd) {
@@ -264,59 +311,64 @@ __device__ __forceinline__ float4 blend4(const float4& a, const float4& b, const
 template <int VT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 feat_cost_fwd_nhwc(const float* __restrict__ fmap, ViewPtrs vp, const float* __restrict__ depth, int depth_kind,
-                   drosfm_cams_t cams, int V, float* __restrict__ cost, int C, int h, int w) {
+                   drosfm_cams_t cams, int V, float* __restrict__ cost, int C, int h, int w, int ppw) {
     __shared__ Cam cam[VT];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    STap* taps = reinterpret_cast<STap*>(dyn_smem);          // [warp][ppw][V]
     const int b = blockIdx.y, P = h * w;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int pbase = (blockIdx.x * kWarpsPerBlock + wid) * 32;
+    const int pbase = (blockIdx.x * kWarpsPerBlock + wid) * ppw;
+    const int npix = max(0, min(ppw, P - pbase));
+    const bool mine = lane < npix;
     const int p = pbase + lane;
-    const bool active = p < P;
-    const float d = active ? to_depth(__ldg(depth + static_cast<size_t>(b) * P + p), depth_kind) : 0.0f;
+    const float draw = mine ? __ldg(depth + static_cast<size_t>(b) * P + p) : 0.0f;
 #pragma unroll
     for (int v = 0; v < VT; ++v)
         if (v < V && threadIdx.x == v) setup_cam(cams, vp.pose[v], b, cam[v]);
     __syncthreads();
-    if (pbase >= P) return;
-    const float wm1 = static_cast<float>(w - 1), hm1 = static_cast<float>(h - 1);
-    int x = 0, y = 0;
-    if (active) pix_xy(p, w, x, y);
-    Taps t[VT];
+    if (npix == 0) return;
+    STap* wt = taps + static_cast<size_t>(wid) * ppw * V;
+    if (mine) {
+        const float d = to_depth(draw, depth_kind);
+        const float wm1 = static_cast<float>(w - 1), hm1 = static_cast<float>(h - 1);
+        int x, y;
+        pix_xy(p, w, x, y);
 #pragma unroll
-    for (int v = 0; v < VT; ++v) {
-        t[v].valid = 0u; t[v].x0 = t[v].y0 = 0; t[v].ax = t[v].ay = 0.0f;
-        if (v < V && active) {
-            Warp wp;
-            warp_pixel(cam[v], x, y, d, wm1, hm1, true, wp);
-            make_taps(wp.p.u, wp.p.v, h, w, DROSFM_PAD_ZEROS, t[v]);
+        for (int v = 0; v < VT; ++v) {
+            if (v < V) {
+                Warp wp;
+                warp_pixel(cam[v], x, y, d, wm1, hm1, true, wp);
+                CTaps t;
+                make_ctaps(wp.p.u, wp.p.v, h, w, t);
+                store_stap(wt + lane * V + v, t);
+            }
         }
     }
-    const int npix = min(32, P - pbase);
+    __syncwarp();
     const float fV = static_cast<float>(V);
     const size_t sample = static_cast<size_t>(b) * P * C;
     for (int cb0 = 0; cb0 < C; cb0 += 128) {
         const int cb = cb0 + lane * 4;
-        const bool chan_ok = cb < C;   // lanes beyond C idle but still take part in the shuffles
-#pragma unroll 2
+        if (cb >= C) continue;
+#pragma unroll 4
         for (int j = 0; j < npix; ++j) {
             const size_t px = sample + static_cast<size_t>(pbase + j) * C + cb;
-            const float4 f = ld4z(fmap + px, chan_ok);
+            const float4 f = ldg4f(fmap + px);
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int v = 0; v < VT; ++v) {
                 if (v < V) {
-                    const TapB tb = bcast(t[v], w, j);
-                    const float* r0 = vp.ref[v] + sample + static_cast<ptrdiff_t>(tb.off) * C + cb;
-                    const float4 a = ld4z(r0, chan_ok && (tb.valid & 1u)), bq = ld4z(r0 + C, chan_ok && (tb.valid & 2u));
-                    const float4 c = ld4z(r0 + static_cast<size_t>(w) * C, chan_ok && (tb.valid & 4u));
-                    const float4 e = ld4z(r0 + static_cast<size_t>(w) * C + C, chan_ok && (tb.valid & 8u));
-                    const float bx = 1.0f - tb.ax, by = 1.0f - tb.ay;
-                    const float4 wv = blend4(a, bq, c, e, bx * by, tb.ax * by, bx * tb.ay, tb.ax * tb.ay);
+                    const STap t = wt[j * V + v];
+                    const float* r0 = vp.ref[v] + sample + static_cast<size_t>(t.o00) * C + cb;
+                    const float4 a = ldg4f(r0), bq = ldg4f(r0 + t.dx * C);
+                    const float4 c = ldg4f(r0 + t.dy * C), e = ldg4f(r0 + (t.dy + t.dx) * C);
+                    const float4 wv = blend4(a, bq, c, e, t.w00, t.w01, t.w10, t.w11);
                     const float dx = f.x - wv.x, dy = f.y - wv.y, dz = f.z - wv.z, dw = f.w - wv.w;
                     acc.x += dx * dx; acc.y += dy * dy; acc.z += dz * dz; acc.w += dw * dw;
                 }
             }
             if (V != 1) { acc.x /= fV; acc.y /= fV; acc.z /= fV; acc.w /= fV; }
-            if (chan_ok) *reinterpret_cast<float4*>(cost + px) = acc;
+            *reinterpret_cast<float4*>(cost + px) = acc;
         }
     }
 }
@@ -326,94 +378,143 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Backward, NHWC: same pixel-to-warp mapping as the forward.  Per pixel and view the warp loads the upstream
+// gradient, the target features and the four taps (six 512-byte accesses), issues four 512-byte
+// red.global.add.v4.f32 into the source gradient and reduces the coordinate gradient with shuffles.  The loads
+// of pixel j+1 are issued before pixel j is consumed (software pipeline), the reductions carry no memory
+// clobber so the compiler may hoist the read-only loads across them.
+struct PixLoad {
+    float4 g, f, a, b, c, e;
+};
+
+__device__ __forceinline__ void red_add4_nc(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d));
+}
+
 template <int VT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ fmap, ViewPtrs vp,
                    const float* __restrict__ depth, int depth_kind, drosfm_cams_t cams, int V,
                    float* __restrict__ g_fmap, ViewGrads vg, float* __restrict__ g_depth, Slot* ws,
-                   int B, int C, int h, int w, int need_coord_grad) {
+                   int B, int C, int h, int w, int ppw, int need_coord_grad) {
     __shared__ Cam cam[VT];
-    __shared__ double red[12 * kWarpsPerBlock];
     __shared__ int flag;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    STap* taps = reinterpret_cast<STap*>(dyn_smem);                                                  // [warp][ppw][V]
+    float2* gxy = reinterpret_cast<float2*>(taps + static_cast<size_t>(kWarpsPerBlock) * ppw * V);   // [warp][ppw][V]
     const int b = blockIdx.y, P = h * w;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int pbase = (blockIdx.x * kWarpsPerBlock + wid) * 32;
+    const int pbase = (blockIdx.x * kWarpsPerBlock + wid) * ppw;
+    const int npix = max(0, min(ppw, P - pbase));
+    const bool mine = lane < npix;
     const int p = pbase + lane;
-    const bool active = p < P;
-    const float draw = active ? __ldg(depth + static_cast<size_t>(b) * P + p) : 0.0f;
+    const float draw = mine ? __ldg(depth + static_cast<size_t>(b) * P + p) : 0.0f;
     const float d = to_depth(draw, depth_kind);
 #pragma unroll
     for (int v = 0; v < VT; ++v)
         if (v < V && threadIdx.x == v) setup_cam(cams, vp.pose[v], b, cam[v]);
     __syncthreads();
     const float wm1 = static_cast<float>(w - 1), hm1 = static_cast<float>(h - 1);
+    STap* wt = taps + static_cast<size_t>(wid) * ppw * V;
+    float2* wg = gxy + static_cast<size_t>(wid) * ppw * V;
     int x = 0, y = 0;
-    if (active) pix_xy(p, w, x, y);
-    Taps t[VT];
-    float gx[VT], gy[VT];
+    float tax[VT], tay[VT];
+    unsigned tvalid[VT];
 #pragma unroll
-    for (int v = 0; v < VT; ++v) {
-        t[v].valid = 0u; t[v].x0 = t[v].y0 = 0; t[v].ax = t[v].ay = 0.0f; t[v].mx = t[v].my = 0.0f;
-        gx[v] = gy[v] = 0.0f;
-        if (v < V && active) {
-            Warp wp;
-            warp_pixel(cam[v], x, y, d, wm1, hm1, true, wp);
-            make_taps(wp.p.u, wp.p.v, h, w, DROSFM_PAD_ZEROS, t[v]);
+    for (int v = 0; v < VT; ++v) { tax[v] = tay[v] = 0.0f; tvalid[v] = 0u; }
+    if (mine) {
+        pix_xy(p, w, x, y);
+#pragma unroll
+        for (int v = 0; v < VT; ++v) {
+            if (v < V) {
+                Warp wp;
+                warp_pixel(cam[v], x, y, d, wm1, hm1, true, wp);
+                CTaps t;
+                make_ctaps(wp.p.u, wp.p.v, h, w, t);
+                store_stap(wt + lane * V + v, t);
+                tax[v] = t.ax; tay[v] = t.ay; tvalid[v] = t.valid;
+            }
         }
     }
-    const int npix = max(0, min(32, P - pbase));
+    __syncwarp();
     const float scale = 2.0f / static_cast<float>(V);
     const size_t sample = static_cast<size_t>(b) * P * C;
     for (int cb0 = 0; cb0 < C; cb0 += 128) {
         const int cb = cb0 + lane * 4;
-        const bool chan_ok = cb < C;   // lanes beyond C idle but still take part in the shuffles
-        for (int j = 0; j < npix; ++j) {
-            const size_t px = sample + static_cast<size_t>(pbase + j) * C + cb;
-            float4 g = make_float4(0.f, 0.f, 0.f, 0.f), f = g;
-            if (chan_ok) {
-                g = __ldg(reinterpret_cast<const float4*>(g_cost + px));
-                f = __ldg(reinterpret_cast<const float4*>(fmap + px));
-            }
-            g.x *= scale; g.y *= scale; g.z *= scale; g.w *= scale;
-            float4 gf = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool chan_ok = cb < C;      // lanes beyond C idle but still take part in the shuffles
+        const int cbs = chan_ok ? cb : 0;
 #pragma unroll
-            for (int v = 0; v < VT; ++v) {
-                if (v < V) {
-                    const TapB tb = bcast(t[v], w, j);
-                    const ptrdiff_t o = static_cast<ptrdiff_t>(tb.off) * C + cb;
-                    const float* r0 = vp.ref[v] + sample + o;
-                    const bool ok = chan_ok;
-                    const float4 a = ld4z(r0, ok && (tb.valid & 1u)), bq = ld4z(r0 + C, ok && (tb.valid & 2u));
-                    const float4 c = ld4z(r0 + static_cast<size_t>(w) * C, ok && (tb.valid & 4u));
-                    const float4 e = ld4z(r0 + static_cast<size_t>(w) * C + C, ok && (tb.valid & 8u));
-                    const float bx = 1.0f - tb.ax, by = 1.0f - tb.ay;
-                    const float wnw = bx * by, wne = tb.ax * by, wsw = bx * tb.ay, wse = tb.ax * tb.ay;
-                    const float4 wv = blend4(a, bq, c, e, wnw, wne, wsw, wse);
-                    const float4 co = make_float4((f.x - wv.x) * g.x, (f.y - wv.y) * g.y, (f.z - wv.z) * g.z,
-                                                  (f.w - wv.w) * g.w);
-                    gf.x += co.x; gf.y += co.y; gf.z += co.z; gf.w += co.w;
-                    if (vg.g_ref[v] != nullptr && ok) {
-                        float* q0 = vg.g_ref[v] + sample + o;
-                        if (tb.valid & 1u) red_add4(q0, -co.x * wnw, -co.y * wnw, -co.z * wnw, -co.w * wnw);
-                        if (tb.valid & 2u) red_add4(q0 + C, -co.x * wne, -co.y * wne, -co.z * wne, -co.w * wne);
-                        if (tb.valid & 4u) red_add4(q0 + static_cast<size_t>(w) * C, -co.x * wsw, -co.y * wsw, -co.z * wsw, -co.w * wsw);
-                        if (tb.valid & 8u) red_add4(q0 + static_cast<size_t>(w) * C + C, -co.x * wse, -co.y * wse, -co.z * wse, -co.w * wse);
-                    }
-                    if (need_coord_grad) {
-                        float sx = co.x * ((bq.x - a.x) * by + (e.x - c.x) * tb.ay) + co.y * ((bq.y - a.y) * by + (e.y - c.y) * tb.ay)
-                                 + co.z * ((bq.z - a.z) * by + (e.z - c.z) * tb.ay) + co.w * ((bq.w - a.w) * by + (e.w - c.w) * tb.ay);
-                        float sy = co.x * ((c.x - a.x) * bx + (e.x - bq.x) * tb.ax) + co.y * ((c.y - a.y) * bx + (e.y - bq.y) * tb.ax)
-                                 + co.z * ((c.z - a.z) * bx + (e.z - bq.z) * tb.ax) + co.w * ((c.w - a.w) * bx + (e.w - bq.w) * tb.ax);
-                        sx = warp_sum(sx);
-                        sy = warp_sum(sy);
-                        if (lane == j) { gx[v] -= sx; gy[v] -= sy; }
+        for (int v = 0; v < VT; ++v) {
+            if (v >= V || npix == 0) continue;
+            float* gref = vg.g_ref[v];
+            const float* ref = vp.ref[v] + sample + cbs;
+            auto fetch = [&](int j, const STap& t) {
+                PixLoad q;
+                const size_t px = sample + static_cast<size_t>(pbase + j) * C + cbs;
+                q.g = ldg4f(g_cost + px);
+                q.f = ldg4f(fmap + px);
+                const float* r0 = ref + static_cast<size_t>(t.o00) * C;
+                q.a = ldg4f(r0);
+                q.b = ldg4f(r0 + t.dx * C);
+                q.c = ldg4f(r0 + t.dy * C);
+                q.e = ldg4f(r0 + (t.dy + t.dx) * C);
+                return q;
+            };
+            STap t = wt[v];
+            PixLoad cur = fetch(0, t);
+            for (int j = 0; j < npix; ++j) {
+                STap tn = t;
+                PixLoad nxt = cur;
+                if (j + 1 < npix) {
+                    tn = wt[(j + 1) * V + v];
+                    nxt = fetch(j + 1, tn);
+                }
+                const size_t px = sample + static_cast<size_t>(pbase + j) * C + cbs;
+                const float4 wv = blend4(cur.a, cur.b, cur.c, cur.e, t.w00, t.w01, t.w10, t.w11);
+                float4 co = make_float4((cur.f.x - wv.x) * cur.g.x * scale, (cur.f.y - wv.y) * cur.g.y * scale,
+                                        (cur.f.z - wv.z) * cur.g.z * scale, (cur.f.w - wv.w) * cur.g.w * scale);
+                if (!chan_ok) co = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g_fmap != nullptr && chan_ok) {
+                    float4* gp = reinterpret_cast<float4*>(g_fmap + px);
+                    if (v == 0) *gp = co;
+                    else { float4 old = *gp; old.x += co.x; old.y += co.y; old.z += co.z; old.w += co.w; *gp = old; }
+                }
+                if (gref != nullptr && chan_ok) {
+                    float* q0 = gref + sample + static_cast<size_t>(t.o00) * C + cbs;
+                    const int odx = t.dx * C, ody = t.dy * C;
+                    if (t.valid & 1u) red_add4_nc(q0, -co.x * t.w00, -co.y * t.w00, -co.z * t.w00, -co.w * t.w00);
+                    if (t.valid & 2u) red_add4_nc(q0 + odx, -co.x * t.w01, -co.y * t.w01, -co.z * t.w01, -co.w * t.w01);
+                    if (t.valid & 4u) red_add4_nc(q0 + ody, -co.x * t.w10, -co.y * t.w10, -co.z * t.w10, -co.w * t.w10);
+                    if (t.valid & 8u) red_add4_nc(q0 + ody + odx, -co.x * t.w11, -co.y * t.w11, -co.z * t.w11, -co.w * t.w11);
+                }
+                if (need_coord_grad) {
+                    // taps outside the source count as zeros in the coordinate gradient
+                    const float m0 = (t.valid & 1u) ? 1.f : 0.f, m1 = (t.valid & 2u) ? 1.f : 0.f;
+                    const float m2 = (t.valid & 4u) ? 1.f : 0.f, m3 = (t.valid & 8u) ? 1.f : 0.f;
+                    const float4 a = make_float4(cur.a.x * m0, cur.a.y * m0, cur.a.z * m0, cur.a.w * m0);
+                    const float4 bq = make_float4(cur.b.x * m1, cur.b.y * m1, cur.b.z * m1, cur.b.w * m1);
+                    const float4 c4 = make_float4(cur.c.x * m2, cur.c.y * m2, cur.c.z * m2, cur.c.w * m2);
+                    const float4 e = make_float4(cur.e.x * m3, cur.e.y * m3, cur.e.z * m3, cur.e.w * m3);
+                    float s01 = co.x * (bq.x - a.x) + co.y * (bq.y - a.y) + co.z * (bq.z - a.z) + co.w * (bq.w - a.w);
+                    float s23 = co.x * (e.x - c4.x) + co.y * (e.y - c4.y) + co.z * (e.z - c4.z) + co.w * (e.w - c4.w);
+                    float s02 = co.x * (c4.x - a.x) + co.y * (c4.y - a.y) + co.z * (c4.z - a.z) + co.w * (c4.w - a.w);
+                    float s13 = co.x * (e.x - bq.x) + co.y * (e.y - bq.y) + co.z * (e.z - bq.z) + co.w * (e.w - bq.w);
+                    s01 = warp_sum(s01); s23 = warp_sum(s23); s02 = warp_sum(s02); s13 = warp_sum(s13);
+                    if (lane == j) {
+                        const float bx = 1.0f - tax[v], by = 1.0f - tay[v];
+                        float2 acc = cb0 == 0 ? make_float2(0.f, 0.f) : wg[lane * V + v];
+                        acc.x -= s01 * by + s23 * tay[v];
+                        acc.y -= s02 * bx + s13 * tax[v];
+                        wg[lane * V + v] = acc;
                     }
                 }
+                cur = nxt;
+                t = tn;
             }
-            if (g_fmap != nullptr && chan_ok) *reinterpret_cast<float4*>(g_fmap + px) = gf;
         }
     }
     if (!need_coord_grad) return;
+    __syncwarp();
     float gd = 0.0f;
 #pragma unroll
     for (int v = 0; v < VT; ++v) {
@@ -421,24 +522,28 @@ feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ f
             float gT[12];
 #pragma unroll
             for (int i = 0; i < 12; ++i) gT[i] = 0.0f;
-            if (active) {
+            if (mine && tvalid[v]) {
+                const float2 gxyv = wg[lane * V + v];
                 Warp wp;
                 warp_pixel(cam[v], x, y, d, wm1, hm1, true, wp);
-                gd += warp_pixel_adjoint(cam[v], wp, d, wm1, hm1, true, gx[v] * t[v].mx, gy[v] * t[v].my, gT);
+                const float mx = 0.5f * static_cast<float>(w - 1), my = 0.5f * static_cast<float>(h - 1);
+                gd += warp_pixel_adjoint(cam[v], wp, d, wm1, hm1, true, gxyv.x * mx, gxyv.y * my, gT);
             }
-            if (vg.g_pose[v] != nullptr) {
-                Slot* slot = ws + (v * B + b);
-                block_accumulate<12>(gT, red, slot->acc);
-                if (last_block(slot, gridDim.x, &flag) && threadIdx.x == 0) {
-                    const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
-                    finish_pose_grad(slot, cams.pose_kind, eul ? vp.pose[v] + b * 6 : nullptr,
-                                     vg.g_pose[v] + b * (eul ? 6 : 16));
-                }
+            if (vg.g_pose[v] != nullptr) warp_accumulate<12>(gT, spread_acc(slot_at(ws, v * B + b)));
+        }
+    }
+    if (mine && g_depth != nullptr)
+        g_depth[static_cast<size_t>(b) * P + p] = depth_kind == DROSFM_INV_DEPTH ? inv2depth_grad(draw, gd) : gd;
+#pragma unroll
+    for (int v = 0; v < VT; ++v) {
+        if (v < V && vg.g_pose[v] != nullptr) {
+            Slot* slot = slot_at(ws, v * B + b);
+            if (last_block(slot, gridDim.x, &flag) && threadIdx.x == 0) {
+                const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
+                finish_pose_grad(slot, cams.pose_kind, eul ? vp.pose[v] + b * 6 : nullptr, vg.g_pose[v] + b * (eul ? 6 : 16));
             }
         }
     }
-    if (active && g_depth != nullptr)
-        g_depth[static_cast<size_t>(b) * P + p] = depth_kind == DROSFM_INV_DEPTH ? inv2depth_grad(draw, gd) : gd;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -461,12 +566,20 @@ static int check_cost_args(const drosfm_cams_t* cams, const float* const* fmap_r
     return DROSFM_OK;
 }
 
+// Channels per thread: 8 by default (all 8 * 4 gathers of a view in flight at once); 16 once the grid is
+// already several waves deep, which halves the redundant coordinate work.
 static int channel_group(int P, int B, int C) {
-    // split channels over blocks until the grid covers the chip a few times
-    const int pix_blocks = ((P + kPixThreads - 1) / kPixThreads) * (B > 0 ? B : 1);
-    int cg = C;
-    while (cg > 8 && pix_blocks * ((C + cg - 1) / cg) < kNumSMs * 4) cg = (cg + 1) / 2;
-    return cg < 1 ? 1 : cg;
+    const long long pix_blocks = static_cast<long long>((P + kPixThreads - 1) / kPixThreads) * (B > 0 ? B : 1);
+    return (pix_blocks * ((C + 15) / 16) >= static_cast<long long>(kNumSMs) * 16) ? 16 : 8;
+}
+
+// NHWC: pixels per warp.  Enough warps to fill the chip several times over wins at small maps (each warp
+// keeps ~5 * ppw 128-bit loads in flight); large maps amortise the per-warp coordinate work over 32 pixels.
+static int pixels_per_warp(int P, int B) {
+    const long long pixels = static_cast<long long>(P) * (B > 0 ? B : 1);
+    int ppw = kMaxPpw;
+    while (ppw > 4 && pixels / ppw < static_cast<long long>(kNumSMs) * 32) ppw /= 2;
+    return ppw;
 }
 
 #define DISPATCH_VT(V, CALL)            \
@@ -497,14 +610,21 @@ int drosfm_feat_cost_fwd(const float* fmap, const float* const* fmap_ref, const 
         DROSFM_REQUIRE(aligned16(fmap) && aligned16(cost), DROSFM_EALIGN, "feat_cost_fwd: NHWC tensors must be 16-byte aligned");
         for (int v = 0; v < n_views; ++v)
             DROSFM_REQUIRE(aligned16(fmap_ref[v]), DROSFM_EALIGN, "feat_cost_fwd: NHWC tensors must be 16-byte aligned");
-        dim3 grid((P + kWarpsPerBlock * 32 - 1) / (kWarpsPerBlock * 32), B);
-#define CALL(VT) feat_cost_fwd_nhwc<VT><<<grid, kWarpsPerBlock * 32, 0, s>>>(fmap, vp, depth, depth_kind, *cams, n_views, cost, C, h, w)
+        const int ppw = pixels_per_warp(P, B);
+        const int per_block = kWarpsPerBlock * ppw;
+        dim3 grid((P + per_block - 1) / per_block, B);
+        const size_t smem = static_cast<size_t>(kWarpsPerBlock) * ppw * n_views * sizeof(STap);
+#define CALL(VT) feat_cost_fwd_nhwc<VT><<<grid, kWarpsPerBlock * 32, smem, s>>>(fmap, vp, depth, depth_kind, *cams, n_views, cost, C, h, w, ppw)
         DISPATCH_VT(n_views, CALL);
 #undef CALL
     } else {
         const int cg = channel_group(P, B, C);
         dim3 grid((P + kPixThreads - 1) / kPixThreads, (C + cg - 1) / cg, B);
-#define CALL(VT) feat_cost_fwd_nchw<VT><<<grid, kPixThreads, 0, s>>>(fmap, vp, depth, depth_kind, *cams, n_views, cost, C, h, w, cg)
+#define CALL(VT)                                                                                                            \
+    do {                                                                                                                    \
+        if (cg == 16) feat_cost_fwd_nchw<VT, 16><<<grid, kPixThreads, 0, s>>>(fmap, vp, depth, depth_kind, *cams, n_views, cost, C, h, w); \
+        else feat_cost_fwd_nchw<VT, 8><<<grid, kPixThreads, 0, s>>>(fmap, vp, depth, depth_kind, *cams, n_views, cost, C, h, w);           \
+    } while (0)
         DISPATCH_VT(n_views, CALL);
 #undef CALL
     }
@@ -538,16 +658,27 @@ int drosfm_feat_cost_bwd(const float* g_cost, const float* fmap, const float* co
         for (int v = 0; v < n_views; ++v)
             DROSFM_REQUIRE(aligned16(fmap_ref[v]) && (!vg.g_ref[v] || aligned16(vg.g_ref[v])), DROSFM_EALIGN,
                            "feat_cost_bwd: NHWC tensors must be 16-byte aligned");
-        dim3 grid((P + kWarpsPerBlock * 32 - 1) / (kWarpsPerBlock * 32), B);
-#define CALL(VT) feat_cost_bwd_nhwc<VT><<<grid, kWarpsPerBlock * 32, 0, s>>>(g_cost, fmap, vp, depth, depth_kind, *cams, n_views, \
-                                                                       g_fmap, vg, g_depth, static_cast<Slot*>(ws), B, C, h, w, need_coord)
+        const int ppw = pixels_per_warp(P, B);
+        const int per_block = kWarpsPerBlock * ppw;
+        dim3 grid((P + per_block - 1) / per_block, B);
+        const size_t smem = static_cast<size_t>(kWarpsPerBlock) * ppw * n_views * (sizeof(STap) + sizeof(float2));
+#define CALL(VT) feat_cost_bwd_nhwc<VT><<<grid, kWarpsPerBlock * 32, smem, s>>>(g_cost, fmap, vp, depth, depth_kind, *cams, n_views, \
+                                                                          g_fmap, vg, g_depth, static_cast<Slot*>(ws), B, C, h, w, ppw, need_coord)
         DISPATCH_VT(n_views, CALL);
 #undef CALL
     } else {
-        const int cg = channel_group(P, B, C);
+        // the backward keeps g, f, gf and 4 taps per channel live: 4 channels per thread (8 for deep grids)
+        const int cg = channel_group(P, B, C) == 16 ? 8 : 4;
         dim3 grid((P + kPixThreads - 1) / kPixThreads, (C + cg - 1) / cg, B);
-#define CALL(VT) feat_cost_bwd_nchw<VT><<<grid, kPixThreads, 0, s>>>(g_cost, fmap, vp, depth, depth_kind, *cams, n_views, g_fmap, vg, \
-                                                                 g_depth, static_cast<Slot*>(ws), B, C, h, w, cg, need_coord)
+#define CALL(VT)                                                                                                            \
+    do {                                                                                                                    \
+        if (cg == 8)                                                                                                        \
+            feat_cost_bwd_nchw<VT, 8><<<grid, kPixThreads, 0, s>>>(g_cost, fmap, vp, depth, depth_kind, *cams, n_views, g_fmap, vg,  \
+                                                                   g_depth, static_cast<Slot*>(ws), B, C, h, w, need_coord);        \
+        else                                                                                                                \
+            feat_cost_bwd_nchw<VT, 4><<<grid, kPixThreads, 0, s>>>(g_cost, fmap, vp, depth, depth_kind, *cams, n_views, g_fmap, vg,  \
+                                                                   g_depth, static_cast<Slot*>(ws), B, C, h, w, need_coord);        \
+    } while (0)
         DISPATCH_VT(n_views, CALL);
 #undef CALL
     }

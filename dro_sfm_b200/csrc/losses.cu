@@ -42,15 +42,14 @@ smooth_mean_kernel(const __grid_constant__ DepthList dl, float* __restrict__ sta
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
-    Slot* slot = ws + ib;
+    Slot* slot = slot_at(ws, ib);
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int k = 0; k < kLossThreads / 32; ++k) t += red[k];
-        atomicAdd(&slot->acc[0], t);
+        atomicAdd(spread_acc(slot), t);
     }
     if (last_block(slot, gridDim.x, &flag) && threadIdx.x == 0) {
-        stats[ib * 4 + 0] = static_cast<float>(__ldcg(&slot->acc[0]) / static_cast<double>(P));
-        slot->acc[0] = 0.0;
+        stats[ib * 4 + 0] = static_cast<float>(take_acc(slot, 0) / static_cast<double>(P));
         slot->ticket = 0ull;
     }
 }
@@ -98,21 +97,19 @@ smooth_fwd_kernel(const float* __restrict__ image, const __grid_constant__ Depth
         if (threadIdx.x < 2) {
             double t = 0.0;
             for (int k = 0; k < kLossThreads / 32; ++k) t += red[2 * k + threadIdx.x];
-            if (t != 0.0) atomicAdd(&ws[i * B + b].acc[threadIdx.x], t);
+            if (t != 0.0) atomicAdd(spread_acc(slot_at(ws, i * B + b)) + threadIdx.x, t);
         }
         __syncthreads();
     }
-    Slot* ticket = ws + n_preds * B;
+    Slot* ticket = slot_at(ws, n_preds * B);
     if (last_block(ticket, gridDim.x * gridDim.y, &flag) && threadIdx.x == 0) {
         const double nx = static_cast<double>(B) * H * (W - 1), ny = static_cast<double>(B) * (H - 1) * W;
         double total = 0.0, pw = 1.0;
         for (int i = 0; i < n_preds; ++i) {
             double tx = 0.0, ty = 0.0;
             for (int bb = 0; bb < B; ++bb) {
-                Slot* s = ws + i * B + bb;
-                const double ax = __ldcg(&s->acc[0]), ay = __ldcg(&s->acc[1]);
-                s->acc[0] = 0.0;
-                s->acc[1] = 0.0;
+                Slot* s = slot_at(ws, i * B + bb);
+                const double ax = take_acc(s, 0), ay = take_acc(s, 1);
                 stats[(i * B + bb) * 4 + 1] = static_cast<float>(ax);
                 stats[(i * B + bb) * 4 + 2] = static_cast<float>(ay);
                 tx += ax;
@@ -235,10 +232,10 @@ reproj_kernel(const float* __restrict__ g_loss, const float* __restrict__ depth,
                 }
             }
             if (MODE == 0) {
-                block_accumulate<1>(&acc, red, ws[i].acc);
+                block_accumulate<1>(&acc, red, spread_acc(slot_at(ws, i)));
             } else if (rp.g_pred[v * n_preds + i] != nullptr) {
-                Slot* slot = ws + ((v * n_preds + i) * B + b);
-                block_accumulate<12>(gT, red, slot->acc);
+                Slot* slot = slot_at(ws, (v * n_preds + i) * B + b);
+                block_accumulate<12>(gT, red, spread_acc(slot));
                 if (last_block(slot, gridDim.x, &flag) && threadIdx.x == 0) {
                     const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
                     finish_pose_grad(slot, cams.pose_kind, eul ? rp.pred[v * n_preds + i] + b * 6 : nullptr,
@@ -249,13 +246,12 @@ reproj_kernel(const float* __restrict__ g_loss, const float* __restrict__ depth,
         __syncthreads();
     }
     if (MODE == 0) {
-        Slot* ticket = ws + n_preds;
+        Slot* ticket = slot_at(ws, n_preds);
         if (last_block(ticket, gridDim.x * gridDim.y, &flag) && threadIdx.x == 0) {
             const double numel = 2.0 * static_cast<double>(B) * P;
             double total = 0.0;
             for (int i = 0; i < n_preds; ++i) {
-                total += static_cast<double>(rp.weight[i]) * (__ldcg(&ws[i].acc[0]) / numel / V);
-                ws[i].acc[0] = 0.0;
+                total += static_cast<double>(rp.weight[i]) * (take_acc(slot_at(ws, i), 0) / numel / V);
             }
             ticket->ticket = 0ull;
             *loss = static_cast<float>(total / static_cast<double>(wsum));

@@ -62,19 +62,22 @@ struct Ssim {
 };
 
 __device__ __forceinline__ Ssim ssim_from(const Win& w, float C1, float C2) {
+    // Plain fp32 with FMA contraction: the variances E[x^2]-mu^2 cancel 3-4 digits, which makes the SSIM
+    // value uncertain at the 1e-4 relative level in ANY fp32 evaluation order (the reference's included),
+    // so the exact rounding sequence of the ATen ops is not worth extra instructions here.
     const float inv9 = 1.0f / 9.0f;
     Ssim r;
-    r.mu_x = __fmul_rn(w.sx, inv9);
-    r.mu_y = __fmul_rn(w.sy, inv9);
-    const float mu_xy = __fmul_rn(r.mu_x, r.mu_y), mu_xx = __fmul_rn(r.mu_x, r.mu_x), mu_yy = __fmul_rn(r.mu_y, r.mu_y);
-    const float sig_x = __fsub_rn(__fmul_rn(w.sxx, inv9), mu_xx);
-    const float sig_y = __fsub_rn(__fmul_rn(w.syy, inv9), mu_yy);
-    const float sig_xy = __fsub_rn(__fmul_rn(w.sxy, inv9), mu_xy);
-    r.A1 = __fadd_rn(__fmul_rn(2.0f, mu_xy), C1);
-    r.A2 = __fadd_rn(__fmul_rn(2.0f, sig_xy), C2);
-    r.B1 = __fadd_rn(__fadd_rn(mu_xx, mu_yy), C1);
-    r.B2 = __fadd_rn(__fadd_rn(sig_x, sig_y), C2);
-    r.s = __fdiv_rn(__fmul_rn(r.A1, r.A2), __fmul_rn(r.B1, r.B2));
+    r.mu_x = w.sx * inv9;
+    r.mu_y = w.sy * inv9;
+    const float mu_xy = r.mu_x * r.mu_y, mu_xx = r.mu_x * r.mu_x, mu_yy = r.mu_y * r.mu_y;
+    const float sig_x = w.sxx * inv9 - mu_xx;
+    const float sig_y = w.syy * inv9 - mu_yy;
+    const float sig_xy = w.sxy * inv9 - mu_xy;
+    r.A1 = 2.0f * mu_xy + C1;
+    r.A2 = 2.0f * sig_xy + C2;
+    r.B1 = mu_xx + mu_yy + C1;
+    r.B2 = sig_x + sig_y + C2;
+    r.s = __fdividef(r.A1 * r.A2, r.B1 * r.B2);
     return r;
 }
 
@@ -105,21 +108,136 @@ __device__ __forceinline__ Win add3(const Win& a, const Win& b, const Win& c) {
 }
 
 // ------------------------------------------------------------------------------------------
+// warped source tile: shared by the forward and backward kernels
+// ------------------------------------------------------------------------------------------
+// Fills xs[3][ROWS][COLS] with the source view sampled at every in-image pixel of the region whose
+// top-left corner is (oy, ox) (zeros elsewhere).  WARP: through the depth/pose warp; otherwise the
+// un-warped source (auto-mask).  Work is batched so that each thread has NB depth loads, then NB*12
+// gathers in flight; the camera lives in registers.
+template <int ROWS, int COLS, int NT, bool WARP>
+__device__ __forceinline__ void fill_source_tile(float* __restrict__ xs, const float* __restrict__ src,
+                                                 const float* __restrict__ invd, int depth_kind, const Cam& cam,
+                                                 int oy, int ox, int H, int W, int P, float wm1, float hm1, int padding) {
+    constexpr int N = ROWS * COLS, NB = 2;
+    constexpr int STEP_Y = NT / COLS, STEP_X = NT % COLS;       // (row, column) advance of idx += NT
+    const int tid = threadIdx.x;
+    int ry = tid / COLS, rx = tid - ry * COLS;
+    for (int base = tid; base < N; base += NT * NB) {
+        int sidx[NB], sxs[NB], sys[NB];
+        bool in[NB];
+        float d[NB];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            const int idx = base + k * NT;
+            sidx[k] = idx;
+            sys[k] = oy + ry;
+            sxs[k] = ox + rx;
+            in[k] = idx < N && sys[k] >= 0 && sys[k] < H && sxs[k] >= 0 && sxs[k] < W;
+            d[k] = 0.0f;
+            if (WARP && in[k]) d[k] = __ldg(invd + sys[k] * W + sxs[k]);
+            rx += STEP_X;
+            ry += STEP_Y;
+            if (rx >= COLS) { rx -= COLS; ++ry; }
+        }
+        // taps: coordinates are clamped into the image and the weight of an out-of-bounds tap is zeroed, so
+        // the gathers below need no predicates
+        int o00[NB], dxo[NB], dyo[NB];
+        float w00[NB], w01[NB], w10[NB], w11[NB];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            o00[k] = 0; dxo[k] = 0; dyo[k] = 0;
+            w00[k] = w01[k] = w10[k] = w11[k] = 0.0f;
+            if (WARP && in[k]) {
+                Warp wp;
+                warp_pixel(cam, sxs[k], sys[k], to_depth(d[k], depth_kind), wm1, hm1, true, wp);
+                Taps t;
+                make_taps(wp.p.u, wp.p.v, H, W, padding, t);
+                if (t.valid) {
+                    const float bx = 1.0f - t.ax, by = 1.0f - t.ay;
+                    w00[k] = (t.valid & 1u) ? bx * by : 0.0f;
+                    w01[k] = (t.valid & 2u) ? t.ax * by : 0.0f;
+                    w10[k] = (t.valid & 4u) ? bx * t.ay : 0.0f;
+                    w11[k] = (t.valid & 8u) ? t.ax * t.ay : 0.0f;
+                    const int x0 = max(t.x0, 0), y0 = max(t.y0, 0);
+                    const int x1 = min(t.x0 + 1, W - 1), y1 = min(t.y0 + 1, H - 1);
+                    o00[k] = y0 * W + x0;
+                    dxo[k] = x1 - x0;
+                    dyo[k] = (y1 - y0) * W;
+                }
+            } else if (!WARP && in[k]) {
+                o00[k] = sys[k] * W + sxs[k];
+            }
+        }
+        float v[NB][12];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* r0 = src + c * P + o00[k];
+                if (WARP) {
+                    v[k][4 * c + 0] = __ldg(r0);
+                    v[k][4 * c + 1] = __ldg(r0 + dxo[k]);
+                    v[k][4 * c + 2] = __ldg(r0 + dyo[k]);
+                    v[k][4 * c + 3] = __ldg(r0 + dyo[k] + dxo[k]);
+                } else {
+                    v[k][c] = in[k] ? __ldg(r0) : 0.0f;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            if (sidx[k] < N) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float o = WARP ? v[k][4 * c] * w00[k] + v[k][4 * c + 1] * w01[k] + v[k][4 * c + 2] * w10[k] +
+                                               v[k][4 * c + 3] * w11[k]
+                                         : v[k][c];
+                    xs[c * N + sidx[k]] = o;
+                }
+            }
+        }
+    }
+}
+
+// Target image tile (zeros outside the image).
+template <int ROWS, int COLS, int NT>
+__device__ __forceinline__ void fill_target_tile(float* __restrict__ ys, const float* __restrict__ img, int oy, int ox,
+                                                 int H, int W, int P) {
+    constexpr int N = ROWS * COLS;
+    constexpr int STEP_Y = NT / COLS, STEP_X = NT % COLS;
+    int ry = threadIdx.x / COLS, rx = threadIdx.x - ry * COLS;
+    for (int idx = threadIdx.x; idx < N; idx += NT) {
+        const int gy = oy + ry, gx = ox + rx;
+        rx += STEP_X;
+        ry += STEP_Y;
+        if (rx >= COLS) { rx -= COLS; ++ry; }
+        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        const int o = gy * W + gx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ys[c * N + idx] = in ? __ldg(img + c * P + o) : 0.0f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // forward (MODE 0) and auto-mask pre-pass (MODE 1)
 // ------------------------------------------------------------------------------------------
-constexpr int FW = 32, FH = 32, FSW = FW + 2, FSH = FH + 2, FRPT = FH / kGroups;
+constexpr int kFwdThreads = 256, kFwdGroups = kFwdThreads / 32;
+constexpr int FW = 32, FH = 64, FSW = FW + 2, FSH = FH + 2, FRPT = FH / kFwdGroups;
+constexpr int kFwdSmemBytes = 2 * 3 * FSH * FSW * static_cast<int>(sizeof(float));
 
 template <int MODE>
-__global__ void __launch_bounds__(kPhotoThreads)
+__global__ void __launch_bounds__(kFwdThreads, 2)
 photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ PhotoPtrs pp, int V, int depth_kind, int n_preds,
                        drosfm_cams_t cams, const float* __restrict__ automask_in, drosfm_photo_opts_t opts,
                        float l1_w, uint8_t* __restrict__ sel_out, float* __restrict__ automask_out,
                        float* __restrict__ loss, Slot* ws, int B, int H, int W) {
-    __shared__ float ys[3][FSH][FSW];
-    __shared__ float xs[3][FSH][FSW];
-    __shared__ Cam cam[MODE == 0 ? DROSFM_MAX_VIEWS : 1];
-    __shared__ double red[kGroups];
+    extern __shared__ float smem[];
+    float* ys = smem;                        // [3][FSH][FSW]
+    float* xs = smem + 3 * FSH * FSW;        // [3][FSH][FSW]
+    __shared__ Cam cam_s[MODE == 0 ? DROSFM_MAX_VIEWS : 1];
+    __shared__ double red[kFwdGroups];
     __shared__ int flag;
+    constexpr int PLANE = FSH * FSW;
     const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
     const int tx0 = blockIdx.x * FW, ty0 = blockIdx.y * FH;
     const int b = MODE == 0 ? static_cast<int>(blockIdx.z) % B : static_cast<int>(blockIdx.z);
@@ -127,22 +245,19 @@ photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ 
     const int P = H * W;
     const float wm1 = static_cast<float>(W - 1), hm1 = static_cast<float>(H - 1);
 
-    for (int idx = tid; idx < 3 * FSH * FSW; idx += kPhotoThreads) {
-        const int c = idx / (FSH * FSW), rem = idx - c * (FSH * FSW);
-        const int ry = rem / FSW, rx = rem - ry * FSW;
-        const int gy = ty0 - 1 + ry, gx = tx0 - 1 + rx;
-        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
-        ys[c][ry][rx] = in ? __ldg(image + (static_cast<size_t>(b) * 3 + c) * P + gy * W + gx) : 0.0f;
-    }
-    if (MODE == 0 && tid < V) setup_cam(cams, pp.pose[tid * n_preds + ip], b, cam[tid]);
+    if (MODE == 0 && tid < V) setup_cam(cams, pp.pose[tid * n_preds + ip], b, cam_s[tid]);
+    fill_target_tile<FSH, FSW, kFwdThreads>(ys, image + static_cast<size_t>(b) * 3 * P, ty0 - 1, tx0 - 1, H, W, P);
     __syncthreads();
 
-    // per-thread stat rows: column gx = tx0 + lane, rows ty0 + grp*FRPT + k
+    // per-thread stat rows: column gx = tx0 + lane, rows gy0 + k; shared-memory offsets are hoisted
     const int gx = tx0 + lane;
     const int gy0 = ty0 + grp * FRPT;
     const int cm = clampi(reflect_idx(gx - 1, W) - tx0 + 1, 0, FSW - 1);
     const int c0 = lane + 1;
     const int cp = clampi(reflect_idx(gx + 1, W) - tx0 + 1, 0, FSW - 1);
+    int roff[FRPT + 2];
+#pragma unroll
+    for (int j = 0; j < FRPT + 2; ++j) roff[j] = clampi(reflect_idx(gy0 - 1 + j, H) - ty0 + 1, 0, FSH - 1) * FSW;
 
     float best[FRPT];
     int sel[FRPT];
@@ -152,36 +267,15 @@ photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ 
         best[k] = use_min ? __int_as_float(0x7f800000) : 0.0f;
         sel[k] = 254;
     }
+    const float* invd = MODE == 0 ? pp.inv_depth[ip] + static_cast<size_t>(b) * P : nullptr;
 
     for (int v = 0; v < V; ++v) {
         // phase A: source view v on tile + halo 1
         const float* src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
-        for (int idx = tid; idx < FSH * FSW; idx += kPhotoThreads) {
-            const int ry = idx / FSW, rx = idx - ry * FSW;
-            const int sy = ty0 - 1 + ry, sx = tx0 - 1 + rx;
-            float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
-            if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
-                if (MODE == 0) {
-                    const float d = to_depth(__ldg(pp.inv_depth[ip] + static_cast<size_t>(b) * P + sy * W + sx), depth_kind);
-                    Warp wp;
-                    warp_pixel(cam[v], sx, sy, d, wm1, hm1, true, wp);
-                    Taps t;
-                    make_taps(wp.p.u, wp.p.v, H, W, opts.padding, t);
-                    if (t.valid) {
-                        const Weights wt = tap_weights(t);
-                        o0 = tap3(src, W, t, wt);
-                        o1 = tap3(src + P, W, t, wt);
-                        o2 = tap3(src + 2 * P, W, t, wt);
-                    }
-                } else {
-                    o0 = __ldg(src + sy * W + sx);
-                    o1 = __ldg(src + P + sy * W + sx);
-                    o2 = __ldg(src + 2 * P + sy * W + sx);
-                }
-            }
-            xs[0][ry][rx] = o0;
-            xs[1][ry][rx] = o1;
-            xs[2][ry][rx] = o2;
+        {
+            const Cam cam = cam_s[MODE == 0 ? v : 0];       // register copy for the sampling loop
+            fill_source_tile<FSH, FSW, kFwdThreads, MODE == 0>(xs, src, invd, depth_kind, cam, ty0 - 1, tx0 - 1, H, W, P, wm1, hm1,
+                                                               opts.padding);
         }
         __syncthreads();
 
@@ -191,23 +285,23 @@ photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ 
         for (int k = 0; k < FRPT; ++k) ssim_acc[k] = l1_acc[k] = 0.0f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
+            const float* xc_ = xs + c * PLANE;
+            const float* yc_ = ys + c * PLANE;
             Win ra, rb;
-            float xca = 0.0f, yca = 0.0f, xcb = 0.0f, ycb = 0.0f;
+            float xcb = 0.0f, ycb = 0.0f;
 #pragma unroll
             for (int j = 0; j < FRPT + 2; ++j) {
-                const int sr = clampi(reflect_idx(gy0 - 1 + j, H) - ty0 + 1, 0, FSH - 1);
                 float xc, yc;
-                const Win rc = row_sums(xs[c][sr], ys[c][sr], cm, c0, cp, xc, yc);
+                const Win rc = row_sums(xc_ + roff[j], yc_ + roff[j], cm, c0, cp, xc, yc);
                 if (j >= 2) {
                     const Ssim s = ssim_from(add3(ra, rb, rc), opts.C1, opts.C2);
-                    const float l = __fmul_rn(__fsub_rn(1.0f, s.s), 0.5f);
+                    const float l = (1.0f - s.s) * 0.5f;
                     ssim_acc[j - 2] += fminf(fmaxf(l, 0.0f), 1.0f);
                     l1_acc[j - 2] += fabsf(xcb - ycb);
                 }
                 ra = rb; rb = rc;
-                xca = xcb; yca = ycb; xcb = xc; ycb = yc;
+                xcb = xc; ycb = yc;
             }
-            (void)xca; (void)yca;
         }
 #pragma unroll
         for (int k = 0; k < FRPT; ++k) {
@@ -249,18 +343,17 @@ photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ 
     __syncthreads();
     if (tid == 0) {
         double s = 0.0;
-        for (int k = 0; k < kGroups; ++k) s += red[k];
-        atomicAdd(&ws[ip].acc[0], s);
+        for (int k = 0; k < kFwdGroups; ++k) s += red[k];
+        atomicAdd(spread_acc(slot_at(ws, ip)), s);
     }
-    Slot* ticket = ws + n_preds;
+    Slot* ticket = slot_at(ws, n_preds);
     if (last_block(ticket, gridDim.x * gridDim.y * gridDim.z, &flag) && tid == 0) {
         double total = 0.0;
         const double denom = static_cast<double>(B) * P * (use_min ? 1.0 : static_cast<double>(V));
         for (int i = 0; i < n_preds; ++i) {
-            const double mean_i = __ldcg(&ws[i].acc[0]) / denom;
+            const double mean_i = take_acc(slot_at(ws, i), 0) / denom;
             // the reference rounds every per-prediction mean to fp32 before the weighted sum
             total += static_cast<double>(pp.weight[i]) * static_cast<double>(static_cast<float>(mean_i));
-            ws[i].acc[0] = 0.0;
         }
         ticket->ticket = 0ull;
         *loss = static_cast<float>(total);
@@ -454,8 +547,8 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
         }
         float* gp = pg.g_pose[v * n_preds + ip];
         if (gp != nullptr) {
-            Slot* slot = ws + ((v * n_preds + ip) * B + b);
-            block_accumulate<12>(gT, red, slot->acc);
+            Slot* slot = slot_at(ws, (v * n_preds + ip) * B + b);
+            block_accumulate<12>(gT, red, spread_acc(slot));
             if (last_block(slot, gridDim.x * gridDim.y, &flag) && tid == 0) {
                 const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
                 finish_pose_grad(slot, cams.pose_kind, eul ? pp.pose[v * n_preds + ip] + b * 6 : nullptr,
@@ -500,6 +593,24 @@ static int check_photo(const float* image, const float* const* context, int n_vi
     return DROSFM_OK;
 }
 
+// Opt in to > 48 KB of dynamic shared memory (per device, done on first use; not a stream operation).
+static int allow_big_smem() {
+    static thread_local int done_for_device = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess && dev != done_for_device) {
+        e = cudaFuncSetAttribute(photometric_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(photometric_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
+        if (e == cudaSuccess) done_for_device = dev;
+    }
+    if (e != cudaSuccess) {
+        set_error("photometric: cannot configure shared memory: %s", cudaGetErrorString(e));
+        return static_cast<int>(e);
+    }
+    return DROSFM_OK;
+}
+
 static float l1_weight(const drosfm_photo_opts_t* opts) {
     // (1 - ssim_loss_weight) is evaluated in double by the reference and rounded when it meets the fp32 tensor
     return static_cast<float>(1.0 - static_cast<double>(opts->ssim_w));
@@ -522,7 +633,8 @@ int drosfm_automask_fwd(const float* image, const float* const* context, int n_v
     o.reduce_op = DROSFM_REDUCE_MIN;
     drosfm_cams_t none{};
     dim3 grid((W + FW - 1) / FW, (H + FH - 1) / FH, B);
-    photometric_fwd_kernel<1><<<grid, kPhotoThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+    if (int e = allow_big_smem()) return e;
+    photometric_fwd_kernel<1><<<grid, kFwdThreads, kFwdSmemBytes, static_cast<cudaStream_t>(stream)>>>(
         image, pp, n_views, DROSFM_DEPTH, 1, none, nullptr, o, l1_weight(opts), nullptr, automask, nullptr, nullptr, B, H, W);
     return launch_status("automask_fwd");
 }
@@ -566,7 +678,8 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
     if (int e = fill_ptrs(pp, context, n_views, inv_depths, n_preds, poses, opts->gamma)) return e;
     DROSFM_REQUIRE(static_cast<long long>(B) * n_preds <= 65535, DROSFM_ERANGE, "photometric_fwd: B * n_preds too large");
     dim3 grid((W + FW - 1) / FW, (H + FH - 1) / FH, B * n_preds);
-    photometric_fwd_kernel<0><<<grid, kPhotoThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+    if (int e = allow_big_smem()) return e;
+    photometric_fwd_kernel<0><<<grid, kFwdThreads, kFwdSmemBytes, static_cast<cudaStream_t>(stream)>>>(
         image, pp, n_views, depth_kind, n_preds, *cams, opts->automask ? automask : nullptr, *opts, l1_weight(opts), sel,
         nullptr, loss, static_cast<Slot*>(ws), B, H, W);
     return launch_status("photometric_fwd");

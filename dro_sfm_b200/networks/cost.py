@@ -7,13 +7,49 @@ Each call is ONE kernel launch: pose vector -> matrix, intrinsics cast/scaling, 
 coordinate chain, the bilinear gather of all source views and the squared-difference reduction are
 fused; nothing but the [B,C,h,w] cost map is written.
 """
+import os
+import weakref
+
+import torch
+
 from .. import ops
 from .. import _lib as L
+
+# The encoder hands over NCHW feature maps, and the same maps are consumed by all 2*V*T cost calls of a
+# forward pass (DepthPoseNet.py:113-115,159-167).  The channels-last kernels move 512 contiguous bytes per
+# tap instead of 4, so each distinct map is converted ONCE per forward (an autograd-visible
+# ``.contiguous(memory_format=channels_last)``; its gradient comes back through the same node) and the copy
+# is remembered for as long as the original tensor object is alive and unmodified.  The returned cost map is
+# a logical [B,C,h,w] tensor in channels_last storage, which is also what cuDNN prefers for the 1x1
+# convolution that consumes it (update.py:81).  DROSFM_COST_LAYOUT=nchw keeps the caller's layout.
+_LAYOUT = os.environ.get("DROSFM_COST_LAYOUT", "nhwc").lower()
+_cl_cache = {}
+
+
+def _channels_last(t):
+    if _LAYOUT != "nhwc" or t.dim() != 4 or t.shape[1] % 4 != 0 or t.shape[1] < 32:
+        return t
+    if t.is_contiguous(memory_format=torch.channels_last):
+        return t
+    key = id(t)
+    hit = _cl_cache.get(key)
+    if hit is not None:
+        ref, version, grad_mode, converted = hit
+        if ref() is t and version == t._version and grad_mode == torch.is_grad_enabled():
+            return converted
+    converted = t.contiguous(memory_format=torch.channels_last)
+    if len(_cl_cache) > 64:
+        for k in [k for k, (r, _, _, _) in _cl_cache.items() if r() is None]:
+            del _cl_cache[k]
+    _cl_cache[key] = (weakref.ref(t, lambda _r, k=key: _cl_cache.pop(k, None)), t._version, torch.is_grad_enabled(), converted)
+    return converted
 
 
 def _cost(pose_list, fmap, fmaps_ref, depth, K, ref_K, scale_factor, inverse_depth):
     # poses arrive as [B,6] euler vectors (Pose.from_vec(pose, "euler") in the reference)
-    return ops.feat_cost(depth, fmap, list(fmaps_ref), list(pose_list), K, ref_K, scale_factor,
+    fmap = _channels_last(fmap)
+    fmaps_ref = [_channels_last(f) for f in fmaps_ref]
+    return ops.feat_cost(depth, fmap, fmaps_ref, list(pose_list), K, ref_K, scale_factor,
                          inverse_depth=inverse_depth)
 
 

@@ -57,6 +57,9 @@ typedef struct {
 
 int drosfm_version(void);
 const char* drosfm_last_error(void);
+/* Number of kernels this library has launched in the process so far (for benchmarks and tests that
+ * must prove the CUDA path ran). */
+unsigned long long drosfm_launch_count(void);
 /* Bytes of zero-initialised workspace for calls that reduce pose gradients or scalar losses over
  * `slots` independent accumulators (one slot = one (sample, view, prediction) pose or one scalar). */
 size_t drosfm_ws_bytes(int slots);
