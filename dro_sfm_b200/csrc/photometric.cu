@@ -25,8 +25,6 @@
 
 namespace drosfm {
 
-constexpr int kPhotoThreads = 128;   // 32 columns x 4 row groups
-constexpr int kGroups = 4;
 
 struct PhotoPtrs {
     const float* context[DROSFM_MAX_VIEWS];
@@ -283,7 +281,7 @@ photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ 
         float ssim_acc[FRPT], l1_acc[FRPT];
 #pragma unroll
         for (int k = 0; k < FRPT; ++k) ssim_acc[k] = l1_acc[k] = 0.0f;
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 3; ++c) {
             const float* xc_ = xs + c * PLANE;
             const float* yc_ = ys + c * PLANE;
@@ -363,25 +361,31 @@ photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------
-constexpr int CW = 32, CH = 20;                 // coefficient region (tile + halo 1)
-constexpr int IW = CW - 2, IH = CH - 2;         // interior pixels owned by the block
-constexpr int BSW = CW + 2, BSH = CH + 2;       // sample region (tile + halo 2)
-constexpr int BRPT = CH / kGroups;              // coefficient rows per thread
+constexpr int kBwdThreads = 256, kBwdGroups = kBwdThreads / 32;
+constexpr int BRPT = 5;                              // coefficient rows per thread
+constexpr int CW = 32, CH = kBwdGroups * BRPT;       // coefficient region (tile + halo 1): 32 x 40
+constexpr int IW = CW - 2, IH = CH - 2;              // interior pixels owned by the block: 30 x 38
+constexpr int BSW = CW + 2, BSH = CH + 2;            // sample region (tile + halo 2): 34 x 42
+constexpr int kBwdSmemFloats = 2 * 3 * BSH * BSW + 3 * CH * CW + 3 * IH * CW;
+constexpr int kBwdSmemBytes = kBwdSmemFloats * static_cast<int>(sizeof(float)) + CH * CW;
 
-__global__ void __launch_bounds__(kPhotoThreads)
+__global__ void __launch_bounds__(kBwdThreads, 2)
 photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict__ image,
                        const __grid_constant__ PhotoPtrs pp, int V,
                        int depth_kind, int n_preds, drosfm_cams_t cams, const uint8_t* __restrict__ sel_in,
                        drosfm_photo_opts_t opts, float l1_w, const __grid_constant__ PhotoGrads pg, Slot* ws,
                        int B, int H, int W) {
-    __shared__ float ys[3][BSH][BSW];
-    __shared__ float xs[3][BSH][BSW];
-    __shared__ float ca[CH][CW], cb[CH][CW], cc[CH][CW];
-    __shared__ float gxs[3][IH][CW];
-    __shared__ uint8_t selt[CH][CW];
-    __shared__ Cam cam[DROSFM_MAX_VIEWS];
-    __shared__ double red[12 * kGroups];
-    __shared__ int flag;
+    extern __shared__ float smem[];
+    constexpr int SPLANE = BSH * BSW, CPLANE = CH * CW;
+    float* ys = smem;                                 // [3][BSH][BSW]
+    float* xs = ys + 3 * SPLANE;                      // [3][BSH][BSW]
+    float* ca = xs + 3 * SPLANE;                      // [CH][CW] x 3 (a, b, c coefficient maps of one channel)
+    float* cb = ca + CPLANE;
+    float* cc = cb + CPLANE;
+    float* gxs = cc + CPLANE;                         // [3][IH][CW] gradient w.r.t. the warped pixel
+    uint8_t* selt = reinterpret_cast<uint8_t*>(gxs + 3 * IH * CW);   // [CH][CW]
+    __shared__ Cam cam_s[DROSFM_MAX_VIEWS];
+    __shared__ int flags[DROSFM_MAX_VIEWS];
     const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
     const int tx0 = blockIdx.x * IW, ty0 = blockIdx.y * IH;          // interior origin
     const int cx0 = tx0 - 1, cy0 = ty0 - 1;                            // coefficient-region origin
@@ -392,124 +396,119 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
     const bool use_min = opts.reduce_op == DROSFM_REDUCE_MIN;
     const float G = __ldg(g_loss) * pp.weight[ip] /
                     (static_cast<float>(B) * static_cast<float>(P) * (use_min ? 1.0f : static_cast<float>(V)));
+    const float kp = G * opts.ssim_w * (-1.0f / 6.0f) * (2.0f / 9.0f);   // d loss / d ssim  x  2/9 of the window derivative
+    const float kl1 = G * l1_w * (1.0f / 3.0f);
 
-    for (int idx = tid; idx < 3 * BSH * BSW; idx += kPhotoThreads) {
-        const int c = idx / (BSH * BSW), rem = idx - c * (BSH * BSW);
-        const int ry = rem / BSW, rx = rem - ry * BSW;
-        const int gy = sy0 + ry, gx = sx0 + rx;
-        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
-        ys[c][ry][rx] = in ? __ldg(image + (static_cast<size_t>(b) * 3 + c) * P + gy * W + gx) : 0.0f;
-    }
-    for (int idx = tid; idx < CH * CW; idx += kPhotoThreads) {
+    if (tid < V) setup_cam(cams, pp.pose[tid * n_preds + ip], b, cam_s[tid]);
+    fill_target_tile<BSH, BSW, kBwdThreads>(ys, image + static_cast<size_t>(b) * 3 * P, sy0, sx0, H, W, P);
+    for (int idx = tid; idx < CH * CW; idx += kBwdThreads) {
         const int ry = idx / CW, rx = idx - ry * CW;
         const int gy = cy0 + ry, gx = cx0 + rx;
         const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
-        selt[ry][rx] = in ? (use_min ? sel_in[(static_cast<size_t>(ip) * B + b) * P + gy * W + gx] : 253) : 254;
+        selt[idx] = in ? (use_min ? sel_in[(static_cast<size_t>(ip) * B + b) * P + gy * W + gx] : 253) : 254;
     }
-    if (tid < V) setup_cam(cams, pp.pose[tid * n_preds + ip], b, cam[tid]);
     __syncthreads();
 
-    // coefficient column / rows of this thread
+    // this thread: coefficient column lane (image column pgx), coefficient rows prow0 .. prow0+BRPT-1
     const int pgx = cx0 + lane;
-    const int prow0 = grp * BRPT;                                    // first coefficient row (region coords)
+    const int prow0 = grp * BRPT;
     const int cm = clampi(reflect_idx(pgx - 1, W) - sx0, 0, BSW - 1);
     const int c0 = lane + 1;
     const int cp = clampi(reflect_idx(pgx + 1, W) - sx0, 0, BSW - 1);
-    // interior pixels of this thread: column lane (1..IW), rows prow0+k with 1 <= row <= IH
+    int roff[BRPT + 2];
+#pragma unroll
+    for (int j = 0; j < BRPT + 2; ++j) roff[j] = clampi(reflect_idx(cy0 + prow0 - 1 + j, H) - sy0, 0, BSH - 1) * BSW;
+    // interior pixels of this thread: column lane in [1, IW], rows r = prow0 + k in [1, IH]
     const bool col_ok = lane >= 1 && lane <= IW && pgx < W;
+    // horizontal multiplicities of the reflected 3x3 window: how often pixel pgx occurs in the window of pgx+dx
+    float wx[3];
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+        const int px = pgx + dx;
+        wx[dx + 1] = (px < 0 || px >= W) ? 0.0f
+                                         : 1.0f + ((px == 0 && pgx == 1) ? 1.0f : 0.0f) + ((px == W - 1 && pgx == W - 2) ? 1.0f : 0.0f);
+    }
+    const int lm = max(lane - 1, 0), lp = min(lane + 1, CW - 1);
     float gd[BRPT];
 #pragma unroll
     for (int k = 0; k < BRPT; ++k) gd[k] = 0.0f;
+    const float* invd = pp.inv_depth[ip] + static_cast<size_t>(b) * P;
 
     for (int v = 0; v < V; ++v) {
         const float* src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
+        const Cam cam = cam_s[v];
         // phase A: warped source on tile + halo 2
-        for (int idx = tid; idx < BSH * BSW; idx += kPhotoThreads) {
-            const int ry = idx / BSW, rx = idx - ry * BSW;
-            const int sy = sy0 + ry, sx = sx0 + rx;
-            float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
-            if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
-                const float d = to_depth(__ldg(pp.inv_depth[ip] + static_cast<size_t>(b) * P + sy * W + sx), depth_kind);
-                Warp wp;
-                warp_pixel(cam[v], sx, sy, d, wm1, hm1, true, wp);
-                Taps t;
-                make_taps(wp.p.u, wp.p.v, H, W, opts.padding, t);
-                if (t.valid) {
-                    const Weights wt = tap_weights(t);
-                    o0 = tap3(src, W, t, wt);
-                    o1 = tap3(src + P, W, t, wt);
-                    o2 = tap3(src + 2 * P, W, t, wt);
-                }
-            }
-            xs[0][ry][rx] = o0;
-            xs[1][ry][rx] = o1;
-            xs[2][ry][rx] = o2;
-        }
+        fill_source_tile<BSH, BSW, kBwdThreads, true>(xs, src, invd, depth_kind, cam, sy0, sx0, H, W, P, wm1, hm1, opts.padding);
         __syncthreads();
 
+#pragma unroll 1
         for (int c = 0; c < 3; ++c) {
-            // phase B: coefficient maps of channel c on tile + halo 1
+            // phase B: coefficient maps of channel c on tile + halo 1 (zero where another map won the min)
             {
+                const float* xc_ = xs + c * SPLANE;
+                const float* yc_ = ys + c * SPLANE;
                 Win ra, rb;
 #pragma unroll
                 for (int j = 0; j < BRPT + 2; ++j) {
-                    const int sr = clampi(reflect_idx(cy0 + prow0 - 1 + j, H) - sy0, 0, BSH - 1);
                     float xc, yc;
-                    const Win rc = row_sums(xs[c][sr], ys[c][sr], cm, c0, cp, xc, yc);
+                    const Win rc = row_sums(xc_ + roff[j], yc_ + roff[j], cm, c0, cp, xc, yc);
                     if (j >= 2) {
                         const int r = prow0 + j - 2;
                         float a = 0.0f, bb = 0.0f, cq = 0.0f;
-                        const int sv = selt[r][lane];
+                        const int sv = selt[r * CW + lane];
                         if (sv == v || sv == 253) {
                             const Ssim s = ssim_from(add3(ra, rb, rc), opts.C1, opts.C2);
                             const float l = (1.0f - s.s) * 0.5f;
                             if (l >= 0.0f && l <= 1.0f) {
-                                const float kp = G * opts.ssim_w * (-1.0f / 6.0f);
-                                const float q = kp * (2.0f / 9.0f) / (s.B1 * s.B2);
+                                const float q = __fdividef(kp, s.B1 * s.B2);
                                 a = q * (s.mu_y * (s.A2 - s.A1) - s.s * s.mu_x * (s.B2 - s.B1));
                                 bb = -q * s.s * s.B1;
                                 cq = q * s.A1;
                             }
                         }
-                        ca[r][lane] = a;
-                        cb[r][lane] = bb;
-                        cc[r][lane] = cq;
+                        ca[r * CW + lane] = a;
+                        cb[r * CW + lane] = bb;
+                        cc[r * CW + lane] = cq;
                     }
                     ra = rb; rb = rc;
                 }
             }
             __syncthreads();
-            // phase C: gradient w.r.t. the warped pixel, channel c
+            // phase C: 3x3 box sums (with the reflection multiplicities) of the three maps -> d loss / d warped pixel
+            {
+                float ha[BRPT + 2], hb[BRPT + 2], hc[BRPT + 2];
 #pragma unroll
-            for (int k = 0; k < BRPT; ++k) {
-                const int r = prow0 + k;                 // coefficient-region row of q
-                const int qy = cy0 + r;
-                if (col_ok && r >= 1 && r <= IH && qy < H) {
-                    float ga = 0.0f, gb = 0.0f, gc = 0.0f;
+                for (int j = 0; j < BRPT + 2; ++j) {
+                    const int row = clampi(prow0 - 1 + j, 0, CH - 1) * CW;
+                    ha[j] = wx[0] * ca[row + lm] + wx[1] * ca[row + lane] + wx[2] * ca[row + lp];
+                    hb[j] = wx[0] * cb[row + lm] + wx[1] * cb[row + lane] + wx[2] * cb[row + lp];
+                    hc[j] = wx[0] * cc[row + lm] + wx[1] * cc[row + lane] + wx[2] * cc[row + lp];
+                }
 #pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy) {
-                        const int py = qy + dy;
-                        if (py < 0 || py >= H) continue;
-                        const float my = 1.0f + ((py == 0 && qy == 1) ? 1.0f : 0.0f) + ((py == H - 1 && qy == H - 2) ? 1.0f : 0.0f);
+                for (int k = 0; k < BRPT; ++k) {
+                    const int r = prow0 + k;
+                    const int qy = cy0 + r;
+                    if (col_ok && r >= 1 && r <= IH && qy < H) {
+                        float ga = 0.0f, gb = 0.0f, gc = 0.0f;
 #pragma unroll
-                        for (int dx = -1; dx <= 1; ++dx) {
-                            const int px = pgx + dx;
-                            if (px < 0 || px >= W) continue;
-                            const float m = my * (1.0f + ((px == 0 && pgx == 1) ? 1.0f : 0.0f) +
-                                                  ((px == W - 1 && pgx == W - 2) ? 1.0f : 0.0f));
-                            ga += m * ca[r + dy][lane + dx];
-                            gb += m * cb[r + dy][lane + dx];
-                            gc += m * cc[r + dy][lane + dx];
+                        for (int dy = -1; dy <= 1; ++dy) {
+                            const int py = qy + dy;
+                            const float wy = (py < 0 || py >= H) ? 0.0f
+                                                                 : 1.0f + ((py == 0 && qy == 1) ? 1.0f : 0.0f) +
+                                                                       ((py == H - 1 && qy == H - 2) ? 1.0f : 0.0f);
+                            ga += wy * ha[k + 1 + dy];
+                            gb += wy * hb[k + 1 + dy];
+                            gc += wy * hc[k + 1 + dy];
                         }
+                        const float xq = xs[c * SPLANE + (r + 1) * BSW + lane + 1], yq = ys[c * SPLANE + (r + 1) * BSW + lane + 1];
+                        float gxv = ga + gb * xq + gc * yq;
+                        const int sv = selt[r * CW + lane];
+                        if (sv == v || sv == 253) {
+                            const float df = xq - yq;
+                            gxv += df > 0.0f ? kl1 : (df < 0.0f ? -kl1 : 0.0f);
+                        }
+                        gxs[(c * IH + r - 1) * CW + lane] = gxv;
                     }
-                    const float xq = xs[c][r + 1][lane + 1], yq = ys[c][r + 1][lane + 1];
-                    float gxv = ga + gb * xq + gc * yq;
-                    const int sv = selt[r][lane];
-                    if (sv == v || sv == 253) {
-                        const float df = xq - yq;
-                        gxv += G * l1_w * (1.0f / 3.0f) * (df > 0.0f ? 1.0f : (df < 0.0f ? -1.0f : 0.0f));
-                    }
-                    gxs[c][r - 1][lane] = gxv;
                 }
             }
             __syncthreads();
@@ -524,38 +523,35 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
             const int r = prow0 + k;
             const int qy = cy0 + r;
             if (col_ok && r >= 1 && r <= IH && qy < H) {
-                const float d = to_depth(__ldg(pp.inv_depth[ip] + static_cast<size_t>(b) * P + qy * W + pgx), depth_kind);
+                const float d = to_depth(__ldg(invd + qy * W + pgx), depth_kind);
                 Warp wp;
-                warp_pixel(cam[v], pgx, qy, d, wm1, hm1, true, wp);
+                warp_pixel(cam, pgx, qy, d, wm1, hm1, true, wp);
                 Taps t;
                 make_taps(wp.p.u, wp.p.v, H, W, opts.padding, t);
                 if (t.valid) {
+                    const int x0 = max(t.x0, 0), y0 = max(t.y0, 0);
+                    const int x1 = min(t.x0 + 1, W - 1), y1 = min(t.y0 + 1, H - 1);
+                    const int o00 = y0 * W + x0, dxo = x1 - x0, dyo = (y1 - y0) * W;
+                    const float m0 = (t.valid & 1u) ? 1.f : 0.f, m1 = (t.valid & 2u) ? 1.f : 0.f;
+                    const float m2 = (t.valid & 4u) ? 1.f : 0.f, m3 = (t.valid & 8u) ? 1.f : 0.f;
                     float gix = 0.0f, giy = 0.0f;
                     const float bx = 1.0f - t.ax, by = 1.0f - t.ay;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        const float* r0 = src + c * P + t.y0 * W + t.x0;
-                        const float v0 = (t.valid & 1u) ? __ldg(r0) : 0.0f, v1 = (t.valid & 2u) ? __ldg(r0 + 1) : 0.0f;
-                        const float v2 = (t.valid & 4u) ? __ldg(r0 + W) : 0.0f, v3 = (t.valid & 8u) ? __ldg(r0 + W + 1) : 0.0f;
-                        const float g = gxs[c][r - 1][lane];
+                        const float* r0 = src + c * P + o00;
+                        const float v0 = __ldg(r0) * m0, v1 = __ldg(r0 + dxo) * m1;
+                        const float v2 = __ldg(r0 + dyo) * m2, v3 = __ldg(r0 + dyo + dxo) * m3;
+                        const float g = gxs[(c * IH + r - 1) * CW + lane];
                         gix += g * ((v1 - v0) * by + (v3 - v2) * t.ay);
                         giy += g * ((v2 - v0) * bx + (v3 - v1) * t.ax);
                     }
-                    gd[k] += warp_pixel_adjoint(cam[v], wp, d, wm1, hm1, true, gix * t.mx, giy * t.my, gT);
+                    gd[k] += warp_pixel_adjoint(cam, wp, d, wm1, hm1, true, gix * t.mx, giy * t.my, gT);
                 }
             }
         }
-        float* gp = pg.g_pose[v * n_preds + ip];
-        if (gp != nullptr) {
-            Slot* slot = slot_at(ws, (v * n_preds + ip) * B + b);
-            block_accumulate<12>(gT, red, spread_acc(slot));
-            if (last_block(slot, gridDim.x * gridDim.y, &flag) && tid == 0) {
-                const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
-                finish_pose_grad(slot, cams.pose_kind, eul ? pp.pose[v * n_preds + ip] + b * 6 : nullptr,
-                                 gp + b * (eul ? 6 : 16));
-            }
-        }
-        __syncthreads();
+        if (pg.g_pose[v * n_preds + ip] != nullptr)
+            warp_accumulate<12>(gT, spread_acc(slot_at(ws, (v * n_preds + ip) * B + b)));
+        __syncthreads();      // gxs / xs are rewritten by the next view
     }
 
     float* gout = pg.g_inv_depth[ip];
@@ -565,13 +561,27 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
             const int r = prow0 + k;
             const int qy = cy0 + r;
             if (col_ok && r >= 1 && r <= IH && qy < H) {
-                const size_t o = static_cast<size_t>(b) * P + qy * W + pgx;
+                const int o = qy * W + pgx;
                 float g = gd[k];
-                if (depth_kind == DROSFM_INV_DEPTH) g = inv2depth_grad(__ldg(pp.inv_depth[ip] + o), g);
-                gout[o] = g;
+                if (depth_kind == DROSFM_INV_DEPTH) g = inv2depth_grad(__ldg(invd + o), g);
+                gout[static_cast<size_t>(b) * P + o] = g;
             }
         }
     }
+    // one ticket per (view, prediction, sample): the last block turns the fp64 sums into the caller's encoding
+    __threadfence();
+    __syncthreads();
+    if (tid < V && pg.g_pose[tid * n_preds + ip] != nullptr) {
+        Slot* slot = slot_at(ws, (tid * n_preds + ip) * B + b);
+        const unsigned long long t = atomicAdd(&slot->ticket, 1ull);
+        if (t == static_cast<unsigned long long>(gridDim.x) * gridDim.y - 1ull) {
+            __threadfence();
+            const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
+            finish_pose_grad(slot, cams.pose_kind, eul ? pp.pose[tid * n_preds + ip] + b * 6 : nullptr,
+                             pg.g_pose[tid * n_preds + ip] + b * (eul ? 6 : 16));
+        }
+    }
+    (void)flags;
 }
 
 static int check_photo(const float* image, const float* const* context, int n_views, const drosfm_photo_opts_t* opts,
@@ -602,6 +612,8 @@ static int allow_big_smem() {
         e = cudaFuncSetAttribute(photometric_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(photometric_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(photometric_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
         if (e == cudaSuccess) done_for_device = dev;
     }
     if (e != cudaSuccess) {
@@ -709,7 +721,8 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
     DROSFM_REQUIRE(!want_pose || ws != nullptr, DROSFM_EINVAL, "photometric_bwd: pose gradients need ws");
     DROSFM_REQUIRE(static_cast<long long>(B) * n_preds <= 65535, DROSFM_ERANGE, "photometric_bwd: B * n_preds too large");
     dim3 grid((W + IW - 1) / IW, (H + IH - 1) / IH, B * n_preds);
-    photometric_bwd_kernel<<<grid, kPhotoThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+    if (int e = allow_big_smem()) return e;
+    photometric_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, static_cast<cudaStream_t>(stream)>>>(
         g_loss, image, pp, n_views, depth_kind, n_preds, *cams, sel, *opts, l1_weight(opts), pg, static_cast<Slot*>(ws), B, H, W);
     return launch_status("photometric_bwd");
 }

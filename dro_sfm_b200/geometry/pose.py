@@ -17,11 +17,28 @@ class Pose:
         if mat.dim() == 2:
             mat = mat.unsqueeze(0)
         assert mat.dim() == 3
-        self.mat = mat
+        self._mat = mat
+        self._vec = None            # euler vector this pose was built from (from_vec), if any
         self._is_identity = False
 
+    @property
+    def mat(self):
+        """[B,4,4] matrix; built on first use when the pose came from ``from_vec`` (one kernel launch)."""
+        if self._mat is None:
+            self._mat = ops.pose_vec2mat(self._vec)
+        return self._mat
+
+    @mat.setter
+    def mat(self, value):
+        self._mat, self._vec = value, None
+
+    def kernel_arg(self):
+        """What the fused kernels consume: the [B,6] euler vector when known (the conversion then runs in
+        the kernel prologue and the gradient lands on the vector directly), else the [B,4,4] matrix."""
+        return self._vec if (self._vec is not None and self._mat is None) else self.mat
+
     def __len__(self):
-        return len(self.mat)
+        return len(self._vec) if self._mat is None else len(self._mat)
 
     @classmethod
     def identity(cls, N=1, device=None, dtype=torch.float):
@@ -37,7 +54,11 @@ class Pose:
         if mode != "euler":
             raise NotImplementedError("dro_sfm_b200: rotation mode {!r} is not supported (configs use 'euler', "
                                       "configs/default_config.py:93)".format(mode))
-        return cls(ops.pose_vec2mat(vec))
+        if not vec.is_cuda or vec.dim() != 2 or vec.shape[-1] != 6:
+            return cls(ops.pose_vec2mat(vec))
+        pose = cls.__new__(cls)
+        pose._mat, pose._vec, pose._is_identity = None, vec, False
+        return pose
 
     @property
     def shape(self):

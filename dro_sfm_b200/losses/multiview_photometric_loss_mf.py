@@ -70,7 +70,11 @@ class MultiViewPhotometricDecayLoss(LossBase):
         for pv in poses:
             if not isinstance(pv, (list, tuple)):
                 pv = [pv] * n
-            out.append([p.mat if hasattr(p, "mat") else p for p in pv])
+            out.append([p.kernel_arg() if hasattr(p, "kernel_arg") else (p.mat if hasattr(p, "mat") else p) for p in pv])
+        # one encoding per call: if euler vectors and matrices are mixed, materialise the matrices
+        if len({t.dim() for row in out for t in row}) > 1:
+            out = [[(p.mat if hasattr(p, "mat") else p) for p in (pv if isinstance(pv, (list, tuple)) else [pv] * n)]
+                   for pv in poses]
         return out
 
     def forward(self, image, context, inv_depths, K, ref_K, poses, return_logs=False, progress=0.0):
