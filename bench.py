@@ -161,21 +161,18 @@ KERNEL_KEYS = {
 
 def run_gpu(args, wl):
     import torch.distributed as dist
-    from dro_sfm_b200 import _lib as L
+    from dro_sfm_b200 import _lib as L, dist_utils as du
     from dro_sfm_b200.hotpath import HotPathStep
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = du.env_rank()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    du.init("nccl", dev)
     L.lib()
     B = args.batch or wl.B
-    step = HotPathStep(wl, dev, B=B, seed=1234 + 1000 * rank, channels_last=(args.layout == "nhwc"))
+    step = HotPathStep(wl, dev, B=B, seed=du.shard_seed(1234, rank), channels_last=(args.layout == "nhwc"))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB of L2
 
     def sync_all():
@@ -192,8 +189,7 @@ def run_gpu(args, wl):
         if e2e:
             step.upload()
         loss = step.step()
-        if world > 1:
-            dist.all_reduce(loss, op=dist.ReduceOp.AVG)        # the only collective on the path: the logged loss
+        du.average_loss(loss.detach())                        # the only collective on the path: the logged loss
         if e2e:
             loss_host.copy_(loss.detach(), non_blocking=True)
         return loss
@@ -228,12 +224,9 @@ def run_gpu(args, wl):
     sync_all()
     ms_e2e = sum(s.elapsed_time(e) for s, e in evs)
     clk = clocks.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
-    frames = B * world * args.steps
-    value, e2e_value = frames / (ms * 1e-3), frames / (ms_e2e * 1e-3)
+    ms, ms_e2e = du.max_over_ranks([ms, ms_e2e], device=dev)
+    value = du.whole_job_rate(B * args.steps, world, ms * 1e-3)
+    e2e_value = du.whole_job_rate(B * args.steps, world, ms_e2e * 1e-3)
 
     # per-kernel durations: the same K steps issued eagerly with CUDA events around every C-ABI launch
     roofline = None
