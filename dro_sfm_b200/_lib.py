@@ -23,6 +23,7 @@ F32, F64 = 0, 1
 DEPTH, INV_DEPTH = 0, 1
 REDUCE_MIN, REDUCE_MEAN = 0, 1
 NCHW, NHWC = 0, 1
+ACCUMULATE_FMAP = 1
 SLOT_BYTES = 128
 
 _vp = ctypes.c_void_p
@@ -67,7 +68,7 @@ SIGNATURES = {
                                    _int, _int, _int, _int, _int, _int, _int, _vp], _int),
     "drosfm_feat_cost_fwd": ([_vp, _pp, _vp, _int, _cp, _pp, _int, _vp, _int, _int, _int, _int, _int, _vp], _int),
     "drosfm_feat_cost_bwd": ([_vp, _vp, _pp, _vp, _int, _cp, _pp, _int, _vp, _pp, _vp, _pp, _vp,
-                              _int, _int, _int, _int, _int, _vp], _int),
+                              _int, _int, _int, _int, _int, _int, _vp], _int),
     "drosfm_automask_fwd": ([_vp, _pp, _int, _op, _vp, _int, _int, _int, _vp], _int),
     "drosfm_photometric_fwd": ([_vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _vp, _vp, _vp,
                                 _int, _int, _int, _vp], _int),

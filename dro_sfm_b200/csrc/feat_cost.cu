@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kPixThreads)
 feat_cost_bwd_nchw(const float* __restrict__ g_cost, const float* __restrict__ fmap, ViewPtrs vp,
                    const float* __restrict__ depth, int depth_kind, drosfm_cams_t cams, int V,
                    float* __restrict__ g_fmap, ViewGrads vg, float* __restrict__ g_depth, Slot* ws,
-                   int B, int C, int h, int w, int need_coord_grad) {
+                   int B, int C, int h, int w, int need_coord_grad, int acc_fmap) {
     __shared__ Cam cam[VT];
     __shared__ int flag;
     const int b = blockIdx.z, P = h * w;
@@ -254,7 +254,10 @@ feat_cost_bwd_nchw(const float* __restrict__ g_cost, const float* __restrict__ f
     if (active && g_fmap != nullptr) {
 #pragma unroll
         for (int k = 0; k < CG; ++k)
-            if (c0 + k < C) g_fmap[base + static_cast<size_t>(k) * P] = gf[k];
+            if (c0 + k < C) {
+                float* gp = g_fmap + base + static_cast<size_t>(k) * P;
+                *gp = acc_fmap ? *gp + gf[k] : gf[k];
+            }
     }
     if (need_coord_grad) {
         // one ticket per block and view: the last block converts the fp64 sums into the caller's encoding
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ fmap, ViewPtrs vp,
                    const float* __restrict__ depth, int depth_kind, drosfm_cams_t cams, int V,
                    float* __restrict__ g_fmap, ViewGrads vg, float* __restrict__ g_depth, Slot* ws,
-                   int B, int C, int h, int w, int ppw, int need_coord_grad) {
+                   int B, int C, int h, int w, int ppw, int need_coord_grad, int acc_fmap) {
     __shared__ Cam cam[VT];
     __shared__ int flag;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -476,7 +479,7 @@ feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ f
                 if (!chan_ok) co = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (g_fmap != nullptr && chan_ok) {
                     float4* gp = reinterpret_cast<float4*>(g_fmap + px);
-                    if (v == 0) *gp = co;
+                    if (v == 0 && !acc_fmap) *gp = co;
                     else { float4 old = *gp; old.x += co.x; old.y += co.y; old.z += co.z; old.w += co.w; *gp = old; }
                 }
                 if (gref != nullptr && chan_ok) {
@@ -634,7 +637,8 @@ int drosfm_feat_cost_fwd(const float* fmap, const float* const* fmap_ref, const 
 int drosfm_feat_cost_bwd(const float* g_cost, const float* fmap, const float* const* fmap_ref, const float* depth,
                          int depth_kind, const drosfm_cams_t* cams, const float* const* poses, int n_views,
                          float* g_fmap, float* const* g_fmap_ref, float* g_depth, float* const* g_poses, void* ws,
-                         int B, int C, int h, int w, int layout, drosfm_stream_t stream) {
+                         int B, int C, int h, int w, int layout, int flags, drosfm_stream_t stream) {
+    const int acc_fmap = (flags & DROSFM_ACCUMULATE_FMAP) ? 1 : 0;
     if (B == 0 || h * w == 0 || C == 0) return DROSFM_OK;
     if (int e = check_cost_args(cams, fmap_ref, poses, n_views, B, C, h, w, layout)) return e;
     DROSFM_REQUIRE(g_cost && fmap && depth, DROSFM_EINVAL, "feat_cost_bwd: NULL argument");
@@ -663,7 +667,7 @@ int drosfm_feat_cost_bwd(const float* g_cost, const float* fmap, const float* co
         dim3 grid((P + per_block - 1) / per_block, B);
         const size_t smem = static_cast<size_t>(kWarpsPerBlock) * ppw * n_views * (sizeof(STap) + sizeof(float2));
 #define CALL(VT) feat_cost_bwd_nhwc<VT><<<grid, kWarpsPerBlock * 32, smem, s>>>(g_cost, fmap, vp, depth, depth_kind, *cams, n_views, \
-                                                                          g_fmap, vg, g_depth, static_cast<Slot*>(ws), B, C, h, w, ppw, need_coord)
+                                                                          g_fmap, vg, g_depth, static_cast<Slot*>(ws), B, C, h, w, ppw, need_coord, acc_fmap)
         DISPATCH_VT(n_views, CALL);
 #undef CALL
     } else {
@@ -674,10 +678,10 @@ int drosfm_feat_cost_bwd(const float* g_cost, const float* fmap, const float* co
     do {                                                                                                                    \
         if (cg == 8)                                                                                                        \
             feat_cost_bwd_nchw<VT, 8><<<grid, kPixThreads, 0, s>>>(g_cost, fmap, vp, depth, depth_kind, *cams, n_views, g_fmap, vg,  \
-                                                                   g_depth, static_cast<Slot*>(ws), B, C, h, w, need_coord);        \
+                                                                   g_depth, static_cast<Slot*>(ws), B, C, h, w, need_coord, acc_fmap);      \
         else                                                                                                                \
             feat_cost_bwd_nchw<VT, 4><<<grid, kPixThreads, 0, s>>>(g_cost, fmap, vp, depth, depth_kind, *cams, n_views, g_fmap, vg,  \
-                                                                   g_depth, static_cast<Slot*>(ws), B, C, h, w, need_coord);        \
+                                                                   g_depth, static_cast<Slot*>(ws), B, C, h, w, need_coord, acc_fmap);      \
     } while (0)
         DISPATCH_VT(n_views, CALL);
 #undef CALL

@@ -37,7 +37,8 @@ def _channels_last(t):
         ref, version, grad_mode, converted = hit
         if ref() is t and version == t._version and grad_mode == torch.is_grad_enabled():
             return converted
-    converted = t.contiguous(memory_format=torch.channels_last)
+    # autograd-visible conversion whose backward hands over the in-kernel sum of all cost gradients
+    converted = ops.to_channels_last_sink(t)
     if len(_cl_cache) > 64:
         for k in [k for k, (r, _, _, _) in _cl_cache.items() if r() is None]:
             del _cl_cache[k]

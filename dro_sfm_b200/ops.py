@@ -299,6 +299,44 @@ def _as_layout(t, layout):
     return t.contiguous(memory_format=torch.channels_last) if layout == L.NHWC else t.contiguous()
 
 
+class GradSink:
+    """Shared gradient accumulator of one feature map over all cost calls of a step.
+
+    ``to_channels_last_sink`` (below) creates one per converted map.  Each cost backward adds its
+    contribution into ``buffer`` inside the kernel (the scatter into the source maps is atomic anyway, the
+    target-map gradient becomes a read-modify-write), instead of returning 2*V*T separate tensors that
+    autograd would have to sum with as many element-wise kernels."""
+    __slots__ = ("buffer", "dummy")
+
+    def __init__(self):
+        self.buffer = None
+        self.dummy = None
+
+
+class _ToChannelsLastSink(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, sink):
+        ctx.sink = sink
+        return t.contiguous(memory_format=torch.channels_last)
+
+    @staticmethod
+    def backward(ctx, g):
+        buf, ctx.sink.buffer = ctx.sink.buffer, None
+        if buf is None:
+            return g, None
+        # g is the zero placeholder returned by the first sink-aware consumer plus whatever ordinary
+        # consumers of the converted tensor contributed
+        return buf.add_(g), None
+
+
+def to_channels_last_sink(t):
+    """channels_last copy of an NCHW feature map whose cost gradients are summed in-kernel (see GradSink)."""
+    sink = GradSink()
+    out = _ToChannelsLastSink.apply(t, sink)
+    out._drosfm_sink = sink if (t.requires_grad and torch.is_grad_enabled()) else None
+    return out
+
+
 class _FeatCost(torch.autograd.Function):
     """inputs: depth, fmap, K, Kref, scale, depth_kind, V, ref_0..ref_{V-1}, pose_0..pose_{V-1}"""
 
@@ -309,8 +347,12 @@ class _FeatCost(torch.autograd.Function):
         layout = _layout_of(fmap)
         if layout == L.NHWC and fmap.shape[1] % 4 != 0:
             layout = L.NCHW
-        fmap = _as_layout(fmap, layout)
-        refs = [_as_layout(r, layout) for r in refs]
+        sinks = [getattr(x, "_drosfm_sink", None) for x in (fmap, *refs)]
+        fmap_l = _as_layout(fmap, layout)
+        refs_l = [_as_layout(r, layout) for r in refs]
+        # a sink only applies when the tensor is used as handed over (no re-layout copy in between)
+        sinks = [s if a is b else None for s, a, b in zip(sinks, (fmap, *refs), (fmap_l, *refs_l))]
+        fmap, refs = fmap_l, refs_l
         poses = [L.f32c(p) for p in poses]
         depth = L.f32c(depth)
         B, C, h, w = fmap.shape
@@ -323,6 +365,7 @@ class _FeatCost(torch.autograd.Function):
                     "feat_cost_fwd")
         ctx.save_for_backward(depth, fmap, keep[0], keep[1], *refs, *poses)
         ctx.cfg = (float(scale), depth_kind, V, kind, layout)
+        ctx.sinks = sinks
         return cost
 
     @staticmethod
@@ -335,27 +378,53 @@ class _FeatCost(torch.autograd.Function):
         B, C, h, w = fmap.shape
         need = ctx.needs_input_grad
         cams, _ = L.make_cams(K, Kref, scale, None, None, None, kind)
-        g_fmap = torch.empty_like(fmap) if need[1] else None
-        # one zero-filled slab for everything the kernel accumulates into (a single memset)
-        n_ref = sum(1 for v in range(V) if need[7 + v])
-        slab = torch.zeros(n_ref * fmap.numel() + (depth.numel() if need[0] else 0), device=fmap.device, dtype=torch.float32)
-        g_refs, off = [], 0
+        sinks = ctx.sinks
+
+        def sink_buffer(sink, like):
+            """(buffer, value to return to autograd): the first consumer of a step allocates the zeroed
+            buffer and returns a zero placeholder so that the sink node runs; later ones return None."""
+            if sink.buffer is None:
+                sink.buffer = torch.zeros_like(like)
+                if sink.dummy is None or sink.dummy.shape != like.shape:
+                    sink.dummy = torch.zeros((), device=like.device, dtype=like.dtype).expand(like.shape)
+                return sink.buffer, sink.dummy
+            return sink.buffer, None
+
+        flags = 0
+        g_fmap = ret_fmap = None
+        if need[1]:
+            if sinks[0] is not None:
+                g_fmap, ret_fmap = sink_buffer(sinks[0], fmap)
+                flags |= L.ACCUMULATE_FMAP
+            else:
+                g_fmap = ret_fmap = torch.empty_like(fmap)
+        # one zero-filled slab for everything else the kernel accumulates into (a single memset)
+        plain = [v for v in range(V) if need[7 + v] and sinks[1 + v] is None]
+        slab = torch.zeros(len(plain) * fmap.numel() + (depth.numel() if need[0] else 0), device=fmap.device, dtype=torch.float32)
+        g_refs, ret_refs, off = [], [], 0
         for v in range(V):
-            if need[7 + v]:
+            if not need[7 + v]:
+                g_refs.append(None)
+                ret_refs.append(None)
+            elif sinks[1 + v] is not None:
+                buf, ret = sink_buffer(sinks[1 + v], refs[v])
+                g_refs.append(buf)
+                ret_refs.append(ret)
+            else:
                 flat = slab[off:off + fmap.numel()]
                 off += fmap.numel()
-                g_refs.append(flat.view(B, h, w, C).permute(0, 3, 1, 2) if layout == L.NHWC else flat.view(B, C, h, w))
-            else:
-                g_refs.append(None)
+                t = flat.view(B, h, w, C).permute(0, 3, 1, 2) if layout == L.NHWC else flat.view(B, C, h, w)
+                g_refs.append(t)
+                ret_refs.append(t)
         g_depth = slab[off:off + depth.numel()].view_as(depth) if need[0] else None
         g_poses = [torch.empty_like(poses[v]) if need[7 + V + v] else None for v in range(V)]
         with torch.cuda.device(fmap.device):
             ws = L.workspace(fmap.device, V * B) if any(p is not None for p in g_poses) else None
             L.check(L.lib().drosfm_feat_cost_bwd(L.ptr(g), L.ptr(fmap), L.ptr_array(refs), L.ptr(depth), depth_kind, cams,
                                                  L.ptr_array(poses), V, L.ptr(g_fmap), L.ptr_array(g_refs), L.ptr(g_depth),
-                                                 L.ptr_array(g_poses), L.ptr(ws), B, C, h, w, layout, L.stream()),
+                                                 L.ptr_array(g_poses), L.ptr(ws), B, C, h, w, layout, flags, L.stream()),
                     "feat_cost_bwd")
-        return (g_depth, g_fmap, None, None, None, None, None, *g_refs, *g_poses)
+        return (g_depth, ret_fmap, None, None, None, None, None, *ret_refs, *g_poses)
 
 
 def feat_cost(depth, fmap, fmaps_ref, poses, K, Kref=None, scale=1.0, inverse_depth=False):

@@ -39,6 +39,7 @@ enum { DROSFM_F32 = 0, DROSFM_F64 = 1 };
 enum { DROSFM_DEPTH = 0, DROSFM_INV_DEPTH = 1 };
 enum { DROSFM_REDUCE_MIN = 0, DROSFM_REDUCE_MEAN = 1 };
 enum { DROSFM_NCHW = 0, DROSFM_NHWC = 1 };
+enum { DROSFM_ACCUMULATE_FMAP = 1 };   /* feat_cost_bwd flags */
 
 typedef void* drosfm_stream_t;  /* cudaStream_t */
 
@@ -119,7 +120,8 @@ int drosfm_view_synthesis_bwd(const float* g_out, const float* src, const float*
  * (V = 1 is get_cost_each).  fmap, fmap_ref[v], cost: [B,C,h,w] in `layout` (NCHW, or NHWC =
  * torch channels_last storage of the same logical tensor).  poses[v]: per-view source pose in
  * cams->pose_kind encoding ([B,4,4] or [B,6]); cams->pose is ignored.
- * bwd: g_fmap written; g_fmap_ref[v] and g_depth accumulated (entries may be NULL);
+ * bwd: g_fmap written (added to when flags & DROSFM_ACCUMULATE_FMAP: lets a caller sum the gradients of
+ * all cost calls of a step in one buffer); g_fmap_ref[v] and g_depth accumulated (entries may be NULL);
  * g_poses[v] written ([B,4,4] or [B,6]; entries may be NULL; ws of drosfm_ws_bytes(V*B)). */
 int drosfm_feat_cost_fwd(const float* fmap, const float* const* fmap_ref, const float* depth, int depth_kind,
                          const drosfm_cams_t* cams, const float* const* poses, int n_views, float* cost,
@@ -128,7 +130,7 @@ int drosfm_feat_cost_bwd(const float* g_cost, const float* fmap, const float* co
                          const float* depth, int depth_kind, const drosfm_cams_t* cams,
                          const float* const* poses, int n_views, float* g_fmap, float* const* g_fmap_ref,
                          float* g_depth, float* const* g_poses, void* ws,
-                         int B, int C, int h, int w, int layout, drosfm_stream_t stream);
+                         int B, int C, int h, int w, int layout, int flags, drosfm_stream_t stream);
 
 /* ---- photometric loss (multiview_photometric_loss_mf.py:15-54,132-269,333-353) ---------------
  * Options shared by the photometric entry points. */

@@ -234,3 +234,42 @@ def test_cost_dropins_match_reference_signature(golden):
     c = depth_cost_calc(cu(g["inv_depth"]), cu(g["fmap"]), (cu(g["fref0"]), cu(g["fref1"])), [cu(g["pose0"]), cu(g["pose1"])],
                         K, K, 1.0 / 8)
     assert_close(c.cpu(), g["depth_f32_cost"], rtol=1e-4, atol=1e-5, what="depth_cost_calc (euler prologue: 1-ulp trig)")
+
+
+def test_cost_gradients_accumulate_through_the_layout_cache():
+    """Several cost calls on the same NCHW feature maps (as DepthPoseNet.forward issues them): the cached
+    channels_last copies collect the gradients in-kernel; the result equals the sum of per-call gradients
+    from the plain NCHW operator."""
+    from dro_sfm_b200 import ops, synthetic as syn
+    from dro_sfm_b200.networks import get_cost_each, depth_cost_calc
+    g = syn.gen(9)
+    B, C, h, w, V = 2, 64, 24, 40, 2
+    K = syn.intrinsics("kitti", B, h * 8, w * 8).to(DEV)
+    fmap0 = syn.features(g, B, C, h, w).to(DEV)
+    frefs0 = [syn.features(g, B, C, h, w).to(DEV) for _ in range(V)]
+    invs = [syn.inv_depth(g, B, h, w, 0.5, 80.0).to(DEV) for _ in range(2)]
+    poses = [[syn.pose_vec(g, B, "kitti").to(DEV) for _ in range(V)] for _ in range(2)]
+    gouts = [torch.randn(B, C, h, w, generator=g).to(DEV) for _ in range(2 * (1 + V))]
+
+    def run(fn_each, fn_depth):
+        fmap = fmap0.clone().requires_grad_(True)
+        frefs = [f.clone().requires_grad_(True) for f in frefs0]
+        outs = []
+        for t in range(2):
+            outs.append(fn_depth(invs[t], fmap, frefs, poses[t]))
+            depth = 1.0 / invs[t]
+            for v in range(V):
+                outs.append(fn_each(poses[t][v], fmap, frefs[v], depth))
+        torch.autograd.backward(outs, gouts)
+        return [fmap.grad] + [f.grad for f in frefs], outs
+
+    g_sink, o_sink = run(lambda p, f, fr, d: get_cost_each(p, f, fr, d, K, K, 0.125),
+                         lambda i, f, frs, ps: depth_cost_calc(i, f, frs, ps, K, K, 0.125))
+    g_plain, o_plain = run(lambda p, f, fr, d: ops.feat_cost(d, f, [fr], [p], K, K, 0.125),
+                           lambda i, f, frs, ps: ops.feat_cost(i, f, frs, ps, K, K, 0.125, inverse_depth=True))
+    for a, b in zip(o_sink, o_plain):
+        assert_close(a.detach().cpu(), b.detach().cpu(), what="cost (nhwc cache vs nchw)")
+    for k, (a, b) in enumerate(zip(g_sink, g_plain)):
+        assert a is not None and a.shape == b.shape
+        scale = float(b.abs().max())
+        assert float((a - b).abs().max()) <= 1e-5 * scale + 1e-6, f"accumulated gradient {k} differs"
