@@ -60,46 +60,53 @@ __device__ __forceinline__ float edge_weight(const float* __restrict__ img, int 
     return expf(-(a / 3.0f));
 }
 
-// pass 2: sums of |dx|*wx and |dy|*wy per (prediction, sample); the last block folds them into the loss
+// pass 2: sums of |dx|*wx and |dy|*wy per (prediction, sample); the last block folds them into the loss.
+// One thread per pixel (grid-stride), the normalisation d / mean is a multiplication by the reciprocal mean
+// (computed once per thread; 1 ulp from the reference's division, far inside the loss tolerance).
 __global__ void __launch_bounds__(kLossThreads)
 smooth_fwd_kernel(const float* __restrict__ image, const __grid_constant__ DepthList dl, int n_preds, float weight,
                   float* __restrict__ stats, float* __restrict__ loss, Slot* ws, int B, int H, int W) {
-    __shared__ double red[2 * (kLossThreads / 32)];
+    __shared__ float red[2 * DROSFM_MAX_PREDS][kLossThreads / 32];
     __shared__ int flag;
     const int b = blockIdx.y, P = H * W;
     const float* img = image + static_cast<size_t>(b) * 3 * P;
-    float sx[DROSFM_MAX_PREDS], sy[DROSFM_MAX_PREDS];
+    float sx[DROSFM_MAX_PREDS], sy[DROSFM_MAX_PREDS], rm[DROSFM_MAX_PREDS];
 #pragma unroll
-    for (int i = 0; i < DROSFM_MAX_PREDS; ++i) sx[i] = sy[i] = 0.0f;
+    for (int i = 0; i < DROSFM_MAX_PREDS; ++i) {
+        sx[i] = sy[i] = 0.0f;
+        rm[i] = i < n_preds ? 1.0f / fmaxf(stats[(i * B + b) * 4], 1e-6f) : 0.0f;
+    }
     for (int p = blockIdx.x * kLossThreads + threadIdx.x; p < P; p += gridDim.x * kLossThreads) {
         const int y = p / W, x = p - y * W;
         const bool hx = x + 1 < W, hy = y + 1 < H;
-        const float wx = hx ? edge_weight(img, P, p, p + 1) : 0.0f;
-        const float wy = hy ? edge_weight(img, P, p, p + W) : 0.0f;
+        const int px = hx ? p + 1 : p, py = hy ? p + W : p;
+        const float wx = hx ? edge_weight(img, P, p, px) : 0.0f;
+        const float wy = hy ? edge_weight(img, P, p, py) : 0.0f;
 #pragma unroll
         for (int i = 0; i < DROSFM_MAX_PREDS; ++i) {
             if (i < n_preds) {
                 const float* d = dl.d[i] + static_cast<size_t>(b) * P;
-                const float m = fmaxf(stats[(i * B + b) * 4], 1e-6f);
-                const float dc = __ldg(d + p) / m;
-                if (hx) sx[i] += fabsf((dc - __ldg(d + p + 1) / m) * wx);
-                if (hy) sy[i] += fabsf((dc - __ldg(d + p + W) / m) * wy);
+                const float dc = __ldg(d + p) * rm[i];
+                sx[i] += fabsf((dc - __ldg(d + px) * rm[i]) * wx);
+                sy[i] += fabsf((dc - __ldg(d + py) * rm[i]) * wy);
             }
         }
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < DROSFM_MAX_PREDS; ++i) {
-        if (i >= n_preds) break;
-        const double a = warp_sum(static_cast<double>(sx[i])), c = warp_sum(static_cast<double>(sy[i]));
-        if (lane == 0) { red[2 * wid] = a; red[2 * wid + 1] = c; }
-        __syncthreads();
-        if (threadIdx.x < 2) {
-            double t = 0.0;
-            for (int k = 0; k < kLossThreads / 32; ++k) t += red[2 * k + threadIdx.x];
-            if (t != 0.0) atomicAdd(spread_acc(slot_at(ws, i * B + b)) + threadIdx.x, t);
+        if (i < n_preds) {
+            const float a = warp_sum(sx[i]), c = warp_sum(sy[i]);
+            if (lane == 0) { red[2 * i][wid] = a; red[2 * i + 1][wid] = c; }
         }
-        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * n_preds) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < kLossThreads / 32; ++k) t += red[threadIdx.x][k];
+        const int i = threadIdx.x >> 1;
+        if (t != 0.0) atomicAdd(spread_acc(slot_at(ws, i * B + b)) + (threadIdx.x & 1), t);
     }
     Slot* ticket = slot_at(ws, n_preds * B);
     if (last_block(ticket, gridDim.x * gridDim.y, &flag) && threadIdx.x == 0) {
@@ -135,29 +142,31 @@ smooth_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict__ im
     const float* img = image + static_cast<size_t>(b) * 3 * P;
     const int y = p / W, x = p - y * W;
     const bool xr = x + 1 < W, xl = x > 0, yd = y + 1 < H, yu = y > 0;
-    const float w_r = xr ? edge_weight(img, P, p, p + 1) : 0.0f;
-    const float w_l = xl ? edge_weight(img, P, p - 1, p) : 0.0f;
-    const float w_d = yd ? edge_weight(img, P, p, p + W) : 0.0f;
-    const float w_u = yu ? edge_weight(img, P, p - W, p) : 0.0f;
+    const int pr = xr ? p + 1 : p, pl = xl ? p - 1 : p, pd = yd ? p + W : p, pu = yu ? p - W : p;
+    const float w_r = xr ? edge_weight(img, P, p, pr) : 0.0f;
+    const float w_l = xl ? edge_weight(img, P, pl, p) : 0.0f;
+    const float w_d = yd ? edge_weight(img, P, p, pd) : 0.0f;
+    const float w_u = yu ? edge_weight(img, P, pu, p) : 0.0f;
     const float g0 = __ldg(g_loss) * weight / static_cast<float>(n_preds);
     const float nx = static_cast<float>(B) * H * (W - 1), ny = static_cast<float>(B) * (H - 1) * W;
+    const float invP = 1.0f / static_cast<float>(P);
     float pw = 1.0f;
     for (int i = 0; i < n_preds; ++i, pw *= 2.0f) {
         float* go = dg.g[i];
         if (go == nullptr) continue;
         const float* d = dl.d[i] + static_cast<size_t>(b) * P;
         const float* st = stats + (i * B + b) * 4;
-        const float mean = st[0], m = fmaxf(mean, 1e-6f);
+        const float mean = st[0], rm = 1.0f / fmaxf(mean, 1e-6f);
         const float kx = nx > 0.0f ? g0 / (pw * nx) : 0.0f, ky = ny > 0.0f ? g0 / (pw * ny) : 0.0f;
-        const float dc = __ldg(d + p) / m;
-        // d L / d dn[p], dn = d / m (the normalised values are formed exactly as in the forward pass)
+        const float dc = __ldg(d + p) * rm;
+        // d L / d dn[p], dn = d * (1/mean) (the normalised values are formed exactly as in the forward pass)
         float h = 0.0f;
-        if (xr) h += kx * w_r * sgn(dc - __ldg(d + p + 1) / m);
-        if (xl) h -= kx * w_l * sgn(__ldg(d + p - 1) / m - dc);
-        if (yd) h += ky * w_d * sgn(dc - __ldg(d + p + W) / m);
-        if (yu) h -= ky * w_u * sgn(__ldg(d + p - W) / m - dc);
-        float g = h / m;
-        if (mean >= 1e-6f) g -= (kx * st[1] + ky * st[2]) / (m * static_cast<float>(P));
+        h += kx * w_r * sgn(dc - __ldg(d + pr) * rm);
+        h -= kx * w_l * sgn(__ldg(d + pl) * rm - dc);
+        h += ky * w_d * sgn(dc - __ldg(d + pd) * rm);
+        h -= ky * w_u * sgn(__ldg(d + pu) * rm - dc);
+        float g = h * rm;
+        if (mean >= 1e-6f) g -= (kx * st[1] + ky * st[2]) * rm * invP;
         const size_t o = static_cast<size_t>(b) * P + p;
         go[o] = accumulate ? go[o] + g : g;
     }
@@ -317,7 +326,9 @@ int drosfm_smoothness_fwd(const float* image, const float* const* inv_depths, in
     if (mb > 64) mb = 64;
     smooth_mean_kernel<<<dim3(mb, n_preds * B), kLossThreads, 0, s>>>(dl, stats, static_cast<Slot*>(ws), B, P);
     if (int e = launch_status("smoothness_fwd (mean)")) return e;
-    smooth_fwd_kernel<<<dim3(strip_blocks(P, B), B), kLossThreads, 0, s>>>(image, dl, n_preds, weight, stats, loss,
+    int fb = (P + kLossThreads * 2 - 1) / (kLossThreads * 2);     // two pixels per thread
+    if (fb < 1) fb = 1;
+    smooth_fwd_kernel<<<dim3(fb, B), kLossThreads, 0, s>>>(image, dl, n_preds, weight, stats, loss,
                                                                            static_cast<Slot*>(ws), B, H, W);
     return launch_status("smoothness_fwd");
 }

@@ -52,20 +52,58 @@ class HotPathStep:
     def _alloc(self):
         wl, h, dev = self.wl, self.host, self.device
         seq_iters = wl.T // wl.seq_len
-        self.image = h["image"].to(dev)
-        self.context = [c.to(dev) for c in h["context"]]
-        self.K = h["K"].to(dev)                                    # float64, as numpy collation delivers it
-        self.fmap = self._feat(h["fmap"]).requires_grad_(True)
-        self.frefs = [self._feat(f).requires_grad_(True) for f in h["fmaps_ref"]]
-        self.inv_lr = [x.to(dev).requires_grad_(True) for x in h["inv_depth_lr"]]
+        # Every forward input of a step lives in ONE flat device buffer (and one pinned host buffer), so the
+        # end-to-end path moves a step's inputs with a single H2D copy into a staging buffer (overlapping
+        # the previous step) and a single device-to-device copy into the tensors the CUDA graph reads.
+        host_list = [h["image"], *h["context"], h["fmap"], *h["fmaps_ref"], *h["inv_depth_lr"], *h["inv_depths"]]
+        host_list += [p for r in h["pose_lr"] for p in r] + [p for r in h["poses"] for p in r]
+        if wl.supervised:
+            host_list += [h["gt_inv_depth"], *h["gt_poses"]]
+        host_list = [t.contiguous().float() for t in host_list]
+        sizes = [t.numel() for t in host_list]
+        offs, total = [], 0
+        for n in sizes:
+            offs.append(total)
+            total += (n + 3) // 4 * 4                       # keep every tensor 16-byte aligned
+        k64 = h["K"].contiguous()                           # float64 intrinsics travel separately (tiny)
+        self.host_flat = torch.zeros(total, dtype=torch.float32)
+        for t, o in zip(host_list, offs):
+            self.host_flat[o:o + t.numel()] = t.reshape(-1)
+        if dev.type == "cuda":
+            self.host_flat = self.host_flat.pin_memory()
+            self.host_K = k64.pin_memory()
+        else:
+            self.host_K = k64
+        self.flat = self.host_flat.to(dev)
+        self.staging = torch.empty_like(self.flat)
+        self.K = k64.to(dev)                                 # float64, as numpy collation delivers it
+        self.K_staging = torch.empty_like(self.K)
+        with torch.no_grad():
+            views = [self.flat[o:o + t.numel()].view(t.shape) for t, o in zip(host_list, offs)]
+        it = iter(views)
+        V, T, n = wl.V, wl.T, wl.n
+
+        def take(k):
+            return [next(it) for _ in range(k)]
+
+        self.image = next(it)
+        self.context = take(V)
+        self.fmap = next(it).requires_grad_(True)
+        self.frefs = [f.requires_grad_(True) for f in take(V)]
+        if self.channels_last:                               # a network that already runs channels_last
+            self.fmap = self.fmap.detach().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+            self.frefs = [f.detach().contiguous(memory_format=torch.channels_last).requires_grad_(True) for f in self.frefs]
+        self.inv_lr = [x.requires_grad_(True) for x in take(T)]
+        self.inv_depths = [x.requires_grad_(True) for x in take(n)]
+        flat_pose_lr = take(T * V)
+        self.pose_lr = [[flat_pose_lr[t * V + v].requires_grad_(True) for v in range(V)] for t in range(T)]
+        flat_poses = take(V * n)
+        self.poses = [[flat_poses[v * n + i].requires_grad_(True) for i in range(n)] for v in range(V)]
+        if wl.supervised:
+            self.gt_inv_depth = next(it)
+            self.gt_poses = take(V)
         # the pose cost sees depth = inv2depth(scale(inv_depth)) built once per outer iteration by the caller
         self.depth_lr = [(1.0 / h["inv_depth_lr"][k * wl.seq_len].clamp(min=1e-6)).to(dev) for k in range(seq_iters)]
-        self.pose_lr = [[p.to(dev).requires_grad_(True) for p in row] for row in h["pose_lr"]]
-        self.inv_depths = [x.to(dev).requires_grad_(True) for x in h["inv_depths"]]
-        self.poses = [[p.to(dev).requires_grad_(True) for p in row] for row in h["poses"]]
-        if wl.supervised:
-            self.gt_inv_depth = h["gt_inv_depth"].to(dev)
-            self.gt_poses = [p.to(dev) for p in h["gt_poses"]]
         g = syn.gen(99)
         hh, ww = wl.H // 8, wl.W // 8
         n_cost = wl.T * (1 + wl.V)
@@ -76,28 +114,34 @@ class HotPathStep:
         if cl:
             self.g_costs = [t.contiguous(memory_format=torch.channels_last) for t in self.g_costs]
         self.one = torch.ones(1, device=dev)
-        # host-resident inputs of a step (pinned) and their device destinations, for the end-to-end timing
-        self._h2d = []
-        pairs = [(h["image"], self.image), (h["K"], self.K), (h["fmap"], self.fmap)]
-        pairs += list(zip(h["context"], self.context)) + list(zip(h["fmaps_ref"], self.frefs))
-        pairs += list(zip(h["inv_depth_lr"], self.inv_lr)) + list(zip(h["inv_depths"], self.inv_depths))
-        pairs += [(p, q) for r, s in zip(h["pose_lr"], self.pose_lr) for p, q in zip(r, s)]
-        pairs += [(p, q) for r, s in zip(h["poses"], self.poses) for p, q in zip(r, s)]
-        if wl.supervised:
-            pairs += [(h["gt_inv_depth"], self.gt_inv_depth)] + list(zip(h["gt_poses"], self.gt_poses))
-        for src, dst in pairs:
-            self._h2d.append((src.contiguous().pin_memory() if self.device.type == "cuda" else src, dst))
-        self.h2d_bytes = sum(_bytes(s) for s, _ in self._h2d)
+        self.h2d_bytes = self.host_flat.numel() * 4 + self.host_K.numel() * 8
 
     def leaves(self):
         out = [self.fmap] + self.frefs + self.inv_lr + [p for r in self.pose_lr for p in r]
         return out + self.inv_depths + [p for r in self.poses for p in r]
 
     def upload(self):
-        """Host -> device copy of every forward input of the step (pinned memory, current stream)."""
+        """Blocking-free host -> device copy of every forward input of the step straight into the tensors the
+        step reads (pinned memory, current stream)."""
         with torch.no_grad():
-            for src, dst in self._h2d:
-                dst.copy_(src, non_blocking=True)      # channels_last destinations are handled by copy_
+            self.flat.copy_(self.host_flat, non_blocking=True)
+            self.K.copy_(self.host_K, non_blocking=True)
+
+    def prefetch(self, stream):
+        """Host -> device copy of the NEXT step's inputs into the staging buffers on `stream` (overlaps the
+        running step); returns the event that marks its completion."""
+        with torch.no_grad(), torch.cuda.stream(stream):
+            self.staging.copy_(self.host_flat, non_blocking=True)
+            self.K_staging.copy_(self.host_K, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return ev
+
+    def commit_staging(self):
+        """Device-to-device move of the staged inputs into the tensors the step reads (current stream)."""
+        with torch.no_grad():
+            self.flat.copy_(self.staging, non_blocking=True)
+            self.K.copy_(self.K_staging, non_blocking=True)
 
     # -- the step --------------------------------------------------------------------------------
     def forward_backward(self):
