@@ -70,9 +70,9 @@ SIGNATURES = {
     "drosfm_feat_cost_bwd": ([_vp, _vp, _pp, _vp, _int, _cp, _pp, _int, _vp, _pp, _vp, _pp, _vp,
                               _int, _int, _int, _int, _int, _int, _vp], _int),
     "drosfm_automask_fwd": ([_vp, _pp, _int, _op, _vp, _int, _int, _int, _vp], _int),
-    "drosfm_photometric_fwd": ([_vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _vp, _vp, _vp,
+    "drosfm_photometric_fwd": ([_vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _vp, _vp, _vp, _vp, _vp,
                                 _int, _int, _int, _vp], _int),
-    "drosfm_photometric_bwd": ([_vp, _vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _pp, _pp, _vp,
+    "drosfm_photometric_bwd": ([_vp, _vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _pp, _pp, _vp, _vp, _vp,
                                 _int, _int, _int, _vp], _int),
     "drosfm_smoothness_fwd": ([_vp, _pp, _int, _f32, _vp, _vp, _vp, _int, _int, _int, _vp], _int),
     "drosfm_smoothness_bwd": ([_vp, _vp, _pp, _int, _f32, _vp, _pp, _int, _int, _int, _int, _vp], _int),

@@ -112,10 +112,20 @@ __device__ __forceinline__ Win add3(const Win& a, const Win& b, const Win& c) {
 // top-left corner is (oy, ox) (zeros elsewhere).  WARP: through the depth/pose warp; otherwise the
 // un-warped source (auto-mask).  Work is batched so that each thread has NB depth loads, then NB*12
 // gathers in flight; the camera lives in registers.
+// What the forward keeps per (prediction, view, sample) for the backward: the warped source (3 planes) and,
+// per pixel, the clamped north-west tap offset, flag bits and the two fractional offsets (16 bytes).
+struct alignas(16) SavedTap {
+    int o00;
+    unsigned flags;     // bits 0-3 tap validity, 4: east tap is a different column, 5: south tap is a different row,
+                        // 6/7: x / y coordinate gradient not clipped away (border padding)
+    float ax, ay;
+};
+
 template <int ROWS, int COLS, int NT, bool WARP>
 __device__ __forceinline__ void fill_source_tile(float* __restrict__ xs, const float* __restrict__ src,
                                                  const float* __restrict__ invd, int depth_kind, const Cam& cam,
-                                                 int oy, int ox, int H, int W, int P, float wm1, float hm1, int padding) {
+                                                 int oy, int ox, int H, int W, int P, float wm1, float hm1, int padding,
+                                                 float* __restrict__ xsave = nullptr, SavedTap* __restrict__ tsave = nullptr) {
     constexpr int N = ROWS * COLS, NB = 2;
     constexpr int STEP_Y = NT / COLS, STEP_X = NT % COLS;       // (row, column) advance of idx += NT
     const int tid = threadIdx.x;
@@ -150,6 +160,21 @@ __device__ __forceinline__ void fill_source_tile(float* __restrict__ xs, const f
                 warp_pixel(cam, sxs[k], sys[k], to_depth(d[k], depth_kind), wm1, hm1, true, wp);
                 Taps t;
                 make_taps(wp.p.u, wp.p.v, H, W, padding, t);
+                if (tsave != nullptr) {
+                    // the tile's own pixels (not the halo) are recorded for the backward pass
+                    const int ry_ = sys[k] - oy, rx_ = sxs[k] - ox;
+                    if (ry_ >= 1 && ry_ <= ROWS - 2 && rx_ >= 1 && rx_ <= COLS - 2) {
+                        SavedTap st;
+                        const int x0 = max(t.x0, 0), y0 = max(t.y0, 0);
+                        st.o00 = t.valid ? y0 * W + x0 : 0;
+                        st.flags = t.valid | ((t.valid && min(t.x0 + 1, W - 1) != x0) ? 16u : 0u) |
+                                   ((t.valid && min(t.y0 + 1, H - 1) != y0) ? 32u : 0u) | (t.mx != 0.0f ? 64u : 0u) |
+                                   (t.my != 0.0f ? 128u : 0u);
+                        st.ax = t.ax;
+                        st.ay = t.ay;
+                        tsave[sys[k] * W + sxs[k]] = st;
+                    }
+                }
                 if (t.valid) {
                     const float bx = 1.0f - t.ax, by = 1.0f - t.ay;
                     w00[k] = (t.valid & 1u) ? bx * by : 0.0f;
@@ -191,6 +216,10 @@ __device__ __forceinline__ void fill_source_tile(float* __restrict__ xs, const f
                                                v[k][4 * c + 3] * w11[k]
                                          : v[k][c];
                     xs[c * N + sidx[k]] = o;
+                    if (WARP && xsave != nullptr && in[k]) {
+                        const int ry_ = sys[k] - oy, rx_ = sxs[k] - ox;
+                        if (ry_ >= 1 && ry_ <= ROWS - 2 && rx_ >= 1 && rx_ <= COLS - 2) xsave[c * P + sys[k] * W + sxs[k]] = o;
+                    }
                 }
             }
         }
@@ -228,7 +257,8 @@ __global__ void __launch_bounds__(kFwdThreads, 2)
 photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ PhotoPtrs pp, int V, int depth_kind, int n_preds,
                        drosfm_cams_t cams, const float* __restrict__ automask_in, drosfm_photo_opts_t opts,
                        float l1_w, uint8_t* __restrict__ sel_out, float* __restrict__ automask_out,
-                       float* __restrict__ loss, Slot* ws, int B, int H, int W) {
+                       float* __restrict__ loss, Slot* ws, float* __restrict__ warped_save, SavedTap* __restrict__ taps_save,
+                       int B, int H, int W) {
     extern __shared__ float smem[];
     float* ys = smem;                        // [3][FSH][FSW]
     float* xs = smem + 3 * FSH * FSW;        // [3][FSH][FSW]
@@ -272,8 +302,11 @@ photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ 
         const float* src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
         {
             const Cam cam = cam_s[MODE == 0 ? v : 0];       // register copy for the sampling loop
+            const size_t slot = (static_cast<size_t>(ip) * V + v) * B + b;
             fill_source_tile<FSH, FSW, kFwdThreads, MODE == 0>(xs, src, invd, depth_kind, cam, ty0 - 1, tx0 - 1, H, W, P, wm1, hm1,
-                                                               opts.padding);
+                                                               opts.padding,
+                                                               (MODE == 0 && warped_save) ? warped_save + slot * 3 * P : nullptr,
+                                                               (MODE == 0 && taps_save) ? taps_save + slot * P : nullptr);
         }
         __syncthreads();
 
@@ -369,11 +402,13 @@ constexpr int BSW = CW + 2, BSH = CH + 2;            // sample region (tile + ha
 constexpr int kBwdSmemFloats = 2 * 3 * BSH * BSW + 3 * CH * CW + 3 * IH * CW;
 constexpr int kBwdSmemBytes = kBwdSmemFloats * static_cast<int>(sizeof(float)) + CH * CW;
 
+template <bool SAVED, bool SAVED_TAPS>
 __global__ void __launch_bounds__(kBwdThreads, 2)
 photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict__ image,
                        const __grid_constant__ PhotoPtrs pp, int V,
                        int depth_kind, int n_preds, drosfm_cams_t cams, const uint8_t* __restrict__ sel_in,
                        drosfm_photo_opts_t opts, float l1_w, const __grid_constant__ PhotoGrads pg, Slot* ws,
+                       const float* __restrict__ warped_save, const SavedTap* __restrict__ taps_save,
                        int B, int H, int W) {
     extern __shared__ float smem[];
     constexpr int SPLANE = BSH * BSW, CPLANE = CH * CW;
@@ -437,8 +472,10 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
     for (int v = 0; v < V; ++v) {
         const float* src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
         const Cam cam = cam_s[v];
-        // phase A: warped source on tile + halo 2
-        fill_source_tile<BSH, BSW, kBwdThreads, true>(xs, src, invd, depth_kind, cam, sy0, sx0, H, W, P, wm1, hm1, opts.padding);
+        // phase A: warped source on tile + halo 2 -- reloaded from the forward's copy, or recomputed
+        const size_t vslot = (static_cast<size_t>(ip) * V + v) * B + b;
+        if (SAVED) fill_target_tile<BSH, BSW, kBwdThreads>(xs, warped_save + vslot * 3 * P, sy0, sx0, H, W, P);
+        else fill_source_tile<BSH, BSW, kBwdThreads, true>(xs, src, invd, depth_kind, cam, sy0, sx0, H, W, P, wm1, hm1, opts.padding);
         __syncthreads();
 
 #pragma unroll 1
@@ -524,28 +561,48 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
             const int qy = cy0 + r;
             if (col_ok && r >= 1 && r <= IH && qy < H) {
                 const float d = to_depth(__ldg(invd + qy * W + pgx), depth_kind);
+                int o00, dxo, dyo;
+                unsigned valid;
+                float ax, ay, mx, my;
                 Warp wp;
-                warp_pixel(cam, pgx, qy, d, wm1, hm1, true, wp);
-                Taps t;
-                make_taps(wp.p.u, wp.p.v, H, W, opts.padding, t);
-                if (t.valid) {
+                if (SAVED_TAPS) {
+                    const int4 raw = __ldg(reinterpret_cast<const int4*>(taps_save + vslot * P + qy * W + pgx));
+                    o00 = raw.x;
+                    const unsigned fl = static_cast<unsigned>(raw.y);
+                    valid = fl & 15u;
+                    dxo = (fl & 16u) ? 1 : 0;
+                    dyo = (fl & 32u) ? W : 0;
+                    ax = __int_as_float(raw.z);
+                    ay = __int_as_float(raw.w);
+                    mx = (fl & 64u) ? 0.5f * wm1 : 0.0f;
+                    my = (fl & 128u) ? 0.5f * hm1 : 0.0f;
+                    if (valid) warp_point(cam, pgx, qy, d, wp);
+                } else {
+                    warp_pixel(cam, pgx, qy, d, wm1, hm1, true, wp);
+                    Taps t;
+                    make_taps(wp.p.u, wp.p.v, H, W, opts.padding, t);
+                    valid = t.valid;
                     const int x0 = max(t.x0, 0), y0 = max(t.y0, 0);
-                    const int x1 = min(t.x0 + 1, W - 1), y1 = min(t.y0 + 1, H - 1);
-                    const int o00 = y0 * W + x0, dxo = x1 - x0, dyo = (y1 - y0) * W;
-                    const float m0 = (t.valid & 1u) ? 1.f : 0.f, m1 = (t.valid & 2u) ? 1.f : 0.f;
-                    const float m2 = (t.valid & 4u) ? 1.f : 0.f, m3 = (t.valid & 8u) ? 1.f : 0.f;
+                    o00 = y0 * W + x0;
+                    dxo = min(t.x0 + 1, W - 1) - x0;
+                    dyo = (min(t.y0 + 1, H - 1) - y0) * W;
+                    ax = t.ax; ay = t.ay; mx = t.mx; my = t.my;
+                }
+                if (valid) {
+                    const float m0 = (valid & 1u) ? 1.f : 0.f, m1 = (valid & 2u) ? 1.f : 0.f;
+                    const float m2 = (valid & 4u) ? 1.f : 0.f, m3 = (valid & 8u) ? 1.f : 0.f;
                     float gix = 0.0f, giy = 0.0f;
-                    const float bx = 1.0f - t.ax, by = 1.0f - t.ay;
+                    const float bx = 1.0f - ax, by = 1.0f - ay;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const float* r0 = src + c * P + o00;
                         const float v0 = __ldg(r0) * m0, v1 = __ldg(r0 + dxo) * m1;
                         const float v2 = __ldg(r0 + dyo) * m2, v3 = __ldg(r0 + dyo + dxo) * m3;
                         const float g = gxs[(c * IH + r - 1) * CW + lane];
-                        gix += g * ((v1 - v0) * by + (v3 - v2) * t.ay);
-                        giy += g * ((v2 - v0) * bx + (v3 - v1) * t.ax);
+                        gix += g * ((v1 - v0) * by + (v3 - v2) * ay);
+                        giy += g * ((v2 - v0) * bx + (v3 - v1) * ax);
                     }
-                    gd[k] += warp_pixel_adjoint(cam, wp, d, wm1, hm1, true, gix * t.mx, giy * t.my, gT);
+                    gd[k] += warp_pixel_adjoint(cam, wp, d, wm1, hm1, true, gix * mx, giy * my, gT);
                 }
             }
         }
@@ -613,7 +670,11 @@ static int allow_big_smem() {
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(photometric_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(photometric_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
+            e = cudaFuncSetAttribute(photometric_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(photometric_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(photometric_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
         if (e == cudaSuccess) done_for_device = dev;
     }
     if (e != cudaSuccess) {
@@ -647,7 +708,8 @@ int drosfm_automask_fwd(const float* image, const float* const* context, int n_v
     dim3 grid((W + FW - 1) / FW, (H + FH - 1) / FH, B);
     if (int e = allow_big_smem()) return e;
     photometric_fwd_kernel<1><<<grid, kFwdThreads, kFwdSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-        image, pp, n_views, DROSFM_DEPTH, 1, none, nullptr, o, l1_weight(opts), nullptr, automask, nullptr, nullptr, B, H, W);
+        image, pp, n_views, DROSFM_DEPTH, 1, none, nullptr, o, l1_weight(opts), nullptr, automask, nullptr, nullptr, nullptr, nullptr,
+        B, H, W);
     return launch_status("automask_fwd");
 }
 
@@ -675,7 +737,7 @@ static int fill_ptrs(PhotoPtrs& pp, const float* const* context, int n_views, co
 int drosfm_photometric_fwd(const float* image, const float* const* context, int n_views, const float* const* inv_depths,
                            int depth_kind, int n_preds, const drosfm_cams_t* cams, const float* const* poses,
                            const float* automask, const drosfm_photo_opts_t* opts, uint8_t* sel, float* loss, void* ws,
-                           int B, int H, int W, drosfm_stream_t stream) {
+                           float* warped_save, void* taps_save, int B, int H, int W, drosfm_stream_t stream) {
     if (int e = check_photo(image, context, n_views, opts, B, H, W)) return e;
     DROSFM_REQUIRE(B > 0 && H * W > 0, DROSFM_EINVAL, "photometric_fwd: empty batch (the mean over zero pixels is undefined)");
     DROSFM_REQUIRE(cams && cams->K && cams->Kref, DROSFM_EINVAL, "photometric_fwd: NULL cams");
@@ -693,15 +755,15 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
     if (int e = allow_big_smem()) return e;
     photometric_fwd_kernel<0><<<grid, kFwdThreads, kFwdSmemBytes, static_cast<cudaStream_t>(stream)>>>(
         image, pp, n_views, depth_kind, n_preds, *cams, opts->automask ? automask : nullptr, *opts, l1_weight(opts), sel,
-        nullptr, loss, static_cast<Slot*>(ws), B, H, W);
+        nullptr, loss, static_cast<Slot*>(ws), warped_save, static_cast<SavedTap*>(taps_save), B, H, W);
     return launch_status("photometric_fwd");
 }
 
 int drosfm_photometric_bwd(const float* g_loss, const float* image, const float* const* context, int n_views,
                            const float* const* inv_depths, int depth_kind, int n_preds, const drosfm_cams_t* cams,
                            const float* const* poses, const uint8_t* sel, const drosfm_photo_opts_t* opts,
-                           float* const* g_inv_depths, float* const* g_poses, void* ws, int B, int H, int W,
-                           drosfm_stream_t stream) {
+                           float* const* g_inv_depths, float* const* g_poses, void* ws, const float* warped_save,
+                           const void* taps_save, int B, int H, int W, drosfm_stream_t stream) {
     if (int e = check_photo(image, context, n_views, opts, B, H, W)) return e;
     if (B == 0 || H * W == 0) return DROSFM_OK;
     DROSFM_REQUIRE(cams && cams->K && cams->Kref, DROSFM_EINVAL, "photometric_bwd: NULL cams");
@@ -722,8 +784,22 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
     DROSFM_REQUIRE(static_cast<long long>(B) * n_preds <= 65535, DROSFM_ERANGE, "photometric_bwd: B * n_preds too large");
     dim3 grid((W + IW - 1) / IW, (H + IH - 1) / IH, B * n_preds);
     if (int e = allow_big_smem()) return e;
-    photometric_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-        g_loss, image, pp, n_views, depth_kind, n_preds, *cams, sel, *opts, l1_weight(opts), pg, static_cast<Slot*>(ws), B, H, W);
+    DROSFM_REQUIRE(taps_save == nullptr || warped_save != nullptr, DROSFM_EINVAL,
+                   "photometric_bwd: taps_save needs warped_save");
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    const SavedTap* ts = static_cast<const SavedTap*>(taps_save);
+    if (warped_save != nullptr && ts != nullptr)
+        photometric_bwd_kernel<true, true><<<grid, kBwdThreads, kBwdSmemBytes, cs>>>(
+            g_loss, image, pp, n_views, depth_kind, n_preds, *cams, sel, *opts, l1_weight(opts), pg, static_cast<Slot*>(ws),
+            warped_save, ts, B, H, W);
+    else if (warped_save != nullptr)
+        photometric_bwd_kernel<true, false><<<grid, kBwdThreads, kBwdSmemBytes, cs>>>(
+            g_loss, image, pp, n_views, depth_kind, n_preds, *cams, sel, *opts, l1_weight(opts), pg, static_cast<Slot*>(ws),
+            warped_save, nullptr, B, H, W);
+    else
+        photometric_bwd_kernel<false, false><<<grid, kBwdThreads, kBwdSmemBytes, cs>>>(
+            g_loss, image, pp, n_views, depth_kind, n_preds, *cams, sel, *opts, l1_weight(opts), pg, static_cast<Slot*>(ws),
+            nullptr, nullptr, B, H, W);
     return launch_status("photometric_bwd");
 }
 

@@ -5,6 +5,8 @@ the C ABI and implements backward with the explicit backward kernel.  No host sy
 CPU path.  Poses are passed either as [B,4,4] matrices (``Pose.mat``) or as [B,6] euler vectors
 (then ``Pose.from_vec(vec, 'euler')``, pose.py:38-45, is evaluated inside the kernel).
 """
+import os
+
 import torch
 
 from . import _lib as L
@@ -444,6 +446,11 @@ def feat_cost(depth, fmap, fmaps_ref, poses, K, Kref=None, scale=1.0, inverse_de
 # ------------------------------------------------------------------------------------------------
 # photometric + smoothness loss
 # ------------------------------------------------------------------------------------------------
+# DROSFM_PHOTO_SAVE_WARP=0 makes the photometric backward re-warp instead of re-reading (saves 12 B per pixel,
+# view and prediction of activation memory at ~15 % more backward time)
+SAVE_WARP = os.environ.get("DROSFM_PHOTO_SAVE_WARP", "1") != "0"
+
+
 def _reduce_op(name):
     if name == "min":
         return L.REDUCE_MIN
@@ -471,6 +478,13 @@ class _PhotoLoss(torch.autograd.Function):
         opts = L.PhotoOpts(ssim_w, C1, C2, padding, reduce_op, int(automask), gamma)
         losses = torch.zeros(2, device=dev, dtype=torch.float32)
         sel = torch.empty(n, B, H, W, device=dev, dtype=torch.uint8) if reduce_op == L.REDUCE_MIN else None
+        # kept for the backward pass (12 bytes per pixel, view and prediction): the kernels are instruction-bound
+        # with HBM idle, so re-reading the warp is cheaper than re-computing it
+        keep_warp = SAVE_WARP and any(ctx.needs_input_grad[6 + V:])
+        wsave = torch.empty(n, V, B, 3, H, W, device=dev, dtype=torch.float32) if keep_warp else None
+        # the bilinear taps can be recorded as well (drosfm_photometric_fwd takes taps_save), but re-deriving them
+        # costs fewer cycles than the 16 B/pixel round trip through HBM (measured on B200), so only the warp is kept
+        tsave = None
         stats = torch.empty(n, B, 4, device=dev, dtype=torch.float32) if smooth_w > 0.0 else None
         lib = L.lib()
         with torch.cuda.device(dev):
@@ -483,12 +497,12 @@ class _PhotoLoss(torch.autograd.Function):
                         "automask_fwd")
             L.check(lib.drosfm_photometric_fwd(L.ptr(image), L.ptr_array(context), V, L.ptr_array(invs), depth_kind, n, cams,
                                                L.ptr_array(poses), L.ptr(amask), opts, L.ptr(sel), L.ptr(losses), L.ptr(ws),
-                                               B, H, W, st), "photometric_fwd")
+                                               L.ptr(wsave), L.ptr(tsave), B, H, W, st), "photometric_fwd")
             if smooth_w > 0.0:
                 L.check(lib.drosfm_smoothness_fwd(L.ptr(image), L.ptr_array(invs), n, smooth_w, L.ptr(stats),
                                                   L.ptr(losses[1:]), L.ptr(ws), B, H, W, st), "smoothness_fwd")
         total = losses.sum().reshape(1)
-        ctx.save_for_backward(image, keep[0], keep[1], sel, stats, *context, *invs, *poses)
+        ctx.save_for_backward(image, keep[0], keep[1], sel, stats, wsave, tsave, *context, *invs, *poses)
         ctx.cfg, ctx.V, ctx.n, ctx.kind = cfg, V, n, kind
         ctx.mark_non_differentiable(losses)
         return total, losses
@@ -497,8 +511,8 @@ class _PhotoLoss(torch.autograd.Function):
     def backward(ctx, g_total, *unused):
         ssim_w, C1, C2, padding, reduce_op, automask, gamma, smooth_w, depth_kind = ctx.cfg
         V, n, kind = ctx.V, ctx.n, ctx.kind
-        image, K, Kref, sel, stats = ctx.saved_tensors[:5]
-        rest = ctx.saved_tensors[5:]
+        image, K, Kref, sel, stats, wsave, tsave = ctx.saved_tensors[:7]
+        rest = ctx.saved_tensors[7:]
         context, invs, poses = rest[:V], rest[V:V + n], rest[V + n:]
         B, _, H, W = image.shape
         dev = image.device
@@ -520,7 +534,8 @@ class _PhotoLoss(torch.autograd.Function):
             st = L.stream()
             L.check(lib.drosfm_photometric_bwd(L.ptr(g), L.ptr(image), L.ptr_array(context), V, L.ptr_array(invs), depth_kind, n,
                                                cams, L.ptr_array(poses), L.ptr(sel), opts, L.ptr_array(g_invs),
-                                               L.ptr_array(g_poses), L.ptr(ws), B, H, W, st), "photometric_bwd")
+                                               L.ptr_array(g_poses), L.ptr(ws), L.ptr(wsave), L.ptr(tsave), B, H, W, st),
+                    "photometric_bwd")
             if smooth_w > 0.0 and any(need_inv):
                 L.check(lib.drosfm_smoothness_bwd(L.ptr(g), L.ptr(image), L.ptr_array(invs), n, smooth_w, L.ptr(stats),
                                                   L.ptr_array(g_invs), 1, B, H, W, st), "smoothness_bwd")

@@ -116,7 +116,7 @@ def test_photometric_loss_vs_oracle_full_size(wl_name, B, n):
     lib = L.lib()
     L.check(lib.drosfm_automask_fwd(L.ptr(img), L.ptr_array(ctx), V, opts, L.ptr(amask), B, H, W, L.stream()))
     L.check(lib.drosfm_photometric_fwd(L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
-                                       L.ptr(amask), opts, L.ptr(sel), L.ptr(loss), L.ptr(ws), B, H, W, L.stream()))
+                                       L.ptr(amask), opts, L.ptr(sel), L.ptr(loss), L.ptr(ws), None, None, B, H, W, L.stream()))
     assert_close(loss.cpu()[0], loss32, what="loss")
     # (2) selection: identical except at near-ties
     flips = 0
@@ -136,11 +136,25 @@ def test_photometric_loss_vs_oracle_full_size(wl_name, B, n):
     one = torch.ones(1, device=dev)
     L.check(lib.drosfm_photometric_bwd(L.ptr(one), L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams,
                                        L.ptr_array(P), L.ptr(sel_forced), opts, L.ptr_array(list(g_inv)), L.ptr_array(list(g_pose)),
-                                       L.ptr(ws), B, H, W, L.stream()))
+                                       L.ptr(ws), None, None, B, H, W, L.stream()))
     for i in range(n):
         assert_close_or_better(g_inv[i].cpu(), g32[i], g64[i], what=f"g_inv{i}")
     for k in range(V * n):
         assert_close_or_better(g_pose[k].cpu(), g32[n + k], g64[n + k], what=f"g_pose{k}")
+    # (4) the backward that re-reads the forward's warp (saved warped sources + taps) agrees with the re-warping one
+    wsave = torch.empty(n, V, B, 3, H, W, device=dev)
+    tsave = torch.empty(n, V, B, H, W, 4, device=dev, dtype=torch.int32)
+    loss2 = torch.zeros(1, device=dev)
+    L.check(lib.drosfm_photometric_fwd(L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
+                                       L.ptr(amask), opts, L.ptr(sel), L.ptr(loss2), L.ptr(ws), L.ptr(wsave), L.ptr(tsave),
+                                       B, H, W, L.stream()))
+    assert torch.equal(loss2, loss)
+    g_inv2, g_pose2 = torch.empty_like(g_inv), torch.empty_like(g_pose)
+    L.check(lib.drosfm_photometric_bwd(L.ptr(one), L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams,
+                                       L.ptr_array(P), L.ptr(sel_forced), opts, L.ptr_array(list(g_inv2)), L.ptr_array(list(g_pose2)),
+                                       L.ptr(ws), L.ptr(wsave), L.ptr(tsave), B, H, W, L.stream()))
+    assert_close(g_inv2.cpu(), g_inv.cpu(), rtol=1e-6, atol=1e-9, what="g_inv (saved warp vs re-warp)")
+    assert_close(g_pose2.cpu(), g_pose.cpu(), rtol=1e-5, atol=1e-8, what="g_pose (saved warp vs re-warp)")
 
 
 def test_photometric_euler_poses_match_matrix_poses():
