@@ -199,10 +199,12 @@ class HotPathStep:
         p = (wl.H // 8) * (wl.W // 8) * B
         P = wl.H * wl.W * B
         V, T, n = wl.V, wl.T, wl.n
+        from . import ops as _ops
+        saved = 12 * V if _ops.SAVE_WARP else 0       # warped sources kept by the forward, re-read by the backward
         out = {
             "feat_cost_fwd_v1": (C * 4 * 3 + 4) * p, "feat_cost_bwd_v1": (C * 4 * 5 + 8) * p,
             "feat_cost_fwd_vN": (C * 4 * (V + 2) + 4) * p, "feat_cost_bwd_vN": (C * 4 * (2 * V + 3) + 8) * p,
-            "photometric_fwd": (16 + 12 * V) * P * n, "photometric_bwd": (20 + 12 * V) * P * n,
+            "photometric_fwd": (16 + 12 * V + saved) * P * n, "photometric_bwd": (20 + 12 * V + saved) * P * n,
             "automask_fwd": (12 + 12 * V + 4) * P,
             "smoothness_fwd": (12 + 8 * n) * P, "smoothness_bwd": (12 + 8 * n) * P,
             "reproj_loss_fwd": 4 * P, "reproj_loss_bwd": 4 * P,
