@@ -179,7 +179,9 @@ class HotPathStep:
         self.zero_grads()
         before = L.lib().drosfm_launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # capture on the warm-up stream: autograd ties every leaf's AccumulateGrad node to the stream of its
+        # first use, and a different capture stream would put cross-stream joins into the graph
+        with torch.cuda.graph(self.graph, stream=s):
             self.loss = self.forward_backward()
         self.launches_per_step = int(L.lib().drosfm_launch_count() - before)
         return self.graph

@@ -35,7 +35,10 @@ def _channels_last(t):
     hit = _cl_cache.get(key)
     if hit is not None:
         ref, version, grad_mode, converted = hit
-        if ref() is t and version == t._version and grad_mode == torch.is_grad_enabled():
+        # valid for the same tensor object, unmodified, in the same grad mode, and only until the backward
+        # pass of the step that created it has run (its autograd node and gradient sink are then spent)
+        if (ref() is t and version == t._version and grad_mode == torch.is_grad_enabled()
+                and not converted._drosfm_sink_state.consumed):
             return converted
     # autograd-visible conversion whose backward hands over the in-kernel sum of all cost gradients
     converted = ops.to_channels_last_sink(t)

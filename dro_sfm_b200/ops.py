@@ -308,11 +308,12 @@ class GradSink:
     contribution into ``buffer`` inside the kernel (the scatter into the source maps is atomic anyway, the
     target-map gradient becomes a read-modify-write), instead of returning 2*V*T separate tensors that
     autograd would have to sum with as many element-wise kernels."""
-    __slots__ = ("buffer", "dummy")
+    __slots__ = ("buffer", "dummy", "consumed")
 
     def __init__(self):
         self.buffer = None
         self.dummy = None
+        self.consumed = False        # set once the backward pass went through: the copy belongs to a finished step
 
 
 class _ToChannelsLastSink(torch.autograd.Function):
@@ -324,6 +325,7 @@ class _ToChannelsLastSink(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         buf, ctx.sink.buffer = ctx.sink.buffer, None
+        ctx.sink.consumed = True
         if buf is None:
             return g, None
         # g is the zero placeholder returned by the first sink-aware consumer plus whatever ordinary
@@ -336,6 +338,7 @@ def to_channels_last_sink(t):
     sink = GradSink()
     out = _ToChannelsLastSink.apply(t, sink)
     out._drosfm_sink = sink if (t.requires_grad and torch.is_grad_enabled()) else None
+    out._drosfm_sink_state = sink
     return out
 
 
