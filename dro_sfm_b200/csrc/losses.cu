@@ -268,6 +268,87 @@ reproj_kernel(const float* __restrict__ g_loss, const float* __restrict__ depth,
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// supervised depth loss: gamma-weighted masked L1 on inverse depth (supervised_loss.py:244-277)
+// ------------------------------------------------------------------------------------------
+struct SupPtrs {
+    const float* d[DROSFM_MAX_PREDS];
+    float* g[DROSFM_MAX_PREDS];
+    float weight[DROSFM_MAX_PREDS];
+};
+
+// MODE 0: loss = sum_i w_i * mean(valid * |gt - d_i|) / sum_i w_i;  MODE 1: gradients w.r.t. every d_i.
+template <int MODE>
+__global__ void __launch_bounds__(kLossThreads)
+sup_depth_kernel(const float* __restrict__ g_loss, const float* __restrict__ gt, const __grid_constant__ SupPtrs sp, int n_preds,
+                 float lo, float hi, float wsum, float* __restrict__ loss, Slot* ws, long long N) {
+    __shared__ double red[DROSFM_MAX_PREDS][kLossThreads / 32];
+    __shared__ int flag;
+    float acc[DROSFM_MAX_PREDS];
+#pragma unroll
+    for (int i = 0; i < DROSFM_MAX_PREDS; ++i) acc[i] = 0.0f;
+    const float gscale = MODE == 1 ? __ldg(g_loss) / (wsum * static_cast<float>(N)) : 0.0f;
+    for (long long p = static_cast<long long>(blockIdx.x) * kLossThreads + threadIdx.x; p < N;
+         p += static_cast<long long>(gridDim.x) * kLossThreads) {
+        const float t = __ldg(gt + p);
+        const bool valid = t > lo && t < hi;
+#pragma unroll
+        for (int i = 0; i < DROSFM_MAX_PREDS; ++i) {
+            if (i < n_preds) {
+                const float df = t - __ldg(sp.d[i] + p);
+                if (MODE == 0) {
+                    if (valid) acc[i] += fabsf(df);
+                } else if (sp.g[i] != nullptr) {
+                    // d|gt - d|/dd = -sign(gt - d)
+                    sp.g[i][p] = valid ? -gscale * sp.weight[i] * (df > 0.0f ? 1.0f : (df < 0.0f ? -1.0f : 0.0f)) : 0.0f;
+                }
+            }
+        }
+    }
+    if (MODE == 1) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < DROSFM_MAX_PREDS; ++i) {
+        if (i < n_preds) {
+            const double s = warp_sum(static_cast<double>(acc[i]));
+            if (lane == 0) red[i][wid] = s;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < n_preds) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < kLossThreads / 32; ++k) t += red[threadIdx.x][k];
+        if (t != 0.0) atomicAdd(spread_acc(slot_at(ws, threadIdx.x)), t);
+    }
+    Slot* ticket = slot_at(ws, n_preds);
+    if (last_block(ticket, gridDim.x, &flag) && threadIdx.x == 0) {
+        double total = 0.0;
+        for (int i = 0; i < n_preds; ++i)
+            total += static_cast<double>(sp.weight[i]) * static_cast<double>(static_cast<float>(take_acc(slot_at(ws, i), 0) / static_cast<double>(N)));
+        ticket->ticket = 0ull;
+        *loss = static_cast<float>(total / static_cast<double>(wsum));
+    }
+}
+
+static int fill_sup(SupPtrs& sp, float& wsum, const float* const* inv_depths, float* const* g, int n_preds, float gamma) {
+    DROSFM_REQUIRE(n_preds >= 1 && n_preds <= DROSFM_MAX_PREDS, DROSFM_ERANGE, "sup_depth_loss: n_preds=%d outside [1,%d]", n_preds,
+                   DROSFM_MAX_PREDS);
+    DROSFM_REQUIRE(inv_depths != nullptr, DROSFM_EINVAL, "sup_depth_loss: NULL prediction array");
+    double sum = 0.0;
+    for (int i = 0; i < n_preds; ++i) {
+        DROSFM_REQUIRE(inv_depths[i] != nullptr, DROSFM_EINVAL, "sup_depth_loss: inv_depths[%d] is NULL", i);
+        sp.d[i] = inv_depths[i];
+        sp.g[i] = g ? g[i] : nullptr;
+        double wgt = 1.0;
+        for (int k = 0; k < n_preds - 1 - i; ++k) wgt *= static_cast<double>(gamma);
+        sp.weight[i] = static_cast<float>(wgt);
+        sum += wgt;
+    }
+    wsum = static_cast<float>(sum);
+    return DROSFM_OK;
+}
+
 static int strip_blocks(int P, int B) {
     int need = (P + kLossThreads - 1) / kLossThreads;
     int cap = (kNumSMs * 4 + B - 1) / (B > 0 ? B : 1);
@@ -351,6 +432,37 @@ int drosfm_smoothness_bwd(const float* g_loss, const float* image, const float* 
     smooth_bwd_kernel<<<dim3((P + kLossThreads - 1) / kLossThreads, B), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         g_loss, image, dl, n_preds, weight, stats, dg, accumulate, B, H, W);
     return launch_status("smoothness_bwd");
+}
+
+int drosfm_sup_depth_loss_fwd(const float* gt_inv_depth, const float* const* inv_depths, int n_preds, float min_depth,
+                              float max_depth, float gamma, float* loss, void* ws, int B, int H, int W,
+                              drosfm_stream_t stream) {
+    DROSFM_REQUIRE(B > 0 && H > 0 && W > 0, DROSFM_EINVAL, "sup_depth_loss_fwd: empty input");
+    DROSFM_REQUIRE(gt_inv_depth && loss && ws, DROSFM_EINVAL, "sup_depth_loss_fwd: NULL argument");
+    SupPtrs sp{};
+    float wsum = 1.0f;
+    if (int e = fill_sup(sp, wsum, inv_depths, nullptr, n_preds, gamma)) return e;
+    const long long N = static_cast<long long>(B) * H * W;
+    long long blocks = (N + kLossThreads * 4 - 1) / (kLossThreads * 4);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    sup_depth_kernel<0><<<static_cast<unsigned>(blocks), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        nullptr, gt_inv_depth, sp, n_preds, 1.0f / max_depth, 1.0f / min_depth, wsum, loss, static_cast<Slot*>(ws), N);
+    return launch_status("sup_depth_loss_fwd");
+}
+
+int drosfm_sup_depth_loss_bwd(const float* g_loss, const float* gt_inv_depth, const float* const* inv_depths, int n_preds,
+                              float min_depth, float max_depth, float gamma, float* const* g_inv_depths, int B, int H, int W,
+                              drosfm_stream_t stream) {
+    DROSFM_REQUIRE(B > 0 && H > 0 && W > 0, DROSFM_EINVAL, "sup_depth_loss_bwd: empty input");
+    DROSFM_REQUIRE(g_loss && gt_inv_depth && g_inv_depths, DROSFM_EINVAL, "sup_depth_loss_bwd: NULL argument");
+    SupPtrs sp{};
+    float wsum = 1.0f;
+    if (int e = fill_sup(sp, wsum, inv_depths, g_inv_depths, n_preds, gamma)) return e;
+    const long long N = static_cast<long long>(B) * H * W;
+    const long long blocks = (N + kLossThreads - 1) / kLossThreads;
+    sup_depth_kernel<1><<<static_cast<unsigned>(blocks), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        g_loss, gt_inv_depth, sp, n_preds, 1.0f / max_depth, 1.0f / min_depth, wsum, nullptr, nullptr, N);
+    return launch_status("sup_depth_loss_bwd");
 }
 
 int drosfm_reproj_loss_fwd(const float* depth, int depth_kind, const drosfm_cams_t* cams, const float* const* gt_poses,

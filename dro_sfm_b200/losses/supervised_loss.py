@@ -2,7 +2,7 @@
 (reference: dro_sfm/losses/supervised_loss.py:201-371).
 
 The reprojection pose loss (get_ref_coords / calc_pose_loss, :279-325) runs as one fused kernel per
-direction; the masked-L1 depth term (:244-277) is a handful of elementwise ops and stays in PyTorch.
+direction, the masked-L1 depth term (:244-277) as one more.
 """
 import torch
 
@@ -29,15 +29,10 @@ class SupervisedDepthPoseLoss(LossBase):
         return {'supervised_num_scales': self.n}
 
     def calculate_loss(self, inv_depths, gt_inv_depths):
-        """gamma-weighted masked L1 on inverse depth (supervised_loss.py:244-277)."""
-        total_loss, total_w, gamma = 0, 0, 0.85
-        min_disp, max_disp = 1.0 / self.max_depth, 1.0 / self.min_depth
-        for i in range(self.n):
-            w = gamma ** (self.n - i - 1)
-            total_w += w
-            valid = ((gt_inv_depths[i] > min_disp) & (gt_inv_depths[i] < max_disp)).detach().squeeze(1)
-            total_loss += w * torch.mean(valid * torch.abs(gt_inv_depths[i] - inv_depths[i]).squeeze(1))
-        return total_loss / total_w
+        """gamma-weighted masked L1 on inverse depth (supervised_loss.py:244-277), one fused kernel.
+        ``gt_inv_depths`` is the per-prediction list the reference builds with match_scales; all entries are
+        the same full-resolution map."""
+        return ops.sup_depth_loss(list(inv_depths[:self.n]), gt_inv_depths[0], self.min_depth, self.max_depth, 0.85)
 
     def get_ref_coords(self, pose, K, ref_K, depth, scale_factor, device):
         """Projected coordinates and their in-range mask (supervised_loss.py:279-291)."""

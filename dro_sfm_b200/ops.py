@@ -12,7 +12,7 @@ import torch
 from . import _lib as L
 
 __all__ = ["pose_vec2mat", "reconstruct", "project", "warp_coords", "grid_gather", "view_synthesis", "feat_cost",
-           "photometric_loss", "reproj_pose_loss"]
+           "photometric_loss", "reproj_pose_loss", "sup_depth_loss"]
 
 
 def _pose_kind(pose):
@@ -633,3 +633,54 @@ def reproj_pose_loss(pred_poses, gt_poses, gt_depth, K, ref_K, min_depth, max_de
     cfg = (float(min_depth), float(max_depth), float(gamma), L.INV_DEPTH if inverse_depth else L.DEPTH)
     flat = [p for pv in pred_poses for p in pv]
     return _ReprojLoss.apply(gt_depth, K, ref_K, cfg, V, n, *gt_poses, *flat)
+
+
+# ------------------------------------------------------------------------------------------------
+# supervised depth loss
+# ------------------------------------------------------------------------------------------------
+class _SupDepthLoss(torch.autograd.Function):
+    """inputs: gt_inv_depth, cfg, n, inv_depth_0..n-1"""
+
+    @staticmethod
+    def forward(ctx, gt, cfg, n, *invs):
+        min_depth, max_depth, gamma = cfg
+        L.require_cuda(gt, *invs)
+        gt = L.f32c(gt)
+        invs = [L.f32c(x) for x in invs]
+        B, _, H, W = gt.shape
+        loss = torch.empty(1, device=gt.device, dtype=torch.float32)
+        with torch.cuda.device(gt.device):
+            ws = L.workspace(gt.device, n + 1)
+            L.check(L.lib().drosfm_sup_depth_loss_fwd(L.ptr(gt), L.ptr_array(invs), n, min_depth, max_depth, gamma, L.ptr(loss),
+                                                      L.ptr(ws), B, H, W, L.stream()), "sup_depth_loss_fwd")
+        ctx.save_for_backward(gt, *invs)
+        ctx.cfg, ctx.n = cfg, n
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        min_depth, max_depth, gamma = ctx.cfg
+        n = ctx.n
+        gt, invs = ctx.saved_tensors[0], ctx.saved_tensors[1:]
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("dro_sfm_b200: the supervised depth loss has no gradient w.r.t. the ground truth")
+        B, _, H, W = gt.shape
+        need = [ctx.needs_input_grad[3 + i] for i in range(n)]
+        slab = torch.empty(n, *invs[0].shape, device=gt.device, dtype=torch.float32)
+        gs = [slab[i] if need[i] else None for i in range(n)]
+        g = L.f32c(g.reshape(1))
+        with torch.cuda.device(gt.device):
+            L.check(L.lib().drosfm_sup_depth_loss_bwd(L.ptr(g), L.ptr(gt), L.ptr_array(invs), n, min_depth, max_depth, gamma,
+                                                      L.ptr_array(gs), B, H, W, L.stream()), "sup_depth_loss_bwd")
+        return (None, None, None, *gs)
+
+
+def sup_depth_loss(inv_depths, gt_inv_depth, min_depth, max_depth, gamma=0.85):
+    """SupervisedDepthPoseLoss.calculate_loss (supervised_loss.py:244-277) for predictions at the GT resolution."""
+    n = len(inv_depths)
+    if not 1 <= n <= L.MAX_PREDS:
+        raise ValueError("sup_depth_loss supports 1..{} predictions".format(L.MAX_PREDS))
+    for d in inv_depths:
+        if tuple(d.shape) != tuple(gt_inv_depth.shape):
+            raise NotImplementedError("dro_sfm_b200: predictions must be at the ground-truth resolution")
+    return _SupDepthLoss.apply(gt_inv_depth, (float(min_depth), float(max_depth), float(gamma)), n, *inv_depths)

@@ -196,6 +196,17 @@ int drosfm_reproj_loss_bwd(const float* g_loss, const float* depth, int depth_ki
                            float min_depth, float max_depth, float gamma, float* const* g_pred_poses, void* ws,
                            int B, int H, int W, drosfm_stream_t stream);
 
+/* ---- supervised depth loss (supervised_loss.py:244-277) ----------------------------------------
+ * loss = sum_i w_i * mean(valid * |gt_inv - inv_depth_i|) / sum_i w_i, valid = 1/max_depth < gt_inv < 1/min_depth,
+ * w_i = gamma^(n-1-i); all maps [B,1,H,W].  fwd: ws of drosfm_ws_bytes(n_preds + 1).
+ * bwd: g_inv_depths[i] written (entries may be NULL). */
+int drosfm_sup_depth_loss_fwd(const float* gt_inv_depth, const float* const* inv_depths, int n_preds, float min_depth,
+                              float max_depth, float gamma, float* loss, void* ws, int B, int H, int W,
+                              drosfm_stream_t stream);
+int drosfm_sup_depth_loss_bwd(const float* g_loss, const float* gt_inv_depth, const float* const* inv_depths, int n_preds,
+                              float min_depth, float max_depth, float gamma, float* const* g_inv_depths, int B, int H, int W,
+                              drosfm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
