@@ -76,8 +76,16 @@ def depth_cost_calc(inv_depth, fmap, fmaps_ref, pose_list, K, ref_K, scale_facto
     return total
 
 
+def upsample_depth(depth, mask, ratio=8):
+    """Convex up-sampling of the low-resolution inverse depth (DepthPoseNet.py:63-74), one fused kernel."""
+    return ops.upsample_depth(depth, mask, ratio)
+
+
 class FeatureMetricCost:
     """Mixin with the reference's method names; ``patch.install`` grafts it onto DepthPoseNet."""
+
+    def upsample_depth(self, depth, mask, ratio=8):
+        return upsample_depth(depth, mask, ratio)
 
     def get_cost_each(self, pose, fmap, fmap_ref, depth, K, ref_K, scale_factor):
         return get_cost_each(pose, fmap, fmap_ref, depth, K, ref_K, scale_factor)

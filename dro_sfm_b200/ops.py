@@ -12,7 +12,7 @@ import torch
 from . import _lib as L
 
 __all__ = ["pose_vec2mat", "reconstruct", "project", "warp_coords", "grid_gather", "view_synthesis", "feat_cost",
-           "photometric_loss", "reproj_pose_loss", "sup_depth_loss"]
+           "photometric_loss", "reproj_pose_loss", "sup_depth_loss", "upsample_depth"]
 
 
 def _pose_kind(pose):
@@ -684,3 +684,44 @@ def sup_depth_loss(inv_depths, gt_inv_depth, min_depth, max_depth, gamma=0.85):
         if tuple(d.shape) != tuple(gt_inv_depth.shape):
             raise NotImplementedError("dro_sfm_b200: predictions must be at the ground-truth resolution")
     return _SupDepthLoss.apply(gt_inv_depth, (float(min_depth), float(max_depth), float(gamma)), n, *inv_depths)
+
+
+# ------------------------------------------------------------------------------------------------
+# convex up-sampling
+# ------------------------------------------------------------------------------------------------
+class _UpsampleDepth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, mask, ratio):
+        L.require_cuda(depth, mask)
+        depth, mask = L.f32c(depth), L.f32c(mask)
+        N, _, H, W = depth.shape
+        out = torch.empty(N, 1, ratio * H, ratio * W, device=depth.device, dtype=torch.float32)
+        with torch.cuda.device(depth.device):
+            L.check(L.lib().drosfm_upsample_depth_fwd(L.ptr(depth), L.ptr(mask), L.ptr(out), N, H, W, ratio, L.stream()),
+                    "upsample_depth_fwd")
+        ctx.save_for_backward(depth, mask)
+        ctx.ratio = ratio
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        depth, mask = ctx.saved_tensors
+        g = L.f32c(g)
+        N, _, H, W = depth.shape
+        gd = torch.zeros_like(depth) if ctx.needs_input_grad[0] else None
+        gm = torch.empty_like(mask) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(depth.device):
+            L.check(L.lib().drosfm_upsample_depth_bwd(L.ptr(g), L.ptr(depth), L.ptr(mask), L.ptr(gd), L.ptr(gm), N, H, W,
+                                                      ctx.ratio, L.stream()), "upsample_depth_bwd")
+        return gd, gm, None
+
+
+def upsample_depth(depth, mask, ratio=8):
+    """DepthPoseNet.upsample_depth (DepthPoseNet.py:63-74): [N,1,H,W] x [N,9*ratio^2,H,W] -> [N,1,ratio*H,ratio*W]."""
+    if depth.dim() != 4 or depth.shape[1] != 1:
+        raise AssertionError("depth must be [N,1,H,W]")
+    if ratio != 8:
+        raise NotImplementedError("dro_sfm_b200: upsample_depth supports ratio 8 (DepthPoseNet.feat_ratio)")
+    if tuple(mask.shape) != (depth.shape[0], 9 * ratio * ratio, depth.shape[2], depth.shape[3]):
+        raise ValueError("mask must be [N,{},H,W], got {}".format(9 * ratio * ratio, tuple(mask.shape)))
+    return _UpsampleDepth.apply(depth, mask, int(ratio))

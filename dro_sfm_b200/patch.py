@@ -8,7 +8,7 @@ Replaces (by name, keeping signatures) the hot-path symbols of the reference:
   dro_sfm.geometry.camera_utils.view_synthesis,
   dro_sfm.losses.multiview_photometric_loss_mf.MultiViewPhotometricDecayLoss,
   dro_sfm.losses.supervised_loss.SupervisedDepthPoseLoss,
-  DepthPoseNet.get_cost_each / depth_cost_calc.
+  DepthPoseNet.get_cost_each / depth_cost_calc / upsample_depth.
 Modules that did `from x import Name` before install() keep their old binding, so the known importers
 (SelfSupModelMF.py:3, SupModelMF.py:3, SemiSupModelMF.py:3-4, DepthPoseNet.py:11, SfmModelMF.py) are
 re-bound too.  Nothing else of the reference is touched: trainer, configs and checkpoints are as-is
@@ -57,4 +57,5 @@ def install():
     if net_mod is not None and hasattr(net_mod, "DepthPoseNet"):
         net_mod.DepthPoseNet.get_cost_each = FeatureMetricCost.get_cost_each
         net_mod.DepthPoseNet.depth_cost_calc = FeatureMetricCost.depth_cost_calc
+        net_mod.DepthPoseNet.upsample_depth = FeatureMetricCost.upsample_depth
     return patched

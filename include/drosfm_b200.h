@@ -207,6 +207,15 @@ int drosfm_sup_depth_loss_bwd(const float* g_loss, const float* gt_inv_depth, co
                               float min_depth, float max_depth, float gamma, float* const* g_inv_depths, int B, int H, int W,
                               drosfm_stream_t stream);
 
+/* ---- convex up-sampling (DepthPoseNet.upsample_depth, DepthPoseNet.py:63-74) ------
+ * depth [N,1,H,W], mask [N,9*ratio*ratio,H,W] -> out [N,1,ratio*H,ratio*W]:
+ * out[8y+i,8x+j] = sum_k softmax_k(mask[k*64+i*8+j, y, x]) * depth_zero_padded[y+k/3-1, x+k%3-1].  ratio must be 8.
+ * bwd: g_mask written, g_depth accumulated (either may be NULL). */
+int drosfm_upsample_depth_fwd(const float* depth, const float* mask, float* out, int N, int H, int W, int ratio,
+                              drosfm_stream_t stream);
+int drosfm_upsample_depth_bwd(const float* g_out, const float* depth, const float* mask, float* g_depth, float* g_mask,
+                              int N, int H, int W, int ratio, drosfm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ __all__ = [
     "inv2depth", "reconstruct", "project", "warp_coords", "grid_gather",
     "view_synthesis", "feat_cost_each", "depth_cost", "ssim", "photometric_map",
     "photometric_loss", "smoothness_loss", "multiview_photometric_decay_loss",
-    "reproj_coords", "reproj_pose_loss", "supervised_depth_loss",
+    "reproj_coords", "reproj_pose_loss", "supervised_depth_loss", "upsample_depth",
 ]
 
 
@@ -331,3 +331,15 @@ def supervised_depth_loss(inv_depths, gt_inv_depth, min_depth, max_depth, gamma=
         valid = ((gt_inv_depth > lo) & (gt_inv_depth < hi)).detach().squeeze(1)
         total = total + w * torch.mean(valid * torch.abs(gt_inv_depth - inv_depths[i]).squeeze(1))
     return total / wsum
+
+
+# ----------------------------------------------------------------------------------------------
+# convex up-sampling
+# ----------------------------------------------------------------------------------------------
+def upsample_depth(depth, mask, ratio=8):
+    """dro_sfm/networks/depth_pose/DepthPoseNet.py:63-74."""
+    N, _, H, W = depth.shape
+    m = torch.softmax(mask.view(N, 1, 9, ratio, ratio, H, W), dim=2)
+    nb = F.unfold(depth, [3, 3], padding=1).view(N, 1, 9, 1, 1, H, W)
+    up = torch.sum(m * nb, dim=2).permute(0, 1, 4, 2, 5, 3)
+    return up.reshape(N, 1, ratio * H, ratio * W)

@@ -272,13 +272,32 @@ def case_supervised(ref):
     save("supervised", **out)
 
 
+def case_upsample(ref):
+    """DepthPoseNet.upsample_depth (DepthPoseNet.py:63-74) with gradients."""
+    g = syn.gen(606)
+    N, H, W = 2, 5, 7
+    depth = syn.inv_depth(g, N, H, W, 0.5, 80.0)
+    mask = torch.randn(N, 576, H, W, generator=g) * 2.0
+    gout = torch.randn(N, 1, 8 * H, 8 * W, generator=g)
+    out = {"depth": depth, "mask": mask, "gout": gout}
+    for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        d, m = leaf(depth, dt), leaf(mask, dt)
+        y = ref.upsample_depth(d, m, ratio=8)
+        y.backward(gout.to(dt))
+        out.update({f"{tag}_out": y, f"{tag}_g_depth": d.grad, f"{tag}_g_mask": m.grad})
+    save("upsample", **out)
+
+
 def main():
     ref = ref_import.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "upsample":
+        return case_upsample(ref)
     case_coords(ref)
     case_view_synthesis(ref)
     case_feat_cost(ref)
     case_photometric(ref)
     case_supervised(ref)
+    case_upsample(ref)
 
 
 if __name__ == "__main__":

@@ -84,4 +84,5 @@ def load():
         SupervisedDepthPoseLoss=SupervisedDepthPoseLoss,
         get_cost_each=lambda *a, **k: DepthPoseNet.get_cost_each(net, *a, **k),
         depth_cost_calc=lambda *a, **k: DepthPoseNet.depth_cost_calc(net, *a, **k),
+        upsample_depth=lambda *a, **k: DepthPoseNet.upsample_depth(net, *a, **k),
     )

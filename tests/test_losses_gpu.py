@@ -299,3 +299,35 @@ def test_cost_gradients_accumulate_through_the_layout_cache():
         assert a is not None and a.shape == b.shape
         scale = float(b.abs().max())
         assert float((a - b).abs().max()) <= 1e-5 * scale + 1e-6, f"accumulated gradient {k} differs"
+
+
+def test_upsample_depth_golden(golden):
+    """Convex up-sampling (DepthPoseNet.upsample_depth) against the reference's fixture."""
+    from dro_sfm_b200.networks import upsample_depth
+    g = golden("upsample")
+    d, m = cu(g["depth"]).requires_grad_(True), cu(g["mask"]).requires_grad_(True)
+    y = upsample_depth(d, m, ratio=8)
+    gd, gm = torch.autograd.grad(y, (d, m), cu(g["gout"]))
+    assert_close(y.detach().cpu(), g["f32_out"], what="out")
+    assert_close_or_better(gm.cpu(), g["f32_g_mask"], g["f64_g_mask"], what="g_mask", reduction=False)
+    assert_close_or_better(gd.cpu(), g["f32_g_depth"], g["f64_g_depth"], what="g_depth")
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 40, 120), (1, 30, 40), (3, 3, 33)])
+def test_upsample_depth_vs_oracle(N, H, W):
+    from dro_sfm_b200 import ops, synthetic as syn
+    g = syn.gen(61)
+    depth = syn.inv_depth(g, N, H, W, 0.5, 80.0)
+    mask = torch.randn(N, 576, H, W, generator=g)
+    gout = torch.randn(N, 1, 8 * H, 8 * W, generator=g)
+    refs = {}
+    for dt in (torch.float32, torch.float64):
+        d, m = depth.to(dt).requires_grad_(True), mask.to(dt).requires_grad_(True)
+        y = oracle.upsample_depth(d, m, 8)
+        refs[dt] = (y.detach(),) + torch.autograd.grad(y, (d, m), gout.to(dt))
+    d, m = depth.to(DEV).requires_grad_(True), mask.to(DEV).requires_grad_(True)
+    y = ops.upsample_depth(d, m, 8)
+    gd, gm = torch.autograd.grad(y, (d, m), gout.to(DEV))
+    assert_close(y.detach().cpu(), refs[torch.float32][0], what="out")
+    assert_close_or_better(gd.cpu(), refs[torch.float32][1], refs[torch.float64][1], what="g_depth")
+    assert_close_or_better(gm.cpu(), refs[torch.float32][2], refs[torch.float64][2], what="g_mask", reduction=False)

@@ -184,3 +184,15 @@ def test_supervised_losses(golden, dt, tag):
         for i in range(n):
             assert_close(grads[k], g[f"{tag}_g_T{v}_{i}"], what=f"g_T{v}_{i}", **gtol)
             k += 1
+
+
+@pytest.mark.parametrize("dt,tag", [(torch.float32, "f32"), (torch.float64, "f64")])
+def test_upsample_depth(golden, dt, tag):
+    g = golden("upsample")
+    d, m = t(g["depth"], dt).requires_grad_(True), t(g["mask"], dt).requires_grad_(True)
+    y = oracle.upsample_depth(d, m, 8)
+    gd, gm = torch.autograd.grad(y, (d, m), t(g["gout"], dt))
+    tol = dict(rtol=1e-6, atol=1e-7) if dt == torch.float32 else dict(rtol=1e-12, atol=1e-13)
+    assert_close(y.detach(), g[f"{tag}_out"], what="out", **tol)
+    assert_close(gd, g[f"{tag}_g_depth"], what="g_depth", **(tol if dt == torch.float64 else dict(rtol=1e-5, atol=1e-6)))
+    assert_close(gm, g[f"{tag}_g_mask"], what="g_mask", **tol)

@@ -29,6 +29,7 @@ def test_install_rebinds_the_hot_path_symbols():
     assert rs.SupervisedDepthPoseLoss is SupervisedDepthPoseLoss
     assert rn.DepthPoseNet.get_cost_each is FeatureMetricCost.get_cost_each
     assert rn.DepthPoseNet.depth_cost_calc is FeatureMetricCost.depth_cost_calc
+    assert rn.DepthPoseNet.upsample_depth is FeatureMetricCost.upsample_depth
 
 
 def test_dropin_signatures_match_the_reference():
@@ -56,4 +57,5 @@ def test_dropin_signatures_match_the_reference():
     assert params(FeatureMetricCost.get_cost_each) == ["self", "pose", "fmap", "fmap_ref", "depth", "K", "ref_K", "scale_factor"]
     assert params(FeatureMetricCost.depth_cost_calc) == ["self", "inv_depth", "fmap", "fmaps_ref", "pose_list", "K", "ref_K",
                                                          "scale_factor"]
+    assert params(FeatureMetricCost.upsample_depth) == ["self", "depth", "mask", "ratio"]
     assert orig_cam is not None and ref is not None
