@@ -58,7 +58,7 @@ def ncu_traffic(kernel_key):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms from the warm-up through the timed regions."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -240,6 +240,9 @@ def run_gpu(args, wl):
             evs.append((s, e))
         return evs
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()                                           # sampled from the warm-up through both timed regions
     for _ in range(max(args.warmup, 3)):
         one_step(False)
         one_step(True)
@@ -248,10 +251,7 @@ def run_gpu(args, wl):
         one_step(False)
         launches_per_step = int(L.lib().drosfm_launch_count() - before)
 
-    clocks = ClockSampler(local)
     sync_all()
-    if rank == 0:
-        clocks.start()
     evs = timed(False, args.steps)
     sync_all()
     ms = sum(s.elapsed_time(e) for s, e in evs)
@@ -325,7 +325,7 @@ def run_gpu(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="train_kitti_mf_selfsup")

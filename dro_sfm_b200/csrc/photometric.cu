@@ -420,7 +420,6 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
     float* gxs = cc + CPLANE;                         // [3][IH][CW] gradient w.r.t. the warped pixel
     uint8_t* selt = reinterpret_cast<uint8_t*>(gxs + 3 * IH * CW);   // [CH][CW]
     __shared__ Cam cam_s[DROSFM_MAX_VIEWS];
-    __shared__ int flags[DROSFM_MAX_VIEWS];
     const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
     const int tx0 = blockIdx.x * IW, ty0 = blockIdx.y * IH;          // interior origin
     const int cx0 = tx0 - 1, cy0 = ty0 - 1;                            // coefficient-region origin
@@ -638,7 +637,6 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
                              pg.g_pose[tid * n_preds + ip] + b * (eul ? 6 : 16));
         }
     }
-    (void)flags;
 }
 
 static int check_photo(const float* image, const float* const* context, int n_views, const drosfm_photo_opts_t* opts,
