@@ -272,7 +272,11 @@ def run_gpu(args, wl):
         L.profile_begin()
         for _ in range(args.steps):
             flush.zero_()
+            # hold the stream back for ~15 ms so the host enqueues the whole step ahead of the device: the events
+            # then bracket device time only, not the Python/ctypes launch latency of an idle GPU
+            torch.cuda._sleep(30_000_000)
             step.step()
+            torch.cuda.synchronize()
         recs = L.profile_end()
         step.graph = graph
         per = {}

@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libdrosfm_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_VIEWS = 8
 MAX_PREDS = 16
 
@@ -70,7 +70,7 @@ SIGNATURES = {
     "drosfm_feat_cost_bwd": ([_vp, _vp, _pp, _vp, _int, _cp, _pp, _int, _vp, _pp, _vp, _pp, _vp,
                               _int, _int, _int, _int, _int, _int, _vp], _int),
     "drosfm_automask_fwd": ([_vp, _pp, _int, _op, _vp, _int, _int, _int, _vp], _int),
-    "drosfm_photometric_fwd": ([_vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _vp, _vp, _vp, _vp, _vp,
+    "drosfm_photometric_fwd": ([_vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _vp, _vp, _vp, _vp,
                                 _int, _int, _int, _vp], _int),
     "drosfm_photometric_bwd": ([_vp, _vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _pp, _pp, _vp, _vp, _vp,
                                 _int, _int, _int, _vp], _int),

@@ -112,20 +112,10 @@ __device__ __forceinline__ Win add3(const Win& a, const Win& b, const Win& c) {
 // top-left corner is (oy, ox) (zeros elsewhere).  WARP: through the depth/pose warp; otherwise the
 // un-warped source (auto-mask).  Work is batched so that each thread has NB depth loads, then NB*12
 // gathers in flight; the camera lives in registers.
-// What the forward keeps per (prediction, view, sample) for the backward: the warped source (3 planes) and,
-// per pixel, the clamped north-west tap offset, flag bits and the two fractional offsets (16 bytes).
-struct alignas(16) SavedTap {
-    int o00;
-    unsigned flags;     // bits 0-3 tap validity, 4: east tap is a different column, 5: south tap is a different row,
-                        // 6/7: x / y coordinate gradient not clipped away (border padding)
-    float ax, ay;
-};
-
 template <int ROWS, int COLS, int NT, bool WARP>
 __device__ __forceinline__ void fill_source_tile(float* __restrict__ xs, const float* __restrict__ src,
                                                  const float* __restrict__ invd, int depth_kind, const Cam& cam,
-                                                 int oy, int ox, int H, int W, int P, float wm1, float hm1, int padding,
-                                                 float* __restrict__ xsave = nullptr, SavedTap* __restrict__ tsave = nullptr) {
+                                                 int oy, int ox, int H, int W, int P, float wm1, float hm1, int padding) {
     constexpr int N = ROWS * COLS, NB = 2;
     constexpr int STEP_Y = NT / COLS, STEP_X = NT % COLS;       // (row, column) advance of idx += NT
     const int tid = threadIdx.x;
@@ -160,21 +150,6 @@ __device__ __forceinline__ void fill_source_tile(float* __restrict__ xs, const f
                 warp_pixel(cam, sxs[k], sys[k], to_depth(d[k], depth_kind), wm1, hm1, true, wp);
                 Taps t;
                 make_taps(wp.p.u, wp.p.v, H, W, padding, t);
-                if (tsave != nullptr) {
-                    // the tile's own pixels (not the halo) are recorded for the backward pass
-                    const int ry_ = sys[k] - oy, rx_ = sxs[k] - ox;
-                    if (ry_ >= 1 && ry_ <= ROWS - 2 && rx_ >= 1 && rx_ <= COLS - 2) {
-                        SavedTap st;
-                        const int x0 = max(t.x0, 0), y0 = max(t.y0, 0);
-                        st.o00 = t.valid ? y0 * W + x0 : 0;
-                        st.flags = t.valid | ((t.valid && min(t.x0 + 1, W - 1) != x0) ? 16u : 0u) |
-                                   ((t.valid && min(t.y0 + 1, H - 1) != y0) ? 32u : 0u) | (t.mx != 0.0f ? 64u : 0u) |
-                                   (t.my != 0.0f ? 128u : 0u);
-                        st.ax = t.ax;
-                        st.ay = t.ay;
-                        tsave[sys[k] * W + sxs[k]] = st;
-                    }
-                }
                 if (t.valid) {
                     const float bx = 1.0f - t.ax, by = 1.0f - t.ay;
                     w00[k] = (t.valid & 1u) ? bx * by : 0.0f;
@@ -216,10 +191,6 @@ __device__ __forceinline__ void fill_source_tile(float* __restrict__ xs, const f
                                                v[k][4 * c + 3] * w11[k]
                                          : v[k][c];
                     xs[c * N + sidx[k]] = o;
-                    if (WARP && xsave != nullptr && in[k]) {
-                        const int ry_ = sys[k] - oy, rx_ = sxs[k] - ox;
-                        if (ry_ >= 1 && ry_ <= ROWS - 2 && rx_ >= 1 && rx_ <= COLS - 2) xsave[c * P + sys[k] * W + sxs[k]] = o;
-                    }
                 }
             }
         }
@@ -248,21 +219,21 @@ __device__ __forceinline__ void fill_target_tile(float* __restrict__ ys, const f
 // ------------------------------------------------------------------------------------------
 // forward (MODE 0) and auto-mask pre-pass (MODE 1)
 // ------------------------------------------------------------------------------------------
-constexpr int kFwdThreads = 256, kFwdGroups = kFwdThreads / 32;
+constexpr int kFwdThreads = 512, kFwdGroups = kFwdThreads / 32;
 constexpr int FW = 32, FH = 64, FSW = FW + 2, FSH = FH + 2, FRPT = FH / kFwdGroups;
 constexpr int kFwdSmemBytes = 2 * 3 * FSH * FSW * static_cast<int>(sizeof(float));
 
-template <int MODE>
-__global__ void __launch_bounds__(kFwdThreads, 2)
+// SAVED: the warped sources come from warp_sources_kernel's output instead of being sampled here.
+template <int MODE, bool SAVED>
+__global__ void __launch_bounds__(kFwdThreads, (SAVED || MODE == 1) ? 2 : 1)
 photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ PhotoPtrs pp, int V, int depth_kind, int n_preds,
                        drosfm_cams_t cams, const float* __restrict__ automask_in, drosfm_photo_opts_t opts,
                        float l1_w, uint8_t* __restrict__ sel_out, float* __restrict__ automask_out,
-                       float* __restrict__ loss, Slot* ws, float* __restrict__ warped_save, SavedTap* __restrict__ taps_save,
-                       int B, int H, int W) {
+                       float* __restrict__ loss, Slot* ws, const float* __restrict__ warped_save, int B, int H, int W) {
     extern __shared__ float smem[];
     float* ys = smem;                        // [3][FSH][FSW]
     float* xs = smem + 3 * FSH * FSW;        // [3][FSH][FSW]
-    __shared__ Cam cam_s[MODE == 0 ? DROSFM_MAX_VIEWS : 1];
+    __shared__ Cam cam_s[(MODE == 0 && !SAVED) ? DROSFM_MAX_VIEWS : 1];
     __shared__ double red[kFwdGroups];
     __shared__ int flag;
     constexpr int PLANE = FSH * FSW;
@@ -273,7 +244,7 @@ photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ 
     const int P = H * W;
     const float wm1 = static_cast<float>(W - 1), hm1 = static_cast<float>(H - 1);
 
-    if (MODE == 0 && tid < V) setup_cam(cams, pp.pose[tid * n_preds + ip], b, cam_s[tid]);
+    if (MODE == 0 && !SAVED && tid < V) setup_cam(cams, pp.pose[tid * n_preds + ip], b, cam_s[tid]);
     fill_target_tile<FSH, FSW, kFwdThreads>(ys, image + static_cast<size_t>(b) * 3 * P, ty0 - 1, tx0 - 1, H, W, P);
     __syncthreads();
 
@@ -299,14 +270,14 @@ photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ 
 
     for (int v = 0; v < V; ++v) {
         // phase A: source view v on tile + halo 1
-        const float* src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
-        {
-            const Cam cam = cam_s[MODE == 0 ? v : 0];       // register copy for the sampling loop
+        if (SAVED) {
             const size_t slot = (static_cast<size_t>(ip) * V + v) * B + b;
+            fill_target_tile<FSH, FSW, kFwdThreads>(xs, warped_save + slot * 3 * P, ty0 - 1, tx0 - 1, H, W, P);
+        } else {
+            const float* src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
+            const Cam cam = cam_s[MODE == 0 ? v : 0];       // register copy for the sampling loop
             fill_source_tile<FSH, FSW, kFwdThreads, MODE == 0>(xs, src, invd, depth_kind, cam, ty0 - 1, tx0 - 1, H, W, P, wm1, hm1,
-                                                               opts.padding,
-                                                               (MODE == 0 && warped_save) ? warped_save + slot * 3 * P : nullptr,
-                                                               (MODE == 0 && taps_save) ? taps_save + slot * P : nullptr);
+                                                               opts.padding);
         }
         __syncthreads();
 
@@ -401,15 +372,18 @@ constexpr int IW = CW - 2, IH = CH - 2;              // interior pixels owned by
 constexpr int BSW = CW + 2, BSH = CH + 2;            // sample region (tile + halo 2): 34 x 42
 constexpr int kBwdSmemFloats = 2 * 3 * BSH * BSW + 3 * CH * CW + 3 * IH * CW;
 constexpr int kBwdSmemBytes = kBwdSmemFloats * static_cast<int>(sizeof(float)) + CH * CW;
+constexpr int kBwdSavedSmemBytes = (2 * 3 * BSH * BSW + 3 * CH * CW) * static_cast<int>(sizeof(float)) + CH * CW;
 
-template <bool SAVED, bool SAVED_TAPS>
-__global__ void __launch_bounds__(kBwdThreads, 2)
+// SAVED = false: the whole backward in one kernel (warp recomputed, nothing kept by the forward).
+// SAVED = true : stage 3 of the staged path -- warped sources are read back from the forward's copy and the
+//                gradient w.r.t. every warped pixel goes to g_warped for warp_sources_adjoint_kernel; no geometry here.
+template <bool SAVED>
+__global__ void __launch_bounds__(kBwdThreads, SAVED ? 3 : 2)
 photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict__ image,
                        const __grid_constant__ PhotoPtrs pp, int V,
                        int depth_kind, int n_preds, drosfm_cams_t cams, const uint8_t* __restrict__ sel_in,
                        drosfm_photo_opts_t opts, float l1_w, const __grid_constant__ PhotoGrads pg, Slot* ws,
-                       const float* __restrict__ warped_save, const SavedTap* __restrict__ taps_save,
-                       int B, int H, int W) {
+                       const float* __restrict__ warped_save, float* __restrict__ g_warped, int B, int H, int W) {
     extern __shared__ float smem[];
     constexpr int SPLANE = BSH * BSW, CPLANE = CH * CW;
     float* ys = smem;                                 // [3][BSH][BSW]
@@ -417,9 +391,10 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
     float* ca = xs + 3 * SPLANE;                      // [CH][CW] x 3 (a, b, c coefficient maps of one channel)
     float* cb = ca + CPLANE;
     float* cc = cb + CPLANE;
-    float* gxs = cc + CPLANE;                         // [3][IH][CW] gradient w.r.t. the warped pixel
-    uint8_t* selt = reinterpret_cast<uint8_t*>(gxs + 3 * IH * CW);   // [CH][CW]
-    __shared__ Cam cam_s[DROSFM_MAX_VIEWS];
+    float* gxs = cc + CPLANE;                         // [3][IH][CW] gradient w.r.t. the warped pixel (fused path only)
+    uint8_t* selt = reinterpret_cast<uint8_t*>(SAVED ? gxs : gxs + 3 * IH * CW);   // [CH][CW]
+    __shared__ Cam cam_s[SAVED ? 1 : DROSFM_MAX_VIEWS];
+    __shared__ unsigned present;                      // bit v: some window of the coefficient region selected view v
     const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
     const int tx0 = blockIdx.x * IW, ty0 = blockIdx.y * IH;          // interior origin
     const int cx0 = tx0 - 1, cy0 = ty0 - 1;                            // coefficient-region origin
@@ -433,13 +408,22 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
     const float kp = G * opts.ssim_w * (-1.0f / 6.0f) * (2.0f / 9.0f);   // d loss / d ssim  x  2/9 of the window derivative
     const float kl1 = G * l1_w * (1.0f / 3.0f);
 
-    if (tid < V) setup_cam(cams, pp.pose[tid * n_preds + ip], b, cam_s[tid]);
+    if (!SAVED && tid < V) setup_cam(cams, pp.pose[tid * n_preds + ip], b, cam_s[tid]);
+    if (tid == 0) present = 0u;
+    __syncthreads();
     fill_target_tile<BSH, BSW, kBwdThreads>(ys, image + static_cast<size_t>(b) * 3 * P, sy0, sx0, H, W, P);
-    for (int idx = tid; idx < CH * CW; idx += kBwdThreads) {
-        const int ry = idx / CW, rx = idx - ry * CW;
-        const int gy = cy0 + ry, gx = cx0 + rx;
-        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
-        selt[idx] = in ? (use_min ? sel_in[(static_cast<size_t>(ip) * B + b) * P + gy * W + gx] : 253) : 254;
+    {
+        unsigned seen = 0u;
+        for (int idx = tid; idx < CH * CW; idx += kBwdThreads) {
+            const int ry = idx / CW, rx = idx - ry * CW;
+            const int gy = cy0 + ry, gx = cx0 + rx;
+            const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+            const int sv = in ? (use_min ? sel_in[(static_cast<size_t>(ip) * B + b) * P + gy * W + gx] : 253) : 254;
+            selt[idx] = static_cast<uint8_t>(sv);
+            seen |= sv == 253 ? 0xffffffffu : (sv < 32 ? 1u << sv : 0u);
+        }
+        seen = __reduce_or_sync(0xffffffffu, seen);
+        if (lane == 0 && seen) atomicOr(&present, seen);
     }
     __syncthreads();
 
@@ -470,9 +454,24 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
 
     for (int v = 0; v < V; ++v) {
         const float* src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
-        const Cam cam = cam_s[v];
-        // phase A: warped source on tile + halo 2 -- reloaded from the forward's copy, or recomputed
+        const Cam cam = cam_s[SAVED ? 0 : v];
         const size_t vslot = (static_cast<size_t>(ip) * V + v) * B + b;
+        float* gw = SAVED ? g_warped + vslot * 3 * P : nullptr;
+        if (!((present >> v) & 1u)) {
+            // no window of this block chose view v: its gradient is identically zero here
+            if (SAVED) {
+#pragma unroll
+                for (int k = 0; k < BRPT; ++k) {
+                    const int r = prow0 + k, qy = cy0 + r;
+                    if (col_ok && r >= 1 && r <= IH && qy < H) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) gw[c * P + qy * W + pgx] = 0.0f;
+                    }
+                }
+            }
+            continue;
+        }
+        // phase A: warped source on tile + halo 2 -- reloaded from the forward's copy, or recomputed
         if (SAVED) fill_target_tile<BSH, BSW, kBwdThreads>(xs, warped_save + vslot * 3 * P, sy0, sx0, H, W, P);
         else fill_source_tile<BSH, BSW, kBwdThreads, true>(xs, src, invd, depth_kind, cam, sy0, sx0, H, W, P, wm1, hm1, opts.padding);
         __syncthreads();
@@ -543,12 +542,15 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
                             const float df = xq - yq;
                             gxv += df > 0.0f ? kl1 : (df < 0.0f ? -kl1 : 0.0f);
                         }
-                        gxs[(c * IH + r - 1) * CW + lane] = gxv;
+                        if (SAVED) gw[c * P + qy * W + pgx] = gxv;
+                        else gxs[(c * IH + r - 1) * CW + lane] = gxv;
                     }
                 }
             }
             __syncthreads();
         }
+
+        if (SAVED) continue;          // stages B and C end with a barrier; the adjoint runs in its own kernel
 
         // phase D: through the bilinear taps and the projection adjoint
         float gT[12];
@@ -560,48 +562,27 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
             const int qy = cy0 + r;
             if (col_ok && r >= 1 && r <= IH && qy < H) {
                 const float d = to_depth(__ldg(invd + qy * W + pgx), depth_kind);
-                int o00, dxo, dyo;
-                unsigned valid;
-                float ax, ay, mx, my;
                 Warp wp;
-                if (SAVED_TAPS) {
-                    const int4 raw = __ldg(reinterpret_cast<const int4*>(taps_save + vslot * P + qy * W + pgx));
-                    o00 = raw.x;
-                    const unsigned fl = static_cast<unsigned>(raw.y);
-                    valid = fl & 15u;
-                    dxo = (fl & 16u) ? 1 : 0;
-                    dyo = (fl & 32u) ? W : 0;
-                    ax = __int_as_float(raw.z);
-                    ay = __int_as_float(raw.w);
-                    mx = (fl & 64u) ? 0.5f * wm1 : 0.0f;
-                    my = (fl & 128u) ? 0.5f * hm1 : 0.0f;
-                    if (valid) warp_point(cam, pgx, qy, d, wp);
-                } else {
-                    warp_pixel(cam, pgx, qy, d, wm1, hm1, true, wp);
-                    Taps t;
-                    make_taps(wp.p.u, wp.p.v, H, W, opts.padding, t);
-                    valid = t.valid;
+                warp_pixel(cam, pgx, qy, d, wm1, hm1, true, wp);
+                Taps t;
+                make_taps(wp.p.u, wp.p.v, H, W, opts.padding, t);
+                if (t.valid) {
                     const int x0 = max(t.x0, 0), y0 = max(t.y0, 0);
-                    o00 = y0 * W + x0;
-                    dxo = min(t.x0 + 1, W - 1) - x0;
-                    dyo = (min(t.y0 + 1, H - 1) - y0) * W;
-                    ax = t.ax; ay = t.ay; mx = t.mx; my = t.my;
-                }
-                if (valid) {
-                    const float m0 = (valid & 1u) ? 1.f : 0.f, m1 = (valid & 2u) ? 1.f : 0.f;
-                    const float m2 = (valid & 4u) ? 1.f : 0.f, m3 = (valid & 8u) ? 1.f : 0.f;
+                    const int o00 = y0 * W + x0, dxo = min(t.x0 + 1, W - 1) - x0, dyo = (min(t.y0 + 1, H - 1) - y0) * W;
+                    const float m0 = (t.valid & 1u) ? 1.f : 0.f, m1 = (t.valid & 2u) ? 1.f : 0.f;
+                    const float m2 = (t.valid & 4u) ? 1.f : 0.f, m3 = (t.valid & 8u) ? 1.f : 0.f;
                     float gix = 0.0f, giy = 0.0f;
-                    const float bx = 1.0f - ax, by = 1.0f - ay;
+                    const float bx = 1.0f - t.ax, by = 1.0f - t.ay;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const float* r0 = src + c * P + o00;
                         const float v0 = __ldg(r0) * m0, v1 = __ldg(r0 + dxo) * m1;
                         const float v2 = __ldg(r0 + dyo) * m2, v3 = __ldg(r0 + dyo + dxo) * m3;
                         const float g = gxs[(c * IH + r - 1) * CW + lane];
-                        gix += g * ((v1 - v0) * by + (v3 - v2) * ay);
-                        giy += g * ((v2 - v0) * bx + (v3 - v1) * ax);
+                        gix += g * ((v1 - v0) * by + (v3 - v2) * t.ay);
+                        giy += g * ((v2 - v0) * bx + (v3 - v1) * t.ax);
                     }
-                    gd[k] += warp_pixel_adjoint(cam, wp, d, wm1, hm1, true, gix * mx, giy * my, gT);
+                    gd[k] += warp_pixel_adjoint(cam, wp, d, wm1, hm1, true, gix * t.mx, giy * t.my, gT);
                 }
             }
         }
@@ -609,6 +590,7 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
             warp_accumulate<12>(gT, spread_acc(slot_at(ws, (v * n_preds + ip) * B + b)));
         __syncthreads();      // gxs / xs are rewritten by the next view
     }
+    if (SAVED) return;
 
     float* gout = pg.g_inv_depth[ip];
     if (gout != nullptr) {
@@ -621,6 +603,197 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
                 float g = gd[k];
                 if (depth_kind == DROSFM_INV_DEPTH) g = inv2depth_grad(__ldg(invd + o), g);
                 gout[static_cast<size_t>(b) * P + o] = g;
+            }
+        }
+    }
+    // one ticket per (view, prediction, sample): the last block turns the fp64 sums into the caller's encoding
+    __threadfence();
+    __syncthreads();
+    if (tid < V && pg.g_pose[tid * n_preds + ip] != nullptr) {
+        Slot* slot = slot_at(ws, (tid * n_preds + ip) * B + b);
+        const unsigned long long t = atomicAdd(&slot->ticket, 1ull);
+        if (t == static_cast<unsigned long long>(gridDim.x) * gridDim.y - 1ull) {
+            __threadfence();
+            const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
+            finish_pose_grad(slot, cams.pose_kind, eul ? pp.pose[tid * n_preds + ip] + b * 6 : nullptr,
+                             pg.g_pose[tid * n_preds + ip] + b * (eul ? 6 : 16));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// staged path: stage 1 (warp every source view once, no halo) and stage 4 (its adjoint)
+// ------------------------------------------------------------------------------------------
+// With a warped_save buffer the loss runs as four lean kernels instead of two fused ones:
+//   1 warp_sources_kernel          inv_depth, pose, source  -> warped [n,V,B,3,H,W]
+//   2 photometric_fwd_kernel<0,1>  warped, target           -> loss, sel
+//   3 photometric_bwd_kernel<1>    warped, target, sel      -> g_warped [n,V,B,3,H,W]
+//   4 warp_sources_adjoint_kernel  g_warped, inv_depth, ... -> g_inv_depth, g_pose
+// The SSIM stages then carry no camera state (fewer registers, more resident warps) and the geometry runs
+// once per pixel instead of once per pixel of every tile + halo.
+constexpr int kFlatThreads = 256, kFlatRows = 8, kFlatNB = 1;
+constexpr int kFlatTileH = (kFlatThreads / 32) * kFlatRows;       // a block covers 32 columns x 64 rows
+
+struct FlatTap {
+    int o00, dxo, dyo;
+    float w00, w01, w10, w11;
+};
+
+__global__ void __launch_bounds__(kFlatThreads, 3)
+warp_sources_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind, int n_preds, drosfm_cams_t cams, int padding,
+                    float* __restrict__ warped, int B, int H, int W) {
+    __shared__ Cam cam_s;
+    const int slot = blockIdx.z;                               // (ip * V + v) * B + b
+    const int b = slot % B, v = (slot / B) % V, ip = slot / (B * V);
+    if (threadIdx.x == 0) setup_cam(cams, pp.pose[v * n_preds + ip], b, cam_s);
+    __syncthreads();
+    const Cam cam = cam_s;
+    const int P = H * W;
+    const float wm1 = static_cast<float>(W - 1), hm1 = static_cast<float>(H - 1);
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y0 = blockIdx.y * kFlatTileH + (threadIdx.x >> 5);
+    const float* __restrict__ invd = pp.inv_depth[ip] + static_cast<size_t>(b) * P;
+    const float* __restrict__ src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
+    float* __restrict__ out = warped + static_cast<size_t>(slot) * 3 * P;
+    if (x >= W) return;
+#pragma unroll 1
+    for (int k0 = 0; k0 < kFlatRows; k0 += kFlatNB) {
+        float d[kFlatNB];
+        bool in[kFlatNB];
+#pragma unroll
+        for (int k = 0; k < kFlatNB; ++k) {
+            const int y = y0 + (k0 + k) * (kFlatThreads / 32);
+            in[k] = y < H;
+            d[k] = in[k] ? __ldg(invd + y * W + x) : 0.0f;
+        }
+        FlatTap tp[kFlatNB];
+#pragma unroll
+        for (int k = 0; k < kFlatNB; ++k) {
+            const int y = y0 + (k0 + k) * (kFlatThreads / 32);
+            tp[k] = FlatTap{0, 0, 0, 0.0f, 0.0f, 0.0f, 0.0f};
+            if (in[k]) {
+                Warp wp;
+                warp_pixel(cam, x, y, to_depth(d[k], depth_kind), wm1, hm1, true, wp);
+                Taps t;
+                make_taps(wp.p.u, wp.p.v, H, W, padding, t);
+                if (t.valid) {
+                    const float bx = 1.0f - t.ax, by = 1.0f - t.ay;
+                    tp[k].w00 = (t.valid & 1u) ? bx * by : 0.0f;
+                    tp[k].w01 = (t.valid & 2u) ? t.ax * by : 0.0f;
+                    tp[k].w10 = (t.valid & 4u) ? bx * t.ay : 0.0f;
+                    tp[k].w11 = (t.valid & 8u) ? t.ax * t.ay : 0.0f;
+                    const int xa = max(t.x0, 0), ya = max(t.y0, 0);
+                    tp[k].o00 = ya * W + xa;
+                    tp[k].dxo = min(t.x0 + 1, W - 1) - xa;
+                    tp[k].dyo = (min(t.y0 + 1, H - 1) - ya) * W;
+                }
+            }
+        }
+        float val[kFlatNB][12];
+#pragma unroll
+        for (int k = 0; k < kFlatNB; ++k) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* r0 = src + c * P + tp[k].o00;
+                val[k][4 * c + 0] = __ldg(r0);
+                val[k][4 * c + 1] = __ldg(r0 + tp[k].dxo);
+                val[k][4 * c + 2] = __ldg(r0 + tp[k].dyo);
+                val[k][4 * c + 3] = __ldg(r0 + tp[k].dyo + tp[k].dxo);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kFlatNB; ++k) {
+            const int y = y0 + (k0 + k) * (kFlatThreads / 32);
+            if (in[k]) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    out[c * P + y * W + x] = val[k][4 * c] * tp[k].w00 + val[k][4 * c + 1] * tp[k].w01 +
+                                             val[k][4 * c + 2] * tp[k].w10 + val[k][4 * c + 3] * tp[k].w11;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFlatThreads, 3)
+warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind, int n_preds, drosfm_cams_t cams,
+                            int padding, const float* __restrict__ g_warped, const __grid_constant__ PhotoGrads pg, Slot* ws,
+                            int B, int H, int W) {
+    __shared__ Cam cam_s[DROSFM_MAX_VIEWS];
+    const int tid = threadIdx.x;
+    const int b = static_cast<int>(blockIdx.z) % B, ip = static_cast<int>(blockIdx.z) / B;
+    if (tid < V) setup_cam(cams, pp.pose[tid * n_preds + ip], b, cam_s[tid]);
+    __syncthreads();
+    const int P = H * W;
+    const float wm1 = static_cast<float>(W - 1), hm1 = static_cast<float>(H - 1);
+    const int x = blockIdx.x * 32 + (tid & 31);
+    const float* __restrict__ invd = pp.inv_depth[ip] + static_cast<size_t>(b) * P;
+    const bool col_ok = x < W;
+    float* gout = pg.g_inv_depth[ip];
+    constexpr int kHalf = 4, kStride = kFlatThreads / 32;
+#pragma unroll 1
+    for (int h = 0; h < kFlatRows / kHalf; ++h) {
+        const int y0 = blockIdx.y * kFlatTileH + h * kHalf * kStride + (tid >> 5);
+        float dv[kHalf], gd[kHalf];
+#pragma unroll
+        for (int k = 0; k < kHalf; ++k) {
+            const int y = y0 + k * kStride;
+            dv[k] = (col_ok && y < H) ? __ldg(invd + y * W + x) : 0.0f;
+            gd[k] = 0.0f;
+        }
+#pragma unroll 1
+        for (int v = 0; v < V; ++v) {
+            const Cam cam = cam_s[v];
+            const float* __restrict__ src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
+            const float* __restrict__ gw = g_warped + ((static_cast<size_t>(ip) * V + v) * B + b) * 3 * P;
+            float gT[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) gT[i] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kHalf; ++k) {
+                const int y = y0 + k * kStride;
+                float g[3] = {0.0f, 0.0f, 0.0f};
+                if (col_ok && y < H) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) g[c] = __ldg(gw + c * P + y * W + x);
+                }
+                // a pixel that no selected window touches has an exactly zero gradient: nothing to push through
+                if (g[0] != 0.0f || g[1] != 0.0f || g[2] != 0.0f) {
+                    const float d = to_depth(dv[k], depth_kind);
+                    Warp wp;
+                    warp_pixel(cam, x, y, d, wm1, hm1, true, wp);
+                    Taps t;
+                    make_taps(wp.p.u, wp.p.v, H, W, padding, t);
+                    if (t.valid) {
+                        const int xa = max(t.x0, 0), ya = max(t.y0, 0);
+                        const int o00 = ya * W + xa, dxo = min(t.x0 + 1, W - 1) - xa, dyo = (min(t.y0 + 1, H - 1) - ya) * W;
+                        const float m0 = (t.valid & 1u) ? 1.f : 0.f, m1 = (t.valid & 2u) ? 1.f : 0.f;
+                        const float m2 = (t.valid & 4u) ? 1.f : 0.f, m3 = (t.valid & 8u) ? 1.f : 0.f;
+                        float gix = 0.0f, giy = 0.0f;
+                        const float bx = 1.0f - t.ax, by = 1.0f - t.ay;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float* r0 = src + c * P + o00;
+                            const float v0 = __ldg(r0) * m0, v1 = __ldg(r0 + dxo) * m1;
+                            const float v2 = __ldg(r0 + dyo) * m2, v3 = __ldg(r0 + dyo + dxo) * m3;
+                            gix += g[c] * ((v1 - v0) * by + (v3 - v2) * t.ay);
+                            giy += g[c] * ((v2 - v0) * bx + (v3 - v1) * t.ax);
+                        }
+                        gd[k] += warp_pixel_adjoint(cam, wp, d, wm1, hm1, true, gix * t.mx, giy * t.my, gT);
+                    }
+                }
+            }
+            if (pg.g_pose[v * n_preds + ip] != nullptr)
+                warp_accumulate<12>(gT, spread_acc(slot_at(ws, (v * n_preds + ip) * B + b)));
+        }
+        if (gout != nullptr) {
+#pragma unroll
+            for (int k = 0; k < kHalf; ++k) {
+                const int y = y0 + k * kStride;
+                if (col_ok && y < H) {
+                    float gg = gd[k];
+                    if (depth_kind == DROSFM_INV_DEPTH) gg = inv2depth_grad(dv[k], gg);
+                    gout[static_cast<size_t>(b) * P + y * W + x] = gg;
+                }
             }
         }
     }
@@ -664,15 +837,15 @@ static int allow_big_smem() {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess && dev != done_for_device) {
-        e = cudaFuncSetAttribute(photometric_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
+        e = cudaFuncSetAttribute(photometric_fwd_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(photometric_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
+            e = cudaFuncSetAttribute(photometric_fwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(photometric_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
+            e = cudaFuncSetAttribute(photometric_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(photometric_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
+            e = cudaFuncSetAttribute(photometric_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSavedSmemBytes);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(photometric_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
+            e = cudaFuncSetAttribute(photometric_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
         if (e == cudaSuccess) done_for_device = dev;
     }
     if (e != cudaSuccess) {
@@ -705,9 +878,8 @@ int drosfm_automask_fwd(const float* image, const float* const* context, int n_v
     drosfm_cams_t none{};
     dim3 grid((W + FW - 1) / FW, (H + FH - 1) / FH, B);
     if (int e = allow_big_smem()) return e;
-    photometric_fwd_kernel<1><<<grid, kFwdThreads, kFwdSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-        image, pp, n_views, DROSFM_DEPTH, 1, none, nullptr, o, l1_weight(opts), nullptr, automask, nullptr, nullptr, nullptr, nullptr,
-        B, H, W);
+    photometric_fwd_kernel<1, false><<<grid, kFwdThreads, kFwdSmemBytes, static_cast<cudaStream_t>(stream)>>>(
+        image, pp, n_views, DROSFM_DEPTH, 1, none, nullptr, o, l1_weight(opts), nullptr, automask, nullptr, nullptr, nullptr, B, H, W);
     return launch_status("automask_fwd");
 }
 
@@ -735,7 +907,7 @@ static int fill_ptrs(PhotoPtrs& pp, const float* const* context, int n_views, co
 int drosfm_photometric_fwd(const float* image, const float* const* context, int n_views, const float* const* inv_depths,
                            int depth_kind, int n_preds, const drosfm_cams_t* cams, const float* const* poses,
                            const float* automask, const drosfm_photo_opts_t* opts, uint8_t* sel, float* loss, void* ws,
-                           float* warped_save, void* taps_save, int B, int H, int W, drosfm_stream_t stream) {
+                           float* warped_save, int B, int H, int W, drosfm_stream_t stream) {
     if (int e = check_photo(image, context, n_views, opts, B, H, W)) return e;
     DROSFM_REQUIRE(B > 0 && H * W > 0, DROSFM_EINVAL, "photometric_fwd: empty batch (the mean over zero pixels is undefined)");
     DROSFM_REQUIRE(cams && cams->K && cams->Kref, DROSFM_EINVAL, "photometric_fwd: NULL cams");
@@ -748,12 +920,22 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
     DROSFM_REQUIRE(!opts->automask || automask != nullptr, DROSFM_EINVAL, "photometric_fwd: automask map is NULL");
     PhotoPtrs pp{};
     if (int e = fill_ptrs(pp, context, n_views, inv_depths, n_preds, poses, opts->gamma)) return e;
-    DROSFM_REQUIRE(static_cast<long long>(B) * n_preds <= 65535, DROSFM_ERANGE, "photometric_fwd: B * n_preds too large");
+    DROSFM_REQUIRE(static_cast<long long>(B) * n_preds * n_views <= 65535, DROSFM_ERANGE, "photometric_fwd: B * n_preds * n_views too large");
     dim3 grid((W + FW - 1) / FW, (H + FH - 1) / FH, B * n_preds);
     if (int e = allow_big_smem()) return e;
-    photometric_fwd_kernel<0><<<grid, kFwdThreads, kFwdSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-        image, pp, n_views, depth_kind, n_preds, *cams, opts->automask ? automask : nullptr, *opts, l1_weight(opts), sel,
-        nullptr, loss, static_cast<Slot*>(ws), warped_save, static_cast<SavedTap*>(taps_save), B, H, W);
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    if (warped_save != nullptr) {
+        dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds * n_views);
+        warp_sources_kernel<<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, opts->padding, warped_save, B, H, W);
+        if (int e = launch_status("photometric_fwd (warp_sources)")) return e;
+        photometric_fwd_kernel<0, true><<<grid, kFwdThreads, kFwdSmemBytes, cs>>>(
+            image, pp, n_views, depth_kind, n_preds, *cams, opts->automask ? automask : nullptr, *opts, l1_weight(opts), sel,
+            nullptr, loss, static_cast<Slot*>(ws), warped_save, B, H, W);
+    } else {
+        photometric_fwd_kernel<0, false><<<grid, kFwdThreads, kFwdSmemBytes, cs>>>(
+            image, pp, n_views, depth_kind, n_preds, *cams, opts->automask ? automask : nullptr, *opts, l1_weight(opts), sel,
+            nullptr, loss, static_cast<Slot*>(ws), nullptr, B, H, W);
+    }
     return launch_status("photometric_fwd");
 }
 
@@ -761,7 +943,7 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
                            const float* const* inv_depths, int depth_kind, int n_preds, const drosfm_cams_t* cams,
                            const float* const* poses, const uint8_t* sel, const drosfm_photo_opts_t* opts,
                            float* const* g_inv_depths, float* const* g_poses, void* ws, const float* warped_save,
-                           const void* taps_save, int B, int H, int W, drosfm_stream_t stream) {
+                           float* g_warped, int B, int H, int W, drosfm_stream_t stream) {
     if (int e = check_photo(image, context, n_views, opts, B, H, W)) return e;
     if (B == 0 || H * W == 0) return DROSFM_OK;
     DROSFM_REQUIRE(cams && cams->K && cams->Kref, DROSFM_EINVAL, "photometric_bwd: NULL cams");
@@ -769,6 +951,8 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
                    "photometric_bwd: pose_kind must be MAT4 or EULER6");
     DROSFM_REQUIRE(g_loss != nullptr, DROSFM_EINVAL, "photometric_bwd: NULL g_loss");
     DROSFM_REQUIRE(opts->reduce_op == DROSFM_REDUCE_MEAN || sel != nullptr, DROSFM_EINVAL, "photometric_bwd: min needs sel");
+    DROSFM_REQUIRE((warped_save == nullptr) == (g_warped == nullptr), DROSFM_EINVAL,
+                   "photometric_bwd: warped_save and g_warped go together (both NULL: fused path)");
     PhotoPtrs pp{};
     if (int e = fill_ptrs(pp, context, n_views, inv_depths, n_preds, poses, opts->gamma)) return e;
     PhotoGrads pg{};
@@ -782,22 +966,20 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
     DROSFM_REQUIRE(static_cast<long long>(B) * n_preds <= 65535, DROSFM_ERANGE, "photometric_bwd: B * n_preds too large");
     dim3 grid((W + IW - 1) / IW, (H + IH - 1) / IH, B * n_preds);
     if (int e = allow_big_smem()) return e;
-    DROSFM_REQUIRE(taps_save == nullptr || warped_save != nullptr, DROSFM_EINVAL,
-                   "photometric_bwd: taps_save needs warped_save");
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
-    const SavedTap* ts = static_cast<const SavedTap*>(taps_save);
-    if (warped_save != nullptr && ts != nullptr)
-        photometric_bwd_kernel<true, true><<<grid, kBwdThreads, kBwdSmemBytes, cs>>>(
+    if (warped_save != nullptr) {
+        photometric_bwd_kernel<true><<<grid, kBwdThreads, kBwdSavedSmemBytes, cs>>>(
             g_loss, image, pp, n_views, depth_kind, n_preds, *cams, sel, *opts, l1_weight(opts), pg, static_cast<Slot*>(ws),
-            warped_save, ts, B, H, W);
-    else if (warped_save != nullptr)
-        photometric_bwd_kernel<true, false><<<grid, kBwdThreads, kBwdSmemBytes, cs>>>(
-            g_loss, image, pp, n_views, depth_kind, n_preds, *cams, sel, *opts, l1_weight(opts), pg, static_cast<Slot*>(ws),
-            warped_save, nullptr, B, H, W);
-    else
-        photometric_bwd_kernel<false, false><<<grid, kBwdThreads, kBwdSmemBytes, cs>>>(
+            warped_save, g_warped, B, H, W);
+        if (int e = launch_status("photometric_bwd (window gradients)")) return e;
+        dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds);
+        warp_sources_adjoint_kernel<<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, opts->padding, g_warped,
+                                                                   pg, static_cast<Slot*>(ws), B, H, W);
+    } else {
+        photometric_bwd_kernel<false><<<grid, kBwdThreads, kBwdSmemBytes, cs>>>(
             g_loss, image, pp, n_views, depth_kind, n_preds, *cams, sel, *opts, l1_weight(opts), pg, static_cast<Slot*>(ws),
             nullptr, nullptr, B, H, W);
+    }
     return launch_status("photometric_bwd");
 }
 

@@ -481,13 +481,10 @@ class _PhotoLoss(torch.autograd.Function):
         opts = L.PhotoOpts(ssim_w, C1, C2, padding, reduce_op, int(automask), gamma)
         losses = torch.zeros(2, device=dev, dtype=torch.float32)
         sel = torch.empty(n, B, H, W, device=dev, dtype=torch.uint8) if reduce_op == L.REDUCE_MIN else None
-        # kept for the backward pass (12 bytes per pixel, view and prediction): the kernels are instruction-bound
-        # with HBM idle, so re-reading the warp is cheaper than re-computing it
+        # staged path (12 bytes per pixel, view and prediction): the sources are warped once by a flat kernel and
+        # the SSIM kernels of both passes read the result; without it everything runs fused and keeps nothing
         keep_warp = SAVE_WARP and any(ctx.needs_input_grad[6 + V:])
         wsave = torch.empty(n, V, B, 3, H, W, device=dev, dtype=torch.float32) if keep_warp else None
-        # the bilinear taps can be recorded as well (drosfm_photometric_fwd takes taps_save), but re-deriving them
-        # costs fewer cycles than the 16 B/pixel round trip through HBM (measured on B200), so only the warp is kept
-        tsave = None
         stats = torch.empty(n, B, 4, device=dev, dtype=torch.float32) if smooth_w > 0.0 else None
         lib = L.lib()
         with torch.cuda.device(dev):
@@ -500,12 +497,12 @@ class _PhotoLoss(torch.autograd.Function):
                         "automask_fwd")
             L.check(lib.drosfm_photometric_fwd(L.ptr(image), L.ptr_array(context), V, L.ptr_array(invs), depth_kind, n, cams,
                                                L.ptr_array(poses), L.ptr(amask), opts, L.ptr(sel), L.ptr(losses), L.ptr(ws),
-                                               L.ptr(wsave), L.ptr(tsave), B, H, W, st), "photometric_fwd")
+                                               L.ptr(wsave), B, H, W, st), "photometric_fwd")
             if smooth_w > 0.0:
                 L.check(lib.drosfm_smoothness_fwd(L.ptr(image), L.ptr_array(invs), n, smooth_w, L.ptr(stats),
                                                   L.ptr(losses[1:]), L.ptr(ws), B, H, W, st), "smoothness_fwd")
         total = losses.sum().reshape(1)
-        ctx.save_for_backward(image, keep[0], keep[1], sel, stats, wsave, tsave, *context, *invs, *poses)
+        ctx.save_for_backward(image, keep[0], keep[1], sel, stats, wsave, *context, *invs, *poses)
         ctx.cfg, ctx.V, ctx.n, ctx.kind = cfg, V, n, kind
         ctx.mark_non_differentiable(losses)
         return total, losses
@@ -514,8 +511,8 @@ class _PhotoLoss(torch.autograd.Function):
     def backward(ctx, g_total, *unused):
         ssim_w, C1, C2, padding, reduce_op, automask, gamma, smooth_w, depth_kind = ctx.cfg
         V, n, kind = ctx.V, ctx.n, ctx.kind
-        image, K, Kref, sel, stats, wsave, tsave = ctx.saved_tensors[:7]
-        rest = ctx.saved_tensors[7:]
+        image, K, Kref, sel, stats, wsave = ctx.saved_tensors[:6]
+        rest = ctx.saved_tensors[6:]
         context, invs, poses = rest[:V], rest[V:V + n], rest[V + n:]
         B, _, H, W = image.shape
         dev = image.device
@@ -531,13 +528,14 @@ class _PhotoLoss(torch.autograd.Function):
         g_invs = [g_inv_slab[i] if need_inv[i] else None for i in range(n)]
         g_pose_slab = torch.empty(V * n, *poses[0].shape, device=dev, dtype=torch.float32) if any(need_pose) else None
         g_poses = [g_pose_slab[k] if need_pose[k] else None for k in range(V * n)]
+        g_warped = torch.empty_like(wsave) if wsave is not None else None     # scratch between the two backward stages
         lib = L.lib()
         with torch.cuda.device(dev):
             ws = L.workspace(dev, max(n * B + 1, V * n * B))
             st = L.stream()
             L.check(lib.drosfm_photometric_bwd(L.ptr(g), L.ptr(image), L.ptr_array(context), V, L.ptr_array(invs), depth_kind, n,
                                                cams, L.ptr_array(poses), L.ptr(sel), opts, L.ptr_array(g_invs),
-                                               L.ptr_array(g_poses), L.ptr(ws), L.ptr(wsave), L.ptr(tsave), B, H, W, st),
+                                               L.ptr_array(g_poses), L.ptr(ws), L.ptr(wsave), L.ptr(g_warped), B, H, W, st),
                     "photometric_bwd")
             if smooth_w > 0.0 and any(need_inv):
                 L.check(lib.drosfm_smoothness_bwd(L.ptr(g), L.ptr(image), L.ptr_array(invs), n, smooth_w, L.ptr(stats),

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DROSFM_ABI_VERSION 1
+#define DROSFM_ABI_VERSION 2
 #define DROSFM_MAX_VIEWS 8      /* source views per call (forward_context + back_context) */
 #define DROSFM_MAX_PREDS 16     /* depth predictions per loss call (GRU iterations seen by the loss) */
 
@@ -152,22 +152,25 @@ int drosfm_automask_fwd(const float* image, const float* const* context, int n_v
  * inv_depths[i]: [B,1,H,W]; poses[v*n_preds+i]: [B,4,4] or [B,6] per cams->pose_kind.
  * sel [n_preds,B,H,W] u8 receives the arg-min view per pixel (255 = auto-mask won); loss: 1 float.
  * ws of drosfm_ws_bytes(n_preds + 1).
- * warped_save [n_preds,V,B,3,H,W] float and taps_save [n_preds,V,B,H,W] x 16 bytes: optional (both NULL or both
- * given) record of the warped sources and their bilinear taps; handing them to drosfm_photometric_bwd saves it the
- * re-warp of every tile + halo (the kernels are instruction-bound, HBM is idle: 28 bytes per pixel, view and
- * prediction buy back ~30 % of the backward). */
+ * warped_save [n_preds,V,B,3,H,W] float, optional: when given, the call runs staged -- one flat kernel warps every
+ * source view once into warped_save (no tile halos, the geometry runs once per pixel), a second one evaluates the
+ * SSIM / L1 / min maps from it -- and the buffer is what drosfm_photometric_bwd wants back.  NULL: one fused
+ * kernel that keeps nothing (inference, or when 12 bytes per pixel, view and prediction are too much). */
 int drosfm_photometric_fwd(const float* image, const float* const* context, int n_views,
                            const float* const* inv_depths, int depth_kind, int n_preds,
                            const drosfm_cams_t* cams, const float* const* poses, const float* automask,
                            const drosfm_photo_opts_t* opts, uint8_t* sel, float* loss, void* ws,
-                           float* warped_save, void* taps_save, int B, int H, int W, drosfm_stream_t stream);
+                           float* warped_save, int B, int H, int W, drosfm_stream_t stream);
 /* g_loss: 1 float on the device (upstream gradient).  g_inv_depths[i] [B,1,H,W] written;
- * g_poses[v*n_preds+i] written ([B,4,4] or [B,6]); ws of drosfm_ws_bytes(n_views*n_preds*B). */
+ * g_poses[v*n_preds+i] written ([B,4,4] or [B,6]); ws of drosfm_ws_bytes(n_views*n_preds*B).
+ * warped_save (the forward's) and g_warped (scratch of the same size, contents undefined on return) go together:
+ * given, the backward runs staged (window-gradient kernel -> g_warped -> flat warp adjoint); both NULL: one fused
+ * kernel that re-warps every tile. */
 int drosfm_photometric_bwd(const float* g_loss, const float* image, const float* const* context, int n_views,
                            const float* const* inv_depths, int depth_kind, int n_preds,
                            const drosfm_cams_t* cams, const float* const* poses, const uint8_t* sel,
                            const drosfm_photo_opts_t* opts, float* const* g_inv_depths, float* const* g_poses,
-                           void* ws, const float* warped_save, const void* taps_save, int B, int H, int W,
+                           void* ws, const float* warped_save, float* g_warped, int B, int H, int W,
                            drosfm_stream_t stream);
 
 /* ---- smoothness loss (multiview_photometric_loss_mf.py:273-299, utils/depth.py:147-199) -------
