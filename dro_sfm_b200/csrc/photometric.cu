@@ -812,6 +812,323 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// staged path, stages 2 and 3 as streaming kernels: no shared-memory tiles, no block barriers
+// ------------------------------------------------------------------------------------------
+// A warp owns a strip of 32 columns (outer 1 or 2 lanes are halo) and walks down a band of rows.  Horizontal
+// neighbours come from warp shuffles, the vertical window from rotating register rows, so every value is loaded
+// once per strip (coalesced 128-byte rows) and the 3x3 statistics cost 2 shuffles + 2 adds per sum.  Reflection
+// padding: the row index is remapped before the load; at the image's first / last column the missing neighbour
+// is the opposite one.
+constexpr int kSsimThreads = 256, kSsimWarps = kSsimThreads / 32;
+constexpr int kFwdStripW = 30, kFwdBandH = 16;       // forward : 1-lane halo, 18 rows loaded for 16 written
+constexpr int kBwdStripW = 28, kBwdBandH = 32;       // backward: 2-lane halo, 36 rows loaded for 32 written
+
+// Left / right neighbour lanes with the reflection at the image's first / last column folded into the source lane.
+struct Lanes {
+    int l, r;
+};
+__device__ __forceinline__ Lanes neighbour_lanes(int lane, bool left_edge, bool right_edge) {
+    Lanes n;
+    n.l = left_edge ? lane + 1 : lane - 1;
+    n.r = right_edge ? lane - 1 : lane + 1;
+    return n;
+}
+__device__ __forceinline__ void neighbours(float c, const Lanes& n, float& l, float& r) {
+    l = __shfl_sync(0xffffffffu, c, n.l);
+    r = __shfl_sync(0xffffffffu, c, n.r);
+}
+// Row gy of the reflection-padded image (one row of padding), clamped for rows beyond the padding.
+__device__ __forceinline__ int padded_row(int gy, int H) { return max(min(abs(gy), 2 * H - 2 - gy), 0); }
+// x / 3 correctly rounded (checked against IEEE division for every float in [0, 8]): the per-pixel channel mean.
+__device__ __forceinline__ float third(float x) {
+    const float r = 1.0f / 3.0f;
+    const float q = __fmul_rn(x, r);
+    return __fmaf_rn(__fmaf_rn(-3.0f, q, x), r, q);
+}
+
+template <int NV>
+struct FwdSums {
+    float sy[3], syy[3], sx[NV][3], sxx[NV][3], sxy[NV][3];
+};
+template <int NV>
+struct FwdRow {
+    FwdSums<NV> s;
+    float yc[3], xc[NV][3];
+};
+
+template <int NV>
+__global__ void __launch_bounds__(kSsimThreads, 2)
+ssim_fwd_stream_kernel(const float* __restrict__ image, const float* __restrict__ warped, const __grid_constant__ PhotoPtrs pp,
+                       int n_preds, const float* __restrict__ automask_in, drosfm_photo_opts_t opts, float l1_w,
+                       uint8_t* __restrict__ sel_out, float* __restrict__ loss, Slot* ws, int B, int H, int W, int nstrips,
+                       int nbands) {
+    __shared__ double red[kSsimWarps];
+    __shared__ int flag;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int wg = blockIdx.x * kSsimWarps + wib;
+    const bool active = wg < nstrips * nbands;
+    const int strip = active ? wg % nstrips : 0, band = active ? wg / nstrips : 0;
+    const int b = static_cast<int>(blockIdx.y) % B, ip = static_cast<int>(blockIdx.y) / B;
+    const int P = H * W;
+    const int gx = strip * kFwdStripW - 1 + lane, gy0 = band * kFwdBandH;
+    const bool col_in = gx >= 0 && gx < W;
+    const bool out_lane = active && lane >= 1 && lane <= kFwdStripW && gx < W;
+    const Lanes nb = neighbour_lanes(lane, gx == 0, gx == W - 1);
+    const int gxc = clampi(gx, 0, W - 1);
+    const bool use_min = opts.reduce_op == DROSFM_REDUCE_MIN;
+    // one base pointer per tensor (already at this lane's column); planes and rows are 32-bit offsets from it
+    const float* __restrict__ ybase = image + static_cast<size_t>(b) * 3 * P + gxc;
+    const float* __restrict__ xbase = warped + (static_cast<size_t>(ip) * NV * B + b) * 3 * P + gxc;
+    const unsigned vstride = static_cast<unsigned>(B) * 3u * static_cast<unsigned>(P);            // < 2^31 (checked by the host)
+
+    float ry[3], rx[NV][3];          // the next row's values, loaded one step ahead
+    auto fetch = [&](int gy) {
+        const unsigned off = static_cast<unsigned>(padded_row(gy, H) * W);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            ry[c] = col_in ? __ldg(ybase + (off + c * P)) : 0.0f;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) rx[v][c] = col_in ? __ldg(xbase + (off + c * P + v * vstride)) : 0.0f;
+        }
+    };
+    float local = 0.0f;
+    FwdSums<NV> s12;
+    FwdRow<NV> ra, rb;
+    auto step = [&](FwdRow<NV>& prev, FwdRow<NV>& cur, int j) {
+        const int gy = gy0 - 1 + j;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            cur.yc[c] = ry[c];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) cur.xc[v][c] = rx[v][c];
+        }
+        fetch(gy + 1);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float yl, yr;
+            neighbours(cur.yc[c], nb, yl, yr);
+            const float y1 = cur.yc[c];
+            cur.s.sy[c] = yl + y1 + yr;
+            cur.s.syy[c] = yl * yl + y1 * y1 + yr * yr;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                float xl, xr;
+                neighbours(cur.xc[v][c], nb, xl, xr);
+                const float x1 = cur.xc[v][c];
+                cur.s.sx[v][c] = xl + x1 + xr;
+                cur.s.sxx[v][c] = xl * xl + x1 * x1 + xr * xr;
+                cur.s.sxy[v][c] = xl * yl + x1 * y1 + xr * yr;
+            }
+        }
+        if (j >= 2) {
+            // window centred on row gy - 1 = rows (gy-2, gy-1) + gy
+            float best = use_min ? __int_as_float(0x7f800000) : 0.0f;
+            int sel = 254;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                float ssim_acc = 0.0f, l1_acc = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    Win w;
+                    w.sx = s12.sx[v][c] + cur.s.sx[v][c];
+                    w.sy = s12.sy[c] + cur.s.sy[c];
+                    w.sxx = s12.sxx[v][c] + cur.s.sxx[v][c];
+                    w.syy = s12.syy[c] + cur.s.syy[c];
+                    w.sxy = s12.sxy[v][c] + cur.s.sxy[v][c];
+                    const Ssim sm = ssim_from(w, opts.C1, opts.C2);
+                    const float l = (1.0f - sm.s) * 0.5f;
+                    ssim_acc += fminf(fmaxf(l, 0.0f), 1.0f);
+                    l1_acc += fabsf(prev.xc[v][c] - prev.yc[c]);
+                }
+                const float pm = __fadd_rn(__fmul_rn(opts.ssim_w, third(ssim_acc)), __fmul_rn(l1_w, third(l1_acc)));
+                if (use_min) {
+                    if (pm < best) { best = pm; sel = v; }
+                } else {
+                    best += pm;
+                }
+            }
+            const int gyo = gy - 1;
+            if (out_lane && gyo < gy0 + kFwdBandH && gyo < H) {
+                const size_t o = static_cast<size_t>(b) * P + gyo * W + gx;
+                if (automask_in != nullptr) {
+                    const float a = __ldg(automask_in + o);
+                    if (a < best) { best = a; sel = 255; }
+                }
+                if (sel_out != nullptr) sel_out[static_cast<size_t>(ip) * B * P + o] = static_cast<uint8_t>(sel);
+                local += best;
+            }
+        }
+        // (prev + cur) is the first half of the next window
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            s12.sy[c] = prev.s.sy[c] + cur.s.sy[c];
+            s12.syy[c] = prev.s.syy[c] + cur.s.syy[c];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                s12.sx[v][c] = prev.s.sx[v][c] + cur.s.sx[v][c];
+                s12.sxx[v][c] = prev.s.sxx[v][c] + cur.s.sxx[v][c];
+                s12.sxy[v][c] = prev.s.sxy[v][c] + cur.s.sxy[v][c];
+            }
+        }
+    };
+    static_assert((kFwdBandH + 2) % 2 == 0, "the row loop is unrolled by two");
+    if (active) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            rb.s.sy[c] = rb.s.syy[c] = 0.0f;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) rb.s.sx[v][c] = rb.s.sxx[v][c] = rb.s.sxy[v][c] = 0.0f;
+        }
+        fetch(gy0 - 1);
+#pragma unroll 1
+        for (int j = 0; j < kFwdBandH + 2; j += 2) {
+            step(rb, ra, j);
+            step(ra, rb, j + 1);
+        }
+    }
+
+    // reduction of the loss, as in the tile kernel
+    double part = warp_sum(static_cast<double>(local));
+    if (lane == 0) red[wib] = part;
+    __syncthreads();
+    if (tid == 0) {
+        double sacc = 0.0;
+        for (int k = 0; k < kSsimWarps; ++k) sacc += red[k];
+        atomicAdd(spread_acc(slot_at(ws, ip)), sacc);
+    }
+    Slot* ticket = slot_at(ws, n_preds);
+    if (last_block(ticket, gridDim.x * gridDim.y, &flag) && tid == 0) {
+        double total = 0.0;
+        const double denom = static_cast<double>(B) * P * (use_min ? 1.0 : static_cast<double>(NV));
+        for (int i = 0; i < n_preds; ++i) {
+            const double mean_i = take_acc(slot_at(ws, i), 0) / denom;
+            total += static_cast<double>(pp.weight[i]) * static_cast<double>(static_cast<float>(mean_i));
+        }
+        ticket->ticket = 0ull;
+        *loss = static_cast<float>(total);
+    }
+}
+
+struct BwdRow {
+    float sy, syy, sx, sxx, sxy;     // horizontal 3-sums of this row
+    float x, y;                      // its centre values
+    float ha, hb, hc;                // horizontal (multiplicity-weighted) 3-sums of the coefficients of the windows centred on it
+};
+
+// One warp: one strip x band of ONE colour channel of one (prediction, view, sample).  Writes d loss / d warped.
+__global__ void __launch_bounds__(kSsimThreads, 4)
+ssim_bwd_stream_kernel(const float* __restrict__ g_loss, const float* __restrict__ image, const float* __restrict__ warped,
+                       const __grid_constant__ PhotoPtrs pp, int V, const uint8_t* __restrict__ sel_in,
+                       drosfm_photo_opts_t opts, float l1_w, float* __restrict__ g_warped, int B, int H, int W, int nstrips,
+                       int nbands) {
+    const int lane = threadIdx.x & 31;
+    const int wg = blockIdx.x * kSsimWarps + (threadIdx.x >> 5);
+    if (wg >= nstrips * nbands) return;
+    const int strip = wg % nstrips, band = wg / nstrips;
+    const int c = static_cast<int>(blockIdx.y) % 3, slot = static_cast<int>(blockIdx.y) / 3;      // slot = (ip * V + v) * B + b
+    const int b = slot % B, v = (slot / B) % V, ip = slot / (B * V);
+    const int P = H * W;
+    const int gx = strip * kBwdStripW - 2 + lane, gy0 = band * kBwdBandH;
+    const bool col_in = gx >= 0 && gx < W;
+    const bool out_lane = lane >= 2 && lane <= kBwdStripW + 1 && gx < W;
+    const Lanes nb = neighbour_lanes(lane, gx == 0, gx == W - 1);
+    const int gxc = clampi(gx, 0, W - 1);
+    const bool use_min = opts.reduce_op == DROSFM_REDUCE_MIN;
+    const float G = __ldg(g_loss) * pp.weight[ip] /
+                    (static_cast<float>(B) * static_cast<float>(P) * (use_min ? 1.0f : static_cast<float>(V)));
+    const float kp = G * opts.ssim_w * (-1.0f / 6.0f) * (2.0f / 9.0f);   // d loss / d ssim  x  2/9 of the window derivative
+    const float kl1 = G * l1_w * (1.0f / 3.0f);
+    const float* __restrict__ ypl = image + (static_cast<size_t>(b) * 3 + c) * P + gxc;
+    const float* __restrict__ xpl = warped + (static_cast<size_t>(slot) * 3 + c) * P + gxc;
+    float* __restrict__ gpl = g_warped + (static_cast<size_t>(slot) * 3 + c) * P + gxc;
+    const uint8_t* __restrict__ spl = sel_in + (static_cast<size_t>(ip) * B + b) * P + gxc;
+    // how often column gx occurs in the (reflected) window centred on gx-1 / gx / gx+1
+    const float wx0 = gx <= 0 ? 0.0f : (gx == 1 ? 2.0f : 1.0f);
+    const float wx2 = gx >= W - 1 ? 0.0f : (gx == W - 2 ? 2.0f : 1.0f);
+
+    float nx, ny;
+    auto fetch = [&](int gy) {
+        const unsigned off = static_cast<unsigned>(padded_row(gy, H) * W);
+        nx = col_in ? __ldg(xpl + off) : 0.0f;
+        ny = col_in ? __ldg(ypl + off) : 0.0f;
+    };
+    int sv_prev = 254;
+    auto step = [&](BwdRow& p2, BwdRow& p1, BwdRow& cur, int j) {
+        const int gy = gy0 - 2 + j;          // row loaded in this step; windows centred on gy-1; gradients of row gy-2
+        const int gc = gy - 1;
+        cur.x = nx;
+        cur.y = ny;
+        fetch(gy + 1);
+        int sv = 254;
+        if (j >= 2 && col_in && gc >= 0 && gc < H) sv = use_min ? static_cast<int>(__ldg(spl + static_cast<unsigned>(gc * W))) : 253;
+        float xl, xr, yl, yr;
+        neighbours(cur.x, nb, xl, xr);
+        neighbours(cur.y, nb, yl, yr);
+        cur.sx = xl + cur.x + xr;
+        cur.sy = yl + cur.y + yr;
+        cur.sxx = xl * xl + cur.x * cur.x + xr * xr;
+        cur.syy = yl * yl + cur.y * cur.y + yr * yr;
+        cur.sxy = xl * yl + cur.x * cur.y + xr * yr;
+        if (j >= 2) {
+            float a = 0.0f, bb = 0.0f, cq = 0.0f;
+            if (sv == v || sv == 253) {
+                Win w;
+                w.sx = p2.sx + p1.sx + cur.sx;
+                w.sy = p2.sy + p1.sy + cur.sy;
+                w.sxx = p2.sxx + p1.sxx + cur.sxx;
+                w.syy = p2.syy + p1.syy + cur.syy;
+                w.sxy = p2.sxy + p1.sxy + cur.sxy;
+                const Ssim sm = ssim_from(w, opts.C1, opts.C2);
+                const float l = (1.0f - sm.s) * 0.5f;
+                if (l >= 0.0f && l <= 1.0f) {
+                    const float q = __fdividef(kp, sm.B1 * sm.B2);
+                    a = q * (sm.mu_y * (sm.A2 - sm.A1) - sm.s * sm.mu_x * (sm.B2 - sm.B1));
+                    bb = -q * sm.s * sm.B1;
+                    cq = q * sm.A1;
+                }
+            }
+            const float al = __shfl_up_sync(0xffffffffu, a, 1), ar = __shfl_down_sync(0xffffffffu, a, 1);
+            const float bl = __shfl_up_sync(0xffffffffu, bb, 1), br = __shfl_down_sync(0xffffffffu, bb, 1);
+            const float cl = __shfl_up_sync(0xffffffffu, cq, 1), cr = __shfl_down_sync(0xffffffffu, cq, 1);
+            p1.ha = wx0 * al + a + wx2 * ar;
+            p1.hb = wx0 * bl + bb + wx2 * br;
+            p1.hc = wx0 * cl + cq + wx2 * cr;
+        }
+        if (j >= 4) {
+            const int gq = gy - 2;
+            if (out_lane && gq < gy0 + kBwdBandH && gq < H) {
+                // vertical multiplicities of row gq in the windows centred on gq-1 / gq / gq+1
+                const float wy0 = gq <= 0 ? 0.0f : (gq == 1 ? 2.0f : 1.0f);
+                const float wy2 = gq >= H - 1 ? 0.0f : (gq == H - 2 ? 2.0f : 1.0f);
+                const float ga = wy0 * cur.ha + p2.ha + wy2 * p1.ha;
+                const float gb = wy0 * cur.hb + p2.hb + wy2 * p1.hb;
+                const float gc_ = wy0 * cur.hc + p2.hc + wy2 * p1.hc;
+                float gxv = ga + gb * p2.x + gc_ * p2.y;
+                if (sv_prev == v || sv_prev == 253) {
+                    const float df = p2.x - p2.y;
+                    // sign(df) * kl1: kl1 with its sign flipped where df is negative
+                    gxv += df == 0.0f ? 0.0f : __int_as_float(__float_as_int(kl1) ^ (__float_as_int(df) & 0x80000000));
+                }
+                gpl[static_cast<unsigned>(gq * W)] = gxv;
+            }
+        }
+        sv_prev = sv;
+    };
+    static_assert((kBwdBandH + 4) % 3 == 0, "the row loop is unrolled by three");
+    BwdRow r0, r1, r2;
+    r0.ha = r0.hb = r0.hc = r1.ha = r1.hb = r1.hc = r2.ha = r2.hb = r2.hc = 0.0f;
+    r0.sx = r0.sy = r0.sxx = r0.syy = r0.sxy = r1.sx = r1.sy = r1.sxx = r1.syy = r1.sxy = 0.0f;
+    r0.x = r0.y = r1.x = r1.y = 0.0f;
+    fetch(gy0 - 2);
+#pragma unroll 1
+    for (int j = 0; j < kBwdBandH + 4; j += 3) {
+        step(r1, r2, r0, j);
+        step(r2, r0, r1, j + 1);
+        step(r0, r1, r2, j + 2);
+    }
+}
+
 static int check_photo(const float* image, const float* const* context, int n_views, const drosfm_photo_opts_t* opts,
                        int B, int H, int W) {
     DROSFM_REQUIRE(B >= 0 && H >= 0 && W >= 0, DROSFM_EINVAL, "photometric: negative dimension");
@@ -928,9 +1245,22 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
         dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds * n_views);
         warp_sources_kernel<<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, opts->padding, warped_save, B, H, W);
         if (int e = launch_status("photometric_fwd (warp_sources)")) return e;
-        photometric_fwd_kernel<0, true><<<grid, kFwdThreads, kFwdSmemBytes, cs>>>(
-            image, pp, n_views, depth_kind, n_preds, *cams, opts->automask ? automask : nullptr, *opts, l1_weight(opts), sel,
-            nullptr, loss, static_cast<Slot*>(ws), warped_save, B, H, W);
+        if (n_views <= 2 && static_cast<long long>(n_views) * B * 3 * H * W < (1ll << 31)) {
+            const int nstrips = (W + kFwdStripW - 1) / kFwdStripW, nbands = (H + kFwdBandH - 1) / kFwdBandH;
+            dim3 sgrid((nstrips * nbands + kSsimWarps - 1) / kSsimWarps, B * n_preds);
+            if (n_views == 1)
+                ssim_fwd_stream_kernel<1><<<sgrid, kSsimThreads, 0, cs>>>(image, warped_save, pp, n_preds, opts->automask ? automask : nullptr,
+                                                                          *opts, l1_weight(opts), sel, loss, static_cast<Slot*>(ws), B, H,
+                                                                          W, nstrips, nbands);
+            else
+                ssim_fwd_stream_kernel<2><<<sgrid, kSsimThreads, 0, cs>>>(image, warped_save, pp, n_preds, opts->automask ? automask : nullptr,
+                                                                          *opts, l1_weight(opts), sel, loss, static_cast<Slot*>(ws), B, H,
+                                                                          W, nstrips, nbands);
+        } else {
+            photometric_fwd_kernel<0, true><<<grid, kFwdThreads, kFwdSmemBytes, cs>>>(
+                image, pp, n_views, depth_kind, n_preds, *cams, opts->automask ? automask : nullptr, *opts, l1_weight(opts), sel,
+                nullptr, loss, static_cast<Slot*>(ws), warped_save, B, H, W);
+        }
     } else {
         photometric_fwd_kernel<0, false><<<grid, kFwdThreads, kFwdSmemBytes, cs>>>(
             image, pp, n_views, depth_kind, n_preds, *cams, opts->automask ? automask : nullptr, *opts, l1_weight(opts), sel,
@@ -968,9 +1298,12 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
     if (int e = allow_big_smem()) return e;
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
     if (warped_save != nullptr) {
-        photometric_bwd_kernel<true><<<grid, kBwdThreads, kBwdSavedSmemBytes, cs>>>(
-            g_loss, image, pp, n_views, depth_kind, n_preds, *cams, sel, *opts, l1_weight(opts), pg, static_cast<Slot*>(ws),
-            warped_save, g_warped, B, H, W);
+        DROSFM_REQUIRE(static_cast<long long>(B) * n_preds * n_views * 3 <= 65535, DROSFM_ERANGE,
+                       "photometric_bwd: B * n_preds * n_views too large");
+        const int nstrips = (W + kBwdStripW - 1) / kBwdStripW, nbands = (H + kBwdBandH - 1) / kBwdBandH;
+        dim3 sgrid((nstrips * nbands + kSsimWarps - 1) / kSsimWarps, B * n_preds * n_views * 3);
+        ssim_bwd_stream_kernel<<<sgrid, kSsimThreads, 0, cs>>>(g_loss, image, warped_save, pp, n_views, sel, *opts, l1_weight(opts),
+                                                               g_warped, B, H, W, nstrips, nbands);
         if (int e = launch_status("photometric_bwd (window gradients)")) return e;
         dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds);
         warp_sources_adjoint_kernel<<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, opts->padding, g_warped,

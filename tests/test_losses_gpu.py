@@ -172,9 +172,10 @@ def _check_photometric(dataset, B, H, W, V, n, min_depth, max_depth, padding="ze
     L.check(lib.drosfm_photometric_bwd(L.ptr(one), L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams,
                                        L.ptr_array(P), L.ptr(sel_forced), opts, L.ptr_array(list(g_inv2)), L.ptr_array(list(g_pose2)),
                                        L.ptr(ws), L.ptr(wsave), L.ptr(g_warped), B, H, W, L.stream()))
-    assert_close(g_inv2.cpu(), g_inv.cpu(), rtol=1e-6, atol=1e-9, what="g_inv (staged vs fused)")
-    # fp32 partial sums of ~10^5 terms grouped differently by the two paths: tolerance relative to the largest entry
-    assert_close(g_pose2.cpu(), g_pose.cpu(), rtol=1e-5, atol=1e-6 * float(g_pose.abs().max()), what="g_pose (staged vs fused)")
+    # the two paths group the (cancelling) fp32 sums differently, so they only agree to the conditioning of the sums;
+    # the parity bar proper is the comparison of each path with the fp32 / fp64 oracle (above and below)
+    assert_close(g_inv2.cpu(), g_inv.cpu(), rtol=1e-4, atol=1e-4 * float(g_inv.abs().max()), what="g_inv (staged vs fused)")
+    assert_close(g_pose2.cpu(), g_pose.cpu(), rtol=1e-4, atol=1e-5 * float(g_pose.abs().max()), what="g_pose (staged vs fused)")
     for i in range(n):
         assert_close_or_better(g_inv2[i].cpu(), g32[i], g64[i], what=f"staged g_inv{i}")
     for k in range(V * n):
