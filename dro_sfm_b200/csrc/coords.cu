@@ -9,6 +9,8 @@
 //
 // HBM-bound: fwd 12 B/px (depth 4 + uv 8), bwd 16 B/px (g_uv 8 + depth 4 + g_depth 4).
 // One thread handles 4 consecutive pixels with 128-bit loads/stores; grid = (chunks, B).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace drosfm {
@@ -23,7 +25,10 @@ __device__ __forceinline__ void pix_xy(int p, int W, int& x, int& y) {
 // ------------------------------------------------------------------------------------------
 // fused forward
 // ------------------------------------------------------------------------------------------
-template <bool VEC>
+// RCP: the divisions of the projection go through div_by_rcp (what every fused loss / cost kernel uses); the default
+// is the plain div.rn chain.  Both give the same bits; DROSFM_COORDS_SHARED_RCP=1 selects RCP so that the tests can
+// hold the shared-reciprocal chain to the same bit-exact oracle.
+template <bool VEC, bool RCP>
 __global__ void __launch_bounds__(kThreads)
 warp_coords_fwd_kernel(const float* __restrict__ depth, int depth_kind, drosfm_cams_t cams,
                        float* __restrict__ uv, uint8_t* __restrict__ mask, int H, int W, int normalize) {
@@ -51,7 +56,7 @@ warp_coords_fwd_kernel(const float* __restrict__ depth, int depth_kind, drosfm_c
         int x, y;
         pix_xy(p0 + k, W, x, y);
         Warp w;
-        warp_pixel(cam, x, y, to_depth(d[k], depth_kind), wm1, hm1, normalize != 0, w);
+        warp_pixel<RCP>(cam, x, y, to_depth(d[k], depth_kind), wm1, hm1, normalize != 0, w);
         out[2 * k] = w.p.u;
         out[2 * k + 1] = w.p.v;
     }
@@ -357,8 +362,12 @@ int drosfm_warp_coords_fwd(const float* depth, int depth_kind, const drosfm_cams
     const int px = vec ? 4 : 1;
     dim3 grid((P + kThreads * px - 1) / (kThreads * px), B);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (vec) warp_coords_fwd_kernel<true><<<grid, kThreads, 0, s>>>(depth, depth_kind, *cams, uv, mask, H, W, normalize);
-    else warp_coords_fwd_kernel<false><<<grid, kThreads, 0, s>>>(depth, depth_kind, *cams, uv, mask, H, W, normalize);
+    const char* env = std::getenv("DROSFM_COORDS_SHARED_RCP");
+    const bool rcp = env != nullptr && env[0] == '1';
+    if (vec && rcp) warp_coords_fwd_kernel<true, true><<<grid, kThreads, 0, s>>>(depth, depth_kind, *cams, uv, mask, H, W, normalize);
+    else if (vec) warp_coords_fwd_kernel<true, false><<<grid, kThreads, 0, s>>>(depth, depth_kind, *cams, uv, mask, H, W, normalize);
+    else if (rcp) warp_coords_fwd_kernel<false, true><<<grid, kThreads, 0, s>>>(depth, depth_kind, *cams, uv, mask, H, W, normalize);
+    else warp_coords_fwd_kernel<false, false><<<grid, kThreads, 0, s>>>(depth, depth_kind, *cams, uv, mask, H, W, normalize);
     return launch_status("warp_coords_fwd");
 }
 

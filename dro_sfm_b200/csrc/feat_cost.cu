@@ -108,7 +108,7 @@ feat_cost_fwd_nchw(const float* __restrict__ fmap, ViewPtrs vp, const float* __r
     for (int v = 0; v < VT; ++v) {
         if (v < V) {
             Warp wp;
-            warp_pixel(cam[v], x, y, d, wm1, hm1, true, wp);
+            warp_pixel<true>(cam[v], x, y, d, wm1, hm1, true, wp);
             CTaps t;
             make_ctaps(wp.p.u, wp.p.v, h, w, t);
             const float* r = vp.ref[v] + (static_cast<size_t>(b) * C + c0) * P + t.o00;
@@ -207,7 +207,7 @@ feat_cost_bwd_nchw(const float* __restrict__ g_cost, const float* __restrict__ f
             t.o00 = t.dx = t.dy = 0; t.w00 = t.w01 = t.w10 = t.w11 = 0.0f; t.ax = t.ay = 0.0f; t.valid = 0u; t.x0 = t.y0 = 0;
             Warp wp;
             if (active) {
-                warp_pixel(cam[v], x, y, d, wm1, hm1, true, wp);
+                warp_pixel<true>(cam[v], x, y, d, wm1, hm1, true, wp);
                 make_ctaps(wp.p.u, wp.p.v, h, w, t);
             }
             const float* r = vp.ref[v] + (static_cast<size_t>(b) * C + c0) * P + t.o00;
@@ -340,7 +340,7 @@ feat_cost_fwd_nhwc(const float* __restrict__ fmap, ViewPtrs vp, const float* __r
         for (int v = 0; v < VT; ++v) {
             if (v < V) {
                 Warp wp;
-                warp_pixel(cam[v], x, y, d, wm1, hm1, true, wp);
+                warp_pixel<true>(cam[v], x, y, d, wm1, hm1, true, wp);
                 CTaps t;
                 make_ctaps(wp.p.u, wp.p.v, h, w, t);
                 store_stap(wt + lane * V + v, t);
@@ -431,7 +431,7 @@ feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ f
         for (int v = 0; v < VT; ++v) {
             if (v < V) {
                 Warp wp;
-                warp_pixel(cam[v], x, y, d, wm1, hm1, true, wp);
+                warp_pixel<true>(cam[v], x, y, d, wm1, hm1, true, wp);
                 CTaps t;
                 make_ctaps(wp.p.u, wp.p.v, h, w, t);
                 store_stap(wt + lane * V + v, t);
@@ -528,7 +528,7 @@ feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ f
             if (mine && tvalid[v]) {
                 const float2 gxyv = wg[lane * V + v];
                 Warp wp;
-                warp_pixel(cam[v], x, y, d, wm1, hm1, true, wp);
+                warp_pixel<true>(cam[v], x, y, d, wm1, hm1, true, wp);
                 const float mx = 0.5f * static_cast<float>(w - 1), my = 0.5f * static_cast<float>(h - 1);
                 gd += warp_pixel_adjoint(cam[v], wp, d, wm1, hm1, true, gxyv.x * mx, gxyv.y * my, gT);
             }

@@ -170,7 +170,7 @@ view_synthesis_fwd_kernel(const float* __restrict__ src, const float* __restrict
         int x, y;
         pix_xy(p0 + k, W, x, y);
         Warp wp;
-        warp_pixel(cam, x, y, to_depth(d[k], depth_kind), wm1, hm1, true, wp);
+        warp_pixel<true>(cam, x, y, to_depth(d[k], depth_kind), wm1, hm1, true, wp);
         make_taps(wp.p.u, wp.p.v, Hs, Ws, padding, t[k]);
         w[k] = tap_weights(t[k]);
     }
@@ -217,7 +217,7 @@ view_synthesis_bwd_kernel(const float* __restrict__ g_out, const float* __restri
             int x, y;
             pix_xy(p, W, x, y);
             dv = __ldg(depth + static_cast<size_t>(b) * P + p);
-            warp_pixel(cam, x, y, to_depth(dv, depth_kind), wm1, hm1, true, wp);
+            warp_pixel<true>(cam, x, y, to_depth(dv, depth_kind), wm1, hm1, true, wp);
             make_taps(wp.p.u, wp.p.v, Hs, Ws, padding, t);
         }
         const Weights w = tap_weights(t);

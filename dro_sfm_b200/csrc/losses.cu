@@ -226,8 +226,8 @@ reproj_kernel(const float* __restrict__ g_loss, const float* __restrict__ depth,
                 const float d = to_depth(__ldg(depth + static_cast<size_t>(b) * P + p), depth_kind);
                 if (!(d > min_depth && d < dmax)) continue;
                 Warp wg, wp;
-                warp_pixel(cgt, x, y, d, wm1, hm1, true, wg);
-                warp_pixel(cpr, x, y, d, wm1, hm1, true, wp);
+                warp_pixel<true>(cgt, x, y, d, wm1, hm1, true, wg);
+                warp_pixel<true>(cpr, x, y, d, wm1, hm1, true, wp);
                 const bool vu = wg.p.u >= -1.0f && wg.p.u <= 1.0f && wp.p.u >= -1.0f && wp.p.u <= 1.0f;
                 const bool vv = wg.p.v >= -1.0f && wg.p.v <= 1.0f && wp.p.v >= -1.0f && wp.p.v <= 1.0f;
                 const float du = wp.p.u - wg.p.u, dv = wp.p.v - wg.p.v;

@@ -147,7 +147,7 @@ __device__ __forceinline__ void fill_source_tile(float* __restrict__ xs, const f
             w00[k] = w01[k] = w10[k] = w11[k] = 0.0f;
             if (WARP && in[k]) {
                 Warp wp;
-                warp_pixel(cam, sxs[k], sys[k], to_depth(d[k], depth_kind), wm1, hm1, true, wp);
+                warp_pixel<true>(cam, sxs[k], sys[k], to_depth(d[k], depth_kind), wm1, hm1, true, wp);
                 Taps t;
                 make_taps(wp.p.u, wp.p.v, H, W, padding, t);
                 if (t.valid) {
@@ -563,7 +563,7 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
             if (col_ok && r >= 1 && r <= IH && qy < H) {
                 const float d = to_depth(__ldg(invd + qy * W + pgx), depth_kind);
                 Warp wp;
-                warp_pixel(cam, pgx, qy, d, wm1, hm1, true, wp);
+                warp_pixel<true>(cam, pgx, qy, d, wm1, hm1, true, wp);
                 Taps t;
                 make_taps(wp.p.u, wp.p.v, H, W, opts.padding, t);
                 if (t.valid) {
@@ -673,7 +673,7 @@ warp_sources_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind,
             tp[k] = FlatTap{0, 0, 0, 0.0f, 0.0f, 0.0f, 0.0f};
             if (in[k]) {
                 Warp wp;
-                warp_pixel(cam, x, y, to_depth(d[k], depth_kind), wm1, hm1, true, wp);
+                warp_pixel<true>(cam, x, y, to_depth(d[k], depth_kind), wm1, hm1, true, wp);
                 Taps t;
                 make_taps(wp.p.u, wp.p.v, H, W, padding, t);
                 if (t.valid) {
@@ -760,7 +760,7 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
                 if (g[0] != 0.0f || g[1] != 0.0f || g[2] != 0.0f) {
                     const float d = to_depth(dv[k], depth_kind);
                     Warp wp;
-                    warp_pixel(cam, x, y, d, wm1, hm1, true, wp);
+                    warp_pixel<true>(cam, x, y, d, wm1, hm1, true, wp);
                     Taps t;
                     make_taps(wp.p.u, wp.p.v, H, W, padding, t);
                     if (t.valid) {
