@@ -16,6 +16,7 @@
 //         128-bit access of a 512-byte contiguous segment, source gradients are red.global.add.v4.f32.
 // The backward pass scatters into the source gradients with atomics; neighbouring lanes that hit the
 // same source pixel are merged with shuffles first (NCHW), pose gradients are reduced in fp64.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace drosfm {
@@ -394,8 +395,10 @@ __device__ __forceinline__ void red_add4_nc(float* p, float a, float b, float c,
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d));
 }
 
+// 5 resident blocks per SM (<= 102 registers): the 40x120x2 maps of the KITTI configuration launch 600 blocks, which
+// must fit the 148 SMs in ONE wave -- at 4 blocks per SM the last 8 blocks ran alone and doubled the kernel time.
 template <int VT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
 feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ fmap, ViewPtrs vp,
                    const float* __restrict__ depth, int depth_kind, drosfm_cams_t cams, int V,
                    float* __restrict__ g_fmap, ViewGrads vg, float* __restrict__ g_depth, Slot* ws,
@@ -582,6 +585,7 @@ static int pixels_per_warp(int P, int B) {
     const long long pixels = static_cast<long long>(P) * (B > 0 ? B : 1);
     int ppw = kMaxPpw;
     while (ppw > 4 && pixels / ppw < static_cast<long long>(kNumSMs) * 32) ppw /= 2;
+    if (const char* e = std::getenv("DROSFM_PPW")) ppw = atoi(e);
     return ppw;
 }
 

@@ -656,60 +656,64 @@ warp_sources_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind,
     const float* __restrict__ src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
     float* __restrict__ out = warped + static_cast<size_t>(slot) * 3 * P;
     if (x >= W) return;
-#pragma unroll 1
-    for (int k0 = 0; k0 < kFlatRows; k0 += kFlatNB) {
-        float d[kFlatNB];
-        bool in[kFlatNB];
+    constexpr int kStride = kFlatThreads / 32;
+    // Software pipeline over the thread's rows: the depths are all requested up front; the twelve gathers of row k
+    // are in flight while the coordinate chain of row k+1 runs.
+    float d[kFlatRows];
 #pragma unroll
-        for (int k = 0; k < kFlatNB; ++k) {
-            const int y = y0 + (k0 + k) * (kFlatThreads / 32);
-            in[k] = y < H;
-            d[k] = in[k] ? __ldg(invd + y * W + x) : 0.0f;
-        }
-        FlatTap tp[kFlatNB];
-#pragma unroll
-        for (int k = 0; k < kFlatNB; ++k) {
-            const int y = y0 + (k0 + k) * (kFlatThreads / 32);
-            tp[k] = FlatTap{0, 0, 0, 0.0f, 0.0f, 0.0f, 0.0f};
-            if (in[k]) {
-                Warp wp;
-                warp_pixel<true>(cam, x, y, to_depth(d[k], depth_kind), wm1, hm1, true, wp);
-                Taps t;
-                make_taps(wp.p.u, wp.p.v, H, W, padding, t);
-                if (t.valid) {
-                    const float bx = 1.0f - t.ax, by = 1.0f - t.ay;
-                    tp[k].w00 = (t.valid & 1u) ? bx * by : 0.0f;
-                    tp[k].w01 = (t.valid & 2u) ? t.ax * by : 0.0f;
-                    tp[k].w10 = (t.valid & 4u) ? bx * t.ay : 0.0f;
-                    tp[k].w11 = (t.valid & 8u) ? t.ax * t.ay : 0.0f;
-                    const int xa = max(t.x0, 0), ya = max(t.y0, 0);
-                    tp[k].o00 = ya * W + xa;
-                    tp[k].dxo = min(t.x0 + 1, W - 1) - xa;
-                    tp[k].dyo = (min(t.y0 + 1, H - 1) - ya) * W;
-                }
+    for (int k = 0; k < kFlatRows; ++k) {
+        const int y = y0 + k * kStride;
+        d[k] = y < H ? __ldg(invd + y * W + x) : 0.0f;
+    }
+    auto taps_of = [&](int k) {
+        const int y = y0 + k * kStride;
+        FlatTap tp{0, 0, 0, 0.0f, 0.0f, 0.0f, 0.0f};
+        if (y < H) {
+            Warp wp;
+            warp_pixel<true>(cam, x, y, to_depth(d[k], depth_kind), wm1, hm1, true, wp);
+            Taps t;
+            make_taps(wp.p.u, wp.p.v, H, W, padding, t);
+            if (t.valid) {
+                const float bx = 1.0f - t.ax, by = 1.0f - t.ay;
+                tp.w00 = (t.valid & 1u) ? bx * by : 0.0f;
+                tp.w01 = (t.valid & 2u) ? t.ax * by : 0.0f;
+                tp.w10 = (t.valid & 4u) ? bx * t.ay : 0.0f;
+                tp.w11 = (t.valid & 8u) ? t.ax * t.ay : 0.0f;
+                const int xa = max(t.x0, 0), ya = max(t.y0, 0);
+                tp.o00 = ya * W + xa;
+                tp.dxo = min(t.x0 + 1, W - 1) - xa;
+                tp.dyo = (min(t.y0 + 1, H - 1) - ya) * W;
             }
         }
-        float val[kFlatNB][12];
+        return tp;
+    };
+    float val[12];
+    auto gather = [&](const FlatTap& tp) {
 #pragma unroll
-        for (int k = 0; k < kFlatNB; ++k) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float* r0 = src + c * P + tp[k].o00;
-                val[k][4 * c + 0] = __ldg(r0);
-                val[k][4 * c + 1] = __ldg(r0 + tp[k].dxo);
-                val[k][4 * c + 2] = __ldg(r0 + tp[k].dyo);
-                val[k][4 * c + 3] = __ldg(r0 + tp[k].dyo + tp[k].dxo);
-            }
+        for (int c = 0; c < 3; ++c) {
+            const float* r0 = src + (static_cast<unsigned>(c * P) + static_cast<unsigned>(tp.o00));
+            val[4 * c + 0] = __ldg(r0);
+            val[4 * c + 1] = __ldg(r0 + tp.dxo);
+            val[4 * c + 2] = __ldg(r0 + tp.dyo);
+            val[4 * c + 3] = __ldg(r0 + tp.dyo + tp.dxo);
         }
+    };
+    FlatTap cur = taps_of(0);
+    gather(cur);
 #pragma unroll
-        for (int k = 0; k < kFlatNB; ++k) {
-            const int y = y0 + (k0 + k) * (kFlatThreads / 32);
-            if (in[k]) {
+    for (int k = 0; k < kFlatRows; ++k) {
+        FlatTap nxt = cur;
+        if (k + 1 < kFlatRows) nxt = taps_of(k + 1);
+        const int y = y0 + k * kStride;
+        if (y < H) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    out[c * P + y * W + x] = val[k][4 * c] * tp[k].w00 + val[k][4 * c + 1] * tp[k].w01 +
-                                             val[k][4 * c + 2] * tp[k].w10 + val[k][4 * c + 3] * tp[k].w11;
-            }
+            for (int c = 0; c < 3; ++c)
+                out[static_cast<unsigned>(c * P + y * W + x)] = val[4 * c] * cur.w00 + val[4 * c + 1] * cur.w01 +
+                                                                  val[4 * c + 2] * cur.w10 + val[4 * c + 3] * cur.w11;
+        }
+        if (k + 1 < kFlatRows) {
+            cur = nxt;
+            gather(cur);
         }
     }
 }
@@ -742,7 +746,7 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
         }
 #pragma unroll 1
         for (int v = 0; v < V; ++v) {
-            const Cam cam = cam_s[v];
+            const Cam& cam = cam_s[v];            // read from shared memory on use: the registers go to occupancy
             const float* __restrict__ src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
             const float* __restrict__ gw = g_warped + ((static_cast<size_t>(ip) * V + v) * B + b) * 3 * P;
             float gT[12];

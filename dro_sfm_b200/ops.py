@@ -404,8 +404,11 @@ class _FeatCost(torch.autograd.Function):
             else:
                 g_fmap = ret_fmap = torch.empty_like(fmap)
         # one zero-filled slab for everything else the kernel accumulates into (a single memset)
+        # (the NHWC kernel writes every depth gradient itself; the NCHW one adds partial sums per channel group)
         plain = [v for v in range(V) if need[7 + v] and sinks[1 + v] is None]
-        slab = torch.zeros(len(plain) * fmap.numel() + (depth.numel() if need[0] else 0), device=fmap.device, dtype=torch.float32)
+        depth_in_slab = need[0] and layout != L.NHWC
+        slab = torch.zeros(len(plain) * fmap.numel() + (depth.numel() if depth_in_slab else 0), device=fmap.device,
+                           dtype=torch.float32)
         g_refs, ret_refs, off = [], [], 0
         for v in range(V):
             if not need[7 + v]:
@@ -421,7 +424,9 @@ class _FeatCost(torch.autograd.Function):
                 t = flat.view(B, h, w, C).permute(0, 3, 1, 2) if layout == L.NHWC else flat.view(B, C, h, w)
                 g_refs.append(t)
                 ret_refs.append(t)
-        g_depth = slab[off:off + depth.numel()].view_as(depth) if need[0] else None
+        g_depth = None
+        if need[0]:
+            g_depth = slab[off:off + depth.numel()].view_as(depth) if depth_in_slab else torch.empty_like(depth)
         g_poses = [torch.empty_like(poses[v]) if need[7 + V + v] else None for v in range(V)]
         with torch.cuda.device(fmap.device):
             ws = L.workspace(fmap.device, V * B) if any(p is not None for p in g_poses) else None
