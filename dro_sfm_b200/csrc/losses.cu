@@ -407,7 +407,7 @@ int drosfm_smoothness_fwd(const float* image, const float* const* inv_depths, in
     if (mb > 64) mb = 64;
     smooth_mean_kernel<<<dim3(mb, n_preds * B), kLossThreads, 0, s>>>(dl, stats, static_cast<Slot*>(ws), B, P);
     if (int e = launch_status("smoothness_fwd (mean)")) return e;
-    int fb = (P + kLossThreads * 2 - 1) / (kLossThreads * 2);     // two pixels per thread
+    int fb = (P + kLossThreads * 8 - 1) / (kLossThreads * 8);     // eight pixels per thread: the 2 n shuffle reductions + atomics of the epilogue are per thread
     if (fb < 1) fb = 1;
     smooth_fwd_kernel<<<dim3(fb, B), kLossThreads, 0, s>>>(image, dl, n_preds, weight, stats, loss,
                                                                            static_cast<Slot*>(ws), B, H, W);

@@ -329,7 +329,10 @@ class _ToChannelsLastSink(torch.autograd.Function):
         if buf is None:
             return g, None
         # g is the zero placeholder returned by the first sink-aware consumer plus whatever ordinary
-        # consumers of the converted tensor contributed
+        # consumers of the converted tensor contributed; the bare placeholder (stride-0 view of one zero) adds nothing
+        dummy = ctx.sink.dummy
+        if dummy is not None and g.data_ptr() == dummy.data_ptr() and all(st == 0 for st in g.stride()):
+            return buf, None
         return buf.add_(g), None
 
 
