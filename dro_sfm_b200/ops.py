@@ -316,11 +316,28 @@ class GradSink:
         self.consumed = False        # set once the backward pass went through: the copy belongs to a finished step
 
 
+def relayout(t, layout):
+    """The same logical [B,C,H,W] tensor in the other dense storage layout (L.NHWC = channels_last, L.NCHW):
+    drosfm_relayout when `t` is a dense fp32 CUDA tensor in the opposite layout, torch's strided copy otherwise."""
+    fmt = torch.channels_last if layout == L.NHWC else torch.contiguous_format
+    if t.is_contiguous(memory_format=fmt):
+        return t
+    other = torch.contiguous_format if layout == L.NHWC else torch.channels_last
+    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.is_contiguous(memory_format=other)):
+        return t.contiguous(memory_format=fmt)
+    B, C, H, W = t.shape
+    out = torch.empty((B, C, H, W), device=t.device, dtype=t.dtype, memory_format=fmt)
+    with torch.cuda.device(t.device):
+        L.check(L.lib().drosfm_relayout(L.ptr(t), L.ptr(out), B, C, H, W, layout, L.stream()), "relayout")
+    return out
+
+
 class _ToChannelsLastSink(torch.autograd.Function):
     @staticmethod
     def forward(ctx, t, sink):
         ctx.sink = sink
-        return t.contiguous(memory_format=torch.channels_last)
+        ctx.nchw_input = t.is_contiguous()
+        return relayout(t, L.NHWC)
 
     @staticmethod
     def backward(ctx, g):
@@ -331,9 +348,11 @@ class _ToChannelsLastSink(torch.autograd.Function):
         # g is the zero placeholder returned by the first sink-aware consumer plus whatever ordinary
         # consumers of the converted tensor contributed; the bare placeholder (stride-0 view of one zero) adds nothing
         dummy = ctx.sink.dummy
-        if dummy is not None and g.data_ptr() == dummy.data_ptr() and all(st == 0 for st in g.stride()):
-            return buf, None
-        return buf.add_(g), None
+        if not (dummy is not None and g.data_ptr() == dummy.data_ptr() and all(st == 0 for st in g.stride())):
+            buf = buf.add_(g)
+        # hand the gradient back in the layout of the input: AccumulateGrad / the producer's backward would
+        # otherwise re-layout it with a generic strided copy
+        return (relayout(buf, L.NCHW) if ctx.nchw_input else buf), None
 
 
 def to_channels_last_sink(t):

@@ -219,6 +219,11 @@ int drosfm_upsample_depth_fwd(const float* depth, const float* mask, float* out,
 int drosfm_upsample_depth_bwd(const float* g_out, const float* depth, const float* mask, float* g_depth, float* g_mask,
                               int N, int H, int W, int ratio, drosfm_stream_t stream);
 
+/* ---- feature-map storage layout (the encoder's maps are NCHW, DepthPoseNet.py:113-115) -----------
+ * Copies a [B,C,H,W] tensor from NCHW storage to NHWC storage (to_layout = DROSFM_NHWC) or back (DROSFM_NCHW);
+ * what `.contiguous(memory_format=torch.channels_last)` / `.contiguous()` do, as a coalesced tiled transpose. */
+int drosfm_relayout(const float* src, float* dst, int B, int C, int H, int W, int to_layout, drosfm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
