@@ -24,6 +24,7 @@ DEPTH, INV_DEPTH = 0, 1
 REDUCE_MIN, REDUCE_MEAN = 0, 1
 NCHW, NHWC = 0, 1
 ACCUMULATE_FMAP = 1
+PHOTO_WARPED_READY, PHOTO_NO_ADJOINT = 1, 2
 SLOT_BYTES = 128
 
 _vp = ctypes.c_void_p
@@ -71,9 +72,12 @@ SIGNATURES = {
                               _int, _int, _int, _int, _int, _int, _vp], _int),
     "drosfm_automask_fwd": ([_vp, _pp, _int, _op, _vp, _int, _int, _int, _vp], _int),
     "drosfm_photometric_fwd": ([_vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _vp, _vp, _vp, _vp,
-                                _int, _int, _int, _vp], _int),
+                                _int, _int, _int, _int, _vp], _int),
     "drosfm_photometric_bwd": ([_vp, _vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _pp, _pp, _vp, _vp, _vp,
-                                _int, _int, _int, _vp], _int),
+                                _int, _int, _int, _int, _vp], _int),
+    "drosfm_warp_sources_fwd": ([_pp, _int, _pp, _int, _int, _cp, _pp, _int, _vp, _int, _int, _int, _vp], _int),
+    "drosfm_warp_sources_bwd": ([_vp, _pp, _int, _pp, _int, _int, _cp, _pp, _int, _pp, _pp, _vp, _int,
+                                 _int, _int, _int, _vp], _int),
     "drosfm_smoothness_fwd": ([_vp, _pp, _int, _f32, _vp, _vp, _vp, _int, _int, _int, _vp], _int),
     "drosfm_smoothness_bwd": ([_vp, _vp, _pp, _int, _f32, _vp, _pp, _int, _int, _int, _int, _vp], _int),
     "drosfm_sup_depth_loss_fwd": ([_vp, _pp, _int, _f32, _f32, _f32, _vp, _vp, _int, _int, _int, _vp], _int),
@@ -227,6 +231,18 @@ def make_cams(K, Kref, sx=1.0, sy=None, Twc=None, pose=None, pose_kind=POSE_IDEN
 
 
 _workspaces = {}
+
+
+_side_streams = {}
+
+
+def side_stream(device):
+    """The library's second stream on `device` (independent parts of a loss run there, joined before returning)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _side_streams.get(idx)
+    if st is None:
+        st = _side_streams[idx] = torch.cuda.Stream(device)
+    return st
 
 
 def workspace(device, slots):

@@ -721,7 +721,7 @@ warp_sources_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind,
 __global__ void __launch_bounds__(kFlatThreads, 3)
 warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind, int n_preds, drosfm_cams_t cams,
                             int padding, const float* __restrict__ g_warped, const __grid_constant__ PhotoGrads pg, Slot* ws,
-                            int B, int H, int W) {
+                            int accumulate, int B, int H, int W) {
     __shared__ Cam cam_s[DROSFM_MAX_VIEWS];
     const int tid = threadIdx.x;
     const int b = static_cast<int>(blockIdx.z) % B, ip = static_cast<int>(blockIdx.z) / B;
@@ -796,7 +796,8 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
                 if (col_ok && y < H) {
                     float gg = gd[k];
                     if (depth_kind == DROSFM_INV_DEPTH) gg = inv2depth_grad(dv[k], gg);
-                    gout[static_cast<size_t>(b) * P + y * W + x] = gg;
+                    float* dst = gout + static_cast<size_t>(b) * P + y * W + x;
+                    *dst = accumulate ? *dst + gg : gg;
                 }
             }
         }
@@ -1228,9 +1229,11 @@ static int fill_ptrs(PhotoPtrs& pp, const float* const* context, int n_views, co
 int drosfm_photometric_fwd(const float* image, const float* const* context, int n_views, const float* const* inv_depths,
                            int depth_kind, int n_preds, const drosfm_cams_t* cams, const float* const* poses,
                            const float* automask, const drosfm_photo_opts_t* opts, uint8_t* sel, float* loss, void* ws,
-                           float* warped_save, int B, int H, int W, drosfm_stream_t stream) {
+                           float* warped_save, int flags, int B, int H, int W, drosfm_stream_t stream) {
     if (int e = check_photo(image, context, n_views, opts, B, H, W)) return e;
     DROSFM_REQUIRE(B > 0 && H * W > 0, DROSFM_EINVAL, "photometric_fwd: empty batch (the mean over zero pixels is undefined)");
+    DROSFM_REQUIRE(!(flags & DROSFM_PHOTO_WARPED_READY) || warped_save != nullptr, DROSFM_EINVAL,
+                   "photometric_fwd: DROSFM_PHOTO_WARPED_READY without a warped buffer");
     DROSFM_REQUIRE(cams && cams->K && cams->Kref, DROSFM_EINVAL, "photometric_fwd: NULL cams");
     DROSFM_REQUIRE(cams->pose_kind == DROSFM_POSE_MAT4 || cams->pose_kind == DROSFM_POSE_EULER6, DROSFM_EINVAL,
                    "photometric_fwd: pose_kind must be MAT4 or EULER6");
@@ -1246,9 +1249,12 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
     if (int e = allow_big_smem()) return e;
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
     if (warped_save != nullptr) {
-        dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds * n_views);
-        warp_sources_kernel<<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, opts->padding, warped_save, B, H, W);
-        if (int e = launch_status("photometric_fwd (warp_sources)")) return e;
+        if (!(flags & DROSFM_PHOTO_WARPED_READY)) {
+            dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds * n_views);
+            warp_sources_kernel<<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, opts->padding, warped_save, B, H,
+                                                               W);
+            if (int e = launch_status("photometric_fwd (warp_sources)")) return e;
+        }
         if (n_views <= 2 && static_cast<long long>(n_views) * B * 3 * H * W < (1ll << 31)) {
             const int nstrips = (W + kFwdStripW - 1) / kFwdStripW, nbands = (H + kFwdBandH - 1) / kFwdBandH;
             dim3 sgrid((nstrips * nbands + kSsimWarps - 1) / kSsimWarps, B * n_preds);
@@ -1277,9 +1283,11 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
                            const float* const* inv_depths, int depth_kind, int n_preds, const drosfm_cams_t* cams,
                            const float* const* poses, const uint8_t* sel, const drosfm_photo_opts_t* opts,
                            float* const* g_inv_depths, float* const* g_poses, void* ws, const float* warped_save,
-                           float* g_warped, int B, int H, int W, drosfm_stream_t stream) {
+                           float* g_warped, int flags, int B, int H, int W, drosfm_stream_t stream) {
     if (int e = check_photo(image, context, n_views, opts, B, H, W)) return e;
     if (B == 0 || H * W == 0) return DROSFM_OK;
+    DROSFM_REQUIRE(!(flags & DROSFM_PHOTO_NO_ADJOINT) || g_warped != nullptr, DROSFM_EINVAL,
+                   "photometric_bwd: DROSFM_PHOTO_NO_ADJOINT needs the staged path (warped_save / g_warped)");
     DROSFM_REQUIRE(cams && cams->K && cams->Kref, DROSFM_EINVAL, "photometric_bwd: NULL cams");
     DROSFM_REQUIRE(cams->pose_kind == DROSFM_POSE_MAT4 || cams->pose_kind == DROSFM_POSE_EULER6, DROSFM_EINVAL,
                    "photometric_bwd: pose_kind must be MAT4 or EULER6");
@@ -1308,16 +1316,72 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
         dim3 sgrid((nstrips * nbands + kSsimWarps - 1) / kSsimWarps, B * n_preds * n_views * 3);
         ssim_bwd_stream_kernel<<<sgrid, kSsimThreads, 0, cs>>>(g_loss, image, warped_save, pp, n_views, sel, *opts, l1_weight(opts),
                                                                g_warped, B, H, W, nstrips, nbands);
+        if (flags & DROSFM_PHOTO_NO_ADJOINT) return launch_status("photometric_bwd (window gradients)");
         if (int e = launch_status("photometric_bwd (window gradients)")) return e;
         dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds);
         warp_sources_adjoint_kernel<<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, opts->padding, g_warped,
-                                                                   pg, static_cast<Slot*>(ws), B, H, W);
+                                                                   pg, static_cast<Slot*>(ws), 0, B, H, W);
     } else {
         photometric_bwd_kernel<false><<<grid, kBwdThreads, kBwdSmemBytes, cs>>>(
             g_loss, image, pp, n_views, depth_kind, n_preds, *cams, sel, *opts, l1_weight(opts), pg, static_cast<Slot*>(ws),
             nullptr, nullptr, B, H, W);
     }
     return launch_status("photometric_bwd");
+}
+
+int drosfm_warp_sources_fwd(const float* const* context, int n_views, const float* const* inv_depths, int depth_kind,
+                            int n_preds, const drosfm_cams_t* cams, const float* const* poses, int padding, float* warped,
+                            int B, int H, int W, drosfm_stream_t stream) {
+    DROSFM_REQUIRE(B >= 0 && H >= 0 && W >= 0, DROSFM_EINVAL, "warp_sources_fwd: negative dimension");
+    DROSFM_REQUIRE(n_views >= 1 && n_views <= DROSFM_MAX_VIEWS, DROSFM_ERANGE, "warp_sources_fwd: n_views=%d outside [1,%d]",
+                   n_views, DROSFM_MAX_VIEWS);
+    DROSFM_REQUIRE(padding == DROSFM_PAD_ZEROS || padding == DROSFM_PAD_BORDER, DROSFM_EINVAL, "warp_sources_fwd: bad padding");
+    if (B == 0 || H * W == 0) return DROSFM_OK;
+    DROSFM_REQUIRE(context != nullptr && warped != nullptr, DROSFM_EINVAL, "warp_sources_fwd: NULL context/warped");
+    for (int v = 0; v < n_views; ++v) DROSFM_REQUIRE(context[v] != nullptr, DROSFM_EINVAL, "warp_sources_fwd: context[%d] is NULL", v);
+    DROSFM_REQUIRE(cams && cams->K && cams->Kref, DROSFM_EINVAL, "warp_sources_fwd: NULL cams");
+    DROSFM_REQUIRE(cams->pose_kind == DROSFM_POSE_MAT4 || cams->pose_kind == DROSFM_POSE_EULER6, DROSFM_EINVAL,
+                   "warp_sources_fwd: pose_kind must be MAT4 or EULER6");
+    DROSFM_REQUIRE(static_cast<long long>(H) * W < (1ll << 28), DROSFM_ERANGE, "warp_sources_fwd: dimension out of range");
+    PhotoPtrs pp{};
+    if (int e = fill_ptrs(pp, context, n_views, inv_depths, n_preds, poses, 1.0f)) return e;
+    DROSFM_REQUIRE(static_cast<long long>(B) * n_preds * n_views <= 65535, DROSFM_ERANGE, "warp_sources_fwd: B * n_preds * n_views too large");
+    dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds * n_views);
+    warp_sources_kernel<<<flat, kFlatThreads, 0, static_cast<cudaStream_t>(stream)>>>(pp, n_views, depth_kind, n_preds, *cams, padding,
+                                                                                      warped, B, H, W);
+    return launch_status("warp_sources_fwd");
+}
+
+int drosfm_warp_sources_bwd(const float* g_warped, const float* const* context, int n_views, const float* const* inv_depths,
+                            int depth_kind, int n_preds, const drosfm_cams_t* cams, const float* const* poses, int padding,
+                            float* const* g_inv_depths, float* const* g_poses, void* ws, int accumulate, int B, int H, int W,
+                            drosfm_stream_t stream) {
+    DROSFM_REQUIRE(B >= 0 && H >= 0 && W >= 0, DROSFM_EINVAL, "warp_sources_bwd: negative dimension");
+    DROSFM_REQUIRE(n_views >= 1 && n_views <= DROSFM_MAX_VIEWS, DROSFM_ERANGE, "warp_sources_bwd: n_views=%d outside [1,%d]",
+                   n_views, DROSFM_MAX_VIEWS);
+    DROSFM_REQUIRE(padding == DROSFM_PAD_ZEROS || padding == DROSFM_PAD_BORDER, DROSFM_EINVAL, "warp_sources_bwd: bad padding");
+    if (B == 0 || H * W == 0) return DROSFM_OK;
+    DROSFM_REQUIRE(context != nullptr && g_warped != nullptr, DROSFM_EINVAL, "warp_sources_bwd: NULL context/g_warped");
+    for (int v = 0; v < n_views; ++v) DROSFM_REQUIRE(context[v] != nullptr, DROSFM_EINVAL, "warp_sources_bwd: context[%d] is NULL", v);
+    DROSFM_REQUIRE(cams && cams->K && cams->Kref, DROSFM_EINVAL, "warp_sources_bwd: NULL cams");
+    DROSFM_REQUIRE(cams->pose_kind == DROSFM_POSE_MAT4 || cams->pose_kind == DROSFM_POSE_EULER6, DROSFM_EINVAL,
+                   "warp_sources_bwd: pose_kind must be MAT4 or EULER6");
+    DROSFM_REQUIRE(static_cast<long long>(H) * W < (1ll << 28), DROSFM_ERANGE, "warp_sources_bwd: dimension out of range");
+    PhotoPtrs pp{};
+    if (int e = fill_ptrs(pp, context, n_views, inv_depths, n_preds, poses, 1.0f)) return e;
+    PhotoGrads pg{};
+    bool want_pose = false;
+    for (int i = 0; i < n_preds; ++i) pg.g_inv_depth[i] = g_inv_depths ? g_inv_depths[i] : nullptr;
+    for (int k = 0; k < n_views * n_preds; ++k) {
+        pg.g_pose[k] = g_poses ? g_poses[k] : nullptr;
+        want_pose |= pg.g_pose[k] != nullptr;
+    }
+    DROSFM_REQUIRE(!want_pose || ws != nullptr, DROSFM_EINVAL, "warp_sources_bwd: pose gradients need ws");
+    DROSFM_REQUIRE(static_cast<long long>(B) * n_preds <= 65535, DROSFM_ERANGE, "warp_sources_bwd: B * n_preds too large");
+    dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds);
+    warp_sources_adjoint_kernel<<<flat, kFlatThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        pp, n_views, depth_kind, n_preds, *cams, padding, g_warped, pg, static_cast<Slot*>(ws), accumulate ? 1 : 0, B, H, W);
+    return launch_status("warp_sources_bwd");
 }
 
 }  // extern "C"

@@ -143,6 +143,10 @@ typedef struct {
     float gamma;         /* decay over predictions: weight_i = gamma^(n-1-i) (0.85) */
 } drosfm_photo_opts_t;
 
+/* flags of drosfm_photometric_fwd / _bwd (staged path only) */
+#define DROSFM_PHOTO_WARPED_READY 1 /* fwd: warped_save already holds drosfm_warp_sources_fwd's output */
+#define DROSFM_PHOTO_NO_ADJOINT 2   /* bwd: stop after g_warped; the caller runs drosfm_warp_sources_bwd itself */
+
 /* Un-warped (auto-mask) pass: automask[b,y,x] = min_v photometric(context_v, image), computed once
  * per step instead of once per prediction (lines 346-351 recompute it n times). */
 int drosfm_automask_fwd(const float* image, const float* const* context, int n_views,
@@ -160,7 +164,7 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
                            const float* const* inv_depths, int depth_kind, int n_preds,
                            const drosfm_cams_t* cams, const float* const* poses, const float* automask,
                            const drosfm_photo_opts_t* opts, uint8_t* sel, float* loss, void* ws,
-                           float* warped_save, int B, int H, int W, drosfm_stream_t stream);
+                           float* warped_save, int flags, int B, int H, int W, drosfm_stream_t stream);
 /* g_loss: 1 float on the device (upstream gradient).  g_inv_depths[i] [B,1,H,W] written;
  * g_poses[v*n_preds+i] written ([B,4,4] or [B,6]); ws of drosfm_ws_bytes(n_views*n_preds*B).
  * warped_save (the forward's) and g_warped (scratch of the same size, contents undefined on return) go together:
@@ -170,8 +174,22 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
                            const float* const* inv_depths, int depth_kind, int n_preds,
                            const drosfm_cams_t* cams, const float* const* poses, const uint8_t* sel,
                            const drosfm_photo_opts_t* opts, float* const* g_inv_depths, float* const* g_poses,
-                           void* ws, const float* warped_save, float* g_warped, int B, int H, int W,
+                           void* ws, const float* warped_save, float* g_warped, int flags, int B, int H, int W,
                            drosfm_stream_t stream);
+
+/* The two warp stages of the staged path on their own, so that a caller can overlap the independent parts of the
+ * loss (auto-mask, smoothness) on a second stream (multiview_photometric_loss_mf.py:132-171, warp_ref_image):
+ * fwd: warped [n_preds,V,B,3,H,W] = view_synthesis(context_v; inv_depth_i, pose_{v,i}) for every (i, v); hand it to
+ *      drosfm_photometric_fwd with DROSFM_PHOTO_WARPED_READY.
+ * bwd: adjoint of that warp for the g_warped a DROSFM_PHOTO_NO_ADJOINT backward left behind: g_inv_depths[i] written
+ *      (accumulate != 0: added to), g_poses[v*n_preds+i] written; ws of drosfm_ws_bytes(n_views*n_preds*B). */
+int drosfm_warp_sources_fwd(const float* const* context, int n_views, const float* const* inv_depths, int depth_kind,
+                            int n_preds, const drosfm_cams_t* cams, const float* const* poses, int padding, float* warped,
+                            int B, int H, int W, drosfm_stream_t stream);
+int drosfm_warp_sources_bwd(const float* g_warped, const float* const* context, int n_views,
+                            const float* const* inv_depths, int depth_kind, int n_preds, const drosfm_cams_t* cams,
+                            const float* const* poses, int padding, float* const* g_inv_depths, float* const* g_poses,
+                            void* ws, int accumulate, int B, int H, int W, drosfm_stream_t stream);
 
 /* ---- smoothness loss (multiview_photometric_loss_mf.py:273-299, utils/depth.py:147-199) -------
  * loss = weight/n * sum_i (mean|dx(d_i/mean(d_i)) * wx| + mean|dy(..) * wy|) / 2^i.

@@ -127,7 +127,7 @@ def _check_photometric(dataset, B, H, W, V, n, min_depth, max_depth, padding="ze
     lib = L.lib()
     L.check(lib.drosfm_automask_fwd(L.ptr(img), L.ptr_array(ctx), V, opts, L.ptr(amask), B, H, W, L.stream()))
     L.check(lib.drosfm_photometric_fwd(L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
-                                       L.ptr(amask), opts, L.ptr(sel), L.ptr(loss), L.ptr(ws), None, B, H, W, L.stream()))
+                                       L.ptr(amask), opts, L.ptr(sel), L.ptr(loss), L.ptr(ws), None, 0, B, H, W, L.stream()))
     assert_close(loss.cpu()[0], loss32, what="loss")
     # (2) selection: identical except at near-ties
     flips = near_ties = 0
@@ -148,7 +148,7 @@ def _check_photometric(dataset, B, H, W, V, n, min_depth, max_depth, padding="ze
     one = torch.ones(1, device=dev)
     L.check(lib.drosfm_photometric_bwd(L.ptr(one), L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams,
                                        L.ptr_array(P), L.ptr(sel_forced), opts, L.ptr_array(list(g_inv)), L.ptr_array(list(g_pose)),
-                                       L.ptr(ws), None, None, B, H, W, L.stream()))
+                                       L.ptr(ws), None, None, 0, B, H, W, L.stream()))
     for i in range(n):
         assert_close_or_better(g_inv[i].cpu(), g32[i], g64[i], what=f"g_inv{i}")
     for k in range(V * n):
@@ -160,7 +160,7 @@ def _check_photometric(dataset, B, H, W, V, n, min_depth, max_depth, padding="ze
     loss2 = torch.zeros(1, device=dev)
     sel2 = torch.empty_like(sel)
     L.check(lib.drosfm_photometric_fwd(L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
-                                       L.ptr(amask), opts, L.ptr(sel2), L.ptr(loss2), L.ptr(ws), L.ptr(wsave), B, H, W, L.stream()))
+                                       L.ptr(amask), opts, L.ptr(sel2), L.ptr(loss2), L.ptr(ws), L.ptr(wsave), 0, B, H, W, L.stream()))
     assert_close(loss2.cpu(), loss.cpu(), rtol=1e-6, atol=0, what="loss (staged vs fused)")
     assert (sel2 != sel).float().mean().item() < 1e-4
     for i in range(n):
@@ -171,7 +171,7 @@ def _check_photometric(dataset, B, H, W, V, n, min_depth, max_depth, padding="ze
     g_inv2, g_pose2 = torch.empty_like(g_inv), torch.empty_like(g_pose)
     L.check(lib.drosfm_photometric_bwd(L.ptr(one), L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams,
                                        L.ptr_array(P), L.ptr(sel_forced), opts, L.ptr_array(list(g_inv2)), L.ptr_array(list(g_pose2)),
-                                       L.ptr(ws), L.ptr(wsave), L.ptr(g_warped), B, H, W, L.stream()))
+                                       L.ptr(ws), L.ptr(wsave), L.ptr(g_warped), 0, B, H, W, L.stream()))
     # the two paths group the (cancelling) fp32 sums differently, so they only agree to the conditioning of the sums;
     # the parity bar proper is the comparison of each path with the fp32 / fp64 oracle (above and below)
     assert_close(g_inv2.cpu(), g_inv.cpu(), rtol=1e-4, atol=1e-4 * float(g_inv.abs().max()), what="g_inv (staged vs fused)")
@@ -180,10 +180,31 @@ def _check_photometric(dataset, B, H, W, V, n, min_depth, max_depth, padding="ze
         assert_close_or_better(g_inv2[i].cpu(), g32[i], g64[i], what=f"staged g_inv{i}")
     for k in range(V * n):
         assert_close_or_better(g_pose2[k].cpu(), g32[n + k], g64[n + k], what=f"staged g_pose{k}")
+    # (5) the stages on their own (what the module uses to overlap auto-mask / smoothness on a second stream):
+    #     warp_sources_fwd + WARPED_READY, NO_ADJOINT + warp_sources_bwd(accumulate) == the single calls above
+    wsave3 = torch.empty_like(wsave)
+    pad = L.PAD_ZEROS if padding == "zeros" else L.PAD_BORDER
+    L.check(lib.drosfm_warp_sources_fwd(L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P), pad,
+                                        L.ptr(wsave3), B, H, W, L.stream()))
+    assert torch.equal(wsave3, wsave)
+    loss3 = torch.zeros(1, device=dev)
+    L.check(lib.drosfm_photometric_fwd(L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
+                                       L.ptr(amask), opts, L.ptr(sel2), L.ptr(loss3), L.ptr(ws), L.ptr(wsave3),
+                                       L.PHOTO_WARPED_READY, B, H, W, L.stream()))
+    assert_close(loss3.cpu(), loss2.cpu(), rtol=1e-6, atol=0, what="loss (split stages)")
+    base = torch.randn_like(g_inv)
+    g_inv3, g_pose3 = base.clone(), torch.empty_like(g_pose)
+    L.check(lib.drosfm_photometric_bwd(L.ptr(one), L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams,
+                                       L.ptr_array(P), L.ptr(sel_forced), opts, None, None, L.ptr(ws), L.ptr(wsave3),
+                                       L.ptr(g_warped), L.PHOTO_NO_ADJOINT, B, H, W, L.stream()))
+    L.check(lib.drosfm_warp_sources_bwd(L.ptr(g_warped), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
+                                        pad, L.ptr_array(list(g_inv3)), L.ptr_array(list(g_pose3)), L.ptr(ws), 1, B, H, W, L.stream()))
+    assert_close((g_inv3 - base).cpu(), g_inv2.cpu(), rtol=1e-4, atol=2e-7 * float(base.abs().max()), what="g_inv (accumulated)")
+    assert_close(g_pose3.cpu(), g_pose2.cpu(), rtol=1e-4, atol=1e-5 * float(g_pose.abs().max()), what="g_pose (split stages)")
     # a half-specified staged call is refused
     rc = lib.drosfm_photometric_bwd(L.ptr(one), L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams,
                                     L.ptr_array(P), L.ptr(sel_forced), opts, L.ptr_array(list(g_inv2)), L.ptr_array(list(g_pose2)),
-                                    L.ptr(ws), L.ptr(wsave), None, B, H, W, L.stream())
+                                    L.ptr(ws), L.ptr(wsave), None, 0, B, H, W, L.stream())
     assert rc < 0 and b"g_warped" in lib.drosfm_last_error()
 
 
@@ -349,3 +370,33 @@ def test_upsample_depth_vs_oracle(N, H, W):
     assert_close(y.detach().cpu(), refs[torch.float32][0], what="out")
     assert_close_or_better(gd.cpu(), refs[torch.float32][1], refs[torch.float64][1], what="g_depth")
     assert_close_or_better(gm.cpu(), refs[torch.float32][2], refs[torch.float64][2], what="g_mask", reduction=False)
+
+
+def test_photometric_loss_second_stream_matches_single_stream(monkeypatch):
+    """The module overlaps auto-mask and smoothness with the warp on a second stream (DROSFM_PHOTO_OVERLAP, default
+    on); loss and gradients equal the single-stream schedule."""
+    from dro_sfm_b200 import ops, synthetic as syn
+    g = syn.gen(11)
+    B, H, W, V, n = 2, 96, 160, 2, 3
+    K = syn.intrinsics("kitti", B, H, W).to(DEV)
+    image = syn.images(g, B, H, W).to(DEV)
+    context = [(0.8 * torch.roll(image.cpu(), v + 1, 3) + 0.2 * syn.images(g, B, H, W)).to(DEV) for v in range(V)]
+    invs0 = [syn.inv_depth(g, B, H, W, 0.5, 80.0).to(DEV) for _ in range(n)]
+    vecs0 = [[(syn.pose_vec(g, B, "kitti") * 0.3).to(DEV) for _ in range(n)] for _ in range(V)]
+
+    def run():
+        invs = [x.clone().requires_grad_(True) for x in invs0]
+        vecs = [[x.clone().requires_grad_(True) for x in tv] for tv in vecs0]
+        total, terms = ops.photometric_loss(image, context, invs, K, K, vecs, smooth_w=0.05)
+        grads = torch.autograd.grad(total, invs + [x for tv in vecs for x in tv])
+        torch.cuda.synchronize()
+        return total.detach(), terms.detach(), grads
+
+    monkeypatch.setattr(ops, "OVERLAP", True)
+    t1, m1, g1 = run()
+    monkeypatch.setattr(ops, "OVERLAP", False)
+    t0, m0, g0 = run()
+    assert_close(t1.cpu(), t0.cpu(), rtol=1e-6, atol=0, what="loss")
+    assert_close(m1.cpu(), m0.cpu(), rtol=1e-6, atol=0, what="terms")
+    for a, b in zip(g1, g0):
+        assert_close(a.cpu(), b.cpu(), rtol=1e-4, atol=1e-5 * float(b.abs().max()), what="gradient")
