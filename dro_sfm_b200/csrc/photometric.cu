@@ -1134,6 +1134,169 @@ ssim_bwd_stream_kernel(const float* __restrict__ g_loss, const float* __restrict
     }
 }
 
+// ---- two views per warp, packed fp32x2 ---------------------------------------------------------
+// These kernels are bound by instruction issue, not by the FMA pipe, and Blackwell's packed fp32x2 arithmetic
+// (fma.rn.f32x2 & co: two IEEE fp32 operations per issued instruction) halves the issue slots of everything that is
+// element-wise over a pair.  The backward stage pairs two source VIEWS in one warp: their statistics, coefficients
+// and box sums travel as float2, and the target-image work (loads, shuffles, sums of y, the sel byte) is shared.
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 shfl2(float2 v, int src) {
+    return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+struct BwdRow2 {
+    float sy, syy;                   // target row: horizontal 3-sums
+    float2 sx, sxx, sxy;             // the two views' rows
+    float2 x;
+    float y;
+    float2 ha, hb, hc;
+};
+
+__global__ void __launch_bounds__(kSsimThreads, 3)
+ssim_bwd_stream2_kernel(const float* __restrict__ g_loss, const float* __restrict__ image, const float* __restrict__ warped,
+                        const __grid_constant__ PhotoPtrs pp, int V, const uint8_t* __restrict__ sel_in,
+                        drosfm_photo_opts_t opts, float l1_w, float* __restrict__ g_warped, int B, int H, int W, int nstrips,
+                        int nbands) {
+    const int lane = threadIdx.x & 31;
+    const int wg = blockIdx.x * kSsimWarps + (threadIdx.x >> 5);
+    if (wg >= nstrips * nbands) return;
+    const int strip = wg % nstrips, band = wg / nstrips;
+    const int c = static_cast<int>(blockIdx.y) % 3, pair = static_cast<int>(blockIdx.y) / 3;      // pair = (ip * V/2 + vp) * B + b
+    const int VP = V >> 1;
+    const int b = pair % B, vp = (pair / B) % VP, ip = pair / (B * VP);
+    const int v0 = 2 * vp;
+    const int P = H * W;
+    const int gx = strip * kBwdStripW - 2 + lane, gy0 = band * kBwdBandH;
+    const bool col_in = gx >= 0 && gx < W;
+    const bool out_lane = lane >= 2 && lane <= kBwdStripW + 1 && gx < W;
+    const Lanes nb = neighbour_lanes(lane, gx == 0, gx == W - 1);
+    const int gxc = clampi(gx, 0, W - 1);
+    const bool use_min = opts.reduce_op == DROSFM_REDUCE_MIN;
+    const float G = __ldg(g_loss) * pp.weight[ip] /
+                    (static_cast<float>(B) * static_cast<float>(P) * (use_min ? 1.0f : static_cast<float>(V)));
+    const float kp = G * opts.ssim_w * (-1.0f / 6.0f) * (2.0f / 9.0f);
+    const float kl1 = G * l1_w * (1.0f / 3.0f);
+    const size_t slot0 = (static_cast<size_t>(ip) * V + v0) * B + b;
+    const unsigned vstride = static_cast<unsigned>(B) * 3u * static_cast<unsigned>(P);     // view v0 + 1 relative to v0
+    const float* __restrict__ ypl = image + (static_cast<size_t>(b) * 3 + c) * P + gxc;
+    const float* __restrict__ xpl = warped + (slot0 * 3 + c) * P + gxc;
+    float* __restrict__ gpl = g_warped + (slot0 * 3 + c) * P + gxc;
+    const uint8_t* __restrict__ spl = sel_in + (static_cast<size_t>(ip) * B + b) * P + gxc;
+    const float2 wx0 = bc2(gx <= 0 ? 0.0f : (gx == 1 ? 2.0f : 1.0f));
+    const float2 wx2 = bc2(gx >= W - 1 ? 0.0f : (gx == W - 2 ? 2.0f : 1.0f));
+    const float2 inv9 = bc2(1.0f / 9.0f), ninv9 = bc2(-1.0f / 9.0f), two = bc2(2.0f);
+    const float2 C1 = bc2(opts.C1), C2 = bc2(opts.C2);
+
+    float2 nx;
+    float ny;
+    auto fetch = [&](int gy) {
+        const unsigned off = static_cast<unsigned>(padded_row(gy, H) * W);
+        nx.x = col_in ? __ldg(xpl + off) : 0.0f;
+        nx.y = col_in ? __ldg(xpl + (off + vstride)) : 0.0f;
+        ny = col_in ? __ldg(ypl + off) : 0.0f;
+    };
+    int sv_prev = 254;
+    auto step = [&](BwdRow2& p2, BwdRow2& p1, BwdRow2& cur, int j) {
+        const int gy = gy0 - 2 + j;
+        const int gc = gy - 1;
+        cur.x = nx;
+        cur.y = ny;
+        fetch(gy + 1);
+        int sv = 254;
+        if (j >= 2 && col_in && gc >= 0 && gc < H) sv = use_min ? static_cast<int>(__ldg(spl + static_cast<unsigned>(gc * W))) : 253;
+        const float2 xl = shfl2(cur.x, nb.l), xr = shfl2(cur.x, nb.r);
+        float yl, yr;
+        neighbours(cur.y, nb, yl, yr);
+        const float2 yl2 = bc2(yl), yc2 = bc2(cur.y), yr2 = bc2(yr);
+        cur.sy = yl + cur.y + yr;
+        cur.syy = yl * yl + cur.y * cur.y + yr * yr;
+        cur.sx = add2(add2(xl, cur.x), xr);
+        cur.sxx = fma2(xr, xr, fma2(cur.x, cur.x, mul2(xl, xl)));
+        cur.sxy = fma2(xr, yr2, fma2(cur.x, yc2, mul2(xl, yl2)));
+        if (j >= 2) {
+            float2 a = bc2(0.0f), bb = a, cq = a;
+            const bool on0 = sv == v0 || sv == 253, on1 = sv == v0 + 1 || sv == 253;
+            if (on0 || on1) {
+                const float2 wsx = add2(add2(p2.sx, p1.sx), cur.sx);
+                const float2 wsxx = add2(add2(p2.sxx, p1.sxx), cur.sxx);
+                const float2 wsxy = add2(add2(p2.sxy, p1.sxy), cur.sxy);
+                const float wsy = p2.sy + p1.sy + cur.sy, wsyy = p2.syy + p1.syy + cur.syy;
+                // statistics as in ssim_from(), two views at a time
+                const float mu_y = wsy * (1.0f / 9.0f);
+                const float mu_yy = mu_y * mu_y;
+                const float sig_y = wsyy * (1.0f / 9.0f) - mu_yy;
+                const float2 mu_y2 = bc2(mu_y);
+                const float2 mu_x = mul2(wsx, inv9), nmu_x = mul2(wsx, ninv9);
+                const float2 mu_xy = mul2(mu_x, mu_y2), mu_xx = mul2(mu_x, mu_x);
+                const float2 sig_x = fma2(nmu_x, mu_x, mul2(wsxx, inv9));
+                const float2 sig_xy = fma2(nmu_x, mu_y2, mul2(wsxy, inv9));
+                const float2 A1 = fma2(two, mu_xy, C1), A2 = fma2(two, sig_xy, C2);
+                const float2 B1 = add2(mu_xx, bc2(mu_yy + opts.C1)), B2 = add2(sig_x, bc2(sig_y + opts.C2));
+                const float2 num = mul2(A1, A2), den = mul2(B1, B2);
+                const float2 rden = make_float2(__fdividef(1.0f, den.x), __fdividef(1.0f, den.y));
+                const float2 sm = mul2(num, rden);
+                const float2 q = mul2(bc2(kp), rden);
+                // a = q (mu_y (A2 - A1) - s mu_x (B2 - B1)),  b = -q s B1,  c = q A1
+                const float2 neg1 = bc2(-1.0f);
+                const float2 dA = fma2(neg1, A1, A2), dB = fma2(neg1, B1, B2);
+                const float2 inner = fma2(mul2(sm, nmu_x), dB, mul2(mu_y2, dA));
+                const float2 a_ = mul2(q, inner);
+                const float2 b_ = mul2(mul2(mul2(bc2(-kp), rden), sm), B1);
+                const float2 c_ = mul2(q, A1);
+                const float l0 = (1.0f - sm.x) * 0.5f, l1 = (1.0f - sm.y) * 0.5f;
+                const bool k0 = on0 && l0 >= 0.0f && l0 <= 1.0f, k1 = on1 && l1 >= 0.0f && l1 <= 1.0f;
+                a = make_float2(k0 ? a_.x : 0.0f, k1 ? a_.y : 0.0f);
+                bb = make_float2(k0 ? b_.x : 0.0f, k1 ? b_.y : 0.0f);
+                cq = make_float2(k0 ? c_.x : 0.0f, k1 ? c_.y : 0.0f);
+            }
+            const int ll = (lane - 1) & 31, lr = (lane + 1) & 31;      // the outermost lanes' sums are never used
+            p1.ha = fma2(wx2, shfl2(a, lr), fma2(wx0, shfl2(a, ll), a));
+            p1.hb = fma2(wx2, shfl2(bb, lr), fma2(wx0, shfl2(bb, ll), bb));
+            p1.hc = fma2(wx2, shfl2(cq, lr), fma2(wx0, shfl2(cq, ll), cq));
+        }
+        if (j >= 4) {
+            const int gq = gy - 2;
+            if (out_lane && gq < gy0 + kBwdBandH && gq < H) {
+                const float2 wy0 = bc2(gq <= 0 ? 0.0f : (gq == 1 ? 2.0f : 1.0f));
+                const float2 wy2 = bc2(gq >= H - 1 ? 0.0f : (gq == H - 2 ? 2.0f : 1.0f));
+                const float2 ga = fma2(wy2, p1.ha, fma2(wy0, cur.ha, p2.ha));
+                const float2 gb = fma2(wy2, p1.hb, fma2(wy0, cur.hb, p2.hb));
+                const float2 gc_ = fma2(wy2, p1.hc, fma2(wy0, cur.hc, p2.hc));
+                float2 gxv = fma2(gc_, bc2(p2.y), fma2(gb, p2.x, ga));
+                const bool q0 = sv_prev == v0 || sv_prev == 253, q1 = sv_prev == v0 + 1 || sv_prev == 253;
+                if (q0) {
+                    const float df = p2.x.x - p2.y;
+                    gxv.x += df == 0.0f ? 0.0f : __int_as_float(__float_as_int(kl1) ^ (__float_as_int(df) & 0x80000000));
+                }
+                if (q1) {
+                    const float df = p2.x.y - p2.y;
+                    gxv.y += df == 0.0f ? 0.0f : __int_as_float(__float_as_int(kl1) ^ (__float_as_int(df) & 0x80000000));
+                }
+                const unsigned o = static_cast<unsigned>(gq * W);
+                gpl[o] = gxv.x;
+                gpl[o + vstride] = gxv.y;
+            }
+        }
+        sv_prev = sv;
+    };
+    BwdRow2 r0, r1, r2;
+    r0.ha = r0.hb = r0.hc = r1.ha = r1.hb = r1.hc = r2.ha = r2.hb = r2.hc = bc2(0.0f);
+    r0.sx = r0.sxx = r0.sxy = r1.sx = r1.sxx = r1.sxy = bc2(0.0f);
+    r0.sy = r0.syy = r1.sy = r1.syy = 0.0f;
+    r0.x = r1.x = bc2(0.0f);
+    r0.y = r1.y = 0.0f;
+    fetch(gy0 - 2);
+#pragma unroll 1
+    for (int j = 0; j < kBwdBandH + 4; j += 3) {
+        step(r1, r2, r0, j);
+        step(r2, r0, r1, j + 1);
+        step(r0, r1, r2, j + 2);
+    }
+}
+
 static int check_photo(const float* image, const float* const* context, int n_views, const drosfm_photo_opts_t* opts,
                        int B, int H, int W) {
     DROSFM_REQUIRE(B >= 0 && H >= 0 && W >= 0, DROSFM_EINVAL, "photometric: negative dimension");
@@ -1314,8 +1477,14 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
                        "photometric_bwd: B * n_preds * n_views too large");
         const int nstrips = (W + kBwdStripW - 1) / kBwdStripW, nbands = (H + kBwdBandH - 1) / kBwdBandH;
         dim3 sgrid((nstrips * nbands + kSsimWarps - 1) / kSsimWarps, B * n_preds * n_views * 3);
-        ssim_bwd_stream_kernel<<<sgrid, kSsimThreads, 0, cs>>>(g_loss, image, warped_save, pp, n_views, sel, *opts, l1_weight(opts),
-                                                               g_warped, B, H, W, nstrips, nbands);
+        if (n_views % 2 == 0 && static_cast<long long>(B) * 3 * H * W < (1ll << 31)) {
+            dim3 pgrid(sgrid.x, B * n_preds * (n_views / 2) * 3);
+            ssim_bwd_stream2_kernel<<<pgrid, kSsimThreads, 0, cs>>>(g_loss, image, warped_save, pp, n_views, sel, *opts,
+                                                                    l1_weight(opts), g_warped, B, H, W, nstrips, nbands);
+        } else {
+            ssim_bwd_stream_kernel<<<sgrid, kSsimThreads, 0, cs>>>(g_loss, image, warped_save, pp, n_views, sel, *opts,
+                                                                   l1_weight(opts), g_warped, B, H, W, nstrips, nbands);
+        }
         if (flags & DROSFM_PHOTO_NO_ADJOINT) return launch_status("photometric_bwd (window gradients)");
         if (int e = launch_status("photometric_bwd (window gradients)")) return e;
         dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds);
