@@ -1015,6 +1015,182 @@ ssim_fwd_stream_kernel(const float* __restrict__ image, const float* __restrict_
     }
 }
 
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 shfl2(float2 v, int src) {
+    return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+
+// Forward, exactly two views: the same walk as ssim_fwd_stream_kernel<2> with the two views' sums, statistics and
+// maps as float2 (half the issue slots for everything that is per view).
+struct FwdSums2 {
+    float sy[3], syy[3];
+    float2 sx[3], sxx[3], sxy[3];
+};
+struct FwdRow2 {
+    FwdSums2 s;
+    float yc[3];
+    float2 xc[3];
+};
+
+__global__ void __launch_bounds__(kSsimThreads, 2)
+ssim_fwd_stream2_kernel(const float* __restrict__ image, const float* __restrict__ warped, const __grid_constant__ PhotoPtrs pp,
+                        int n_preds, const float* __restrict__ automask_in, drosfm_photo_opts_t opts, float l1_w,
+                        uint8_t* __restrict__ sel_out, float* __restrict__ loss, Slot* ws, int B, int H, int W, int nstrips,
+                        int nbands) {
+    __shared__ double red[kSsimWarps];
+    __shared__ int flag;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int wg = blockIdx.x * kSsimWarps + wib;
+    const bool active = wg < nstrips * nbands;
+    const int strip = active ? wg % nstrips : 0, band = active ? wg / nstrips : 0;
+    const int b = static_cast<int>(blockIdx.y) % B, ip = static_cast<int>(blockIdx.y) / B;
+    const int P = H * W;
+    const int gx = strip * kFwdStripW - 1 + lane, gy0 = band * kFwdBandH;
+    const bool col_in = gx >= 0 && gx < W;
+    const bool out_lane = active && lane >= 1 && lane <= kFwdStripW && gx < W;
+    const Lanes nb = neighbour_lanes(lane, gx == 0, gx == W - 1);
+    const int gxc = clampi(gx, 0, W - 1);
+    const bool use_min = opts.reduce_op == DROSFM_REDUCE_MIN;
+    const float* __restrict__ ybase = image + static_cast<size_t>(b) * 3 * P + gxc;
+    const float* __restrict__ xbase = warped + (static_cast<size_t>(ip) * 2 * B + b) * 3 * P + gxc;
+    const unsigned vstride = static_cast<unsigned>(B) * 3u * static_cast<unsigned>(P);
+    const float2 inv9 = bc2(1.0f / 9.0f), ninv9 = bc2(-1.0f / 9.0f), two = bc2(2.0f);
+    const float2 C1 = bc2(opts.C1), C2 = bc2(opts.C2);
+
+    float ry[3];
+    float2 rx[3];
+    auto fetch = [&](int gy) {
+        const unsigned off = static_cast<unsigned>(padded_row(gy, H) * W);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            ry[c] = col_in ? __ldg(ybase + (off + c * P)) : 0.0f;
+            rx[c].x = col_in ? __ldg(xbase + (off + c * P)) : 0.0f;
+            rx[c].y = col_in ? __ldg(xbase + (off + c * P + vstride)) : 0.0f;
+        }
+    };
+    float local = 0.0f;
+    FwdSums2 s12;
+    FwdRow2 ra, rb;
+    auto step = [&](FwdRow2& prev, FwdRow2& cur, int j) {
+        const int gy = gy0 - 1 + j;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            cur.yc[c] = ry[c];
+            cur.xc[c] = rx[c];
+        }
+        fetch(gy + 1);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float yl, yr;
+            neighbours(cur.yc[c], nb, yl, yr);
+            const float y1 = cur.yc[c];
+            cur.s.sy[c] = yl + y1 + yr;
+            cur.s.syy[c] = yl * yl + y1 * y1 + yr * yr;
+            const float2 xl = shfl2(cur.xc[c], nb.l), xr = shfl2(cur.xc[c], nb.r), x1 = cur.xc[c];
+            cur.s.sx[c] = add2(add2(xl, x1), xr);
+            cur.s.sxx[c] = fma2(xr, xr, fma2(x1, x1, mul2(xl, xl)));
+            cur.s.sxy[c] = fma2(xr, bc2(yr), fma2(x1, bc2(y1), mul2(xl, bc2(yl))));
+        }
+        if (j >= 2) {
+            float2 ssim_acc = bc2(0.0f), l1_acc = bc2(0.0f);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float2 wsx = add2(s12.sx[c], cur.s.sx[c]);
+                const float2 wsxx = add2(s12.sxx[c], cur.s.sxx[c]);
+                const float2 wsxy = add2(s12.sxy[c], cur.s.sxy[c]);
+                const float wsy = s12.sy[c] + cur.s.sy[c], wsyy = s12.syy[c] + cur.s.syy[c];
+                const float mu_y = wsy * (1.0f / 9.0f);
+                const float mu_yy = mu_y * mu_y;
+                const float sig_y = wsyy * (1.0f / 9.0f) - mu_yy;
+                const float2 mu_y2 = bc2(mu_y);
+                const float2 mu_x = mul2(wsx, inv9), nmu_x = mul2(wsx, ninv9);
+                const float2 mu_xy = mul2(mu_x, mu_y2), mu_xx = mul2(mu_x, mu_x);
+                const float2 sig_x = fma2(nmu_x, mu_x, mul2(wsxx, inv9));
+                const float2 sig_xy = fma2(nmu_x, mu_y2, mul2(wsxy, inv9));
+                const float2 A1 = fma2(two, mu_xy, C1), A2 = fma2(two, sig_xy, C2);
+                const float2 B1 = add2(mu_xx, bc2(mu_yy + opts.C1)), B2 = add2(sig_x, bc2(sig_y + opts.C2));
+                const float2 num = mul2(A1, A2), den = mul2(B1, B2);
+                const float2 sm = make_float2(__fdividef(num.x, den.x), __fdividef(num.y, den.y));
+                // clamp((1 - s) / 2, 0, 1)
+                const float2 l = fma2(sm, bc2(-0.5f), bc2(0.5f));
+                ssim_acc.x += fminf(fmaxf(l.x, 0.0f), 1.0f);
+                ssim_acc.y += fminf(fmaxf(l.y, 0.0f), 1.0f);
+                const float2 df = fma2(bc2(-1.0f), bc2(prev.yc[c]), prev.xc[c]);
+                l1_acc.x += fabsf(df.x);
+                l1_acc.y += fabsf(df.y);
+            }
+            const float pm0 = __fadd_rn(__fmul_rn(opts.ssim_w, third(ssim_acc.x)), __fmul_rn(l1_w, third(l1_acc.x)));
+            const float pm1 = __fadd_rn(__fmul_rn(opts.ssim_w, third(ssim_acc.y)), __fmul_rn(l1_w, third(l1_acc.y)));
+            float best;
+            int sel;
+            if (use_min) {
+                best = __int_as_float(0x7f800000);
+                sel = 254;
+                if (pm0 < best) { best = pm0; sel = 0; }
+                if (pm1 < best) { best = pm1; sel = 1; }
+            } else {
+                best = pm0 + pm1;
+                sel = 254;
+            }
+            const int gyo = gy - 1;
+            if (out_lane && gyo < gy0 + kFwdBandH && gyo < H) {
+                const size_t o = static_cast<size_t>(b) * P + gyo * W + gx;
+                if (automask_in != nullptr) {
+                    const float a = __ldg(automask_in + o);
+                    if (a < best) { best = a; sel = 255; }
+                }
+                if (sel_out != nullptr) sel_out[static_cast<size_t>(ip) * B * P + o] = static_cast<uint8_t>(sel);
+                local += best;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            s12.sy[c] = prev.s.sy[c] + cur.s.sy[c];
+            s12.syy[c] = prev.s.syy[c] + cur.s.syy[c];
+            s12.sx[c] = add2(prev.s.sx[c], cur.s.sx[c]);
+            s12.sxx[c] = add2(prev.s.sxx[c], cur.s.sxx[c]);
+            s12.sxy[c] = add2(prev.s.sxy[c], cur.s.sxy[c]);
+        }
+    };
+    if (active) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            rb.s.sy[c] = rb.s.syy[c] = 0.0f;
+            rb.s.sx[c] = rb.s.sxx[c] = rb.s.sxy[c] = bc2(0.0f);
+        }
+        fetch(gy0 - 1);
+#pragma unroll 1
+        for (int j = 0; j < kFwdBandH + 2; j += 2) {
+            step(rb, ra, j);
+            step(ra, rb, j + 1);
+        }
+    }
+
+    double part = warp_sum(static_cast<double>(local));
+    if (lane == 0) red[wib] = part;
+    __syncthreads();
+    if (tid == 0) {
+        double sacc = 0.0;
+        for (int k = 0; k < kSsimWarps; ++k) sacc += red[k];
+        atomicAdd(spread_acc(slot_at(ws, ip)), sacc);
+    }
+    Slot* ticket = slot_at(ws, n_preds);
+    if (last_block(ticket, gridDim.x * gridDim.y, &flag) && tid == 0) {
+        double total = 0.0;
+        const double denom = static_cast<double>(B) * P * (use_min ? 1.0 : 2.0);
+        for (int i = 0; i < n_preds; ++i) {
+            const double mean_i = take_acc(slot_at(ws, i), 0) / denom;
+            total += static_cast<double>(pp.weight[i]) * static_cast<double>(static_cast<float>(mean_i));
+        }
+        ticket->ticket = 0ull;
+        *loss = static_cast<float>(total);
+    }
+}
+
 struct BwdRow {
     float sy, syy, sx, sxx, sxy;     // horizontal 3-sums of this row
     float x, y;                      // its centre values
@@ -1139,14 +1315,6 @@ ssim_bwd_stream_kernel(const float* __restrict__ g_loss, const float* __restrict
 // (fma.rn.f32x2 & co: two IEEE fp32 operations per issued instruction) halves the issue slots of everything that is
 // element-wise over a pair.  The backward stage pairs two source VIEWS in one warp: their statistics, coefficients
 // and box sums travel as float2, and the target-image work (loads, shuffles, sums of y, the sel byte) is shared.
-__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
-__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ float2 shfl2(float2 v, int src) {
-    return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
-}
-
 struct BwdRow2 {
     float sy, syy;                   // target row: horizontal 3-sums
     float2 sx, sxx, sxy;             // the two views' rows
@@ -1426,9 +1594,9 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
                                                                           *opts, l1_weight(opts), sel, loss, static_cast<Slot*>(ws), B, H,
                                                                           W, nstrips, nbands);
             else
-                ssim_fwd_stream_kernel<2><<<sgrid, kSsimThreads, 0, cs>>>(image, warped_save, pp, n_preds, opts->automask ? automask : nullptr,
-                                                                          *opts, l1_weight(opts), sel, loss, static_cast<Slot*>(ws), B, H,
-                                                                          W, nstrips, nbands);
+                ssim_fwd_stream2_kernel<<<sgrid, kSsimThreads, 0, cs>>>(image, warped_save, pp, n_preds, opts->automask ? automask : nullptr,
+                                                                        *opts, l1_weight(opts), sel, loss, static_cast<Slot*>(ws), B, H, W,
+                                                                        nstrips, nbands);
         } else {
             photometric_fwd_kernel<0, true><<<grid, kFwdThreads, kFwdSmemBytes, cs>>>(
                 image, pp, n_views, depth_kind, n_preds, *cams, opts->automask ? automask : nullptr, *opts, l1_weight(opts), sel,
