@@ -266,10 +266,10 @@ feat_cost_bwd_nchw(const float* __restrict__ g_cost, const float* __restrict__ f
         for (int v = 0; v < VT; ++v) {
             if (v < V && vg.g_pose[v] != nullptr) {
                 Slot* slot = slot_at(ws, v * B + b);
-                if (last_block(slot, gridDim.x * gridDim.y, &flag) && threadIdx.x == 0) {
+                if (last_block(slot, gridDim.x * gridDim.y, &flag) && threadIdx.x < 32) {
                     const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
-                    finish_pose_grad(slot, cams.pose_kind, eul ? vp.pose[v] + b * 6 : nullptr,
-                                     vg.g_pose[v] + b * (eul ? 6 : 16));
+                    finish_pose_grad_warp(slot, cams.pose_kind, eul ? vp.pose[v] + b * 6 : nullptr,
+                                          vg.g_pose[v] + b * (eul ? 6 : 16));
                 }
             }
         }
@@ -545,9 +545,9 @@ feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ f
     for (int v = 0; v < VT; ++v) {
         if (v < V && vg.g_pose[v] != nullptr) {
             Slot* slot = slot_at(ws, v * B + b);
-            if (last_block(slot, gridDim.x, &flag) && threadIdx.x == 0) {
+            if (last_block(slot, gridDim.x, &flag) && threadIdx.x < 32) {
                 const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
-                finish_pose_grad(slot, cams.pose_kind, eul ? vp.pose[v] + b * 6 : nullptr, vg.g_pose[v] + b * (eul ? 6 : 16));
+                finish_pose_grad_warp(slot, cams.pose_kind, eul ? vp.pose[v] + b * 6 : nullptr, vg.g_pose[v] + b * (eul ? 6 : 16));
             }
         }
     }
