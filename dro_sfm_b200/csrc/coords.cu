@@ -126,9 +126,9 @@ warp_coords_bwd_kernel(const float* __restrict__ g_uv, const float* __restrict__
     if (g_pose == nullptr) return;
     Slot* slot = slot_at(ws, b);
     block_accumulate<12>(gT, red, spread_acc(slot));
-    if (last_block(slot, gridDim.x, &flag) && threadIdx.x == 0) {
+    if (last_block(slot, gridDim.x, &flag) && threadIdx.x < 32) {
         const int stride = cams.pose_kind == DROSFM_POSE_EULER6 ? 6 : 16;
-        finish_pose_grad(slot, cams.pose_kind, cams.pose_kind == DROSFM_POSE_EULER6 ? cams.pose + b * 6 : nullptr,
+        finish_pose_grad_warp(slot, cams.pose_kind, cams.pose_kind == DROSFM_POSE_EULER6 ? cams.pose + b * 6 : nullptr,
                          g_pose + b * stride);
     }
 }
@@ -269,8 +269,8 @@ project_bwd_kernel(const float* __restrict__ g_uv, const float* __restrict__ poi
     if (g_Tcw == nullptr) return;
     Slot* slot = slot_at(ws, b);
     block_accumulate<12>(gT, red, spread_acc(slot));
-    if (last_block(slot, gridDim.x, &flag) && threadIdx.x == 0)
-        finish_pose_grad(slot, DROSFM_POSE_MAT4, nullptr, g_Tcw + b * 16);
+    if (last_block(slot, gridDim.x, &flag) && threadIdx.x < 32)
+        finish_pose_grad_warp(slot, DROSFM_POSE_MAT4, nullptr, g_Tcw + b * 16);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -109,24 +109,31 @@ smooth_fwd_kernel(const float* __restrict__ image, const __grid_constant__ Depth
         if (t != 0.0) atomicAdd(spread_acc(slot_at(ws, i * B + b)) + (threadIdx.x & 1), t);
     }
     Slot* ticket = slot_at(ws, n_preds * B);
-    if (last_block(ticket, gridDim.x * gridDim.y, &flag) && threadIdx.x == 0) {
-        const double nx = static_cast<double>(B) * H * (W - 1), ny = static_cast<double>(B) * (H - 1) * W;
-        double total = 0.0, pw = 1.0;
-        for (int i = 0; i < n_preds; ++i) {
-            double tx = 0.0, ty = 0.0;
-            for (int bb = 0; bb < B; ++bb) {
-                Slot* s = slot_at(ws, i * B + bb);
-                const double ax = take_acc(s, 0), ay = take_acc(s, 1);
-                stats[(i * B + bb) * 4 + 1] = static_cast<float>(ax);
-                stats[(i * B + bb) * 4 + 2] = static_cast<float>(ay);
-                tx += ax;
-                ty += ay;
-            }
-            total += ((nx > 0 ? tx / nx : 0.0) + (ny > 0 ? ty / ny : 0.0)) / pw;
-            pw *= 2.0;
+    if (last_block(ticket, gridDim.x * gridDim.y, &flag)) {
+        // every thread of the last block collects (prediction, sample) pairs, so the 2 n B accumulators are read with
+        // one round trip; the per-prediction totals meet in shared memory (fp64), thread 0 folds them into the loss
+        __shared__ double tot[2 * DROSFM_MAX_PREDS];
+        if (threadIdx.x < 2 * DROSFM_MAX_PREDS) tot[threadIdx.x] = 0.0;
+        __syncthreads();
+        for (int k = threadIdx.x; k < n_preds * B; k += kLossThreads) {
+            Slot* s = slot_at(ws, k);                          // k = i * B + bb
+            const double ax = take_acc(s, 0), ay = take_acc(s, 1);
+            stats[k * 4 + 1] = static_cast<float>(ax);
+            stats[k * 4 + 2] = static_cast<float>(ay);
+            atomicAdd(&tot[2 * (k / B)], ax);
+            atomicAdd(&tot[2 * (k / B) + 1], ay);
         }
-        ticket->ticket = 0ull;
-        *loss = static_cast<float>(static_cast<double>(weight) * (total / n_preds));
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double nx = static_cast<double>(B) * H * (W - 1), ny = static_cast<double>(B) * (H - 1) * W;
+            double total = 0.0, pw = 1.0;
+            for (int i = 0; i < n_preds; ++i) {
+                total += ((nx > 0 ? tot[2 * i] / nx : 0.0) + (ny > 0 ? tot[2 * i + 1] / ny : 0.0)) / pw;
+                pw *= 2.0;
+            }
+            ticket->ticket = 0ull;
+            *loss = static_cast<float>(static_cast<double>(weight) * (total / n_preds));
+        }
     }
 }
 
@@ -245,10 +252,10 @@ reproj_kernel(const float* __restrict__ g_loss, const float* __restrict__ depth,
             } else if (rp.g_pred[v * n_preds + i] != nullptr) {
                 Slot* slot = slot_at(ws, (v * n_preds + i) * B + b);
                 block_accumulate<12>(gT, red, spread_acc(slot));
-                if (last_block(slot, gridDim.x, &flag) && threadIdx.x == 0) {
+                if (last_block(slot, gridDim.x, &flag) && threadIdx.x < 32) {
                     const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
-                    finish_pose_grad(slot, cams.pose_kind, eul ? rp.pred[v * n_preds + i] + b * 6 : nullptr,
-                                     rp.g_pred[v * n_preds + i] + b * (eul ? 6 : 16));
+                    finish_pose_grad_warp(slot, cams.pose_kind, eul ? rp.pred[v * n_preds + i] + b * 6 : nullptr,
+                                          rp.g_pred[v * n_preds + i] + b * (eul ? 6 : 16));
                 }
             }
         }
@@ -256,14 +263,18 @@ reproj_kernel(const float* __restrict__ g_loss, const float* __restrict__ depth,
     }
     if (MODE == 0) {
         Slot* ticket = slot_at(ws, n_preds);
-        if (last_block(ticket, gridDim.x * gridDim.y, &flag) && threadIdx.x == 0) {
+        if (last_block(ticket, gridDim.x * gridDim.y, &flag) && threadIdx.x < 32) {
+            // lane i collects prediction i (all loads in flight together), lane 0 adds them in order
+            const int lane = threadIdx.x;
             const double numel = 2.0 * static_cast<double>(B) * P;
+            double term = 0.0;
+            if (lane < n_preds) term = static_cast<double>(rp.weight[lane]) * (take_acc(slot_at(ws, lane), 0) / numel / V);
             double total = 0.0;
-            for (int i = 0; i < n_preds; ++i) {
-                total += static_cast<double>(rp.weight[i]) * (take_acc(slot_at(ws, i), 0) / numel / V);
+            for (int i = 0; i < n_preds; ++i) total += __shfl_sync(0xffffffffu, term, i);
+            if (lane == 0) {
+                ticket->ticket = 0ull;
+                *loss = static_cast<float>(total / static_cast<double>(wsum));
             }
-            ticket->ticket = 0ull;
-            *loss = static_cast<float>(total / static_cast<double>(wsum));
         }
     }
 }
@@ -322,12 +333,18 @@ sup_depth_kernel(const float* __restrict__ g_loss, const float* __restrict__ gt,
         if (t != 0.0) atomicAdd(spread_acc(slot_at(ws, threadIdx.x)), t);
     }
     Slot* ticket = slot_at(ws, n_preds);
-    if (last_block(ticket, gridDim.x, &flag) && threadIdx.x == 0) {
+    if (last_block(ticket, gridDim.x, &flag) && threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        double term = 0.0;
+        if (lane < n_preds)
+            term = static_cast<double>(sp.weight[lane]) *
+                   static_cast<double>(static_cast<float>(take_acc(slot_at(ws, lane), 0) / static_cast<double>(N)));
         double total = 0.0;
-        for (int i = 0; i < n_preds; ++i)
-            total += static_cast<double>(sp.weight[i]) * static_cast<double>(static_cast<float>(take_acc(slot_at(ws, i), 0) / static_cast<double>(N)));
-        ticket->ticket = 0ull;
-        *loss = static_cast<float>(total / static_cast<double>(wsum));
+        for (int i = 0; i < n_preds; ++i) total += __shfl_sync(0xffffffffu, term, i);
+        if (lane == 0) {
+            ticket->ticket = 0ull;
+            *loss = static_cast<float>(total / static_cast<double>(wsum));
+        }
     }
 }
 

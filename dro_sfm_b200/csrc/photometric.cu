@@ -349,17 +349,9 @@ photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ 
         atomicAdd(spread_acc(slot_at(ws, ip)), s);
     }
     Slot* ticket = slot_at(ws, n_preds);
-    if (last_block(ticket, gridDim.x * gridDim.y * gridDim.z, &flag) && tid == 0) {
-        double total = 0.0;
-        const double denom = static_cast<double>(B) * P * (use_min ? 1.0 : static_cast<double>(V));
-        for (int i = 0; i < n_preds; ++i) {
-            const double mean_i = take_acc(slot_at(ws, i), 0) / denom;
-            // the reference rounds every per-prediction mean to fp32 before the weighted sum
-            total += static_cast<double>(pp.weight[i]) * static_cast<double>(static_cast<float>(mean_i));
-        }
-        ticket->ticket = 0ull;
-        *loss = static_cast<float>(total);
-    }
+    if (last_block(ticket, gridDim.x * gridDim.y * gridDim.z, &flag) && tid < 32)
+        finish_weighted_means(ws, n_preds, pp.weight, static_cast<double>(B) * P * (use_min ? 1.0 : static_cast<double>(V)), ticket,
+                              loss);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -607,18 +599,15 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
         }
     }
     // one ticket per (view, prediction, sample): the last block turns the fp64 sums into the caller's encoding
-    __threadfence();
-    __syncthreads();
-    if (tid < V && pg.g_pose[tid * n_preds + ip] != nullptr) {
-        Slot* slot = slot_at(ws, (tid * n_preds + ip) * B + b);
-        const unsigned long long t = atomicAdd(&slot->ticket, 1ull);
-        if (t == static_cast<unsigned long long>(gridDim.x) * gridDim.y - 1ull) {
-            __threadfence();
+    __shared__ unsigned last_mask;
+    finish_last_slots(
+        V, static_cast<unsigned long long>(gridDim.x) * gridDim.y, &last_mask,
+        [&](int v) { return pg.g_pose[v * n_preds + ip] != nullptr ? slot_at(ws, (v * n_preds + ip) * B + b) : nullptr; },
+        [&](int v, Slot* slot) {
             const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
-            finish_pose_grad(slot, cams.pose_kind, eul ? pp.pose[tid * n_preds + ip] + b * 6 : nullptr,
-                             pg.g_pose[tid * n_preds + ip] + b * (eul ? 6 : 16));
-        }
-    }
+            finish_pose_grad_warp(slot, cams.pose_kind, eul ? pp.pose[v * n_preds + ip] + b * 6 : nullptr,
+                                  pg.g_pose[v * n_preds + ip] + b * (eul ? 6 : 16));
+        });
 }
 
 // ------------------------------------------------------------------------------------------
@@ -803,18 +792,15 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
         }
     }
     // one ticket per (view, prediction, sample): the last block turns the fp64 sums into the caller's encoding
-    __threadfence();
-    __syncthreads();
-    if (tid < V && pg.g_pose[tid * n_preds + ip] != nullptr) {
-        Slot* slot = slot_at(ws, (tid * n_preds + ip) * B + b);
-        const unsigned long long t = atomicAdd(&slot->ticket, 1ull);
-        if (t == static_cast<unsigned long long>(gridDim.x) * gridDim.y - 1ull) {
-            __threadfence();
+    __shared__ unsigned last_mask;
+    finish_last_slots(
+        V, static_cast<unsigned long long>(gridDim.x) * gridDim.y, &last_mask,
+        [&](int v) { return pg.g_pose[v * n_preds + ip] != nullptr ? slot_at(ws, (v * n_preds + ip) * B + b) : nullptr; },
+        [&](int v, Slot* slot) {
             const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
-            finish_pose_grad(slot, cams.pose_kind, eul ? pp.pose[tid * n_preds + ip] + b * 6 : nullptr,
-                             pg.g_pose[tid * n_preds + ip] + b * (eul ? 6 : 16));
-        }
-    }
+            finish_pose_grad_warp(slot, cams.pose_kind, eul ? pp.pose[v * n_preds + ip] + b * 6 : nullptr,
+                                  pg.g_pose[v * n_preds + ip] + b * (eul ? 6 : 16));
+        });
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1003,16 +989,9 @@ ssim_fwd_stream_kernel(const float* __restrict__ image, const float* __restrict_
         atomicAdd(spread_acc(slot_at(ws, ip)), sacc);
     }
     Slot* ticket = slot_at(ws, n_preds);
-    if (last_block(ticket, gridDim.x * gridDim.y, &flag) && tid == 0) {
-        double total = 0.0;
-        const double denom = static_cast<double>(B) * P * (use_min ? 1.0 : static_cast<double>(NV));
-        for (int i = 0; i < n_preds; ++i) {
-            const double mean_i = take_acc(slot_at(ws, i), 0) / denom;
-            total += static_cast<double>(pp.weight[i]) * static_cast<double>(static_cast<float>(mean_i));
-        }
-        ticket->ticket = 0ull;
-        *loss = static_cast<float>(total);
-    }
+    if (last_block(ticket, gridDim.x * gridDim.y, &flag) && tid < 32)
+        finish_weighted_means(ws, n_preds, pp.weight, static_cast<double>(B) * P * (use_min ? 1.0 : static_cast<double>(NV)), ticket,
+                              loss);
 }
 
 __device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
@@ -1179,16 +1158,8 @@ ssim_fwd_stream2_kernel(const float* __restrict__ image, const float* __restrict
         atomicAdd(spread_acc(slot_at(ws, ip)), sacc);
     }
     Slot* ticket = slot_at(ws, n_preds);
-    if (last_block(ticket, gridDim.x * gridDim.y, &flag) && tid == 0) {
-        double total = 0.0;
-        const double denom = static_cast<double>(B) * P * (use_min ? 1.0 : 2.0);
-        for (int i = 0; i < n_preds; ++i) {
-            const double mean_i = take_acc(slot_at(ws, i), 0) / denom;
-            total += static_cast<double>(pp.weight[i]) * static_cast<double>(static_cast<float>(mean_i));
-        }
-        ticket->ticket = 0ull;
-        *loss = static_cast<float>(total);
-    }
+    if (last_block(ticket, gridDim.x * gridDim.y, &flag) && tid < 32)
+        finish_weighted_means(ws, n_preds, pp.weight, static_cast<double>(B) * P * (use_min ? 1.0 : 2.0), ticket, loss);
 }
 
 struct BwdRow {
