@@ -275,7 +275,9 @@ def run_gpu(args, wl):
     # per-kernel durations: the same K steps issued eagerly with CUDA events around every C-ABI launch
     roofline = None
     if rank == 0:
+        from dro_sfm_b200 import ops as _ops
         graph, step.graph = step.graph, None
+        overlap, _ops.OVERLAP = _ops.OVERLAP, False      # one stream: concurrent kernels would stretch each other's events
         step.step()
         torch.cuda.synchronize()
         n_inst = min(args.steps, 10)
@@ -289,6 +291,7 @@ def run_gpu(args, wl):
             torch.cuda.synchronize()
         recs = L.profile_end()
         step.graph = graph
+        _ops.OVERLAP = overlap
         if os.environ.get("DROSFM_BENCH_DUMP"):
             n_one = len(recs) // n_inst
             for name, a, t_ms in recs[n_one:2 * n_one]:
