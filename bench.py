@@ -37,8 +37,8 @@ def measured_peaks():
 
 
 # C-ABI call -> the CUDA kernels it launches (names as in the ncu reports); the staged photometric calls are two each
-NCU_NAMES = {"photometric_bwd": ["ssim_bwd_stream_kernel", "warp_sources_adjoint_kernel"],
-             "photometric_fwd": ["warp_sources_kernel", "ssim_fwd_stream_kernel<2>"],
+NCU_NAMES = {"photometric_bwd": ["ssim_bwd_stream", "warp_sources_adjoint_kernel"],
+             "photometric_fwd": ["warp_sources_kernel", "ssim_fwd_stream"],
              "feat_cost_fwd_v1": ["feat_cost_fwd_nhwc<1>"], "feat_cost_bwd_v1": ["feat_cost_bwd_nhwc<1>"],
              "feat_cost_fwd_vN": ["feat_cost_fwd_nhwc<2>"], "feat_cost_bwd_vN": ["feat_cost_bwd_nhwc<2>"],
              "automask_fwd": ["photometric_fwd_kernel<1, 0>"], "smoothness_fwd": ["smooth_mean_kernel", "smooth_fwd_kernel"],
