@@ -719,38 +719,46 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
     const int P = H * W;
     const float wm1 = static_cast<float>(W - 1), hm1 = static_cast<float>(H - 1);
     const int x = blockIdx.x * 32 + (tid & 31);
-    const float* __restrict__ invd = pp.inv_depth[ip] + static_cast<size_t>(b) * P;
     const bool col_ok = x < W;
-    float* gout = pg.g_inv_depth[ip];
+    // per-sample planes; everything below is a 32-bit offset from one of these (the host checks the ranges)
+    const float* __restrict__ invd = pp.inv_depth[ip] + static_cast<size_t>(b) * P;
+    float* __restrict__ gout = pg.g_inv_depth[ip] != nullptr ? pg.g_inv_depth[ip] + static_cast<size_t>(b) * P : nullptr;
+    const float* __restrict__ gw0 = g_warped + (static_cast<size_t>(ip) * V * B + b) * 3 * P;      // view v: + v * vstride
+    const unsigned vstride = static_cast<unsigned>(B) * 3u * static_cast<unsigned>(P);
     constexpr int kHalf = 4, kStride = kFlatThreads / 32;
 #pragma unroll 1
     for (int h = 0; h < kFlatRows / kHalf; ++h) {
         const int y0 = blockIdx.y * kFlatTileH + h * kHalf * kStride + (tid >> 5);
-        float dv[kHalf], gd[kHalf];
+        float dv[kHalf], gd[kHalf], old[kHalf];
+        unsigned off[kHalf];
+        bool in[kHalf];
 #pragma unroll
         for (int k = 0; k < kHalf; ++k) {
             const int y = y0 + k * kStride;
-            dv[k] = (col_ok && y < H) ? __ldg(invd + y * W + x) : 0.0f;
+            in[k] = col_ok && y < H;
+            off[k] = in[k] ? static_cast<unsigned>(y * W + x) : 0u;
+            dv[k] = in[k] ? __ldg(invd + off[k]) : 0.0f;
+            old[k] = (in[k] && accumulate && gout != nullptr) ? gout[off[k]] : 0.0f;      // requested now, needed at the end
             gd[k] = 0.0f;
         }
 #pragma unroll 1
         for (int v = 0; v < V; ++v) {
             const Cam& cam = cam_s[v];            // read from shared memory on use: the registers go to occupancy
             const float* __restrict__ src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
-            const float* __restrict__ gw = g_warped + ((static_cast<size_t>(ip) * V + v) * B + b) * 3 * P;
+            // all twelve upstream gradients of this view's rows are requested before the first one is used
+            float g[kHalf][3];
+#pragma unroll
+            for (int k = 0; k < kHalf; ++k)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) g[k][c] = in[k] ? __ldg(gw0 + (v * vstride + c * P + off[k])) : 0.0f;
             float gT[12];
 #pragma unroll
             for (int i = 0; i < 12; ++i) gT[i] = 0.0f;
 #pragma unroll
             for (int k = 0; k < kHalf; ++k) {
-                const int y = y0 + k * kStride;
-                float g[3] = {0.0f, 0.0f, 0.0f};
-                if (col_ok && y < H) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) g[c] = __ldg(gw + c * P + y * W + x);
-                }
                 // a pixel that no selected window touches has an exactly zero gradient: nothing to push through
-                if (g[0] != 0.0f || g[1] != 0.0f || g[2] != 0.0f) {
+                if (g[k][0] != 0.0f || g[k][1] != 0.0f || g[k][2] != 0.0f) {
+                    const int y = y0 + k * kStride;
                     const float d = to_depth(dv[k], depth_kind);
                     Warp wp;
                     warp_pixel<true>(cam, x, y, d, wm1, hm1, true, wp);
@@ -758,18 +766,20 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
                     make_taps(wp.p.u, wp.p.v, H, W, padding, t);
                     if (t.valid) {
                         const int xa = max(t.x0, 0), ya = max(t.y0, 0);
-                        const int o00 = ya * W + xa, dxo = min(t.x0 + 1, W - 1) - xa, dyo = (min(t.y0 + 1, H - 1) - ya) * W;
+                        const unsigned o00 = static_cast<unsigned>(ya * W + xa);
+                        const unsigned dxo = static_cast<unsigned>(min(t.x0 + 1, W - 1) - xa);
+                        const unsigned dyo = static_cast<unsigned>((min(t.y0 + 1, H - 1) - ya) * W);
                         const float m0 = (t.valid & 1u) ? 1.f : 0.f, m1 = (t.valid & 2u) ? 1.f : 0.f;
                         const float m2 = (t.valid & 4u) ? 1.f : 0.f, m3 = (t.valid & 8u) ? 1.f : 0.f;
                         float gix = 0.0f, giy = 0.0f;
                         const float bx = 1.0f - t.ax, by = 1.0f - t.ay;
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            const float* r0 = src + c * P + o00;
-                            const float v0 = __ldg(r0) * m0, v1 = __ldg(r0 + dxo) * m1;
-                            const float v2 = __ldg(r0 + dyo) * m2, v3 = __ldg(r0 + dyo + dxo) * m3;
-                            gix += g[c] * ((v1 - v0) * by + (v3 - v2) * t.ay);
-                            giy += g[c] * ((v2 - v0) * bx + (v3 - v1) * t.ax);
+                            const unsigned oc = o00 + static_cast<unsigned>(c * P);
+                            const float v0 = __ldg(src + oc) * m0, v1 = __ldg(src + (oc + dxo)) * m1;
+                            const float v2 = __ldg(src + (oc + dyo)) * m2, v3 = __ldg(src + (oc + dyo + dxo)) * m3;
+                            gix += g[k][c] * ((v1 - v0) * by + (v3 - v2) * t.ay);
+                            giy += g[k][c] * ((v2 - v0) * bx + (v3 - v1) * t.ax);
                         }
                         gd[k] += warp_pixel_adjoint(cam, wp, d, wm1, hm1, true, gix * t.mx, giy * t.my, gT);
                     }
@@ -781,12 +791,10 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
         if (gout != nullptr) {
 #pragma unroll
             for (int k = 0; k < kHalf; ++k) {
-                const int y = y0 + k * kStride;
-                if (col_ok && y < H) {
+                if (in[k]) {
                     float gg = gd[k];
                     if (depth_kind == DROSFM_INV_DEPTH) gg = inv2depth_grad(dv[k], gg);
-                    float* dst = gout + static_cast<size_t>(b) * P + y * W + x;
-                    *dst = accumulate ? *dst + gg : gg;
+                    gout[off[k]] = old[k] + gg;
                 }
             }
         }
@@ -1625,6 +1633,8 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
                                                                    l1_weight(opts), g_warped, B, H, W, nstrips, nbands);
         }
         if (flags & DROSFM_PHOTO_NO_ADJOINT) return launch_status("photometric_bwd (window gradients)");
+        DROSFM_REQUIRE(static_cast<long long>(n_views) * B * 3 * H * W < (1ll << 32), DROSFM_ERANGE,
+                       "photometric_bwd: one prediction's warped views exceed 2^32 elements");
         if (int e = launch_status("photometric_bwd (window gradients)")) return e;
         dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds);
         warp_sources_adjoint_kernel<<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, opts->padding, g_warped,
@@ -1686,6 +1696,8 @@ int drosfm_warp_sources_bwd(const float* g_warped, const float* const* context, 
     }
     DROSFM_REQUIRE(!want_pose || ws != nullptr, DROSFM_EINVAL, "warp_sources_bwd: pose gradients need ws");
     DROSFM_REQUIRE(static_cast<long long>(B) * n_preds <= 65535, DROSFM_ERANGE, "warp_sources_bwd: B * n_preds too large");
+    DROSFM_REQUIRE(static_cast<long long>(n_views) * B * 3 * H * W < (1ll << 32), DROSFM_ERANGE,
+                   "warp_sources_bwd: one prediction's warped views exceed 2^32 elements");
     dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds);
     warp_sources_adjoint_kernel<<<flat, kFlatThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         pp, n_views, depth_kind, n_preds, *cams, padding, g_warped, pg, static_cast<Slot*>(ws), accumulate ? 1 : 0, B, H, W);
