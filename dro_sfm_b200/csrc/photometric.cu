@@ -1302,13 +1302,16 @@ struct BwdRow2 {
     float2 ha, hb, hc;
 };
 
-__global__ void __launch_bounds__(kSsimThreads, 3)
+// 128-thread blocks, 5 per SM: 102 registers hold the packed state without spills at 20 resident warps
+constexpr int kBwd2Threads = 128, kBwd2Warps = kBwd2Threads / 32;
+
+__global__ void __launch_bounds__(kBwd2Threads, 5)
 ssim_bwd_stream2_kernel(const float* __restrict__ g_loss, const float* __restrict__ image, const float* __restrict__ warped,
                         const __grid_constant__ PhotoPtrs pp, int V, const uint8_t* __restrict__ sel_in,
                         drosfm_photo_opts_t opts, float l1_w, float* __restrict__ g_warped, int B, int H, int W, int nstrips,
                         int nbands) {
     const int lane = threadIdx.x & 31;
-    const int wg = blockIdx.x * kSsimWarps + (threadIdx.x >> 5);
+    const int wg = blockIdx.x * kBwd2Warps + (threadIdx.x >> 5);
     if (wg >= nstrips * nbands) return;
     const int strip = wg % nstrips, band = wg / nstrips;
     const int c = static_cast<int>(blockIdx.y) % 3, pair = static_cast<int>(blockIdx.y) / 3;      // pair = (ip * V/2 + vp) * B + b
@@ -1625,8 +1628,8 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
         const int nstrips = (W + kBwdStripW - 1) / kBwdStripW, nbands = (H + kBwdBandH - 1) / kBwdBandH;
         dim3 sgrid((nstrips * nbands + kSsimWarps - 1) / kSsimWarps, B * n_preds * n_views * 3);
         if (n_views % 2 == 0 && static_cast<long long>(B) * 3 * H * W < (1ll << 31)) {
-            dim3 pgrid(sgrid.x, B * n_preds * (n_views / 2) * 3);
-            ssim_bwd_stream2_kernel<<<pgrid, kSsimThreads, 0, cs>>>(g_loss, image, warped_save, pp, n_views, sel, *opts,
+            dim3 pgrid((nstrips * nbands + kBwd2Warps - 1) / kBwd2Warps, B * n_preds * (n_views / 2) * 3);
+            ssim_bwd_stream2_kernel<<<pgrid, kBwd2Threads, 0, cs>>>(g_loss, image, warped_save, pp, n_views, sel, *opts,
                                                                     l1_weight(opts), g_warped, B, H, W, nstrips, nbands);
         } else {
             ssim_bwd_stream_kernel<<<sgrid, kSsimThreads, 0, cs>>>(g_loss, image, warped_save, pp, n_views, sel, *opts,
