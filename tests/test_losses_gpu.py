@@ -68,9 +68,11 @@ def test_photometric_loss_vs_oracle_full_size(wl_name, B, n):
 
 
 @pytest.mark.parametrize("B,H,W,V,n,padding", [(3, 37, 53, 1, 1, "zeros"), (1, 66, 35, 3, 2, "border"), (2, 2, 2, 2, 1, "zeros"),
-                                               (1, 40, 31, 8, 1, "zeros")])
+                                               (1, 40, 31, 8, 1, "zeros"), (1, 33, 57, 2, 2, "border"), (2, 17, 61, 4, 1, "zeros"),
+                                               (1, 35, 28, 2, 1, "zeros")])
 def test_photometric_loss_ragged_shapes(B, H, W, V, n, padding):
-    """Tile-unaligned and degenerate sizes (2x2 is the smallest image reflection padding allows), 1..8 views."""
+    """Tile-, strip- and band-unaligned and degenerate sizes (2x2 is the smallest image reflection padding allows),
+    1..8 views: every SSIM kernel variant (tile, streaming scalar, streaming packed pairs) is exercised."""
     _check_photometric("scannet", B, H, W, V, n, 0.2, 10.0, padding=padding)
 
 
@@ -162,7 +164,7 @@ def _check_photometric(dataset, B, H, W, V, n, min_depth, max_depth, padding="ze
     L.check(lib.drosfm_photometric_fwd(L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
                                        L.ptr(amask), opts, L.ptr(sel2), L.ptr(loss2), L.ptr(ws), L.ptr(wsave), 0, B, H, W, L.stream()))
     assert_close(loss2.cpu(), loss.cpu(), rtol=1e-6, atol=0, what="loss (staged vs fused)")
-    assert (sel2 != sel).float().mean().item() < 1e-4
+    assert int((sel2 != sel).sum()) <= max(2, int(1e-4 * sel.numel()))      # near-ties only (see the docstring)
     for i in range(n):
         for v in range(V):
             with torch.no_grad():
