@@ -301,6 +301,17 @@ def _as_layout(t, layout):
     return t.contiguous(memory_format=torch.channels_last) if layout == L.NHWC else t.contiguous()
 
 
+_ZEROS = {}
+
+
+def _zero_scalar(device):
+    """One fp32 zero per device (the stride-0 placeholder gradients of the sinks expand it; never written)."""
+    z = _ZEROS.get(device)
+    if z is None:
+        z = _ZEROS[device] = torch.zeros((), device=device, dtype=torch.float32)
+    return z
+
+
 class GradSink:
     """Shared gradient accumulator of one feature map over all cost calls of a step.
 
@@ -413,7 +424,7 @@ class _FeatCost(torch.autograd.Function):
             if sink.buffer is None:
                 sink.buffer = torch.zeros_like(like)
                 if sink.dummy is None or sink.dummy.shape != like.shape:
-                    sink.dummy = torch.zeros((), device=like.device, dtype=like.dtype).expand(like.shape)
+                    sink.dummy = _zero_scalar(like.device).expand(like.shape)
                 return sink.buffer, sink.dummy
             return sink.buffer, None
 
@@ -508,7 +519,8 @@ class _PhotoLoss(torch.autograd.Function):
         kind = _pose_kind(poses[0])
         cams, keep = L.make_cams(K, Kref, 1.0, None, None, None, kind)
         opts = L.PhotoOpts(ssim_w, C1, C2, padding, reduce_op, int(automask), gamma)
-        losses = torch.zeros(2, device=dev, dtype=torch.float32)
+        # [photometric, smoothness]: each written by its kernel's finisher (zero only if there is no smoothness term)
+        losses = (torch.empty if smooth_w > 0.0 else torch.zeros)(2, device=dev, dtype=torch.float32)
         sel = torch.empty(n, B, H, W, device=dev, dtype=torch.uint8) if reduce_op == L.REDUCE_MIN else None
         # staged path (12 bytes per pixel, view and prediction): the sources are warped once by a flat kernel and
         # the SSIM kernels of both passes read the result; without it everything runs fused and keeps nothing
