@@ -199,6 +199,7 @@ def run_gpu(args, wl):
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_cpus = du.bind_host_to_gpu(local) if world > 1 else None      # NUMA-local pinned staging buffers (e2e leg)
     du.init("nccl", dev)
     L.lib()
     B = args.batch or wl.B
@@ -335,7 +336,7 @@ def run_gpu(args, wl):
             "config": {"workload": wl.name, "H": wl.H, "W": wl.W, "views": wl.V, "gru_steps": wl.T, "predictions": wl.n,
                        "batch_per_gpu": B, "global_batch": B * world, "feature_layout": args.layout,
                        "cuda_graph": not args.no_graph, "l2": "flushed between timed iterations (256 MiB write)",
-                       "parallelism": "dp%d" % world},
+                       "parallelism": "dp%d" % world, "host_cpus_rank0": (len(host_cpus) if host_cpus else None)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": step.h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,

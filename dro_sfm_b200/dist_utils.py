@@ -51,3 +51,23 @@ def max_over_ranks(values, device="cpu"):
 def whole_job_rate(units_per_rank, world, seconds):
     """Aggregate throughput of a weak-scaling run: all ranks' units over the slowest rank's time."""
     return units_per_rank * world / seconds
+
+
+def bind_host_to_gpu(local_rank):
+    """Best effort: run this process on the CPUs NVML reports as local to its GPU, so that the pinned staging buffers
+    it allocates afterwards (first touch) live on the GPU's NUMA node and the per-step H2D copies of the ranks do not
+    all cross the inter-socket link.  Returns the CPU set applied, or None (no NVML, no affinity API, empty mask)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64 + 16)
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = local & allowed
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None

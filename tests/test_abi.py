@@ -57,3 +57,15 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_relayout_of_host_tensors_is_torchs_copy():
+    """ops.relayout only calls the library for dense fp32 CUDA tensors; everything else takes torch's strided copy."""
+    import torch
+    from dro_sfm_b200 import ops, _lib
+    x = torch.randn(2, 8, 3, 5)
+    cl = ops.relayout(x, _lib.NHWC)
+    assert cl.is_contiguous(memory_format=torch.channels_last) and torch.equal(cl, x)
+    assert ops.relayout(cl, _lib.NHWC) is cl
+    back = ops.relayout(cl, _lib.NCHW)
+    assert back.is_contiguous() and torch.equal(back, x)

@@ -66,3 +66,15 @@ def test_whole_job_rate_is_weak_scaling():
     from dro_sfm_b200 import dist_utils as du
     assert du.whole_job_rate(units_per_rank=20, world=8, seconds=0.5) == 320.0
     assert du.shard_seed(1234, 3, 2) == 1234 + 3000 + 2
+
+
+def test_bind_host_to_gpu_is_best_effort():
+    """Without NVML / a GPU the NUMA binding is a no-op that reports None and leaves the affinity alone."""
+    import os
+    from dro_sfm_b200 import dist_utils as du
+    before = os.sched_getaffinity(0)
+    cpus = du.bind_host_to_gpu(0)
+    assert cpus is None or set(cpus) <= before
+    if cpus is None:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
