@@ -37,8 +37,8 @@ def measured_peaks():
 
 
 # C-ABI call -> the CUDA kernels it launches (names as in the ncu reports); the staged photometric calls are two each
-NCU_NAMES = {"photometric_bwd": ["ssim_bwd_stream", "warp_sources_adjoint_kernel"],
-             "photometric_fwd": ["warp_sources_kernel", "ssim_fwd_stream"],
+NCU_NAMES = {"photometric_bwd": ["ssim_bwd_stream"], "photometric_fwd": ["ssim_fwd_stream"],
+             "warp_sources_fwd": ["warp_sources_kernel"], "warp_sources_bwd": ["warp_sources_adjoint_kernel"],
              "feat_cost_fwd_v1": ["feat_cost_fwd_nhwc<1>"], "feat_cost_bwd_v1": ["feat_cost_bwd_nhwc<1>"],
              "feat_cost_fwd_vN": ["feat_cost_fwd_nhwc<2>"], "feat_cost_bwd_vN": ["feat_cost_bwd_nhwc<2>"],
              "automask_fwd": ["photometric_fwd_kernel<1, 0>"], "smoothness_fwd": ["smooth_mean_kernel", "smooth_fwd_kernel"],
@@ -186,6 +186,7 @@ KERNEL_KEYS = {
     "drosfm_smoothness_bwd": lambda a: "smoothness_bwd", "drosfm_reproj_loss_fwd": lambda a: "reproj_loss_fwd",
     "drosfm_reproj_loss_bwd": lambda a: "reproj_loss_bwd", "drosfm_pose_vec2mat_fwd": lambda a: "pose_vec2mat_fwd",
     "drosfm_pose_vec2mat_bwd": lambda a: "pose_vec2mat_bwd",
+    "drosfm_warp_sources_fwd": lambda a: "warp_sources_fwd", "drosfm_warp_sources_bwd": lambda a: "warp_sources_bwd",
 }
 
 
@@ -278,7 +279,8 @@ def run_gpu(args, wl):
     if rank == 0:
         from dro_sfm_b200 import ops as _ops
         graph, step.graph = step.graph, None
-        overlap, _ops.OVERLAP = _ops.OVERLAP, False      # one stream: concurrent kernels would stretch each other's events
+        # the same split calls on ONE stream: concurrent kernels would stretch each other's events
+        overlap, _ops.OVERLAP = _ops.OVERLAP, ("serial" if _ops.OVERLAP else False)
         step.step()
         torch.cuda.synchronize()
         n_inst = min(args.steps, 10)
@@ -319,7 +321,12 @@ def run_gpu(args, wl):
                     "timed_steps": n_inst,
                     "share_of_kernel_time": totals[dom] / sum(totals.values()),
                     "step_algorithmic_GBps": alg["step_total"] / (ms / args.steps * 1e-3) / 1e9,
-                    "kernel_ms_per_step": {k: round(v / n_inst, 4) for k, v in sorted(totals.items())}}
+                    "kernel_ms_per_step": {k: round(v / n_inst, 4) for k, v in sorted(totals.items())},
+                    # the same roofline for every call of the step: algorithmic GB/s and fraction of the peak
+                    "per_call": {k: {"launches": len(per[k]) // n_inst, "avg_ms": round(totals[k] / len(per[k]), 5),
+                                     "GBps": round(alg[k] / (totals[k] / len(per[k]) * 1e-3) / 1e9, 1),
+                                     "frac": round(alg[k] / (totals[k] / len(per[k]) * 1e-3) / 1e9 / peak, 4)}
+                                 for k in sorted(totals) if k in alg}}
 
     if rank == 0:
         cpu = None

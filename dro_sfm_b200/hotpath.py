@@ -203,10 +203,16 @@ class HotPathStep:
         V, T, n = wl.V, wl.T, wl.n
         from . import ops as _ops
         saved = 12 * V if _ops.SAVE_WARP else 0       # warped sources kept by the forward, re-read by the backward
+        split = bool(_ops.SAVE_WARP and _ops.OVERLAP)  # the loss is issued as separate warp / SSIM calls
         out = {
             "feat_cost_fwd_v1": (C * 4 * 3 + 4) * p, "feat_cost_bwd_v1": (C * 4 * 5 + 8) * p,
             "feat_cost_fwd_vN": (C * 4 * (V + 2) + 4) * p, "feat_cost_bwd_vN": (C * 4 * (2 * V + 3) + 8) * p,
-            "photometric_fwd": (16 + 12 * V + saved) * P * n, "photometric_bwd": (20 + 12 * V + saved) * P * n,
+            # one fused call each, or (split) the warp stages on their own: warp fwd reads depth + sources and writes
+            # the warped copy; SSIM fwd reads target + warped + auto-mask, writes sel; SSIM bwd reads target + warped +
+            # sel, writes g_warped; warp bwd reads g_warped + depth + sources, writes g_inv_depth
+            "photometric_fwd": ((17 + 12 * V) if split else (16 + 12 * V + saved)) * P * n,
+            "photometric_bwd": ((13 + 24 * V) if split else (20 + 12 * V + saved)) * P * n,
+            "warp_sources_fwd": (4 + 24 * V) * P * n, "warp_sources_bwd": (8 + 24 * V) * P * n,
             "automask_fwd": (12 + 12 * V + 4) * P,
             "smoothness_fwd": (12 + 8 * n) * P, "smoothness_bwd": (12 + 8 * n) * P,
             "reproj_loss_fwd": 4 * P, "reproj_loss_bwd": 4 * P,
@@ -216,6 +222,6 @@ class HotPathStep:
             total = sum(out[k] * calls[k] for k in calls) + out["reproj_loss_fwd"] + out["reproj_loss_bwd"]
         else:
             total = sum(out[k] * calls[k] for k in calls) + sum(out[k] for k in (
-                "photometric_fwd", "photometric_bwd", "automask_fwd", "smoothness_fwd", "smoothness_bwd"))
+                "automask_fwd", "smoothness_fwd", "smoothness_bwd")) + (16 + 12 * V + saved + 20 + 12 * V + saved) * P * n
         out["step_total"] = total
         return out

@@ -490,7 +490,8 @@ def feat_cost(depth, fmap, fmaps_ref, poses, K, Kref=None, scale=1.0, inverse_de
 # DROSFM_PHOTO_SAVE_WARP=0 makes the photometric backward re-warp instead of re-reading (saves 12 B per pixel,
 # view and prediction of activation memory at ~15 % more backward time)
 SAVE_WARP = os.environ.get("DROSFM_PHOTO_SAVE_WARP", "1") != "0"
-# DROSFM_PHOTO_OVERLAP=0 keeps the whole loss on the caller's stream (no second stream for auto-mask / smoothness)
+# DROSFM_PHOTO_OVERLAP=0 keeps the whole loss on the caller's stream (no second stream for auto-mask / smoothness).
+# OVERLAP may also be set to "serial" (bench.py's per-kernel timing pass): the same split calls, on one stream.
 OVERLAP = os.environ.get("DROSFM_PHOTO_OVERLAP", "1") != "0"
 
 
@@ -528,7 +529,8 @@ class _PhotoLoss(torch.autograd.Function):
         wsave = torch.empty(n, V, B, 3, H, W, device=dev, dtype=torch.float32) if keep_warp else None
         stats = torch.empty(n, B, 4, device=dev, dtype=torch.float32) if smooth_w > 0.0 else None
         lib = L.lib()
-        staged = wsave is not None and OVERLAP
+        staged = wsave is not None and bool(OVERLAP)        # split calls
+        two_streams = staged and OVERLAP is True            # OVERLAP == "serial": split calls, one stream
         with torch.cuda.device(dev):
             ws = L.workspace(dev, max(n * B + 1, V * n * B))
             st = L.stream()
@@ -540,7 +542,7 @@ class _PhotoLoss(torch.autograd.Function):
                 if automask:
                     L.check(lib.drosfm_automask_fwd(pc, pa, V, opts, L.ptr(amask), B, H, W, L.stream()), "automask_fwd")
                 ev = None
-                if staged:
+                if two_streams:
                     ev = torch.cuda.Event()
                     ev.record()
                 if smooth_w > 0.0:
@@ -551,20 +553,24 @@ class _PhotoLoss(torch.autograd.Function):
             if staged:
                 # the flat warp of all sources runs on the caller's stream while a second stream produces the
                 # auto-mask map (needed by the SSIM stage) and the smoothness term (needed at the end)
-                main, side = torch.cuda.current_stream(dev), L.side_stream(dev)
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    ev_mask = side_work()
+                if two_streams:
+                    main, side = torch.cuda.current_stream(dev), L.side_stream(dev)
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        ev_mask = side_work()
+                else:
+                    side_work()
                 L.check(lib.drosfm_warp_sources_fwd(pa, V, pi, depth_kind, n, cams, pp_, padding, L.ptr(wsave), B, H, W, st),
                         "warp_sources_fwd")
-                main.wait_event(ev_mask)
+                if two_streams:
+                    main.wait_event(ev_mask)
                 flags = L.PHOTO_WARPED_READY
             else:
                 side_work()
                 flags = 0
             L.check(lib.drosfm_photometric_fwd(pc, pa, V, pi, depth_kind, n, cams, pp_, L.ptr(amask), opts, L.ptr(sel),
                                                L.ptr(losses), L.ptr(ws), L.ptr(wsave), flags, B, H, W, st), "photometric_fwd")
-            if staged:
+            if two_streams:
                 main.wait_stream(side)
         total = losses.sum().reshape(1)
         ctx.save_for_backward(image, keep[0], keep[1], sel, stats, wsave, *context, *invs, *poses)
@@ -603,15 +609,18 @@ class _PhotoLoss(torch.autograd.Function):
             if wsave is not None and OVERLAP and smooth:
                 # the smoothness gradient is written by a second stream while the window-gradient stage runs; the warp
                 # adjoint then adds its share to the same buffers
-                main, side = torch.cuda.current_stream(dev), L.side_stream(dev)
-                side.wait_stream(main)
+                two_streams = OVERLAP is True
+                main, side = torch.cuda.current_stream(dev), (L.side_stream(dev) if two_streams else torch.cuda.current_stream(dev))
+                if two_streams:
+                    side.wait_stream(main)
                 with torch.cuda.stream(side):
                     L.check(lib.drosfm_smoothness_bwd(L.ptr(g), pc, pi, n, smooth_w, L.ptr(stats), L.ptr_array(g_invs), 0, B, H, W,
                                                       L.stream()), "smoothness_bwd")
                 L.check(lib.drosfm_photometric_bwd(L.ptr(g), pc, pa, V, pi, depth_kind, n, cams, pp_, L.ptr(sel), opts, None, None,
                                                    L.ptr(ws), L.ptr(wsave), L.ptr(g_warped), L.PHOTO_NO_ADJOINT, B, H, W, st),
                         "photometric_bwd")
-                main.wait_stream(side)
+                if two_streams:
+                    main.wait_stream(side)
                 L.check(lib.drosfm_warp_sources_bwd(L.ptr(g_warped), pa, V, pi, depth_kind, n, cams, pp_, padding,
                                                     L.ptr_array(g_invs), L.ptr_array(g_poses), L.ptr(ws), 1, B, H, W, st),
                         "warp_sources_bwd")
