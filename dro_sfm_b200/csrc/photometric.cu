@@ -1340,23 +1340,31 @@ ssim_bwd_stream2_kernel(const float* __restrict__ g_loss, const float* __restric
     const float2 inv9 = bc2(1.0f / 9.0f), ninv9 = bc2(-1.0f / 9.0f), two = bc2(2.0f);
     const float2 C1 = bc2(opts.C1), C2 = bc2(opts.C2);
 
-    float2 nx;
-    float ny;
-    auto fetch = [&](int gy) {
-        const unsigned off = static_cast<unsigned>(padded_row(gy, H) * W);
-        nx.x = col_in ? __ldg(xpl + off) : 0.0f;
-        nx.y = col_in ? __ldg(xpl + (off + vstride)) : 0.0f;
-        ny = col_in ? __ldg(ypl + off) : 0.0f;
+    // rows are requested two steps before they are used (three rotating buffers); the sel byte of a row travels with it
+    // and is consumed one step later still, when that row is the window centre
+    struct Pre {
+        float2 x;
+        float y;
+        int sel;
     };
+    Pre f0, f1, f2;
+    auto fetch = [&](int gy, Pre& f) {
+        const unsigned off = static_cast<unsigned>(padded_row(gy, H) * W);
+        f.x.x = col_in ? __ldg(xpl + off) : 0.0f;
+        f.x.y = col_in ? __ldg(xpl + (off + vstride)) : 0.0f;
+        f.y = col_in ? __ldg(ypl + off) : 0.0f;
+        f.sel = 254;
+        if (col_in && gy >= 0 && gy < H) f.sel = use_min ? static_cast<int>(__ldg(spl + static_cast<unsigned>(gy * W))) : 253;
+    };
+    int sel_row = 254;      // sel of the row loaded in the previous step = the centre row of this step
     int sv_prev = 254;
-    auto step = [&](BwdRow2& p2, BwdRow2& p1, BwdRow2& cur, int j) {
+    auto step = [&](BwdRow2& p2, BwdRow2& p1, BwdRow2& cur, Pre& mine, Pre& refill, int j) {
         const int gy = gy0 - 2 + j;
-        const int gc = gy - 1;
-        cur.x = nx;
-        cur.y = ny;
-        fetch(gy + 1);
-        int sv = 254;
-        if (j >= 2 && col_in && gc >= 0 && gc < H) sv = use_min ? static_cast<int>(__ldg(spl + static_cast<unsigned>(gc * W))) : 253;
+        cur.x = mine.x;
+        cur.y = mine.y;
+        const int sv = j >= 2 ? sel_row : 254;
+        sel_row = mine.sel;
+        fetch(gy + 2, refill);
         const float2 xl = shfl2(cur.x, nb.l), xr = shfl2(cur.x, nb.r);
         float yl, yr;
         neighbours(cur.y, nb, yl, yr);
@@ -1438,12 +1446,13 @@ ssim_bwd_stream2_kernel(const float* __restrict__ g_loss, const float* __restric
     r0.sy = r0.syy = r1.sy = r1.syy = 0.0f;
     r0.x = r1.x = bc2(0.0f);
     r0.y = r1.y = 0.0f;
-    fetch(gy0 - 2);
+    fetch(gy0 - 2, f0);
+    fetch(gy0 - 1, f1);
 #pragma unroll 1
     for (int j = 0; j < kBwdBandH + 4; j += 3) {
-        step(r1, r2, r0, j);
-        step(r2, r0, r1, j + 1);
-        step(r0, r1, r2, j + 2);
+        step(r1, r2, r0, f0, f2, j);
+        step(r2, r0, r1, f1, f0, j + 1);
+        step(r0, r1, r2, f2, f1, j + 2);
     }
 }
 
