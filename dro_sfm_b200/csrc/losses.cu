@@ -38,7 +38,22 @@ smooth_mean_kernel(const __grid_constant__ DepthList dl, float* __restrict__ sta
     const int i = ib / B, b = ib - i * B;
     const float* d = dl.d[i] + static_cast<size_t>(b) * P;
     double s = 0.0;
-    for (int p = blockIdx.x * kLossThreads + threadIdx.x; p < P; p += gridDim.x * kLossThreads) s += __ldg(d + p);
+    if ((P & 3) == 0 && (reinterpret_cast<size_t>(d) & 15) == 0) {
+        // 128-bit loads, two in flight per thread and iteration
+        const float4* d4 = reinterpret_cast<const float4*>(d);
+        const int P4 = P >> 2, stride = gridDim.x * kLossThreads;
+        int p = blockIdx.x * kLossThreads + threadIdx.x;
+        for (; p + stride < P4; p += 2 * stride) {
+            const float4 a = __ldg(d4 + p), c = __ldg(d4 + p + stride);
+            s += static_cast<double>((a.x + a.y) + (a.z + a.w)) + static_cast<double>((c.x + c.y) + (c.z + c.w));
+        }
+        if (p < P4) {
+            const float4 a = __ldg(d4 + p);
+            s += static_cast<double>((a.x + a.y) + (a.z + a.w));
+        }
+    } else {
+        for (int p = blockIdx.x * kLossThreads + threadIdx.x; p < P; p += gridDim.x * kLossThreads) s += __ldg(d + p);
+    }
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
