@@ -103,37 +103,49 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm (oracle port, PyTorch CPU) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_step(wl, batch, threads):
+def cpu_step(wl, batch, threads, dtype=torch.float32, return_grads=False, pose_to_T=None):
     """One frame-batch of the same hot-path work with the CPU oracle (test infrastructure used here only
-    as the reported baseline): 2*V*T cost evaluations fwd+bwd + the loss fwd+bwd."""
+    as the reported baseline / checker): 2*V*T cost evaluations fwd+bwd + the loss fwd+bwd.
+
+    return_grads: also return the gradient of every leaf in HotPathStep.leaves() order.  pose_to_T: how a [B,6] pose
+    vector becomes a [B,4,4] matrix (default: the oracle's Pose.from_vec on the CPU)."""
     import oracle
     torch.set_num_threads(threads)
-    K = batch["K"]
-    fmap = batch["fmap"].clone().requires_grad_(True)
-    frefs = [f.clone().requires_grad_(True) for f in batch["fmaps_ref"]]
+    to_T = pose_to_T or oracle.pose_vec_to_T
+    c = lambda x: x.to(dtype)                                                    # noqa: E731
+    K = batch["K"].float().to(dtype)                                             # the reference casts K.float() first
+    fmap = c(batch["fmap"]).clone().requires_grad_(True)
+    frefs = [c(f).clone().requires_grad_(True) for f in batch["fmaps_ref"]]
     B, C, h, w = fmap.shape
     g = torch.Generator().manual_seed(99)
-    gout = torch.randn(B, C, h, w, generator=g)
-    outs = []
+    n_cost = wl.T * (1 + wl.V)
+    gouts = [c(torch.randn(B, C, h, w, generator=g)) for _ in range(n_cost)] if return_grads else \
+        [c(torch.randn(B, C, h, w, generator=g))] * n_cost
+    outs, inv_lr, pose_lr = [], [], []
     for t in range(wl.T):
-        inv = batch["inv_depth_lr"][t].clone().requires_grad_(True)
-        outs.append(oracle.depth_cost(inv, fmap, frefs, [p for p in batch["pose_lr"][t]], K, K, 0.125))
-        depth = oracle.inv2depth(batch["inv_depth_lr"][(t // wl.seq_len) * wl.seq_len])
+        inv = c(batch["inv_depth_lr"][t]).clone().requires_grad_(True)
+        inv_lr.append(inv)
+        outs.append(oracle.depth_cost(inv, fmap, frefs, [to_T(c(p)) for p in batch["pose_lr"][t]], K, K, 0.125))
+        depth = oracle.inv2depth(c(batch["inv_depth_lr"][(t // wl.seq_len) * wl.seq_len]))
         for v in range(wl.V):
-            pose = batch["pose_lr"][t][v].clone().requires_grad_(True)
-            outs.append(oracle.feat_cost_each(pose, fmap, frefs[v], depth, K, K, 0.125))
-    invs = [x.clone().requires_grad_(True) for x in batch["inv_depths"]]
-    pvec = [[p.clone().requires_grad_(True) for p in row] for row in batch["poses"]]
-    Ts = [[oracle.pose_vec_to_T(p) for p in row] for row in pvec]
+            pose = c(batch["pose_lr"][t][v]).clone().requires_grad_(True)
+            pose_lr.append(pose)
+            outs.append(oracle.feat_cost_each(to_T(pose), fmap, frefs[v], depth, K, K, 0.125))
+    invs = [c(x).clone().requires_grad_(True) for x in batch["inv_depths"]]
+    pvec = [[c(p).clone().requires_grad_(True) for p in row] for row in batch["poses"]]
+    Ts = [[to_T(p) for p in row] for row in pvec]
     if wl.supervised:
-        loss = oracle.reproj_pose_loss(Ts, [oracle.pose_vec_to_T(p) for p in batch["gt_poses"]],
-                                       oracle.inv2depth(batch["gt_inv_depth"]), K, K, wl.min_depth, wl.max_depth) \
-            + oracle.supervised_depth_loss(invs, batch["gt_inv_depth"], wl.min_depth, wl.max_depth)
+        loss = oracle.reproj_pose_loss(Ts, [to_T(c(p)) for p in batch["gt_poses"]],
+                                       oracle.inv2depth(c(batch["gt_inv_depth"])), K, K, wl.min_depth, wl.max_depth) \
+            + oracle.supervised_depth_loss(invs, c(batch["gt_inv_depth"]), wl.min_depth, wl.max_depth)
     else:
-        loss, _ = oracle.multiview_photometric_decay_loss(batch["image"], batch["context"], invs, K, K, Ts, smooth_w=0.001,
-                                                          automask=True, reduce_op="min")
-    torch.autograd.backward([loss.sum()] + outs, [torch.ones(())] + [gout] * len(outs))
-    return float(loss.sum())
+        loss, _ = oracle.multiview_photometric_decay_loss(c(batch["image"]), [c(x) for x in batch["context"]], invs, K, K, Ts,
+                                                          smooth_w=0.001, automask=True, reduce_op="min")
+    torch.autograd.backward([loss.sum()] + outs, [torch.ones((), dtype=dtype)] + gouts)
+    if not return_grads:
+        return float(loss.detach().sum())
+    leaves = [fmap] + frefs + inv_lr + pose_lr + invs + [p for row in pvec for p in row]
+    return float(loss.detach().sum()), [x.grad for x in leaves]
 
 
 def time_cpu(wl, B, reps, threads):

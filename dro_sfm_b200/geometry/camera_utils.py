@@ -27,7 +27,9 @@ def view_synthesis(ref_image, depth, ref_cam, cam, mode='bilinear', padding_mode
     assert depth.size(1) == 1
     if mode != 'bilinear':
         raise NotImplementedError("dro_sfm_b200: interpolation mode {!r} is not supported".format(mode))
-    if cam.Tcw._is_identity:
+    # `_is_identity` is set by Pose.identity() and cleared by the mat setter; an in-place edit of the matrix storage
+    # (pose.mat[:, :3, 3] = t) bumps the tensor's version counter, which is checked here
+    if cam.Tcw._is_identity and cam.Tcw.mat._version == 0:
         return ops.view_synthesis(ref_image, depth, ref_cam.Tcw.mat, cam.K, ref_cam.K, 1.0, padding_mode)
     world_points = cam.reconstruct(depth, frame='w')
     ref_coords = ref_cam.project(world_points, frame='w')

@@ -30,7 +30,9 @@ class Pose:
 
     @mat.setter
     def mat(self, value):
-        self._mat, self._vec = value, None
+        # a new matrix is no longer known to be the identity (view_synthesis picks its fused kernel on that flag);
+        # to() / repeat() restore the flag themselves because they keep the values
+        self._mat, self._vec, self._is_identity = value, None, False
 
     def kernel_arg(self):
         """What the fused kernels consume: the [B,6] euler vector when known (the conversion then runs in
@@ -68,7 +70,9 @@ class Pose:
         return self.mat
 
     def repeat(self, *args, **kwargs):
+        ident = self._is_identity
         self.mat = self.mat.repeat(*args, **kwargs)
+        self._is_identity = ident
         return self
 
     def inverse(self):
@@ -82,7 +86,9 @@ class Pose:
         return out
 
     def to(self, *args, **kwargs):
+        ident = self._is_identity
         self.mat = self.mat.to(*args, **kwargs)
+        self._is_identity = ident
         return self
 
     def transform_pose(self, pose):

@@ -54,7 +54,8 @@ class SupervisedDepthPoseLoss(LossBase):
             if tuple(d.shape) != tuple(gt_inv_depth.shape):
                 raise NotImplementedError("dro_sfm_b200: predictions must be at the ground-truth resolution")
         loss_depth = self.calculate_loss(inv_depths, [gt_inv_depth] * self.n)
-        preds = [[p.mat if hasattr(p, "mat") else p for p in pv] for pv in poses]
+        # calc_pose_loss (and the reference, supervised_loss.py:306-312) use the first self.n predictions of every view
+        preds = [[p.mat if hasattr(p, "mat") else p for p in pv[:self.n]] for pv in poses]
         gts = [g.mat if hasattr(g, "mat") else g for g in gt_pose_context]
         # inv2depth of the GT map is fused into the kernel
         loss_pose = ops.reproj_pose_loss(preds, gts, gt_inv_depth, K, ref_K, self.min_depth, self.max_depth, 0.85,

@@ -419,12 +419,20 @@ class _FeatCost(torch.autograd.Function):
         sinks = ctx.sinks
 
         def sink_buffer(sink, like):
-            """(buffer, value to return to autograd): the first consumer of a step allocates the zeroed
-            buffer and returns a zero placeholder so that the sink node runs; later ones return None."""
+            """(buffer, value to return to autograd): the first consumer of a backward pass allocates the zeroed
+            buffer and returns a zero placeholder so that the sink node runs; later ones return None.  The buffer
+            belongs to ONE backward pass: a callback at the end of the pass drops it if the sink node was not reached
+            (torch.autograd.grad(cost, inputs=[pose]) or an aborted pass), so partial sums never leak into the next."""
             if sink.buffer is None:
                 sink.buffer = torch.zeros_like(like)
                 if sink.dummy is None or sink.dummy.shape != like.shape:
                     sink.dummy = _zero_scalar(like.device).expand(like.shape)
+                buf = sink.buffer
+
+                def end_of_pass(sink=sink, buf=buf):
+                    if sink.buffer is buf:
+                        sink.buffer = None
+                torch.autograd.Variable._execution_engine.queue_callback(end_of_pass)
                 return sink.buffer, sink.dummy
             return sink.buffer, None
 

@@ -71,3 +71,15 @@ def warp_coords(depth, K, Kref, T, sx=1.0, sy=None, normalize=True, want_mask=Fa
     lib().drosfm_oracle_warp_coords(_p(depth), _p(K), _p(Kref), _p(T), ctypes.c_float(sx), ctypes.c_float(sy),
                                     _p(uv), _p(mask, _u8), B, H, W, int(normalize))
     return (uv, mask.astype(bool)) if want_mask else uv
+
+
+def euler_from_trig(trig, angle_z, fma=False):
+    """(sin x, cos x, sin y, cos y, sin z, cos z) [N,6] + z angles [N] -> R [N,3,3] in euler2mat's operation order.
+    fma=False: the accumulation of torch's CPU bmm; fma=True: the FMA chain of a CUDA bmm (see coords_oracle.c)."""
+    trig, angle_z = _c(trig), _c(angle_z)
+    N = trig.shape[0]
+    out = np.empty((N, 3, 3), np.float32)
+    fn = lib().drosfm_oracle_euler_from_trig
+    for i in range(N):
+        fn(_p(trig[i]), ctypes.c_float(float(angle_z[i])), int(bool(fma)), _p(out[i]))
+    return out

@@ -147,3 +147,33 @@ void drosfm_oracle_warp_coords(const float* depth, const float* K, const float* 
             }
     }
 }
+
+/* euler2mat (dro_sfm/geometry/pose_utils.py:38-69) AFTER the six trigonometric evaluations:
+ * trig = (sin x, cos x, sin y, cos y, sin z, cos z) as produced by torch.sin / torch.cos (they depend on the math
+ * library of the device that runs the reference -- SLEEF on the CPU, the CUDA math library on the GPU -- so they are
+ * INPUTS here), angle_z = the z angle itself (the reference's `zeros` is z * 0, a SIGNED zero, `ones` is zeros + 1).
+ * R = (Rx . Ry) . Rz, every entry of both 3x3 products computed with zero and one entries included.  Accumulation:
+ *   use_fma == 0   (a0*b0 + a1*b1) + a2*b2 with every product rounded -- what torch 2.11's CPU bmm does for
+ *                  [B,3,3] x [B,3,3] operands (pinned by tests/test_oracle_golden.py::test_euler_restatement_*);
+ *   use_fma != 0   fma(a2,b2, fma(a1,b1, a0*b0)) -- what the reference's bmm evaluates on a CUDA device (pinned on the
+ *                  B200 by tests/test_kernels_gpu.py::test_pose_vec2mat_bit_exact_vs_torch_cuda).
+ * R is row-major [9]. */
+static void mat3_mul(const float* A, const float* B, float* C, int use_fma) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            const float* a = A + 3 * i;
+            if (use_fma) C[3 * i + j] = fmaf(a[2], B[6 + j], fmaf(a[1], B[3 + j], a[0] * B[j]));
+            else C[3 * i + j] = (a[0] * B[j] + a[1] * B[3 + j]) + a[2] * B[6 + j];
+        }
+}
+
+void drosfm_oracle_euler_from_trig(const float* trig, float angle_z, int use_fma, float* R) {
+    const float sx = trig[0], cx = trig[1], sy = trig[2], cy = trig[3], sz = trig[4], cz = trig[5];
+    const float zero = angle_z * 0.0f, one = zero + 1.0f;
+    const float Rx[9] = {one, zero, zero, zero, cx, -sx, zero, sx, cx};
+    const float Ry[9] = {cy, zero, sy, zero, one, zero, -sy, zero, cy};
+    const float Rz[9] = {cz, -sz, zero, sz, cz, zero, zero, zero, one};
+    float Rxy[9];
+    mat3_mul(Rx, Ry, Rxy, use_fma);
+    mat3_mul(Rxy, Rz, R, use_fma);
+}

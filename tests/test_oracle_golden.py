@@ -196,3 +196,23 @@ def test_upsample_depth(golden, dt, tag):
     assert_close(y.detach(), g[f"{tag}_out"], what="out", **tol)
     assert_close(gd, g[f"{tag}_g_depth"], what="g_depth", **(tol if dt == torch.float64 else dict(rtol=1e-5, atol=1e-6)))
     assert_close(gm, g[f"{tag}_g_mask"], what="g_mask", **tol)
+
+
+@pytest.mark.parametrize("scale", [0.01, 0.05, 2.0])
+def test_euler_restatement_matches_torch_cpu(scale):
+    """oracle/coords_oracle.c:drosfm_oracle_euler_from_trig (non-FMA accumulation) reproduces euler2mat as torch
+    evaluates it on the CPU bit for bit -- signed zeros included -- when fed torch's own sin / cos."""
+    import numpy as np
+    torch.manual_seed(11)
+    ang = (torch.randn(4096, 3) * scale).float()
+    ang[:64] = -ang[:64].abs()
+    ang[64:72] = 0.0
+    ang[72:80] = -0.0
+    R = oracle.euler_to_R(ang).numpy()
+    x, y, z = ang[:, 0], ang[:, 1], ang[:, 2]
+    trig = torch.stack([torch.sin(x), torch.cos(x), torch.sin(y), torch.cos(y), torch.sin(z), torch.cos(z)], 1).numpy()
+    Rc = c_oracle.euler_from_trig(trig, z.numpy(), fma=False)
+    assert np.array_equal(R.view(np.uint32), Rc.view(np.uint32))
+    # the FMA accumulation (what a CUDA bmm evaluates) differs from it by at most one ulp of 1.0
+    Rf = c_oracle.euler_from_trig(trig, z.numpy(), fma=True)
+    assert np.abs(Rf.astype(np.float64) - R).max() <= 1.2e-7
