@@ -148,16 +148,57 @@ def cpu_step(wl, batch, threads, dtype=torch.float32, return_grads=False, pose_t
     return float(loss.detach().sum()), [x.grad for x in leaves]
 
 
+def cpu_arm():
+    """(kind, step function) of the CPU arm: the UNMODIFIED reference's own functions when its package is staged
+    (baseline/_ref, oracle/stage_reference.py; kind "reference"), else the oracle port (kind "port"; bit-equal to the
+    reference on the CPU, tests/test_oracle_vs_reference.py)."""
+    from oracle import reference
+    if reference.available():
+        def ref_step(wl, batch, threads):
+            torch.set_num_threads(threads)
+            return reference.hot_path_step(wl, batch, "cpu")
+        return "reference", ref_step
+    return "port", cpu_step
+
+
 def time_cpu(wl, B, reps, threads):
+    """Returns (frames/s, seconds per step, loss, kind)."""
     from dro_sfm_b200 import synthetic as syn
+    kind, fn = cpu_arm()
     batch = syn.hot_path_batch(wl, seed=1234, C=128, B=B)
-    cpu_step(wl, batch, threads)                     # warm-up
+    loss = fn(wl, batch, threads)                    # warm-up
     best = float("inf")
     for _ in range(reps):
         t0 = time.perf_counter()
-        cpu_step(wl, batch, threads)
+        fn(wl, batch, threads)
         best = min(best, time.perf_counter() - t0)
-    return B / best, best
+    return B / best, best, loss, kind
+
+
+def time_gpu_aten_reference(wl, B, dev, steps=3):
+    """The REFERENCE's own cost + loss calls (stock ATen ops, TF32 off) on the same GPU: the like-for-like comparator of
+    SURVEY.md section 8(d).  None when the reference package is not staged."""
+    from oracle import reference
+    if not reference.available():
+        return None
+    from dro_sfm_b200 import synthetic as syn
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        batch = syn.hot_path_batch(wl, seed=1234, C=128, B=B)
+        for _ in range(2):
+            loss = reference.hot_path_step(wl, batch, dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            reference.hot_path_step(wl, batch, dev)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    return {"value": B / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "batch": B, "steps": steps, "loss": loss,
+            "what": "the unmodified reference's get_cost_each / depth_cost_calc / loss modules (stock ATen, eager, TF32 off) "
+                    "on the same B200, same inputs and call sequence, inputs resident on the device"}
 
 
 def run_reference(args, wl):
@@ -167,22 +208,25 @@ def run_reference(args, wl):
     threads = os.cpu_count() or 1
     from dro_sfm_b200 import synthetic as syn
     B = 1
+    kind, fn = cpu_arm()
     batch = syn.hot_path_batch(wl, seed=1234, C=128, B=B)
     for _ in range(min(args.warmup, 1)):
-        cpu_step(wl, batch, threads)
+        fn(wl, batch, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_step(wl, batch, threads)
+        fn(wl, batch, threads)
     dt = (time.perf_counter() - t0) / args.steps
     value = B / dt
-    sample = "B=1 frame of %s per step (all %d cost calls + loss, fwd+bwd), PyTorch-CPU oracle port" % (wl.name, 2 * wl.V * wl.T)
+    sample = "B=1 frame of %s per step (all %d cost calls + loss, fwd+bwd), %s" % (
+        wl.name, 2 * wl.V * wl.T, "the unmodified reference's own functions on PyTorch-CPU (baseline/_ref)" if kind == "reference"
+        else "PyTorch-CPU oracle port of the reference")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl.name, "H": wl.H, "W": wl.W, "views": wl.V, "gru_steps": wl.T, "predictions": wl.n,
                    "batch_per_step": B, "device": "cpu"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -341,13 +385,22 @@ def run_gpu(args, wl):
                                  for k in sorted(totals) if k in alg}}
 
     if rank == 0:
-        cpu = None
+        cpu = parity = aten = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, best = time_cpu(wl, 1, 3, threads)
-            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": "B=1 frame of %s (all %d cost calls + loss, fwd+bwd), best of 3 after 1 warm-up, %.2f s each; "
-                             "PyTorch-CPU oracle port of the reference" % (wl.name, 2 * wl.V * wl.T, best)}
+            v, best, cpu_loss, kind = time_cpu(wl, 1, 3, threads)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                   "sample": "B=1 frame of %s (all %d cost calls + loss, fwd+bwd), best of 3 after 1 warm-up, %.2f s each; %s"
+                             % (wl.name, 2 * wl.V * wl.T, best, "the unmodified reference's own functions on PyTorch-CPU"
+                                if kind == "reference" else "PyTorch-CPU oracle port of the reference")}
+            # the timed GPU step and the CPU arm compute the same thing: loss of the SAME B=1 inputs on both
+            chk = HotPathStep(wl, dev, B=1, seed=1234, channels_last=(args.layout == "nhwc"))
+            gpu_loss = float(chk.step().detach())
+            parity = {"gpu_loss": gpu_loss, "cpu_loss": cpu_loss, "rel_err": abs(gpu_loss - cpu_loss) / max(abs(cpu_loss), 1e-30),
+                      "inputs": "B=1, seed 1234 of %s on both arms; full-step gradients are compared in "
+                                "tests/test_hotpath_parity_gpu.py" % wl.name}
+            del chk
+            aten = time_gpu_aten_reference(wl, B, dev)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -360,7 +413,7 @@ def run_gpu(args, wl):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
-            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity, "gpu_aten_reference": aten,
         }
         print(json.dumps(out))
     if world > 1:
