@@ -103,12 +103,13 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm (oracle port, PyTorch CPU) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_step(wl, batch, threads, dtype=torch.float32, return_grads=False, pose_to_T=None):
+def cpu_step(wl, batch, threads, dtype=torch.float32, return_grads=False, pose_to_T=None, forced_sel=None, maps_out=None):
     """One frame-batch of the same hot-path work with the CPU oracle (test infrastructure used here only
     as the reported baseline / checker): 2*V*T cost evaluations fwd+bwd + the loss fwd+bwd.
 
     return_grads: also return the gradient of every leaf in HotPathStep.leaves() order.  pose_to_T: how a [B,6] pose
-    vector becomes a [B,4,4] matrix (default: the oracle's Pose.from_vec on the CPU)."""
+    vector becomes a [B,4,4] matrix (default: the oracle's Pose.from_vec on the CPU).  forced_sel / maps_out: see
+    oracle.photometric_loss (checker-only: the per-pixel arg-min of the photometric loss taken from another evaluation)."""
     import oracle
     torch.set_num_threads(threads)
     to_T = pose_to_T or oracle.pose_vec_to_T
@@ -140,7 +141,8 @@ def cpu_step(wl, batch, threads, dtype=torch.float32, return_grads=False, pose_t
             + oracle.supervised_depth_loss(invs, c(batch["gt_inv_depth"]), wl.min_depth, wl.max_depth)
     else:
         loss, _ = oracle.multiview_photometric_decay_loss(c(batch["image"]), [c(x) for x in batch["context"]], invs, K, K, Ts,
-                                                          smooth_w=0.001, automask=True, reduce_op="min")
+                                                          smooth_w=0.001, automask=True, reduce_op="min",
+                                                          forced_sel=forced_sel, maps_out=maps_out)
     torch.autograd.backward([loss.sum()] + outs, [torch.ones((), dtype=dtype)] + gouts)
     if not return_grads:
         return float(loss.detach().sum())

@@ -13,9 +13,10 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libdrosfm_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_VIEWS = 8
 MAX_PREDS = 16
+MAX_COST_JOBS = 9
 
 POSE_IDENTITY, POSE_MAT4, POSE_EULER6 = 0, 1, 2
 PAD_ZEROS, PAD_BORDER = 0, 1
@@ -45,8 +46,22 @@ class PhotoOpts(ctypes.Structure):
                 ("reduce_op", ctypes.c_int32), ("automask", ctypes.c_int32), ("gamma", _f32)]
 
 
+class CostJob(ctypes.Structure):
+    """drosfm_cost_job_t"""
+    _fields_ = [("fmap", _vp), ("fmap_ref", _pp), ("depth", _vp), ("depth_kind", ctypes.c_int32), ("poses", _pp),
+                ("n_views", ctypes.c_int32), ("cost", _vp)]
+
+
+class CostJobGrads(ctypes.Structure):
+    """drosfm_cost_job_grads_t"""
+    _fields_ = [("g_cost", _vp), ("g_fmap", _vp), ("g_fmap_ref", _pp), ("g_depth", _vp), ("g_poses", _pp),
+                ("flags", ctypes.c_int32)]
+
+
 _cp = ctypes.POINTER(Cams)
 _op = ctypes.POINTER(PhotoOpts)
+_jp = ctypes.POINTER(CostJob)
+_gp = ctypes.POINTER(CostJobGrads)
 
 # name -> argtypes; every symbol include/drosfm_b200.h declares (tests check the export list)
 SIGNATURES = {
@@ -70,6 +85,8 @@ SIGNATURES = {
     "drosfm_feat_cost_fwd": ([_vp, _pp, _vp, _int, _cp, _pp, _int, _vp, _int, _int, _int, _int, _int, _vp], _int),
     "drosfm_feat_cost_bwd": ([_vp, _vp, _pp, _vp, _int, _cp, _pp, _int, _vp, _pp, _vp, _pp, _vp,
                               _int, _int, _int, _int, _int, _int, _vp], _int),
+    "drosfm_feat_cost_batch_fwd": ([_jp, _int, _cp, _int, _int, _int, _int, _int, _vp], _int),
+    "drosfm_feat_cost_batch_bwd": ([_jp, _gp, _int, _cp, _vp, _int, _int, _int, _int, _int, _vp], _int),
     "drosfm_automask_fwd": ([_vp, _pp, _int, _op, _vp, _int, _int, _int, _vp], _int),
     "drosfm_photometric_fwd": ([_vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _vp, _vp, _vp, _vp,
                                 _int, _int, _int, _int, _vp], _int),

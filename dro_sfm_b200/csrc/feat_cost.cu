@@ -289,9 +289,35 @@ feat_cost_bwd_nchw(const float* __restrict__ g_cost, const float* __restrict__ f
 // Lanes 0..ppw-1 first compute the taps of "their" pixel and park them in shared memory; the warp then
 // walks over the pixels with all lanes on the channel axis.  ppw is chosen by the host: small for small
 // maps (more warps in flight), 32 for large ones (coordinate work amortised over more bytes).
+//
+// One launch evaluates a BATCH of independent cost calls ("jobs", blockIdx.z): within one step of the recurrent
+// optimiser the depth cost (V views, mean) and the V per-view pose costs depend only on the state at the start of the
+// step (DepthPoseNet.py:159-167 builds all cost closures before either update block runs), so a caller that advances
+// the update blocks in lock-step submits them together.  At the training shapes a single call is a one-wave launch
+// bound by the latency of one warp's chain; three or more jobs per launch overlap each other's phases.
 // ------------------------------------------------------------------------------------------
 constexpr int kWarpsPerBlock = 4;
 constexpr int kMaxPpw = 32;
+constexpr int kMaxJobs = DROSFM_MAX_COST_JOBS;
+
+struct CostJob {
+    const float* fmap;
+    const float* depth;
+    float* cost;
+    const float* ref[DROSFM_MAX_VIEWS];
+    const float* pose[DROSFM_MAX_VIEWS];
+    int V, depth_kind;
+};
+struct CostJobGrad {
+    const float* g_cost;
+    float* g_fmap;
+    float* g_depth;
+    float* g_ref[DROSFM_MAX_VIEWS];
+    float* g_pose[DROSFM_MAX_VIEWS];
+    int acc_fmap, need_coord, slot0, pad_;      // slot0: first workspace slot of the job (V * B slots)
+};
+struct CostJobs { CostJob j[kMaxJobs]; };
+struct CostJobGrads { CostJobGrad j[kMaxJobs]; };
 
 struct alignas(16) STap {      // 32 bytes: two broadcast LDS.128 per pixel and view
     int o00, dx, dy;           // element offsets (pixel units, to be multiplied by C)
@@ -312,34 +338,47 @@ __device__ __forceinline__ float4 blend4(const float4& a, const float4& b, const
                        a.z * wa + b.z * wb + c.z * wc + d.z * wd, a.w * wa + b.w * wb + c.w * wc + d.w * wd);
 }
 
+// Camera set-up of a block for the V views of its job.  Several views: the three parts of every view's set-up run in
+// three warps (measured: -0.3 / -1.2 us per call); one view: a second barrier costs more than the split saves.
+template <int VT>
+__device__ __forceinline__ void setup_cams_block(const drosfm_cams_t& cams, const CostJob& job, int b, Cam* cam) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, V = job.V;
+    if constexpr (VT >= 2) {
+        if (V >= 2) {
+            if (wid < 3 && lane < V) setup_cam_part(cams, job.pose[lane], b, cam[lane], wid);      // kWarpsPerBlock >= 3
+            __syncthreads();
+            if (threadIdx.x < V) setup_cam_finish(cam[threadIdx.x]);
+        } else if (threadIdx.x == 0) {
+            setup_cam(cams, job.pose[0], b, cam[0]);
+        }
+    } else {
+        if (threadIdx.x == 0) setup_cam(cams, job.pose[0], b, cam[0]);
+    }
+    __syncthreads();
+}
+
 template <int VT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-feat_cost_fwd_nhwc(const float* __restrict__ fmap, ViewPtrs vp, const float* __restrict__ depth, int depth_kind,
-                   drosfm_cams_t cams, int V, float* __restrict__ cost, int C, int h, int w, int ppw) {
+feat_cost_fwd_nhwc(const __grid_constant__ CostJobs jobs, drosfm_cams_t cams, int C, int h, int w, int ppw) {
     __shared__ Cam cam[VT];
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    STap* taps = reinterpret_cast<STap*>(dyn_smem);          // [warp][ppw][V]
+    STap* taps = reinterpret_cast<STap*>(dyn_smem);          // [warp][ppw][VT]
+    const CostJob& job = jobs.j[blockIdx.z];
+    const int V = job.V;
+    const float* __restrict__ fmap = job.fmap;
+    float* __restrict__ cost = job.cost;
     const int b = blockIdx.y, P = h * w;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int pbase = (blockIdx.x * kWarpsPerBlock + wid) * ppw;
     const int npix = max(0, min(ppw, P - pbase));
     const bool mine = lane < npix;
     const int p = pbase + lane;
-    const float draw = mine ? __ldg(depth + static_cast<size_t>(b) * P + p) : 0.0f;
-    if constexpr (VT >= 2) {
-        // several views: the three parts of every view's set-up run in three warps (measured: -0.3 / -1.2 us per call)
-        if (wid < 3 && lane < V) setup_cam_part(cams, vp.pose[lane], b, cam[lane], wid);      // kWarpsPerBlock >= 3
-        __syncthreads();
-        if (threadIdx.x < V) setup_cam_finish(cam[threadIdx.x]);
-    } else {
-        // one view: a second barrier costs more than the split saves
-        if (threadIdx.x == 0 && V > 0) setup_cam(cams, vp.pose[0], b, cam[0]);
-    }
-    __syncthreads();
+    const float draw = mine ? __ldg(job.depth + static_cast<size_t>(b) * P + p) : 0.0f;
+    setup_cams_block<VT>(cams, job, b, cam);
     if (npix == 0) return;
-    STap* wt = taps + static_cast<size_t>(wid) * ppw * V;
+    STap* wt = taps + static_cast<size_t>(wid) * ppw * VT;
     if (mine) {
-        const float d = to_depth(draw, depth_kind);
+        const float d = to_depth(draw, job.depth_kind);
         const float wm1 = static_cast<float>(w - 1), hm1 = static_cast<float>(h - 1);
         int x, y;
         pix_xy(p, w, x, y);
@@ -350,7 +389,7 @@ feat_cost_fwd_nhwc(const float* __restrict__ fmap, ViewPtrs vp, const float* __r
                 warp_pixel<true>(cam[v], x, y, d, wm1, hm1, true, wp);
                 CTaps t;
                 make_ctaps(wp.p.u, wp.p.v, h, w, t);
-                store_stap(wt + lane * V + v, t);
+                store_stap(wt + lane * VT + v, t);
             }
         }
     }
@@ -368,8 +407,8 @@ feat_cost_fwd_nhwc(const float* __restrict__ fmap, ViewPtrs vp, const float* __r
 #pragma unroll
             for (int v = 0; v < VT; ++v) {
                 if (v < V) {
-                    const STap t = wt[j * V + v];
-                    const float* r0 = vp.ref[v] + sample + static_cast<size_t>(t.o00) * C + cb;
+                    const STap t = wt[j * VT + v];
+                    const float* r0 = job.ref[v] + sample + static_cast<size_t>(t.o00) * C + cb;
                     const float4 a = ldg4f(r0), bq = ldg4f(r0 + t.dx * C);
                     const float4 c = ldg4f(r0 + t.dy * C), e = ldg4f(r0 + (t.dy + t.dx) * C);
                     const float4 wv = blend4(a, bq, c, e, t.w00, t.w01, t.w10, t.w11);
@@ -383,63 +422,58 @@ feat_cost_fwd_nhwc(const float* __restrict__ fmap, ViewPtrs vp, const float* __r
     }
 }
 
-// red.global.add.v4.f32 (sm_90+): one 16-byte reduction per lane, 512 contiguous bytes per warp
-__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// red.global.add.v4.f32 (sm_90+): one 16-byte reduction per lane, 512 contiguous bytes per warp.  Neither this nor the
+// store below carries a memory clobber, so the compiler may hoist the read-only loads of the next pixel across them;
+// both are `asm volatile`, which keeps them in program order RELATIVE TO EACH OTHER (the first view's plain store of a
+// target-map gradient is followed by the other views' reductions into the same address).
+__device__ __forceinline__ void red_add4_nc(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d));
+}
+__device__ __forceinline__ void st_global4_nc(float* p, float a, float b, float c, float d) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d));
 }
 
 // Backward, NHWC: same pixel-to-warp mapping as the forward.  Per pixel and view the warp loads the upstream
 // gradient, the target features and the four taps (six 512-byte accesses), issues four 512-byte
 // red.global.add.v4.f32 into the source gradient and reduces the coordinate gradient with shuffles.  The loads
-// of pixel j+1 are issued before pixel j is consumed (software pipeline), the reductions carry no memory
-// clobber so the compiler may hoist the read-only loads across them.
+// of pixel j+1 are issued before pixel j is consumed (software pipeline).
 struct PixLoad {
     float4 g, f, a, b, c, e;
 };
 
-__device__ __forceinline__ void red_add4_nc(float* p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d));
-}
+// Register budget per template: one and two views fit 5 blocks per SM (<= 102 registers; the 40x120x2 maps of the
+// KITTI configuration launch 600 blocks per job, 4 per SM left a tail wave); four and eight views keep per-view state
+// (fractional offsets, validity) for every view and get 4 / 3 blocks per SM instead of spilling.
+template <int VT> struct BwdBlocks { static constexpr int value = VT <= 2 ? 5 : (VT <= 4 ? 4 : 3); };
 
-// 5 resident blocks per SM (<= 102 registers): the 40x120x2 maps of the KITTI configuration launch 600 blocks, which
-// must fit the 148 SMs in ONE wave -- at 4 blocks per SM the last 8 blocks ran alone and doubled the kernel time.
 template <int VT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
-feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ fmap, ViewPtrs vp,
-                   const float* __restrict__ depth, int depth_kind, drosfm_cams_t cams, int V,
-                   float* __restrict__ g_fmap, ViewGrads vg, float* __restrict__ g_depth, Slot* ws,
-                   int B, int C, int h, int w, int ppw, int need_coord_grad, int acc_fmap) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, BwdBlocks<VT>::value)
+feat_cost_bwd_nhwc(const __grid_constant__ CostJobs jobs, const __grid_constant__ CostJobGrads grads, drosfm_cams_t cams,
+                   Slot* ws, int B, int C, int h, int w, int ppw) {
     __shared__ Cam cam[VT];
     __shared__ int flag;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    STap* taps = reinterpret_cast<STap*>(dyn_smem);                                                  // [warp][ppw][V]
-    float2* gxy = reinterpret_cast<float2*>(taps + static_cast<size_t>(kWarpsPerBlock) * ppw * V);   // [warp][ppw][V]
+    STap* taps = reinterpret_cast<STap*>(dyn_smem);                                                   // [warp][ppw][VT]
+    float2* gxy = reinterpret_cast<float2*>(taps + static_cast<size_t>(kWarpsPerBlock) * ppw * VT);   // [warp][ppw][VT]
+    const CostJob& job = jobs.j[blockIdx.z];
+    const CostJobGrad& jg = grads.j[blockIdx.z];
+    const int V = job.V, depth_kind = job.depth_kind, need_coord_grad = jg.need_coord, acc_fmap = jg.acc_fmap;
+    const float* __restrict__ g_cost = jg.g_cost;
+    const float* __restrict__ fmap = job.fmap;
+    float* __restrict__ g_fmap = jg.g_fmap;
     const int b = blockIdx.y, P = h * w;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int pbase = (blockIdx.x * kWarpsPerBlock + wid) * ppw;
     const int npix = max(0, min(ppw, P - pbase));
     const bool mine = lane < npix;
     const int p = pbase + lane;
-    const float draw = mine ? __ldg(depth + static_cast<size_t>(b) * P + p) : 0.0f;
+    const float draw = mine ? __ldg(job.depth + static_cast<size_t>(b) * P + p) : 0.0f;
     const float d = to_depth(draw, depth_kind);
-    if constexpr (VT >= 2) {
-        // several views: the three parts of every view's set-up run in three warps (measured: -0.3 / -1.2 us per call)
-        if (wid < 3 && lane < V) setup_cam_part(cams, vp.pose[lane], b, cam[lane], wid);      // kWarpsPerBlock >= 3
-        __syncthreads();
-        if (threadIdx.x < V) setup_cam_finish(cam[threadIdx.x]);
-    } else {
-        // one view: a second barrier costs more than the split saves
-        if (threadIdx.x == 0 && V > 0) setup_cam(cams, vp.pose[0], b, cam[0]);
-    }
-    __syncthreads();
+    setup_cams_block<VT>(cams, job, b, cam);
     const float wm1 = static_cast<float>(w - 1), hm1 = static_cast<float>(h - 1);
-    STap* wt = taps + static_cast<size_t>(wid) * ppw * V;
-    float2* wg = gxy + static_cast<size_t>(wid) * ppw * V;
+    STap* wt = taps + static_cast<size_t>(wid) * ppw * VT;
+    float2* wg = gxy + static_cast<size_t>(wid) * ppw * VT;
     int x = 0, y = 0;
-    float tax[VT], tay[VT];
-    unsigned tvalid[VT];
-#pragma unroll
-    for (int v = 0; v < VT; ++v) { tax[v] = tay[v] = 0.0f; tvalid[v] = 0u; }
     if (mine) {
         pix_xy(p, w, x, y);
 #pragma unroll
@@ -449,14 +483,18 @@ feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ f
                 warp_pixel<true>(cam[v], x, y, d, wm1, hm1, true, wp);
                 CTaps t;
                 make_ctaps(wp.p.u, wp.p.v, h, w, t);
-                store_stap(wt + lane * V + v, t);
-                tax[v] = t.ax; tay[v] = t.ay; tvalid[v] = t.valid;
+                store_stap(wt + lane * VT + v, t);
+                // the fractional offsets (needed once per pixel by the coordinate gradient) wait in shared memory
+                wg[lane * VT + v] = make_float2(t.ax, t.ay);
             }
         }
     }
     __syncwarp();
     const float scale = 2.0f / static_cast<float>(V);
     const size_t sample = static_cast<size_t>(b) * P * C;
+    float2 acc_g[VT];           // lane j: coordinate gradient of pixel j (d cost / d ix, d cost / d iy) per view
+#pragma unroll
+    for (int v = 0; v < VT; ++v) acc_g[v] = make_float2(0.f, 0.f);
     for (int cb0 = 0; cb0 < C; cb0 += 128) {
         const int cb = cb0 + lane * 4;
         const bool chan_ok = cb < C;      // lanes beyond C idle but still take part in the shuffles
@@ -464,8 +502,8 @@ feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ f
 #pragma unroll
         for (int v = 0; v < VT; ++v) {
             if (v >= V || npix == 0) continue;
-            float* gref = vg.g_ref[v];
-            const float* ref = vp.ref[v] + sample + cbs;
+            float* gref = jg.g_ref[v];
+            const float* ref = job.ref[v] + sample + cbs;
             auto fetch = [&](int j, const STap& t) {
                 PixLoad q;
                 const size_t px = sample + static_cast<size_t>(pbase + j) * C + cbs;
@@ -480,11 +518,12 @@ feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ f
             };
             STap t = wt[v];
             PixLoad cur = fetch(0, t);
+            const float2 frac = mine ? wg[lane * VT + v] : make_float2(0.f, 0.f);
             for (int j = 0; j < npix; ++j) {
                 STap tn = t;
                 PixLoad nxt = cur;
                 if (j + 1 < npix) {
-                    tn = wt[(j + 1) * V + v];
+                    tn = wt[(j + 1) * VT + v];
                     nxt = fetch(j + 1, tn);
                 }
                 const size_t px = sample + static_cast<size_t>(pbase + j) * C + cbs;
@@ -495,7 +534,7 @@ feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ f
                 if (g_fmap != nullptr && chan_ok) {
                     // accumulation as a fire-and-forget reduction: a read-modify-write would put one exposed L2 round
                     // trip per pixel on the warp's critical path (21 % of the stall samples before this change)
-                    if (v == 0 && !acc_fmap) *reinterpret_cast<float4*>(g_fmap + px) = co;
+                    if (v == 0 && !acc_fmap) st_global4_nc(g_fmap + px, co.x, co.y, co.z, co.w);
                     else red_add4_nc(g_fmap + px, co.x, co.y, co.z, co.w);
                 }
                 if (gref != nullptr && chan_ok) {
@@ -520,11 +559,8 @@ feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ f
                     float s13 = co.x * (e.x - bq.x) + co.y * (e.y - bq.y) + co.z * (e.z - bq.z) + co.w * (e.w - bq.w);
                     s01 = warp_sum(s01); s23 = warp_sum(s23); s02 = warp_sum(s02); s13 = warp_sum(s13);
                     if (lane == j) {
-                        const float bx = 1.0f - tax[v], by = 1.0f - tay[v];
-                        float2 acc = cb0 == 0 ? make_float2(0.f, 0.f) : wg[lane * V + v];
-                        acc.x -= s01 * by + s23 * tay[v];
-                        acc.y -= s02 * bx + s13 * tax[v];
-                        wg[lane * V + v] = acc;
+                        acc_g[v].x -= s01 * (1.0f - frac.y) + s23 * frac.y;
+                        acc_g[v].y -= s02 * (1.0f - frac.x) + s13 * frac.x;
                     }
                 }
                 cur = nxt;
@@ -533,7 +569,6 @@ feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ f
         }
     }
     if (!need_coord_grad) return;
-    __syncwarp();
     float gd = 0.0f;
 #pragma unroll
     for (int v = 0; v < VT; ++v) {
@@ -541,25 +576,24 @@ feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ f
             float gT[12];
 #pragma unroll
             for (int i = 0; i < 12; ++i) gT[i] = 0.0f;
-            if (mine && tvalid[v]) {
-                const float2 gxyv = wg[lane * V + v];
+            if (mine && wt[lane * VT + v].valid) {
                 Warp wp;
                 warp_pixel<true>(cam[v], x, y, d, wm1, hm1, true, wp);
                 const float mx = 0.5f * static_cast<float>(w - 1), my = 0.5f * static_cast<float>(h - 1);
-                gd += warp_pixel_adjoint(cam[v], wp, d, wm1, hm1, true, gxyv.x * mx, gxyv.y * my, gT);
+                gd += warp_pixel_adjoint(cam[v], wp, d, wm1, hm1, true, acc_g[v].x * mx, acc_g[v].y * my, gT);
             }
-            if (vg.g_pose[v] != nullptr) warp_accumulate<12>(gT, spread_acc(slot_at(ws, v * B + b)));
+            if (jg.g_pose[v] != nullptr) warp_accumulate<12>(gT, spread_acc(slot_at(ws, jg.slot0 + v * B + b)));
         }
     }
-    if (mine && g_depth != nullptr)
-        g_depth[static_cast<size_t>(b) * P + p] = depth_kind == DROSFM_INV_DEPTH ? inv2depth_grad(draw, gd) : gd;
+    if (mine && jg.g_depth != nullptr)
+        jg.g_depth[static_cast<size_t>(b) * P + p] = depth_kind == DROSFM_INV_DEPTH ? inv2depth_grad(draw, gd) : gd;
 #pragma unroll
     for (int v = 0; v < VT; ++v) {
-        if (v < V && vg.g_pose[v] != nullptr) {
-            Slot* slot = slot_at(ws, v * B + b);
+        if (v < V && jg.g_pose[v] != nullptr) {
+            Slot* slot = slot_at(ws, jg.slot0 + v * B + b);
             if (last_block(slot, gridDim.x, &flag) && threadIdx.x < 32) {
                 const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
-                finish_pose_grad_warp(slot, cams.pose_kind, eul ? vp.pose[v] + b * 6 : nullptr, vg.g_pose[v] + b * (eul ? 6 : 16));
+                finish_pose_grad_warp(slot, cams.pose_kind, eul ? job.pose[v] + b * 6 : nullptr, jg.g_pose[v] + b * (eul ? 6 : 16));
             }
         }
     }
@@ -568,18 +602,23 @@ feat_cost_bwd_nhwc(const float* __restrict__ g_cost, const float* __restrict__ f
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static int check_cost_args(const drosfm_cams_t* cams, const float* const* fmap_ref, const float* const* poses,
-                           int n_views, int B, int C, int h, int w, int layout) {
+static_assert(sizeof(drosfm_cost_job_t) == 56 && sizeof(drosfm_cost_job_grads_t) == 48, "ABI layout (see dro_sfm_b200/_lib.py)");
+
+static int check_cost_dims(const drosfm_cams_t* cams, int B, int C, int h, int w, int layout) {
     DROSFM_REQUIRE(cams && cams->K && cams->Kref, DROSFM_EINVAL, "feat_cost: NULL cams");
-    DROSFM_REQUIRE(n_views >= 1 && n_views <= DROSFM_MAX_VIEWS, DROSFM_ERANGE, "feat_cost: n_views=%d outside [1,%d]",
-                   n_views, DROSFM_MAX_VIEWS);
     DROSFM_REQUIRE(B >= 0 && C >= 0 && h >= 0 && w >= 0, DROSFM_EINVAL, "feat_cost: negative dimension");
     DROSFM_REQUIRE(B <= 65535 && static_cast<long long>(h) * w < (1ll << 26), DROSFM_ERANGE, "feat_cost: dimension out of range");
     DROSFM_REQUIRE(layout == DROSFM_NCHW || layout == DROSFM_NHWC, DROSFM_EINVAL, "feat_cost: bad layout %d", layout);
     DROSFM_REQUIRE(layout == DROSFM_NCHW || C % 4 == 0, DROSFM_ENOTSUP, "feat_cost: NHWC layout needs C %% 4 == 0 (C=%d)", C);
-    DROSFM_REQUIRE(fmap_ref != nullptr && poses != nullptr, DROSFM_EINVAL, "feat_cost: NULL view arrays");
     DROSFM_REQUIRE(cams->pose_kind == DROSFM_POSE_MAT4 || cams->pose_kind == DROSFM_POSE_EULER6, DROSFM_EINVAL,
                    "feat_cost: pose_kind must be MAT4 or EULER6");
+    return DROSFM_OK;
+}
+
+static int check_cost_views(const float* const* fmap_ref, const float* const* poses, int n_views) {
+    DROSFM_REQUIRE(n_views >= 1 && n_views <= DROSFM_MAX_VIEWS, DROSFM_ERANGE, "feat_cost: n_views=%d outside [1,%d]",
+                   n_views, DROSFM_MAX_VIEWS);
+    DROSFM_REQUIRE(fmap_ref != nullptr && poses != nullptr, DROSFM_EINVAL, "feat_cost: NULL view arrays");
     for (int v = 0; v < n_views; ++v)
         DROSFM_REQUIRE(fmap_ref[v] != nullptr && poses[v] != nullptr, DROSFM_EINVAL, "feat_cost: view %d has a NULL pointer", v);
     return DROSFM_OK;
@@ -594,11 +633,14 @@ static int channel_group(int P, int B, int C) {
 
 // NHWC: pixels per warp.  Enough warps to fill the chip several times over wins at small maps (each warp
 // keeps ~5 * ppw 128-bit loads in flight); large maps amortise the per-warp coordinate work over 32 pixels.
-static int pixels_per_warp(int P, int B) {
-    const long long pixels = static_cast<long long>(P) * (B > 0 ? B : 1);
+// `units` = pixel-views of the whole launch (all jobs).
+static int pixels_per_warp(long long units) {
     int ppw = kMaxPpw;
-    while (ppw > 4 && pixels / ppw < static_cast<long long>(kNumSMs) * 32) ppw /= 2;
-    if (const char* e = std::getenv("DROSFM_PPW")) ppw = atoi(e);
+    while (ppw > 4 && units / ppw < static_cast<long long>(kNumSMs) * 32) ppw /= 2;
+    if (const char* e = std::getenv("DROSFM_PPW")) {        // tuning knob; anything but a supported value is ignored
+        const int v = atoi(e);
+        if (v == 4 || v == 8 || v == 16 || v == 32) ppw = v;
+    }
     return ppw;
 }
 
@@ -610,44 +652,138 @@ static int pixels_per_warp(int P, int B) {
         else { CALL(8); }               \
     } while (0)
 
+static int vt_of(int v) { return v == 1 ? 1 : (v == 2 ? 2 : (v <= 4 ? 4 : 8)); }
+
+// Validates a batch and fills the device-side job tables.  grads == nullptr: forward.
+static int fill_jobs(const drosfm_cost_job_t* jobs, const drosfm_cost_job_grads_t* grads, int n_jobs, int B, void* ws,
+                     CostJobs& cj, CostJobGrads& cg, int& max_v, long long& units, const char* who) {
+    DROSFM_REQUIRE(jobs != nullptr && n_jobs >= 1 && n_jobs <= kMaxJobs, DROSFM_ERANGE, "%s: n_jobs=%d outside [1,%d]", who, n_jobs,
+                   kMaxJobs);
+    max_v = 0;
+    units = 0;
+    int slot = 0;
+    for (int k = 0; k < n_jobs; ++k) {
+        const drosfm_cost_job_t& in = jobs[k];
+        if (int e = check_cost_views(in.fmap_ref, in.poses, in.n_views)) return e;
+        DROSFM_REQUIRE(in.fmap && in.depth && (grads != nullptr || in.cost), DROSFM_EINVAL, "%s: job %d has a NULL argument", who, k);
+        DROSFM_REQUIRE(aligned16(in.fmap) && aligned16(in.cost), DROSFM_EALIGN, "%s: NHWC tensors must be 16-byte aligned", who);
+        CostJob& o = cj.j[k];
+        o.fmap = in.fmap; o.depth = in.depth; o.cost = in.cost; o.V = in.n_views; o.depth_kind = in.depth_kind;
+        for (int v = 0; v < in.n_views; ++v) {
+            DROSFM_REQUIRE(aligned16(in.fmap_ref[v]), DROSFM_EALIGN, "%s: NHWC tensors must be 16-byte aligned", who);
+            o.ref[v] = in.fmap_ref[v];
+            o.pose[v] = in.poses[v];
+        }
+        max_v = in.n_views > max_v ? in.n_views : max_v;
+        units += in.n_views;
+        if (grads != nullptr) {
+            const drosfm_cost_job_grads_t& gi = grads[k];
+            CostJobGrad& g = cg.j[k];
+            DROSFM_REQUIRE(gi.g_cost != nullptr && aligned16(gi.g_cost) && (!gi.g_fmap || aligned16(gi.g_fmap)), DROSFM_EALIGN,
+                           "%s: job %d: g_cost is NULL or a gradient tensor is not 16-byte aligned", who, k);
+            g.g_cost = gi.g_cost; g.g_fmap = gi.g_fmap; g.g_depth = gi.g_depth;
+            g.acc_fmap = (gi.flags & DROSFM_ACCUMULATE_FMAP) ? 1 : 0;
+            bool want_pose = false;
+            for (int v = 0; v < in.n_views; ++v) {
+                g.g_ref[v] = gi.g_fmap_ref ? gi.g_fmap_ref[v] : nullptr;
+                g.g_pose[v] = gi.g_poses ? gi.g_poses[v] : nullptr;
+                DROSFM_REQUIRE(!g.g_ref[v] || aligned16(g.g_ref[v]), DROSFM_EALIGN, "%s: NHWC tensors must be 16-byte aligned", who);
+                want_pose |= g.g_pose[v] != nullptr;
+            }
+            DROSFM_REQUIRE(!want_pose || ws != nullptr, DROSFM_EINVAL, "%s: pose gradients need ws", who);
+            g.need_coord = (want_pose || g.g_depth != nullptr) ? 1 : 0;
+            g.slot0 = slot;
+            g.pad_ = 0;
+            slot += in.n_views * B;
+        }
+    }
+    return DROSFM_OK;
+}
+
+static int launch_cost_fwd_nhwc(const CostJobs& cj, int n_jobs, int max_v, long long units, const drosfm_cams_t* cams,
+                                int B, int C, int h, int w, cudaStream_t s) {
+    const int P = h * w, VT = vt_of(max_v);
+    const int ppw = pixels_per_warp(static_cast<long long>(P) * B * units);
+    const int per_block = kWarpsPerBlock * ppw;
+    dim3 grid((P + per_block - 1) / per_block, B, n_jobs);
+    const size_t smem = static_cast<size_t>(kWarpsPerBlock) * ppw * VT * sizeof(STap);
+#define CALL(VT_) feat_cost_fwd_nhwc<VT_><<<grid, kWarpsPerBlock * 32, smem, s>>>(cj, *cams, C, h, w, ppw)
+    DISPATCH_VT(max_v, CALL);
+#undef CALL
+    return launch_status("feat_cost_fwd");
+}
+
+static int launch_cost_bwd_nhwc(const CostJobs& cj, const CostJobGrads& cg, int n_jobs, int max_v, long long units,
+                                const drosfm_cams_t* cams, void* ws, int B, int C, int h, int w, cudaStream_t s) {
+    const int P = h * w, VT = vt_of(max_v);
+    const int ppw = pixels_per_warp(static_cast<long long>(P) * B * units);
+    const int per_block = kWarpsPerBlock * ppw;
+    dim3 grid((P + per_block - 1) / per_block, B, n_jobs);
+    const size_t smem = static_cast<size_t>(kWarpsPerBlock) * ppw * VT * (sizeof(STap) + sizeof(float2));
+#define CALL(VT_) feat_cost_bwd_nhwc<VT_><<<grid, kWarpsPerBlock * 32, smem, s>>>(cj, cg, *cams, static_cast<Slot*>(ws), B, C, h, w, ppw)
+    DISPATCH_VT(max_v, CALL);
+#undef CALL
+    return launch_status("feat_cost_bwd");
+}
+
 }  // namespace drosfm
 
 using namespace drosfm;
 
 extern "C" {
 
+int drosfm_feat_cost_batch_fwd(const drosfm_cost_job_t* jobs, int n_jobs, const drosfm_cams_t* cams,
+                               int B, int C, int h, int w, int layout, drosfm_stream_t stream) {
+    if (B == 0 || C == 0 || h * w == 0 || n_jobs == 0) return DROSFM_OK;
+    if (int e = check_cost_dims(cams, B, C, h, w, layout)) return e;
+    DROSFM_REQUIRE(layout == DROSFM_NHWC, DROSFM_ENOTSUP, "feat_cost_batch_fwd: batches run on the NHWC (channels_last) layout only");
+    CostJobs cj{};
+    CostJobGrads cg{};
+    int max_v;
+    long long units;
+    if (int e = fill_jobs(jobs, nullptr, n_jobs, B, nullptr, cj, cg, max_v, units, "feat_cost_batch_fwd")) return e;
+    return launch_cost_fwd_nhwc(cj, n_jobs, max_v, units, cams, B, C, h, w, static_cast<cudaStream_t>(stream));
+}
+
+int drosfm_feat_cost_batch_bwd(const drosfm_cost_job_t* jobs, const drosfm_cost_job_grads_t* grads, int n_jobs,
+                               const drosfm_cams_t* cams, void* ws, int B, int C, int h, int w, int layout,
+                               drosfm_stream_t stream) {
+    if (B == 0 || C == 0 || h * w == 0 || n_jobs == 0) return DROSFM_OK;
+    if (int e = check_cost_dims(cams, B, C, h, w, layout)) return e;
+    DROSFM_REQUIRE(layout == DROSFM_NHWC, DROSFM_ENOTSUP, "feat_cost_batch_bwd: batches run on the NHWC (channels_last) layout only");
+    DROSFM_REQUIRE(grads != nullptr, DROSFM_EINVAL, "feat_cost_batch_bwd: NULL grads");
+    CostJobs cj{};
+    CostJobGrads cg{};
+    int max_v;
+    long long units;
+    if (int e = fill_jobs(jobs, grads, n_jobs, B, ws, cj, cg, max_v, units, "feat_cost_batch_bwd")) return e;
+    return launch_cost_bwd_nhwc(cj, cg, n_jobs, max_v, units, cams, ws, B, C, h, w, static_cast<cudaStream_t>(stream));
+}
+
 int drosfm_feat_cost_fwd(const float* fmap, const float* const* fmap_ref, const float* depth, int depth_kind,
                          const drosfm_cams_t* cams, const float* const* poses, int n_views, float* cost,
                          int B, int C, int h, int w, int layout, drosfm_stream_t stream) {
     if (B == 0 || C == 0 || h * w == 0) return DROSFM_OK;
-    if (int e = check_cost_args(cams, fmap_ref, poses, n_views, B, C, h, w, layout)) return e;
+    if (int e = check_cost_dims(cams, B, C, h, w, layout)) return e;
+    if (int e = check_cost_views(fmap_ref, poses, n_views)) return e;
     DROSFM_REQUIRE(fmap && depth && cost, DROSFM_EINVAL, "feat_cost_fwd: NULL argument");
+    if (layout == DROSFM_NHWC) {
+        const drosfm_cost_job_t job{fmap, fmap_ref, depth, depth_kind, poses, n_views, cost};
+        return drosfm_feat_cost_batch_fwd(&job, 1, cams, B, C, h, w, layout, stream);
+    }
     ViewPtrs vp{};
     for (int v = 0; v < n_views; ++v) { vp.ref[v] = fmap_ref[v]; vp.pose[v] = poses[v]; }
     const int P = h * w;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (layout == DROSFM_NHWC) {
-        DROSFM_REQUIRE(aligned16(fmap) && aligned16(cost), DROSFM_EALIGN, "feat_cost_fwd: NHWC tensors must be 16-byte aligned");
-        for (int v = 0; v < n_views; ++v)
-            DROSFM_REQUIRE(aligned16(fmap_ref[v]), DROSFM_EALIGN, "feat_cost_fwd: NHWC tensors must be 16-byte aligned");
-        const int ppw = pixels_per_warp(P, B);
-        const int per_block = kWarpsPerBlock * ppw;
-        dim3 grid((P + per_block - 1) / per_block, B);
-        const size_t smem = static_cast<size_t>(kWarpsPerBlock) * ppw * n_views * sizeof(STap);
-#define CALL(VT) feat_cost_fwd_nhwc<VT><<<grid, kWarpsPerBlock * 32, smem, s>>>(fmap, vp, depth, depth_kind, *cams, n_views, cost, C, h, w, ppw)
-        DISPATCH_VT(n_views, CALL);
-#undef CALL
-    } else {
-        const int cg = channel_group(P, B, C);
-        dim3 grid((P + kPixThreads - 1) / kPixThreads, (C + cg - 1) / cg, B);
+    const int cg = channel_group(P, B, C);
+    dim3 grid((P + kPixThreads - 1) / kPixThreads, (C + cg - 1) / cg, B);
 #define CALL(VT)                                                                                                            \
     do {                                                                                                                    \
         if (cg == 16) feat_cost_fwd_nchw<VT, 16><<<grid, kPixThreads, 0, s>>>(fmap, vp, depth, depth_kind, *cams, n_views, cost, C, h, w); \
         else feat_cost_fwd_nchw<VT, 8><<<grid, kPixThreads, 0, s>>>(fmap, vp, depth, depth_kind, *cams, n_views, cost, C, h, w);           \
     } while (0)
-        DISPATCH_VT(n_views, CALL);
+    DISPATCH_VT(n_views, CALL);
 #undef CALL
-    }
     return launch_status("feat_cost_fwd");
 }
 
@@ -657,8 +793,14 @@ int drosfm_feat_cost_bwd(const float* g_cost, const float* fmap, const float* co
                          int B, int C, int h, int w, int layout, int flags, drosfm_stream_t stream) {
     const int acc_fmap = (flags & DROSFM_ACCUMULATE_FMAP) ? 1 : 0;
     if (B == 0 || h * w == 0 || C == 0) return DROSFM_OK;
-    if (int e = check_cost_args(cams, fmap_ref, poses, n_views, B, C, h, w, layout)) return e;
+    if (int e = check_cost_dims(cams, B, C, h, w, layout)) return e;
+    if (int e = check_cost_views(fmap_ref, poses, n_views)) return e;
     DROSFM_REQUIRE(g_cost && fmap && depth, DROSFM_EINVAL, "feat_cost_bwd: NULL argument");
+    if (layout == DROSFM_NHWC) {
+        const drosfm_cost_job_t job{fmap, fmap_ref, depth, depth_kind, poses, n_views, nullptr};
+        const drosfm_cost_job_grads_t jg{g_cost, g_fmap, g_fmap_ref, g_depth, g_poses, flags};
+        return drosfm_feat_cost_batch_bwd(&job, &jg, 1, cams, ws, B, C, h, w, layout, stream);
+    }
     ViewPtrs vp{};
     ViewGrads vg{};
     bool want_pose = false;
@@ -673,24 +815,9 @@ int drosfm_feat_cost_bwd(const float* g_cost, const float* fmap, const float* co
     const int need_coord = (want_pose || g_depth != nullptr) ? 1 : 0;
     const int P = h * w;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (layout == DROSFM_NHWC) {
-        DROSFM_REQUIRE(aligned16(fmap) && aligned16(g_cost) && (!g_fmap || aligned16(g_fmap)), DROSFM_EALIGN,
-                       "feat_cost_bwd: NHWC tensors must be 16-byte aligned");
-        for (int v = 0; v < n_views; ++v)
-            DROSFM_REQUIRE(aligned16(fmap_ref[v]) && (!vg.g_ref[v] || aligned16(vg.g_ref[v])), DROSFM_EALIGN,
-                           "feat_cost_bwd: NHWC tensors must be 16-byte aligned");
-        const int ppw = pixels_per_warp(P, B);
-        const int per_block = kWarpsPerBlock * ppw;
-        dim3 grid((P + per_block - 1) / per_block, B);
-        const size_t smem = static_cast<size_t>(kWarpsPerBlock) * ppw * n_views * (sizeof(STap) + sizeof(float2));
-#define CALL(VT) feat_cost_bwd_nhwc<VT><<<grid, kWarpsPerBlock * 32, smem, s>>>(g_cost, fmap, vp, depth, depth_kind, *cams, n_views, \
-                                                                          g_fmap, vg, g_depth, static_cast<Slot*>(ws), B, C, h, w, ppw, need_coord, acc_fmap)
-        DISPATCH_VT(n_views, CALL);
-#undef CALL
-    } else {
-        // the backward keeps g, f, gf and 4 taps per channel live: 4 channels per thread (8 for deep grids)
-        const int cg = channel_group(P, B, C) == 16 ? 8 : 4;
-        dim3 grid((P + kPixThreads - 1) / kPixThreads, (C + cg - 1) / cg, B);
+    // the backward keeps g, f, gf and 4 taps per channel live: 4 channels per thread (8 for deep grids)
+    const int cg = channel_group(P, B, C) == 16 ? 8 : 4;
+    dim3 grid((P + kPixThreads - 1) / kPixThreads, (C + cg - 1) / cg, B);
 #define CALL(VT)                                                                                                            \
     do {                                                                                                                    \
         if (cg == 8)                                                                                                        \
@@ -700,9 +827,8 @@ int drosfm_feat_cost_bwd(const float* g_cost, const float* fmap, const float* co
             feat_cost_bwd_nchw<VT, 4><<<grid, kPixThreads, 0, s>>>(g_cost, fmap, vp, depth, depth_kind, *cams, n_views, g_fmap, vg,  \
                                                                    g_depth, static_cast<Slot*>(ws), B, C, h, w, need_coord, acc_fmap);      \
     } while (0)
-        DISPATCH_VT(n_views, CALL);
+    DISPATCH_VT(n_views, CALL);
 #undef CALL
-    }
     return launch_status("feat_cost_bwd");
 }
 

@@ -6,7 +6,10 @@ into the replaced subsystems:
 
   * ``DepthPoseNet.forward`` (DepthPoseNet.py:154-192): for each of the T GRU steps one
     ``depth_cost_calc`` (V views, gradients to inverse depth and features) and V ``get_cost_each``
-    calls (gradients to the pose vector and features) -- 2*V*T cost evaluations forward and backward;
+    calls (gradients to the pose vector and features) -- 2*V*T cost evaluations forward and backward.
+    With the lock-step schedule that ``patch.install()`` grafts onto DepthPoseNet (networks/lockstep.py; default) the
+    1 + V evaluations of a GRU step are one ``cost_batch`` call; ``lockstep=False`` issues them one by one as the
+    reference's own schedule does;
   * ``SelfSupModelMF`` / ``SupModelMF``: ``Pose.from_vec`` for every (view, prediction), then
     ``MultiViewPhotometricDecayLoss.forward`` or ``SupervisedDepthPoseLoss.forward`` and their backward.
 
@@ -19,7 +22,7 @@ from . import _lib as L
 from . import synthetic as syn
 from .geometry import Pose
 from .losses import MultiViewPhotometricDecayLoss, SupervisedDepthPoseLoss
-from .networks import depth_cost_calc, get_cost_each
+from .networks import cost_batch, depth_cost_calc, get_cost_each
 
 
 def _bytes(t):
@@ -29,8 +32,9 @@ def _bytes(t):
 class HotPathStep:
     """Static device buffers + the step function (eager or CUDA-graph replay)."""
 
-    def __init__(self, wl, device, B=None, C=128, seed=1234, channels_last=False):
+    def __init__(self, wl, device, B=None, C=128, seed=1234, channels_last=False, lockstep=True):
         self.wl, self.device, self.C = wl, torch.device(device), C
+        self.lockstep = lockstep
         self.B = wl.B if B is None else B
         self.channels_last = channels_last
         self.host = syn.hot_path_batch(wl, seed=seed, C=C, B=self.B)
@@ -149,8 +153,13 @@ class HotPathStep:
         costs = []
         for t in range(wl.T):
             poses_t = [p.detach() for p in self.pose_lr[t]]          # DepthPoseNet.py:156
-            costs.append(depth_cost_calc(self.inv_lr[t], self.fmap, self.frefs, poses_t, self.K, self.K, 1.0 / 8))
             depth = self.depth_lr[t // wl.seq_len]
+            if self.lockstep:
+                jobs = [(self.inv_lr[t], self.fmap, self.frefs, poses_t, True)]
+                jobs += [(depth, self.fmap, [self.frefs[v]], [self.pose_lr[t][v]], False) for v in range(wl.V)]
+                costs += cost_batch(jobs, self.K, self.K, 1.0 / 8)
+                continue
+            costs.append(depth_cost_calc(self.inv_lr[t], self.fmap, self.frefs, poses_t, self.K, self.K, 1.0 / 8))
             for v in range(wl.V):
                 costs.append(get_cost_each(self.pose_lr[t][v], self.fmap, self.frefs[v], depth, self.K, self.K, 1.0 / 8))
         poses = [[Pose.from_vec(p, 'euler') for p in row] for row in self.poses]   # SfmModelMF.py:169-182

@@ -49,6 +49,9 @@ class MultiViewPhotometricDecayLoss(LossBase):
         self.padding_mode = padding_mode
         self.automask_loss = automask_loss
         self.progressive_scaling = ProgressiveScaling(progressive_scaling, self.n)
+        # diagnostic of the last forward: [n,B,H,W] uint8, the source view that won the per-pixel min (255: an un-warped
+        # map, i.e. the pixel is auto-masked); None for the 'mean' reduce op
+        self.last_selection = None
         if self.automask_loss:
             assert self.photometric_reduce_op == 'min', \
                 'For automasking only the min photometric_reduce_op is supported.'
@@ -80,11 +83,11 @@ class MultiViewPhotometricDecayLoss(LossBase):
     def forward(self, image, context, inv_depths, K, ref_K, poses, return_logs=False, progress=0.0):
         """Same contract as the reference (lines 303-361): returns {'loss': [1], 'metrics': {...}}."""
         self.n = len(inv_depths)
-        total, terms = ops.photometric_loss(
+        total, terms, self.last_selection = ops.photometric_loss(
             image, list(context), list(inv_depths), K, ref_K, self._pose_mats(poses, self.n),
             ssim_w=self.ssim_loss_weight, C1=self.C1, C2=self.C2, reduce_op=self.photometric_reduce_op,
             padding_mode=self.padding_mode, automask=self.automask_loss, smooth_w=self.smooth_loss_weight,
-            gamma=0.85, inverse_depth=True)
+            gamma=0.85, inverse_depth=True, want_selection=True)
         if self.smooth_loss_weight > 0.0:
             self.add_metric('smoothness_loss', terms[1])
             # reference quirk: 'photometric_loss' aliases the tensor that `loss += smoothness` then

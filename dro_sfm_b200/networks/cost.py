@@ -76,6 +76,16 @@ def depth_cost_calc(inv_depth, fmap, fmaps_ref, pose_list, K, ref_K, scale_facto
     return total
 
 
+def cost_batch(jobs, K, ref_K, scale_factor):
+    """Several independent cost evaluations in ONE kernel launch (forward) and one more (backward).
+
+    jobs: (depth_or_inv_depth, fmap, fmaps_ref, pose_list, is_inverse_depth) tuples -- a depth_cost_calc call is
+    (inv_depth, fmap, fmaps_ref, pose_list, True), a get_cost_each call (depth, fmap, [fmap_ref], [pose], False).
+    Used by the lock-step schedule (networks/lockstep.py); results equal the individual calls."""
+    prepared = [(d, _channels_last(f), [_channels_last(r) for r in frs], list(ps), inv) for d, f, frs, ps, inv in jobs]
+    return ops.feat_cost_batch(prepared, K, ref_K, scale_factor)
+
+
 def upsample_depth(depth, mask, ratio=8):
     """Convex up-sampling of the low-resolution inverse depth (DepthPoseNet.py:63-74), one fused kernel."""
     return ops.upsample_depth(depth, mask, ratio)

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib as L
 
-__all__ = ["pose_vec2mat", "reconstruct", "project", "warp_coords", "grid_gather", "view_synthesis", "feat_cost",
+__all__ = ["pose_vec2mat", "reconstruct", "project", "warp_coords", "grid_gather", "view_synthesis", "feat_cost", "feat_cost_batch",
            "photometric_loss", "reproj_pose_loss", "sup_depth_loss", "upsample_depth"]
 
 
@@ -375,6 +375,25 @@ def to_channels_last_sink(t):
     return out
 
 
+def sink_buffer(sink, like):
+    """(buffer, value to return to autograd): the first consumer of a backward pass allocates the zeroed
+    buffer and returns a zero placeholder so that the sink node runs; later ones return None.  The buffer
+    belongs to ONE backward pass: a callback at the end of the pass drops it if the sink node was not reached
+    (torch.autograd.grad(cost, inputs=[pose]) or an aborted pass), so partial sums never leak into the next."""
+    if sink.buffer is None:
+        sink.buffer = torch.zeros_like(like)
+        if sink.dummy is None or sink.dummy.shape != like.shape:
+            sink.dummy = _zero_scalar(like.device).expand(like.shape)
+        buf = sink.buffer
+
+        def end_of_pass(sink=sink, buf=buf):
+            if sink.buffer is buf:
+                sink.buffer = None
+        torch.autograd.Variable._execution_engine.queue_callback(end_of_pass)
+        return sink.buffer, sink.dummy
+    return sink.buffer, None
+
+
 class _FeatCost(torch.autograd.Function):
     """inputs: depth, fmap, K, Kref, scale, depth_kind, V, ref_0..ref_{V-1}, pose_0..pose_{V-1}"""
 
@@ -417,24 +436,6 @@ class _FeatCost(torch.autograd.Function):
         need = ctx.needs_input_grad
         cams, _ = L.make_cams(K, Kref, scale, None, None, None, kind)
         sinks = ctx.sinks
-
-        def sink_buffer(sink, like):
-            """(buffer, value to return to autograd): the first consumer of a backward pass allocates the zeroed
-            buffer and returns a zero placeholder so that the sink node runs; later ones return None.  The buffer
-            belongs to ONE backward pass: a callback at the end of the pass drops it if the sink node was not reached
-            (torch.autograd.grad(cost, inputs=[pose]) or an aborted pass), so partial sums never leak into the next."""
-            if sink.buffer is None:
-                sink.buffer = torch.zeros_like(like)
-                if sink.dummy is None or sink.dummy.shape != like.shape:
-                    sink.dummy = _zero_scalar(like.device).expand(like.shape)
-                buf = sink.buffer
-
-                def end_of_pass(sink=sink, buf=buf):
-                    if sink.buffer is buf:
-                        sink.buffer = None
-                torch.autograd.Variable._execution_engine.queue_callback(end_of_pass)
-                return sink.buffer, sink.dummy
-            return sink.buffer, None
 
         flags = 0
         g_fmap = ret_fmap = None
@@ -490,6 +491,135 @@ def feat_cost(depth, fmap, fmaps_ref, poses, K, Kref=None, scale=1.0, inverse_de
     _no_grad_for("K", K)
     return _FeatCost.apply(depth, fmap, K, Kref, float(scale), L.INV_DEPTH if inverse_depth else L.DEPTH, V,
                            *fmaps_ref, *poses)
+
+
+class _FeatCostBatch(torch.autograd.Function):
+    """Several independent cost calls in one launch (drosfm_feat_cost_batch_*; channels_last tensors only).
+    inputs: K, Kref, scale, spec = ((V, depth_kind), ...), then per job: depth, fmap, ref_0..ref_{V-1}, pose_0..pose_{V-1}.
+    outputs: one cost map per job."""
+
+    @staticmethod
+    def _split(spec, tensors):
+        jobs, pos = [], 0
+        for V, dk in spec:
+            jobs.append((tensors[pos], tensors[pos + 1], tensors[pos + 2:pos + 2 + V], tensors[pos + 2 + V:pos + 2 + 2 * V], dk))
+            pos += 2 + 2 * V
+        return jobs
+
+    @staticmethod
+    def forward(ctx, K, Kref, scale, spec, *tensors):
+        L.require_cuda(K, Kref, *tensors)
+        jobs = _FeatCostBatch._split(spec, tensors)
+        B, C, h, w = jobs[0][1].shape
+        kind = _pose_kind(jobs[0][3][0])
+        cams, keep = L.make_cams(K, Kref, scale, None, None, None, kind)
+        table = (L.CostJob * len(jobs))()
+        saved, sinks, costs, hold = [], [], [], []
+        for k, (depth, fmap, refs, poses, dk) in enumerate(jobs):
+            if tuple(fmap.shape) != (B, C, h, w) or _pose_kind(poses[0]) != kind:
+                raise ValueError("feat_cost_batch: all jobs must share the feature-map shape and the pose encoding")
+            sinks.append([getattr(x, "_drosfm_sink", None) for x in (fmap, *refs)])
+            depth, poses = L.f32c(depth), [L.f32c(p) for p in poses]
+            cost = torch.empty_like(fmap)
+            ra, pa = L.ptr_array(list(refs)), L.ptr_array(poses)
+            hold += [ra, pa]
+            j = table[k]
+            j.fmap, j.fmap_ref, j.depth, j.depth_kind = fmap.data_ptr(), ra, depth.data_ptr(), dk
+            j.poses, j.n_views, j.cost = pa, len(refs), cost.data_ptr()
+            saved += [depth, fmap, *refs, *poses]
+            costs.append(cost)
+        with torch.cuda.device(jobs[0][1].device):
+            L.check(L.lib().drosfm_feat_cost_batch_fwd(table, len(jobs), cams, B, C, h, w, L.NHWC, L.stream()), "feat_cost_batch_fwd")
+        ctx.save_for_backward(keep[0], keep[1], *saved)
+        ctx.cfg = (float(scale), spec, kind)
+        ctx.sinks = sinks
+        ctx.set_materialize_grads(False)
+        return tuple(costs)
+
+    @staticmethod
+    def backward(ctx, *g_costs):
+        scale, spec, kind = ctx.cfg
+        K, Kref = ctx.saved_tensors[:2]
+        jobs = _FeatCostBatch._split(spec, ctx.saved_tensors[2:])
+        B, C, h, w = jobs[0][1].shape
+        dev = jobs[0][1].device
+        cams, _ = L.make_cams(K, Kref, scale, None, None, None, kind)
+        need = ctx.needs_input_grad[4:]
+        live = [k for k in range(len(jobs)) if g_costs[k] is not None]
+        rets = [None] * len(need)
+        if not live:
+            return (None, None, None, None, *rets)
+        jt, gt = (L.CostJob * len(live))(), (L.CostJobGrads * len(live))()
+        hold, pos_of, pos, slots = [], [], 0, 0
+        for V, _ in spec:
+            pos_of.append(pos)
+            pos += 2 + 2 * V
+        # every plain (non-sink) source-map gradient of the launch lives in one zero-filled slab: a single memset
+        n_plain = sum(1 for k in live for v in range(spec[k][0]) if need[pos_of[k] + 2 + v] and ctx.sinks[k][1 + v] is None)
+        slab = torch.zeros(n_plain * B * C * h * w, device=dev, dtype=torch.float32) if n_plain else None
+        off = 0
+        for row, k in enumerate(live):
+            depth, fmap, refs, poses, dk = jobs[k]
+            V, p0, sinks = spec[k][0], pos_of[k], ctx.sinks[k]
+            g = g_costs[k]
+            g = g if g.is_contiguous(memory_format=torch.channels_last) and g.dtype == torch.float32 else _as_layout(g, L.NHWC)
+            flags, g_fmap = 0, None
+            if need[p0 + 1]:
+                if sinks[0] is not None:
+                    g_fmap, rets[p0 + 1] = sink_buffer(sinks[0], fmap)
+                    flags |= L.ACCUMULATE_FMAP
+                else:
+                    g_fmap = rets[p0 + 1] = torch.empty_like(fmap)
+            g_refs = []
+            for v in range(V):
+                if not need[p0 + 2 + v]:
+                    g_refs.append(None)
+                elif sinks[1 + v] is not None:
+                    buf, rets[p0 + 2 + v] = sink_buffer(sinks[1 + v], refs[v])
+                    g_refs.append(buf)
+                else:
+                    t = slab[off:off + fmap.numel()].view(B, h, w, C).permute(0, 3, 1, 2)
+                    off += fmap.numel()
+                    g_refs.append(t)
+                    rets[p0 + 2 + v] = t
+            g_depth = rets[p0] = torch.empty_like(depth) if need[p0] else None
+            g_poses = [torch.empty_like(poses[v]) if need[p0 + 2 + V + v] else None for v in range(V)]
+            for v in range(V):
+                rets[p0 + 2 + V + v] = g_poses[v]
+            ra, pa, gra, gpa = L.ptr_array(list(refs)), L.ptr_array(list(poses)), L.ptr_array(g_refs), L.ptr_array(g_poses)
+            hold += [ra, pa, gra, gpa, g]
+            j, q = jt[row], gt[row]
+            j.fmap, j.fmap_ref, j.depth, j.depth_kind, j.poses, j.n_views, j.cost = fmap.data_ptr(), ra, depth.data_ptr(), dk, pa, V, None
+            q.g_cost, q.g_fmap, q.g_fmap_ref = g.data_ptr(), (None if g_fmap is None else g_fmap.data_ptr()), gra
+            q.g_depth, q.g_poses, q.flags = (None if g_depth is None else g_depth.data_ptr()), gpa, flags
+            slots += V * B
+        with torch.cuda.device(dev):
+            ws = L.workspace(dev, slots)
+            L.check(L.lib().drosfm_feat_cost_batch_bwd(jt, gt, len(live), cams, L.ptr(ws), B, C, h, w, L.NHWC, L.stream()),
+                    "feat_cost_batch_bwd")
+        return (None, None, None, None, *rets)
+
+
+def feat_cost_batch(jobs, K, Kref=None, scale=1.0):
+    """Several independent feature-metric cost calls in ONE launch.
+
+    jobs: sequence of (depth, fmap, fmaps_ref, poses, inverse_depth) -- the arguments of `feat_cost` -- sharing K, Kref,
+    scale, the feature-map shape and the pose encoding.  Returns one cost map per job.  The batched kernels run on
+    channels_last maps; any other input falls back to one `feat_cost` call per job (same results)."""
+    jobs = [(d, f, list(fr), list(ps), bool(inv)) for d, f, fr, ps, inv in jobs]
+    Kref = K if Kref is None else Kref
+    _no_grad_for("K", K)
+
+    def nhwc(t):
+        return t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.shape[1] % 4 == 0 and _layout_of(t) == L.NHWC
+
+    ok = 1 <= len(jobs) <= L.MAX_COST_JOBS and all(
+        nhwc(f) and all(nhwc(r) for r in fr) and 1 <= len(fr) <= L.MAX_VIEWS and len(ps) == len(fr) for _, f, fr, ps, _ in jobs)
+    if not ok or len(jobs) == 1:
+        return [feat_cost(d, f, fr, ps, K, Kref, scale, inverse_depth=inv) for d, f, fr, ps, inv in jobs]
+    spec = tuple((len(fr), L.INV_DEPTH if inv else L.DEPTH) for _, _, fr, _, inv in jobs)
+    flat = [t for d, f, fr, ps, _ in jobs for t in (d, f, *fr, *ps)]
+    return list(_FeatCostBatch.apply(K, Kref, float(scale), spec, *flat))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -584,7 +714,10 @@ class _PhotoLoss(torch.autograd.Function):
         ctx.save_for_backward(image, keep[0], keep[1], sel, stats, wsave, *context, *invs, *poses)
         ctx.cfg, ctx.V, ctx.n, ctx.kind = cfg, V, n, kind
         ctx.mark_non_differentiable(losses)
-        return total, losses
+        if sel is None:
+            return total, losses
+        ctx.mark_non_differentiable(sel)
+        return total, losses, sel
 
     @staticmethod
     def backward(ctx, g_total, *unused):
@@ -643,11 +776,13 @@ class _PhotoLoss(torch.autograd.Function):
 
 
 def photometric_loss(image, context, inv_depths, K, ref_K, poses, ssim_w=0.85, C1=1e-4, C2=9e-4, reduce_op="min",
-                     padding_mode="zeros", automask=True, smooth_w=0.001, gamma=0.85, inverse_depth=True):
+                     padding_mode="zeros", automask=True, smooth_w=0.001, gamma=0.85, inverse_depth=True, want_selection=False):
     """MultiViewPhotometricDecayLoss.forward (multiview_photometric_loss_mf.py:303-361), fused.
 
     context: V source images; inv_depths: n predictions [B,1,H,W]; poses[v][i]: [B,4,4] or [B,6].
-    Returns (total [1], terms [2]) with terms = detached [photometric, smoothness] values."""
+    Returns (total [1], terms [2]) with terms = detached [photometric, smoothness] values; with want_selection also
+    the arg-min view per pixel of every prediction ([n,B,H,W] uint8; 255 = an un-warped / auto-mask map won; None for the
+    'mean' reduce op)."""
     V, n = len(context), len(inv_depths)
     if not (1 <= V <= L.MAX_VIEWS and 1 <= n <= L.MAX_PREDS):
         raise ValueError("photometric_loss supports 1..{} views and 1..{} predictions".format(L.MAX_VIEWS, L.MAX_PREDS))
@@ -664,7 +799,10 @@ def photometric_loss(image, context, inv_depths, K, ref_K, poses, ssim_w=0.85, C
     cfg = (float(ssim_w), float(C1), float(C2), _padding(padding_mode), _reduce_op(reduce_op), bool(automask), float(gamma),
            float(smooth_w), L.INV_DEPTH if inverse_depth else L.DEPTH)
     flat = [p for pv in poses for p in pv]
-    return _PhotoLoss.apply(image, K, ref_K, cfg, V, n, *context, *inv_depths, *flat)
+    out = _PhotoLoss.apply(image, K, ref_K, cfg, V, n, *context, *inv_depths, *flat)
+    if want_selection:
+        return out[0], out[1], (out[2] if len(out) > 2 else None)
+    return out[0], out[1]
 
 
 # ------------------------------------------------------------------------------------------------

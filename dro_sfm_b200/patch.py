@@ -8,7 +8,9 @@ Replaces (by name, keeping signatures) the hot-path symbols of the reference:
   dro_sfm.geometry.camera_utils.view_synthesis,
   dro_sfm.losses.multiview_photometric_loss_mf.MultiViewPhotometricDecayLoss,
   dro_sfm.losses.supervised_loss.SupervisedDepthPoseLoss,
-  DepthPoseNet.get_cost_each / depth_cost_calc / upsample_depth.
+  DepthPoseNet.get_cost_each / depth_cost_calc / upsample_depth, and (lockstep=True, the default) DepthPoseNet.forward
+  by the lock-step schedule of networks/lockstep.py: the same sub-modules and arithmetic, with the 1 + V cost
+  evaluations of every inner step of the recurrent optimiser submitted as one kernel launch.
 Modules that did `from x import Name` before install() keep their old binding, so the known importers
 (SelfSupModelMF.py:3, SupModelMF.py:3, SemiSupModelMF.py:3-4, DepthPoseNet.py:11, SfmModelMF.py) are
 re-bound too.  Nothing else of the reference is touched: trainer, configs and checkpoints are as-is
@@ -29,7 +31,7 @@ def _rebind(module_name, **symbols):
     return True
 
 
-def install():
+def install(lockstep=True):
     """Returns the list of reference modules that were patched."""
     from .geometry import Camera, Pose, view_synthesis
     from .losses import MultiViewPhotometricDecayLoss, SupervisedDepthPoseLoss
@@ -58,4 +60,7 @@ def install():
         net_mod.DepthPoseNet.get_cost_each = FeatureMetricCost.get_cost_each
         net_mod.DepthPoseNet.depth_cost_calc = FeatureMetricCost.depth_cost_calc
         net_mod.DepthPoseNet.upsample_depth = FeatureMetricCost.upsample_depth
+        if lockstep:
+            from .networks import lockstep as _lockstep
+            net_mod.DepthPoseNet.forward = _lockstep.forward
     return patched

@@ -28,9 +28,10 @@
 extern "C" {
 #endif
 
-#define DROSFM_ABI_VERSION 2
+#define DROSFM_ABI_VERSION 3
 #define DROSFM_MAX_VIEWS 8      /* source views per call (forward_context + back_context) */
 #define DROSFM_MAX_PREDS 16     /* depth predictions per loss call (GRU iterations seen by the loss) */
+#define DROSFM_MAX_COST_JOBS 9  /* cost evaluations per batched launch: one depth cost + one pose cost per view */
 
 enum { DROSFM_OK = 0, DROSFM_EINVAL = -1, DROSFM_ERANGE = -2, DROSFM_EALIGN = -3, DROSFM_ENOTSUP = -4 };
 enum { DROSFM_POSE_IDENTITY = 0, DROSFM_POSE_MAT4 = 1, DROSFM_POSE_EULER6 = 2 };
@@ -131,6 +132,38 @@ int drosfm_feat_cost_bwd(const float* g_cost, const float* fmap, const float* co
                          const float* const* poses, int n_views, float* g_fmap, float* const* g_fmap_ref,
                          float* g_depth, float* const* g_poses, void* ws,
                          int B, int C, int h, int w, int layout, int flags, drosfm_stream_t stream);
+
+/* ---- a batch of independent feature-metric cost calls in ONE launch ---------------------------
+ * Within one step of the recurrent optimiser the depth cost (depth_cost_calc: V views, mean) and the V per-view pose
+ * costs (get_cost_each) depend only on the state at the start of the step: DepthPoseNet.forward builds every cost
+ * closure (DepthPoseNet.py:159-167) before either update block runs (:171-192, update.py:161,189).  A caller that
+ * advances the update blocks in lock-step (dro_sfm_b200/networks/lockstep.py) hands all of them over at once; at the
+ * training shapes one call alone is a one-wave launch bound by latency.  Each job is one drosfm_feat_cost_{fwd,bwd}
+ * call with the same B, C, h, w, cams (intrinsics, scale, pose encoding) and the NHWC layout; jobs may share feature
+ * maps.  Gradient buffers shared by several jobs must be zero-filled and flagged DROSFM_ACCUMULATE_FMAP (g_fmap) --
+ * g_fmap_ref / g_depth follow the rules of drosfm_feat_cost_bwd.  ws: drosfm_ws_bytes(B * sum of n_views). */
+typedef struct {
+    const float* fmap;               /* [B,C,h,w] target features (NHWC storage)                   */
+    const float* const* fmap_ref;    /* n_views source maps                                         */
+    const float* depth;              /* [B,1,h,w] depth or inverse depth                            */
+    int32_t depth_kind;              /* DROSFM_DEPTH | DROSFM_INV_DEPTH                             */
+    const float* const* poses;       /* n_views poses in cams->pose_kind encoding                   */
+    int32_t n_views;                 /* 1 = get_cost_each, V = depth_cost_calc (mean over views)    */
+    float* cost;                     /* [B,C,h,w] output (ignored by the backward)                  */
+} drosfm_cost_job_t;
+typedef struct {
+    const float* g_cost;             /* upstream gradient of the job's cost map                     */
+    float* g_fmap;                   /* written, or added to with DROSFM_ACCUMULATE_FMAP; may be NULL */
+    float* const* g_fmap_ref;        /* accumulated; entries / the array may be NULL                */
+    float* g_depth;                  /* written; may be NULL                                        */
+    float* const* g_poses;           /* written; entries / the array may be NULL                    */
+    int32_t flags;                   /* DROSFM_ACCUMULATE_FMAP                                      */
+} drosfm_cost_job_grads_t;
+int drosfm_feat_cost_batch_fwd(const drosfm_cost_job_t* jobs, int n_jobs, const drosfm_cams_t* cams,
+                               int B, int C, int h, int w, int layout, drosfm_stream_t stream);
+int drosfm_feat_cost_batch_bwd(const drosfm_cost_job_t* jobs, const drosfm_cost_job_grads_t* grads, int n_jobs,
+                               const drosfm_cams_t* cams, void* ws, int B, int C, int h, int w, int layout,
+                               drosfm_stream_t stream);
 
 /* ---- photometric loss (multiview_photometric_loss_mf.py:15-54,132-269,333-353) ---------------
  * Options shared by the photometric entry points. */

@@ -233,11 +233,17 @@ def photometric_map(est, image, ssim_w=0.85, C1=1e-4, C2=9e-4, clip=0.0):
 
 
 def photometric_loss(image, context, inv_depths, K, ref_K, poses, ssim_w=0.85, C1=1e-4, C2=9e-4,
-                     reduce_op="min", clip=0.0, padding_mode="zeros", automask=True, gamma=0.85):
+                     reduce_op="min", clip=0.0, padding_mode="zeros", automask=True, gamma=0.85,
+                     forced_sel=None, maps_out=None):
     """multiview_photometric_loss_mf.py:132-171,231-269,333-353.
 
     ``poses[v][i]`` is the [B,4,4] target->source transform of view v at prediction i.
     Map order per prediction is [warp_0, unwarp_0, warp_1, unwarp_1, ...] (lines 343-351).
+
+    Checker-only extras ('min' reduce): ``maps_out`` (a list) receives the detached [B,2V,H,W] map stack of every
+    prediction; ``forced_sel[i]`` ([B,H,W] long: source view v >= 0, -1 = an un-warped / auto-mask map) replaces the
+    per-pixel arg-min, so that gradients of two fp32 evaluations can be compared for the SAME selection (the per-pixel
+    min is discontinuous: at a near-tie the winner -- and with it a whole gradient term -- may differ).
     """
     n = len(inv_depths)
     per_pred = [[] for _ in range(n)]
@@ -254,7 +260,17 @@ def photometric_loss(image, context, inv_depths, K, ref_K, poses, ssim_w=0.85, C
         if reduce_op == "mean":
             li = sum([m.mean() for m in per_pred[i]]) / len(per_pred[i])
         elif reduce_op == "min":
-            li = torch.cat(per_pred[i], 1).min(1, True)[0].mean()
+            stack = torch.cat(per_pred[i], 1)
+            if maps_out is not None:
+                maps_out.append(stack.detach())
+            if forced_sel is None:
+                li = stack.min(1, True)[0].mean()
+            else:
+                idx = forced_sel[i].long()
+                if automask:
+                    auto = stack[:, 1::2].argmin(1) * 2 + 1
+                    idx = torch.where(idx < 0, auto, idx * 2)
+                li = stack.gather(1, idx.unsqueeze(1)).mean()
         else:
             raise NotImplementedError("Unknown photometric_reduce_op: {}".format(reduce_op))
         total = total + gamma ** (n - i - 1) * li
