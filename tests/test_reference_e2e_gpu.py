@@ -86,10 +86,14 @@ def _step_float64(build_model, net, batch):
     intrinsics with K.float() (DepthPoseNet.py:84-85, multiview_photometric_loss_mf.py:162-163); for this pass only,
     Tensor.float is a cast to double.  Returns None if the reference cannot run in float64."""
     import copy
-    orig = torch.Tensor.float
+    import dro_sfm.geometry.pose as ref_pose
+    orig, orig_identity = torch.Tensor.float, ref_pose.Pose.__dict__["identity"]
     try:
         net64 = copy.deepcopy(net).double()
         torch.Tensor.float = lambda t, *a, **k: t.double()
+        # Pose.identity's dtype default is torch.float (pose.py:28); the identity target pose must be double here
+        ref_pose.Pose.identity = classmethod(lambda cls, N=1, device=None, dtype=torch.float64:
+                                             orig_identity.__func__(cls, N, device, torch.float64))
         model = build_model(net64).double()
         b64 = {k: ([x.double() for x in v] if isinstance(v, list) else v.double()) for k, v in batch.items()}
         return _step(model, b64)
@@ -98,6 +102,7 @@ def _step_float64(build_model, net, batch):
         return None
     finally:
         torch.Tensor.float = orig
+        ref_pose.Pose.identity = orig_identity
 
 
 def _rel(a, b):
