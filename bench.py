@@ -38,6 +38,9 @@ def measured_peaks():
 
 # C-ABI call -> the CUDA kernels it launches (names as in the ncu reports); the staged photometric calls are two each
 NCU_NAMES = {"photometric_bwd": ["ssim_bwd_stream"], "photometric_fwd": ["ssim_fwd_stream"],
+             "feat_cost_batch_fwd": ["feat_cost_fwd_nhwc<2>"], "feat_cost_batch_bwd": ["feat_cost_bwd_nhwc<2>"],
+             "photometric_loss_fwd": ["photometric_fwd_kernel<1, 0>", "warp_sources_kernel", "ssim_fwd_stream"],
+             "photometric_loss_bwd": ["ssim_bwd_stream", "warp_sources_adjoint_kernel"],
              "warp_sources_fwd": ["warp_sources_kernel"], "warp_sources_bwd": ["warp_sources_adjoint_kernel"],
              "feat_cost_fwd_v1": ["feat_cost_fwd_nhwc<1>"], "feat_cost_bwd_v1": ["feat_cost_bwd_nhwc<1>"],
              "feat_cost_fwd_vN": ["feat_cost_fwd_nhwc<2>"], "feat_cost_bwd_vN": ["feat_cost_bwd_nhwc<2>"],
@@ -245,7 +248,12 @@ KERNEL_KEYS = {
     "drosfm_reproj_loss_bwd": lambda a: "reproj_loss_bwd", "drosfm_pose_vec2mat_fwd": lambda a: "pose_vec2mat_fwd",
     "drosfm_pose_vec2mat_bwd": lambda a: "pose_vec2mat_bwd",
     "drosfm_warp_sources_fwd": lambda a: "warp_sources_fwd", "drosfm_warp_sources_bwd": lambda a: "warp_sources_bwd",
+    "drosfm_feat_cost_batch_fwd": lambda a: "feat_cost_batch_fwd", "drosfm_feat_cost_batch_bwd": lambda a: "feat_cost_batch_bwd",
 }
+# The photometric loss is ONE operator per direction in SURVEY.md section 8(d); the staged path implements it with several
+# launches.  The roofline treats each direction as a unit: SURVEY bytes over the summed duration of its launches.
+UNITS = {"photometric_loss_fwd": ["automask_fwd", "warp_sources_fwd", "photometric_fwd"],
+         "photometric_loss_bwd": ["photometric_bwd", "warp_sources_bwd"]}
 
 
 def run_gpu(args, wl):
@@ -278,6 +286,7 @@ def run_gpu(args, wl):
     copy_stream = torch.cuda.Stream(dev)
     main = torch.cuda.current_stream(dev)
     pending = {"ev": None}
+    counter, log_every = {"n": 0}, max(1, args.log_every)
 
     def one_step(e2e):
         """e2e: the step consumes inputs that came from pinned host memory.  The H2D copy of the NEXT step's
@@ -292,7 +301,11 @@ def run_gpu(args, wl):
             copy_stream.wait_stream(main)
             pending["ev"] = step.prefetch(copy_stream)
         loss = step.step()
-        du.average_loss(loss.detach())                        # the only collective on the path: the logged loss
+        # the only collective on the path is the LOGGED loss (utils/reduce.py:10-30 reduces what the progress bar
+        # shows): averaged over the ranks every `log_every` steps, off the per-step critical path
+        counter["n"] += 1
+        if counter["n"] % log_every == 0:
+            du.average_loss(loss.detach())
         if e2e:
             loss_host.copy_(loss.detach(), non_blocking=True)
             main.wait_event(pending["ev"])
@@ -362,29 +375,55 @@ def run_gpu(args, wl):
             key = KERNEL_KEYS.get(name, lambda _a: name)(a)
             per.setdefault(key, []).append(t_ms)
         alg = step.algorithmic_bytes()
+        stage = alg.pop("stage_operands")
         totals = {k: sum(v) for k, v in per.items()}
-        dom = max((k for k in totals if k in alg), key=lambda k: totals[k])
-        avg_ms = totals[dom] / len(per[dom])
+        counts = {k: len(v) // n_inst for k, v in per.items()}
+        # launch units: single C-ABI calls, except the photometric loss (one unit per direction, see UNITS)
+        unit_ms, unit_launches, unit_kernels = {}, {}, {}
+        grouped = set()
+        for unit, members in UNITS.items():
+            present = [m for m in members if m in totals]
+            if present:
+                unit_ms[unit] = sum(totals[m] for m in present) / n_inst
+                unit_launches[unit] = sum(counts[m] for m in present)
+                unit_kernels[unit] = present
+                grouped.update(present)
+        for k in totals:
+            if k not in grouped and k in alg:
+                unit_ms[k] = totals[k] / len(per[k])            # per launch
+                unit_launches[k] = counts[k]
+                unit_kernels[k] = [k]
+        per_step_ms = {k: (unit_ms[k] if k in UNITS else unit_ms[k] * unit_launches[k]) for k in unit_ms}
+        dom = max(per_step_ms, key=lambda k: per_step_ms[k])
         peak, peak_src = measured_peaks()
-        achieved = alg[dom] / (avg_ms * 1e-3) / 1e9
+        achieved = alg[dom] / (unit_ms[dom] * 1e-3) / 1e9
         traffic, traffic_src = ncu_traffic(dom)
+
+        def entry(k):
+            gbps = alg[k] / (unit_ms[k] * 1e-3) / 1e9
+            return {"launches_per_step": unit_launches[k], "ms": round(unit_ms[k], 5), "bytes": alg[k], "GBps": round(gbps, 1),
+                    "frac": round(gbps / peak, 4), "share_of_step_kernel_time": round(per_step_ms[k] / sum(per_step_ms.values()), 4),
+                    "c_abi_calls": unit_kernels[k]}
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                    "note": "per C-ABI call (CUDA events around the call, device held back so that host launch latency is "
-                            "excluded; the staged photometric calls are 2 CUDA launches each); the SSIM / warp kernels are "
-                            "instruction-issue bound on B200 (ncu: issue slots 50-75% busy, DRAM < 15%), so frac -- algorithmic "
-                            "bytes over measured copy bandwidth -- is low by construction",
-                    "bytes_per_launch": alg[dom], "avg_launch_ms": avg_ms,
-                    "launches": len(per[dom]) // n_inst, "cuda_kernels": NCU_NAMES.get(dom),
-                    "timed_steps": n_inst,
-                    "share_of_kernel_time": totals[dom] / sum(totals.values()),
+                    "note": "algorithmic bytes = SURVEY.md 8(d) figures (every distinct operand of the OPERATOR once); unit = one "
+                            "C-ABI launch, except the photometric loss, which SURVEY defines as one fused operator per "
+                            "direction: its unit is the direction's launches together (the staged path's warped copy and "
+                            "g_warped are this design's traffic and are NOT counted).  Durations: CUDA events around every "
+                            "C-ABI call of the step, eager, one stream, device held back so that host launch latency is "
+                            "excluded, L2 flushed before each step.  The loss kernels are instruction-issue bound (ncu: "
+                            "issue slots 50-75 % busy, DRAM < 15 %)",
+                    "bytes_per_launch": alg[dom], "avg_launch_ms": unit_ms[dom], "launches": unit_launches[dom],
+                    "c_abi_calls": unit_kernels[dom], "cuda_kernels": NCU_NAMES.get(dom), "timed_steps": n_inst,
+                    "share_of_kernel_time": per_step_ms[dom] / sum(per_step_ms.values()),
                     "step_algorithmic_GBps": alg["step_total"] / (ms / args.steps * 1e-3) / 1e9,
+                    "step_frac": alg["step_total"] / (ms / args.steps * 1e-3) / 1e9 / peak,
                     "kernel_ms_per_step": {k: round(v / n_inst, 4) for k, v in sorted(totals.items())},
-                    # the same roofline for every call of the step: algorithmic GB/s and fraction of the peak
-                    "per_call": {k: {"launches": len(per[k]) // n_inst, "avg_ms": round(totals[k] / len(per[k]), 5),
-                                     "GBps": round(alg[k] / (totals[k] / len(per[k]) * 1e-3) / 1e9, 1),
-                                     "frac": round(alg[k] / (totals[k] / len(per[k]) * 1e-3) / 1e9 / peak, 4)}
-                                 for k in sorted(totals) if k in alg}}
+                    "per_unit": {k: entry(k) for k in sorted(unit_ms)},
+                    # individual stages of the staged photometric path against their own operand bytes (orientation only)
+                    "per_stage_operands": {k: {"ms": round(totals[k] / len(per[k]), 5), "operand_bytes": stage[k],
+                                               "GBps": round(stage[k] / (totals[k] / len(per[k]) * 1e-3) / 1e9, 1)}
+                                           for k in sorted(stage) if k in totals}}
 
     if rank == 0:
         cpu = parity = aten = None
@@ -412,7 +451,12 @@ def run_gpu(args, wl):
                        "cuda_graph": not args.no_graph, "l2": "flushed between timed iterations (256 MiB write)",
                        "parallelism": "dp%d" % world, "host_cpus_rank0": (len(host_cpus) if host_cpus else None)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": step.h2d_bytes, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "h2d_GBps_per_rank": step.h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9,
+                    "host_batch": "what the data loader delivers per step, in pinned memory: target + source pictures as uint8 "
+                                  "(converted on the device by drosfm_images_u8_to_f32 inside the timed step), float64 "
+                                  "intrinsics, GT depth / poses for supervised workloads; feature maps, inverse depths and pose "
+                                  "vectors are produced on the device by the networks and stay resident"},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity, "gpu_aten_reference": aten,
@@ -432,6 +476,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the YAML's batch_size)")
     ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--log-every", type=int, default=10, help="all-reduce the logged loss every k steps (multi-GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     from dro_sfm_b200 import synthetic as syn

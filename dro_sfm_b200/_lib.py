@@ -100,6 +100,7 @@ SIGNATURES = {
     "drosfm_sup_depth_loss_fwd": ([_vp, _pp, _int, _f32, _f32, _f32, _vp, _vp, _int, _int, _int, _vp], _int),
     "drosfm_sup_depth_loss_bwd": ([_vp, _vp, _pp, _int, _f32, _f32, _f32, _pp, _int, _int, _int, _vp], _int),
     "drosfm_relayout": ([_vp, _vp, _int, _int, _int, _int, _int, _vp], _int),
+    "drosfm_images_u8_to_f32": ([_vp, _vp, ctypes.c_size_t, _vp], _int),
     "drosfm_upsample_depth_fwd": ([_vp, _vp, _vp, _int, _int, _int, _int, _vp], _int),
     "drosfm_upsample_depth_bwd": ([_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp], _int),
     "drosfm_reproj_loss_fwd": ([_vp, _int, _cp, _pp, _pp, _int, _int, _f32, _f32, _f32, _vp, _vp,

@@ -31,6 +31,27 @@ transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int row
     }
 }
 
+// uint8 pictures -> float32 in [0,1]: x / 255 with the IEEE division ToTensor performs (datasets/augmentations.py:149-152).
+// 16 pixels per thread: one 128-bit load, four 128-bit stores.
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t n) {
+    const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 16;
+    if (i + 16 <= n) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + i));
+        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float4 o;
+            o.x = __fdiv_rn(static_cast<float>(w[k] & 0xffu), 255.0f);
+            o.y = __fdiv_rn(static_cast<float>((w[k] >> 8) & 0xffu), 255.0f);
+            o.z = __fdiv_rn(static_cast<float>((w[k] >> 16) & 0xffu), 255.0f);
+            o.w = __fdiv_rn(static_cast<float>(w[k] >> 24), 255.0f);
+            __stcs(reinterpret_cast<float4*>(dst + i + 4 * k), o);
+        }
+    } else {
+        for (size_t j = i; j < n; ++j) dst[j] = __fdiv_rn(static_cast<float>(src[j]), 255.0f);
+    }
+}
+
 }  // namespace drosfm
 
 using namespace drosfm;
@@ -51,6 +72,16 @@ int drosfm_relayout(const float* src, float* dst, int B, int C, int H, int W, in
     DROSFM_REQUIRE(grid.y <= 65535, DROSFM_ERANGE, "relayout: too many rows");
     transpose_kernel<<<grid, kTile * kTileRows, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, rows, cols);
     return launch_status("relayout");
+}
+
+int drosfm_images_u8_to_f32(const uint8_t* src, float* dst, size_t n, drosfm_stream_t stream) {
+    if (n == 0) return DROSFM_OK;
+    DROSFM_REQUIRE(src != nullptr && dst != nullptr, DROSFM_EINVAL, "images_u8_to_f32: NULL buffer");
+    DROSFM_REQUIRE(aligned16(src) && aligned16(dst), DROSFM_EALIGN, "images_u8_to_f32: buffers must be 16-byte aligned");
+    const size_t threads = (n + 15) / 16;
+    DROSFM_REQUIRE(threads / 256 < (1ull << 31), DROSFM_ERANGE, "images_u8_to_f32: too many elements");
+    u8_to_f32_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, n);
+    return launch_status("images_u8_to_f32");
 }
 
 }  // extern "C"

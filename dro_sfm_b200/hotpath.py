@@ -56,9 +56,8 @@ class HotPathStep:
     def _alloc(self):
         wl, h, dev = self.wl, self.host, self.device
         seq_iters = wl.T // wl.seq_len
-        # Every forward input of a step lives in ONE flat device buffer (and one pinned host buffer), so the
-        # end-to-end path moves a step's inputs with a single H2D copy into a staging buffer (overlapping
-        # the previous step) and a single device-to-device copy into the tensors the CUDA graph reads.
+        # Every forward input of a step lives in ONE flat device buffer: pictures first, GT tensors last (the two
+        # regions the end-to-end path refreshes from the host every step, see below).
         host_list = [h["image"], *h["context"], h["fmap"], *h["fmaps_ref"], *h["inv_depth_lr"], *h["inv_depths"]]
         host_list += [p for r in h["pose_lr"] for p in r] + [p for r in h["poses"] for p in r]
         if wl.supervised:
@@ -73,13 +72,24 @@ class HotPathStep:
         self.host_flat = torch.zeros(total, dtype=torch.float32)
         for t, o in zip(host_list, offs):
             self.host_flat[o:o + t.numel()] = t.reshape(-1)
+        # What a data loader delivers per step (the end-to-end leg of bench.py moves exactly this, every step):
+        #   * the target and source pictures as uint8 (they are 8-bit images, synthetic.quantise8; the device turns them
+        #     into the float32 tensors the loss reads with drosfm_images_u8_to_f32 == ToTensor's x / 255),
+        #   * the float64 intrinsics, and for supervised workloads the GT inverse depth and GT poses (float32).
+        # Feature maps, inverse depths and pose vectors are produced ON the device by the networks in a training step
+        # (DepthPoseNet.py:113-205); they stay resident and are not part of the host batch.
+        self.n_img = (1 + wl.V) * self.B * 3 * wl.H * wl.W                       # image + contexts lead the flat buffer
+        assert offs[1 + wl.V] == self.n_img
+        self.host_u8 = torch.round(self.host_flat[:self.n_img] * 255.0).to(torch.uint8)
+        self.extra_lo = offs[len(host_list) - (1 + wl.V)] if wl.supervised else total     # GT tensors trail the flat buffer
+        self.host_extra = self.host_flat[self.extra_lo:].clone()
         if dev.type == "cuda":
-            self.host_flat = self.host_flat.pin_memory()
-            self.host_K = k64.pin_memory()
+            self.host_u8, self.host_extra, self.host_K = self.host_u8.pin_memory(), self.host_extra.pin_memory(), k64.pin_memory()
         else:
             self.host_K = k64
         self.flat = self.host_flat.to(dev)
-        self.staging = torch.empty_like(self.flat)
+        self.staging_u8 = torch.empty(self.host_u8.shape, dtype=torch.uint8, device=dev)
+        self.staging_extra = torch.empty(self.host_extra.shape, dtype=torch.float32, device=dev)
         self.K = k64.to(dev)                                 # float64, as numpy collation delivers it
         self.K_staging = torch.empty_like(self.K)
         with torch.no_grad():
@@ -118,33 +128,32 @@ class HotPathStep:
         if cl:
             self.g_costs = [t.contiguous(memory_format=torch.channels_last) for t in self.g_costs]
         self.one = torch.ones(1, device=dev)
-        self.h2d_bytes = self.host_flat.numel() * 4 + self.host_K.numel() * 8
+        self.h2d_bytes = self.host_u8.numel() + self.host_extra.numel() * 4 + self.host_K.numel() * 8
 
     def leaves(self):
         out = [self.fmap] + self.frefs + self.inv_lr + [p for r in self.pose_lr for p in r]
         return out + self.inv_depths + [p for r in self.poses for p in r]
 
-    def upload(self):
-        """Blocking-free host -> device copy of every forward input of the step straight into the tensors the
-        step reads (pinned memory, current stream)."""
-        with torch.no_grad():
-            self.flat.copy_(self.host_flat, non_blocking=True)
-            self.K.copy_(self.host_K, non_blocking=True)
-
     def prefetch(self, stream):
-        """Host -> device copy of the NEXT step's inputs into the staging buffers on `stream` (overlaps the
-        running step); returns the event that marks its completion."""
+        """Host -> device copy of the NEXT step's batch (uint8 pictures, intrinsics, GT tensors; pinned memory) into the
+        staging buffers on `stream` (overlaps the running step); returns the event that marks its completion."""
         with torch.no_grad(), torch.cuda.stream(stream):
-            self.staging.copy_(self.host_flat, non_blocking=True)
+            self.staging_u8.copy_(self.host_u8, non_blocking=True)
+            if self.staging_extra.numel():
+                self.staging_extra.copy_(self.host_extra, non_blocking=True)
             self.K_staging.copy_(self.host_K, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(stream)
         return ev
 
     def commit_staging(self):
-        """Device-to-device move of the staged inputs into the tensors the step reads (current stream)."""
+        """The staged batch becomes the tensors the step reads (current stream): the pictures are converted to float32
+        by one kernel, the small tensors are copied device-to-device."""
+        from . import ops
         with torch.no_grad():
-            self.flat.copy_(self.staging, non_blocking=True)
+            ops.images_u8_to_f32(self.staging_u8, out=self.flat[:self.n_img])
+            if self.staging_extra.numel():
+                self.flat[self.extra_lo:].copy_(self.staging_extra, non_blocking=True)
             self.K.copy_(self.K_staging, non_blocking=True)
 
     # -- the step --------------------------------------------------------------------------------
@@ -205,32 +214,39 @@ class HotPathStep:
 
     # -- bookkeeping for the roofline ---------------------------------------------------------------
     def algorithmic_bytes(self):
-        """every distinct input read once, every output written once per call."""
+        """Algorithmic bytes per launch unit, SURVEY.md section 8(d): every distinct input read once and every output
+        written once per operator call, fp32.  Keys with a SURVEY figure:
+          feat_cost_*            (V+2)*4C+4 fwd, (2V+3)*4C+8 bwd per feature pixel; a batched launch is the sum of its jobs;
+          photometric_loss_fwd   (16+12V) B per pixel and prediction -- the loss forward as ONE fused operator (target,
+                                 depth, V sources; auto-mask and min included), however many kernels implement it;
+          photometric_loss_bwd   (20+12V) B per pixel and prediction;
+          smoothness_fwd / _bwd  the operands of the pass over all n predictions: image once + n maps (+ n gradients);
+          reproj_loss_*          4 B per pixel.
+        Keys under "stage_operands" are the operand bytes of the individual stages of the staged photometric path
+        (warped copy, g_warped: traffic of THIS design, no SURVEY figure) -- reported per call for orientation only."""
         wl, B, C = self.wl, self.B, self.C
         p = (wl.H // 8) * (wl.W // 8) * B
         P = wl.H * wl.W * B
         V, T, n = wl.V, wl.T, wl.n
-        from . import ops as _ops
-        saved = 12 * V if _ops.SAVE_WARP else 0       # warped sources kept by the forward, re-read by the backward
-        split = bool(_ops.SAVE_WARP and _ops.OVERLAP)  # the loss is issued as separate warp / SSIM calls
         out = {
             "feat_cost_fwd_v1": (C * 4 * 3 + 4) * p, "feat_cost_bwd_v1": (C * 4 * 5 + 8) * p,
             "feat_cost_fwd_vN": (C * 4 * (V + 2) + 4) * p, "feat_cost_bwd_vN": (C * 4 * (2 * V + 3) + 8) * p,
-            # one fused call each, or (split) the warp stages on their own: warp fwd reads depth + sources and writes
-            # the warped copy; SSIM fwd reads target + warped + auto-mask, writes sel; SSIM bwd reads target + warped +
-            # sel, writes g_warped; warp bwd reads g_warped + depth + sources, writes g_inv_depth
-            "photometric_fwd": ((17 + 12 * V) if split else (16 + 12 * V + saved)) * P * n,
-            "photometric_bwd": ((13 + 24 * V) if split else (20 + 12 * V + saved)) * P * n,
-            "warp_sources_fwd": (4 + 24 * V) * P * n, "warp_sources_bwd": (8 + 24 * V) * P * n,
-            "automask_fwd": (12 + 12 * V + 4) * P,
-            "smoothness_fwd": (12 + 8 * n) * P, "smoothness_bwd": (12 + 8 * n) * P,
+            "photometric_loss_fwd": (16 + 12 * V) * P * n, "photometric_loss_bwd": (20 + 12 * V) * P * n,
+            "smoothness_fwd": (12 + 4 * n) * P, "smoothness_bwd": (12 + 8 * n) * P,
             "reproj_loss_fwd": 4 * P, "reproj_loss_bwd": 4 * P,
         }
-        calls = {"feat_cost_fwd_v1": V * T, "feat_cost_bwd_v1": V * T, "feat_cost_fwd_vN": T, "feat_cost_bwd_vN": T}
+        out["feat_cost_batch_fwd"] = out["feat_cost_fwd_vN"] + V * out["feat_cost_fwd_v1"]
+        out["feat_cost_batch_bwd"] = out["feat_cost_bwd_vN"] + V * out["feat_cost_bwd_v1"]
+        out["stage_operands"] = {
+            "warp_sources_fwd": (4 + 24 * V) * P * n, "photometric_fwd": (17 + 12 * V) * P * n,
+            "photometric_bwd": (13 + 24 * V) * P * n, "warp_sources_bwd": (8 + 24 * V) * P * n,
+            "automask_fwd": (12 + 12 * V + 4) * P,
+        }
+        cost = T * (out["feat_cost_fwd_vN"] + out["feat_cost_bwd_vN"]) + V * T * (out["feat_cost_fwd_v1"] + out["feat_cost_bwd_v1"])
         if wl.supervised:
-            total = sum(out[k] * calls[k] for k in calls) + out["reproj_loss_fwd"] + out["reproj_loss_bwd"]
+            total = cost + out["reproj_loss_fwd"] + out["reproj_loss_bwd"]
         else:
-            total = sum(out[k] * calls[k] for k in calls) + sum(out[k] for k in (
-                "automask_fwd", "smoothness_fwd", "smoothness_bwd")) + (16 + 12 * V + saved + 20 + 12 * V + saved) * P * n
+            # SURVEY 8(d) per prediction: photometric 16+12V / 20+12V, smoothness 16 / 20 bytes per pixel
+            total = cost + out["photometric_loss_fwd"] + out["photometric_loss_bwd"] + 36 * P * n
         out["step_total"] = total
         return out

@@ -12,7 +12,7 @@ import torch
 from . import _lib as L
 
 __all__ = ["pose_vec2mat", "reconstruct", "project", "warp_coords", "grid_gather", "view_synthesis", "feat_cost", "feat_cost_batch",
-           "photometric_loss", "reproj_pose_loss", "sup_depth_loss", "upsample_depth"]
+           "photometric_loss", "reproj_pose_loss", "sup_depth_loss", "upsample_depth", "images_u8_to_f32"]
 
 
 def _pose_kind(pose):
@@ -919,6 +919,25 @@ def sup_depth_loss(inv_depths, gt_inv_depth, min_depth, max_depth, gamma=0.85):
         if tuple(d.shape) != tuple(gt_inv_depth.shape):
             raise NotImplementedError("dro_sfm_b200: predictions must be at the ground-truth resolution")
     return _SupDepthLoss.apply(gt_inv_depth, (float(min_depth), float(max_depth), float(gamma)), n, *inv_depths)
+
+
+# ------------------------------------------------------------------------------------------------
+# 8-bit pictures
+# ------------------------------------------------------------------------------------------------
+def images_u8_to_f32(src, out=None):
+    """uint8 pictures -> float32 / 255 (ToTensor, datasets/augmentations.py:149-152) on the device, one launch.
+    `out`: optional float32 tensor with the same number of elements (written in place)."""
+    L.require_cuda(src)
+    if src.dtype != torch.uint8:
+        raise ValueError("images_u8_to_f32 expects a uint8 tensor")
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty(src.shape, device=src.device, dtype=torch.float32)
+    elif out.dtype != torch.float32 or out.numel() != src.numel() or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float32 tensor with as many elements as src")
+    with torch.cuda.device(src.device):
+        L.check(L.lib().drosfm_images_u8_to_f32(L.ptr(src), L.ptr(out), src.numel(), L.stream()), "images_u8_to_f32")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -77,6 +77,11 @@ def images(g, B, H, W):
     return (0.95 * smooth_noise(g, B, 3, H, W) + 0.05 * torch.rand(B, 3, H, W, generator=g)).contiguous()
 
 
+def quantise8(x):
+    """The same image as a decoded 8-bit picture: k / 255 (what ToTensor delivers, datasets/augmentations.py:149-152)."""
+    return torch.round(x.clamp(0, 1) * 255.0).div(255.0)
+
+
 def inv_depth(g, B, H, W, min_depth, max_depth, frac_nonpos=0.0):
     """[B,1,H,W] inverse depth in (1/max_depth, 1/min_depth) (layers.py:11-20 range).
     ``frac_nonpos`` injects values <= 0 to exercise the inv2depth mask (utils/depth.py:119-121)."""
@@ -118,8 +123,9 @@ def hot_path_batch(wl, seed=1234, C=128, B=None):
     g = gen(seed)
     h, w = wl.H // 8, wl.W // 8
     out = {
-        "image": images(g, B, wl.H, wl.W),
-        "context": [images(g, B, wl.H, wl.W) for _ in range(wl.V)],
+        # 8-bit pictures (k / 255): the end-to-end path ships them as uint8, the way a dataset stores them
+        "image": quantise8(images(g, B, wl.H, wl.W)),
+        "context": [quantise8(images(g, B, wl.H, wl.W)) for _ in range(wl.V)],
         "K": intrinsics(wl.dataset, B, wl.H, wl.W),
         "fmap": features(g, B, C, h, w),
         "fmaps_ref": [features(g, B, C, h, w) for _ in range(wl.V)],

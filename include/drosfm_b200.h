@@ -275,6 +275,11 @@ int drosfm_upsample_depth_bwd(const float* g_out, const float* depth, const floa
  * what `.contiguous(memory_format=torch.channels_last)` / `.contiguous()` do, as a coalesced tiled transpose. */
 int drosfm_relayout(const float* src, float* dst, int B, int C, int H, int W, int to_layout, drosfm_stream_t stream);
 
+/* ---- 8-bit pictures -> float32 (ToTensor, dro_sfm/datasets/augmentations.py:149-152) ---------------
+ * dst[i] = src[i] / 255 (IEEE division) for n elements: lets a data loader ship the target and source pictures as
+ * uint8 (a quarter of the host-to-device bytes) and convert them in one launch on the device. */
+int drosfm_images_u8_to_f32(const uint8_t* src, float* dst, size_t n, drosfm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
