@@ -77,6 +77,7 @@ SIGNATURES = {
     "drosfm_project_bwd": ([_vp, _vp, _vp, _int, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp], _int),
     "drosfm_warp_coords_fwd": ([_vp, _int, _cp, _vp, _vp, _int, _int, _int, _int, _vp], _int),
     "drosfm_warp_coords_bwd": ([_vp, _vp, _int, _cp, _vp, _vp, _vp, _int, _int, _int, _int, _vp], _int),
+    "drosfm_selftest_rcp": ([_vp, _vp], _int),
     "drosfm_grid_gather_fwd": ([_vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp], _int),
     "drosfm_grid_gather_bwd": ([_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp], _int),
     "drosfm_view_synthesis_fwd": ([_vp, _vp, _int, _cp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp], _int),
@@ -92,8 +93,8 @@ SIGNATURES = {
                                 _int, _int, _int, _int, _vp], _int),
     "drosfm_photometric_bwd": ([_vp, _vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _pp, _pp, _vp, _vp, _vp,
                                 _int, _int, _int, _int, _vp], _int),
-    "drosfm_warp_sources_fwd": ([_pp, _int, _pp, _int, _int, _cp, _pp, _int, _vp, _int, _int, _int, _vp], _int),
-    "drosfm_warp_sources_bwd": ([_vp, _pp, _int, _pp, _int, _int, _cp, _pp, _int, _pp, _pp, _vp, _int,
+    "drosfm_warp_sources_fwd": ([_pp, _int, _pp, _int, _int, _cp, _pp, _int, _vp, _vp, _int, _int, _int, _vp], _int),
+    "drosfm_warp_sources_bwd": ([_vp, _pp, _int, _pp, _int, _int, _cp, _pp, _int, _vp, _pp, _pp, _vp, _int,
                                  _int, _int, _int, _vp], _int),
     "drosfm_smoothness_fwd": ([_vp, _pp, _int, _f32, _vp, _vp, _vp, _int, _int, _int, _vp], _int),
     "drosfm_smoothness_bwd": ([_vp, _vp, _pp, _int, _f32, _vp, _pp, _int, _int, _int, _int, _vp], _int),

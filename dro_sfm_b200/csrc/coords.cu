@@ -25,10 +25,11 @@ __device__ __forceinline__ void pix_xy(int p, int W, int& x, int& y) {
 // ------------------------------------------------------------------------------------------
 // fused forward
 // ------------------------------------------------------------------------------------------
-// RCP: the divisions of the projection go through div_by_rcp (what every fused loss / cost kernel uses); the default
-// is the plain div.rn chain.  Both give the same bits; DROSFM_COORDS_SHARED_RCP=1 selects RCP so that the tests can
-// hold the shared-reciprocal chain to the same bit-exact oracle.
-template <bool VEC, bool RCP>
+// CHAIN 0: the plain div.rn chain (default).  1: the divisions of the projection go through div_by_rcp (supervised
+// losses, fused tile kernels).  2: warp_pixel_fast, the branch-free variant of the flat warp / cost kernels.  All give the
+// same bits (2: wherever |coordinate| < 1e30); DROSFM_COORDS_SHARED_RCP=1|2 selects them so that the tests can hold
+// every chain the fused kernels use to the same bit-exact oracle.
+template <bool VEC, int CHAIN>
 __global__ void __launch_bounds__(kThreads)
 warp_coords_fwd_kernel(const float* __restrict__ depth, int depth_kind, drosfm_cams_t cams,
                        float* __restrict__ uv, uint8_t* __restrict__ mask, int H, int W, int normalize) {
@@ -56,7 +57,8 @@ warp_coords_fwd_kernel(const float* __restrict__ depth, int depth_kind, drosfm_c
         int x, y;
         pix_xy(p0 + k, W, x, y);
         Warp w;
-        warp_pixel<RCP>(cam, x, y, to_depth(d[k], depth_kind), wm1, hm1, normalize != 0, w);
+        if constexpr (CHAIN == 2) warp_pixel_fast(cam, x, y, to_depth_fast(d[k], depth_kind), make_norm(W, H), normalize != 0, w);
+        else warp_pixel<CHAIN == 1>(cam, x, y, to_depth(d[k], depth_kind), wm1, hm1, normalize != 0, w);
         out[2 * k] = w.p.u;
         out[2 * k + 1] = w.p.v;
     }
@@ -304,6 +306,20 @@ __global__ void pose_vec2mat_bwd_kernel(const float* __restrict__ g_mat, const f
     for (int k = 0; k < 6; ++k) g_vec[i * 6 + k] = static_cast<float>(gv[k]);
 }
 
+// drosfm_selftest_rcp: rcp_rn_normal(x) against __frcp_rn(x) for EVERY float with 2^-126 <= |x| < 2^126
+__global__ void __launch_bounds__(256) selftest_rcp_kernel(unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned long long i = blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += stride) {
+        const unsigned bits = static_cast<unsigned>(i);
+        const unsigned e = (bits >> 23) & 0xffu;
+        if (e < 1u || e > 252u) continue;
+        const float x = __uint_as_float(bits);
+        if (__float_as_uint(rcp_rn_normal(x)) != __float_as_uint(__frcp_rn(x))) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 static int check_dims(int B, int H, int W) {
     DROSFM_REQUIRE(B >= 0 && H >= 0 && W >= 0, DROSFM_EINVAL, "negative dimension B=%d H=%d W=%d", B, H, W);
     DROSFM_REQUIRE(static_cast<long long>(H) * W < (1ll << 30) && B <= 65535, DROSFM_ERANGE,
@@ -363,12 +379,18 @@ int drosfm_warp_coords_fwd(const float* depth, int depth_kind, const drosfm_cams
     dim3 grid((P + kThreads * px - 1) / (kThreads * px), B);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const char* env = std::getenv("DROSFM_COORDS_SHARED_RCP");
-    const bool rcp = env != nullptr && env[0] == '1';
-    if (vec && rcp) warp_coords_fwd_kernel<true, true><<<grid, kThreads, 0, s>>>(depth, depth_kind, *cams, uv, mask, H, W, normalize);
-    else if (vec) warp_coords_fwd_kernel<true, false><<<grid, kThreads, 0, s>>>(depth, depth_kind, *cams, uv, mask, H, W, normalize);
-    else if (rcp) warp_coords_fwd_kernel<false, true><<<grid, kThreads, 0, s>>>(depth, depth_kind, *cams, uv, mask, H, W, normalize);
-    else warp_coords_fwd_kernel<false, false><<<grid, kThreads, 0, s>>>(depth, depth_kind, *cams, uv, mask, H, W, normalize);
+    const int chain = env == nullptr ? 0 : (env[0] == '1' ? 1 : (env[0] == '2' ? 2 : 0));
+#define COORDS(VEC_, CH_) warp_coords_fwd_kernel<VEC_, CH_><<<grid, kThreads, 0, s>>>(depth, depth_kind, *cams, uv, mask, H, W, normalize)
+    if (vec) { if (chain == 2) COORDS(true, 2); else if (chain == 1) COORDS(true, 1); else COORDS(true, 0); }
+    else { if (chain == 2) COORDS(false, 2); else if (chain == 1) COORDS(false, 1); else COORDS(false, 0); }
+#undef COORDS
     return launch_status("warp_coords_fwd");
+}
+
+int drosfm_selftest_rcp(unsigned long long* mismatches, drosfm_stream_t stream) {
+    DROSFM_REQUIRE(mismatches != nullptr, DROSFM_EINVAL, "selftest_rcp: NULL counter");
+    selftest_rcp_kernel<<<kNumSMs * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(mismatches);
+    return launch_status("selftest_rcp");
 }
 
 int drosfm_warp_coords_bwd(const float* g_uv, const float* depth, int depth_kind, const drosfm_cams_t* cams,

@@ -378,15 +378,15 @@ feat_cost_fwd_nhwc(const __grid_constant__ CostJobs jobs, drosfm_cams_t cams, in
     if (npix == 0) return;
     STap* wt = taps + static_cast<size_t>(wid) * ppw * VT;
     if (mine) {
-        const float d = to_depth(draw, job.depth_kind);
-        const float wm1 = static_cast<float>(w - 1), hm1 = static_cast<float>(h - 1);
+        const float d = to_depth_fast(draw, job.depth_kind);
+        const Norm nm = make_norm(w, h);
         int x, y;
         pix_xy(p, w, x, y);
 #pragma unroll
         for (int v = 0; v < VT; ++v) {
             if (v < V) {
                 Warp wp;
-                warp_pixel<true>(cam[v], x, y, d, wm1, hm1, true, wp);
+                warp_pixel_fast(cam[v], x, y, d, nm, true, wp);
                 CTaps t;
                 make_ctaps(wp.p.u, wp.p.v, h, w, t);
                 store_stap(wt + lane * VT + v, t);
@@ -468,9 +468,10 @@ feat_cost_bwd_nhwc(const __grid_constant__ CostJobs jobs, const __grid_constant_
     const bool mine = lane < npix;
     const int p = pbase + lane;
     const float draw = mine ? __ldg(job.depth + static_cast<size_t>(b) * P + p) : 0.0f;
-    const float d = to_depth(draw, depth_kind);
+    const float d = to_depth_fast(draw, depth_kind);
     setup_cams_block<VT>(cams, job, b, cam);
-    const float wm1 = static_cast<float>(w - 1), hm1 = static_cast<float>(h - 1);
+    const Norm nm = make_norm(w, h);
+    const float wm1 = nm.wm1, hm1 = nm.hm1;
     STap* wt = taps + static_cast<size_t>(wid) * ppw * VT;
     float2* wg = gxy + static_cast<size_t>(wid) * ppw * VT;
     int x = 0, y = 0;
@@ -480,7 +481,7 @@ feat_cost_bwd_nhwc(const __grid_constant__ CostJobs jobs, const __grid_constant_
         for (int v = 0; v < VT; ++v) {
             if (v < V) {
                 Warp wp;
-                warp_pixel<true>(cam[v], x, y, d, wm1, hm1, true, wp);
+                warp_pixel_fast(cam[v], x, y, d, nm, true, wp);
                 CTaps t;
                 make_ctaps(wp.p.u, wp.p.v, h, w, t);
                 store_stap(wt + lane * VT + v, t);
@@ -578,7 +579,7 @@ feat_cost_bwd_nhwc(const __grid_constant__ CostJobs jobs, const __grid_constant_
             for (int i = 0; i < 12; ++i) gT[i] = 0.0f;
             if (mine && wt[lane * VT + v].valid) {
                 Warp wp;
-                warp_pixel<true>(cam[v], x, y, d, wm1, hm1, true, wp);
+                warp_pixel_fast(cam[v], x, y, d, nm, true, wp);
                 const float mx = 0.5f * static_cast<float>(w - 1), my = 0.5f * static_cast<float>(h - 1);
                 gd += warp_pixel_adjoint(cam[v], wp, d, wm1, hm1, true, acc_g[v].x * mx, acc_g[v].y * my, gT);
             }

@@ -620,17 +620,44 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
 //   4 warp_sources_adjoint_kernel  g_warped, inv_depth, ... -> g_inv_depth, g_pose
 // The SSIM stages then carry no camera state (fewer registers, more resident warps) and the geometry runs
 // once per pixel instead of once per pixel of every tile + halo.
-constexpr int kFlatThreads = 256, kFlatRows = 8, kFlatNB = 1;
+constexpr int kFlatThreads = 256, kFlatRows = 8;
 constexpr int kFlatTileH = (kFlatThreads / 32) * kFlatRows;       // a block covers 32 columns x 64 rows
 
+// Source pictures as RGBx texels ([V][B][H][W][4] floats, x = 0): every bilinear tap of the flat warp and of its adjoint
+// is ONE 128-bit gather instead of three 32-bit ones from three planes (a third of the load instructions and address
+// arithmetic; the two horizontal taps of a pixel share a 32-byte sector).  Written once per step.
+__global__ void __launch_bounds__(256)
+pack_rgbx_kernel(const __grid_constant__ PhotoPtrs pp, int B, int P, float* __restrict__ rgbx) {
+    const int v = blockIdx.z, b = blockIdx.y;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= P) return;
+    const float* __restrict__ src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
+    const float4 t = make_float4(__ldg(src + p), __ldg(src + P + p), __ldg(src + 2 * P + p), 0.0f);
+    reinterpret_cast<float4*>(rgbx)[(static_cast<size_t>(v) * B + b) * P + p] = t;
+}
+
 struct FlatTap {
-    int o00, dxo, dyo;
+    int o00, dxo, dyo;                 // element offsets (pixels): north-west tap, +east, +south
     float w00, w01, w10, w11;
 };
 
+__device__ __forceinline__ FlatTap flat_taps(float u, float v, int H, int W, int padding) {
+    float mx, my;
+    const ATap tx = axis_taps(unnormalize(u, W, padding, mx), W);
+    const ATap ty = axis_taps(unnormalize(v, H, padding, my), H);
+    FlatTap tp;
+    tp.o00 = ty.i0 * W + tx.i0;
+    tp.dxo = tx.step;
+    tp.dyo = ty.step * W;
+    tp.w00 = tx.w0 * ty.w0; tp.w01 = tx.w1 * ty.w0; tp.w10 = tx.w0 * ty.w1; tp.w11 = tx.w1 * ty.w1;
+    return tp;
+}
+
+// PACKED: the sources are read as RGBx texels (`rgbx`), otherwise as the caller's three planes.
+template <bool PACKED>
 __global__ void __launch_bounds__(kFlatThreads, 3)
 warp_sources_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind, int n_preds, drosfm_cams_t cams, int padding,
-                    float* __restrict__ warped, int B, int H, int W) {
+                    const float* __restrict__ rgbx, float* __restrict__ warped, int B, int H, int W) {
     __shared__ Cam cam_s;
     const int slot = blockIdx.z;                               // (ip * V + v) * B + b
     const int b = slot % B, v = (slot / B) % V, ip = slot / (B * V);
@@ -638,15 +665,16 @@ warp_sources_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind,
     __syncthreads();
     const Cam cam = cam_s;
     const int P = H * W;
-    const float wm1 = static_cast<float>(W - 1), hm1 = static_cast<float>(H - 1);
+    const Norm nm = make_norm(W, H);
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y0 = blockIdx.y * kFlatTileH + (threadIdx.x >> 5);
     const float* __restrict__ invd = pp.inv_depth[ip] + static_cast<size_t>(b) * P;
     const float* __restrict__ src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
+    const float4* __restrict__ tex = reinterpret_cast<const float4*>(rgbx) + (static_cast<size_t>(v) * B + b) * P;
     float* __restrict__ out = warped + static_cast<size_t>(slot) * 3 * P;
     if (x >= W) return;
     constexpr int kStride = kFlatThreads / 32;
-    // Software pipeline over the thread's rows: the depths are all requested up front; the twelve gathers of row k
+    // Software pipeline over the thread's rows: the depths are all requested up front; the gathers of row k
     // are in flight while the coordinate chain of row k+1 runs.
     float d[kFlatRows];
 #pragma unroll
@@ -655,36 +683,29 @@ warp_sources_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind,
         d[k] = y < H ? __ldg(invd + y * W + x) : 0.0f;
     }
     auto taps_of = [&](int k) {
-        const int y = y0 + k * kStride;
-        FlatTap tp{0, 0, 0, 0.0f, 0.0f, 0.0f, 0.0f};
-        if (y < H) {
-            Warp wp;
-            warp_pixel<true>(cam, x, y, to_depth(d[k], depth_kind), wm1, hm1, true, wp);
-            Taps t;
-            make_taps(wp.p.u, wp.p.v, H, W, padding, t);
-            if (t.valid) {
-                const float bx = 1.0f - t.ax, by = 1.0f - t.ay;
-                tp.w00 = (t.valid & 1u) ? bx * by : 0.0f;
-                tp.w01 = (t.valid & 2u) ? t.ax * by : 0.0f;
-                tp.w10 = (t.valid & 4u) ? bx * t.ay : 0.0f;
-                tp.w11 = (t.valid & 8u) ? t.ax * t.ay : 0.0f;
-                const int xa = max(t.x0, 0), ya = max(t.y0, 0);
-                tp.o00 = ya * W + xa;
-                tp.dxo = min(t.x0 + 1, W - 1) - xa;
-                tp.dyo = (min(t.y0 + 1, H - 1) - ya) * W;
-            }
-        }
-        return tp;
+        // rows beyond the image run the chain on depth 0 (in-range addresses, results discarded): no divergence
+        Warp wp;
+        warp_pixel_fast(cam, x, y0 + k * kStride, to_depth_fast(d[k], depth_kind), nm, true, wp);
+        return flat_taps(wp.p.u, wp.p.v, H, W, padding);
     };
     float val[12];
+    float4 tex4[4];
     auto gather = [&](const FlatTap& tp) {
+        if constexpr (PACKED) {
+            const float4* r0 = tex + tp.o00;
+            tex4[0] = __ldg(r0);
+            tex4[1] = __ldg(r0 + tp.dxo);
+            tex4[2] = __ldg(r0 + tp.dyo);
+            tex4[3] = __ldg(r0 + tp.dyo + tp.dxo);
+        } else {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float* r0 = src + (static_cast<unsigned>(c * P) + static_cast<unsigned>(tp.o00));
-            val[4 * c + 0] = __ldg(r0);
-            val[4 * c + 1] = __ldg(r0 + tp.dxo);
-            val[4 * c + 2] = __ldg(r0 + tp.dyo);
-            val[4 * c + 3] = __ldg(r0 + tp.dyo + tp.dxo);
+            for (int c = 0; c < 3; ++c) {
+                const float* r0 = src + (static_cast<unsigned>(c * P) + static_cast<unsigned>(tp.o00));
+                val[4 * c + 0] = __ldg(r0);
+                val[4 * c + 1] = __ldg(r0 + tp.dxo);
+                val[4 * c + 2] = __ldg(r0 + tp.dyo);
+                val[4 * c + 3] = __ldg(r0 + tp.dyo + tp.dxo);
+            }
         }
     };
     FlatTap cur = taps_of(0);
@@ -695,10 +716,17 @@ warp_sources_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind,
         if (k + 1 < kFlatRows) nxt = taps_of(k + 1);
         const int y = y0 + k * kStride;
         if (y < H) {
+            const unsigned o = static_cast<unsigned>(y * W + x);
+            if constexpr (PACKED) {
+                out[o] = tex4[0].x * cur.w00 + tex4[1].x * cur.w01 + tex4[2].x * cur.w10 + tex4[3].x * cur.w11;
+                out[o + P] = tex4[0].y * cur.w00 + tex4[1].y * cur.w01 + tex4[2].y * cur.w10 + tex4[3].y * cur.w11;
+                out[o + 2 * P] = tex4[0].z * cur.w00 + tex4[1].z * cur.w01 + tex4[2].z * cur.w10 + tex4[3].z * cur.w11;
+            } else {
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-                out[static_cast<unsigned>(c * P + y * W + x)] = val[4 * c] * cur.w00 + val[4 * c + 1] * cur.w01 +
-                                                                  val[4 * c + 2] * cur.w10 + val[4 * c + 3] * cur.w11;
+                for (int c = 0; c < 3; ++c)
+                    out[o + static_cast<unsigned>(c * P)] = val[4 * c] * cur.w00 + val[4 * c + 1] * cur.w01 +
+                                                             val[4 * c + 2] * cur.w10 + val[4 * c + 3] * cur.w11;
+            }
         }
         if (k + 1 < kFlatRows) {
             cur = nxt;
@@ -707,108 +735,145 @@ warp_sources_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind,
     }
 }
 
+// red.global.add.f32: fire-and-forget accumulation of one view's depth gradient
+__device__ __forceinline__ void red_add1(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+
+// Adjoint of the flat warp.  Like the forward, one block owns a 32 x 64 tile of ONE (prediction, view, sample): a thread
+// walks down 8 rows of its column, pushes the upstream gradient of the warped pixel through the bilinear taps and the
+// projection chain, and keeps the 12 pose-gradient terms in registers over all its rows -- one warp-level
+// reduce-scatter (13 shuffles) and 12 fp64 atomics per warp and block.  The depth gradients of the V views of a pixel
+// meet in g_inv_depth through red.global.add (ADD) or are stored (V == 1, nothing to add to).
+// A row is skipped when no lane of the warp has a non-zero upstream gradient (un-selected view / auto-masked region).
+template <bool PACKED, bool ADD>
 __global__ void __launch_bounds__(kFlatThreads, 3)
 warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind, int n_preds, drosfm_cams_t cams,
-                            int padding, const float* __restrict__ g_warped, const __grid_constant__ PhotoGrads pg, Slot* ws,
-                            int accumulate, int B, int H, int W) {
-    __shared__ Cam cam_s[DROSFM_MAX_VIEWS];
+                            int padding, const float* __restrict__ rgbx, const float* __restrict__ g_warped,
+                            const __grid_constant__ PhotoGrads pg, Slot* ws, int B, int H, int W) {
+    __shared__ Cam cam_s;
+    __shared__ int flag;
     const int tid = threadIdx.x;
-    const int b = static_cast<int>(blockIdx.z) % B, ip = static_cast<int>(blockIdx.z) / B;
-    if (tid < V) setup_cam(cams, pp.pose[tid * n_preds + ip], b, cam_s[tid]);
+    const int slot = blockIdx.z;                               // (ip * V + v) * B + b
+    const int b = slot % B, v = (slot / B) % V, ip = slot / (B * V);
+    if (tid == 0) setup_cam(cams, pp.pose[v * n_preds + ip], b, cam_s);
     __syncthreads();
+    const Cam& cam = cam_s;                                    // read from shared memory on use: the registers go to occupancy
     const int P = H * W;
-    const float wm1 = static_cast<float>(W - 1), hm1 = static_cast<float>(H - 1);
+    const Norm nm = make_norm(W, H);
     const int x = blockIdx.x * 32 + (tid & 31);
+    const int y0 = blockIdx.y * kFlatTileH + (tid >> 5);
     const bool col_ok = x < W;
-    // per-sample planes; everything below is a 32-bit offset from one of these (the host checks the ranges)
+    constexpr int kStride = kFlatThreads / 32;
     const float* __restrict__ invd = pp.inv_depth[ip] + static_cast<size_t>(b) * P;
     float* __restrict__ gout = pg.g_inv_depth[ip] != nullptr ? pg.g_inv_depth[ip] + static_cast<size_t>(b) * P : nullptr;
-    const float* __restrict__ gw0 = g_warped + (static_cast<size_t>(ip) * V * B + b) * 3 * P;      // view v: + v * vstride
-    const unsigned vstride = static_cast<unsigned>(B) * 3u * static_cast<unsigned>(P);
-    constexpr int kHalf = 4, kStride = kFlatThreads / 32;
-#pragma unroll 1
-    for (int h = 0; h < kFlatRows / kHalf; ++h) {
-        const int y0 = blockIdx.y * kFlatTileH + h * kHalf * kStride + (tid >> 5);
-        float dv[kHalf], gd[kHalf], old[kHalf];
-        unsigned off[kHalf];
-        bool in[kHalf];
+    const float* __restrict__ gw = g_warped + static_cast<size_t>(slot) * 3 * P;
+    const float* __restrict__ src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
+    const float4* __restrict__ tex = reinterpret_cast<const float4*>(rgbx) + (static_cast<size_t>(v) * B + b) * P;
+    float gT[12];
 #pragma unroll
-        for (int k = 0; k < kHalf; ++k) {
-            const int y = y0 + k * kStride;
-            in[k] = col_ok && y < H;
-            off[k] = in[k] ? static_cast<unsigned>(y * W + x) : 0u;
-            dv[k] = in[k] ? __ldg(invd + off[k]) : 0.0f;
-            old[k] = (in[k] && accumulate && gout != nullptr) ? gout[off[k]] : 0.0f;      // requested now, needed at the end
-            gd[k] = 0.0f;
-        }
-#pragma unroll 1
-        for (int v = 0; v < V; ++v) {
-            const Cam& cam = cam_s[v];            // read from shared memory on use: the registers go to occupancy
-            const float* __restrict__ src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
-            // all twelve upstream gradients of this view's rows are requested before the first one is used
-            float g[kHalf][3];
+    for (int i = 0; i < 12; ++i) gT[i] = 0.0f;
+    // the depths of all rows are requested up front, the upstream gradients one row ahead
+    float dv[kFlatRows];
 #pragma unroll
-            for (int k = 0; k < kHalf; ++k)
+    for (int k = 0; k < kFlatRows; ++k) {
+        const int y = y0 + k * kStride;
+        dv[k] = (col_ok && y < H) ? __ldg(invd + y * W + x) : 0.0f;
+    }
+    float gn[3];
+    auto fetch_g = [&](int k) {
+        const int y = y0 + k * kStride;
+        const bool in = col_ok && y < H;
+        const unsigned o = in ? static_cast<unsigned>(y * W + x) : 0u;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) g[k][c] = in[k] ? __ldg(gw0 + (v * vstride + c * P + off[k])) : 0.0f;
-            float gT[12];
+        for (int c = 0; c < 3; ++c) gn[c] = in ? __ldg(gw + (o + static_cast<unsigned>(c * P))) : 0.0f;
+    };
+    fetch_g(0);
 #pragma unroll
-            for (int i = 0; i < 12; ++i) gT[i] = 0.0f;
+    for (int k = 0; k < kFlatRows; ++k) {
+        const float g0 = gn[0], g1 = gn[1], g2 = gn[2];
+        if (k + 1 < kFlatRows) fetch_g(k + 1);
+        const int y = y0 + k * kStride;
+        const bool in = col_ok && y < H;
+        float gd = 0.0f;
+        if (__any_sync(0xffffffffu, g0 != 0.0f || g1 != 0.0f || g2 != 0.0f)) {
+            const float d = to_depth_fast(dv[k], depth_kind);
+            Warp wp;
+            warp_pixel_fast(cam, x, y, d, nm, true, wp);
+            float mx, my;
+            const ATap tx = axis_taps(unnormalize(wp.p.u, W, padding, mx), W);
+            const ATap ty = axis_taps(unnormalize(wp.p.v, H, padding, my), H);
+            const unsigned o00 = static_cast<unsigned>(ty.i0 * W + tx.i0);
+            const unsigned dxo = static_cast<unsigned>(tx.step), dyo = static_cast<unsigned>(ty.step * W);
+            // d(sample)/d(ix) = (ne - nw) wy0 + (se - sw) wy1 and d(sample)/d(iy) = (sw - nw) wx0 + (se - ne) wx1, a tap
+            // outside the source counting as zero: four coefficients per direction, shared by the channels
+            const float kx0 = -tx.f0 * ty.w0, kx1 = tx.f1 * ty.w0, kx2 = -tx.f0 * ty.w1, kx3 = tx.f1 * ty.w1;
+            const float ky0 = -ty.f0 * tx.w0, ky1 = -ty.f0 * tx.w1, ky2 = ty.f1 * tx.w0, ky3 = ty.f1 * tx.w1;
+            float gix, giy;
+            if constexpr (PACKED) {
+                const float4 t0 = __ldg(tex + o00), t1 = __ldg(tex + (o00 + dxo));
+                const float4 t2 = __ldg(tex + (o00 + dyo)), t3 = __ldg(tex + (o00 + dyo + dxo));
+                gix = g0 * (t0.x * kx0 + t1.x * kx1 + t2.x * kx2 + t3.x * kx3) + g1 * (t0.y * kx0 + t1.y * kx1 + t2.y * kx2 + t3.y * kx3) +
+                      g2 * (t0.z * kx0 + t1.z * kx1 + t2.z * kx2 + t3.z * kx3);
+                giy = g0 * (t0.x * ky0 + t1.x * ky1 + t2.x * ky2 + t3.x * ky3) + g1 * (t0.y * ky0 + t1.y * ky1 + t2.y * ky2 + t3.y * ky3) +
+                      g2 * (t0.z * ky0 + t1.z * ky1 + t2.z * ky2 + t3.z * ky3);
+            } else {
+                gix = giy = 0.0f;
+                const float gc[3] = {g0, g1, g2};
 #pragma unroll
-            for (int k = 0; k < kHalf; ++k) {
-                // a pixel that no selected window touches has an exactly zero gradient: nothing to push through
-                if (g[k][0] != 0.0f || g[k][1] != 0.0f || g[k][2] != 0.0f) {
-                    const int y = y0 + k * kStride;
-                    const float d = to_depth(dv[k], depth_kind);
-                    Warp wp;
-                    warp_pixel<true>(cam, x, y, d, wm1, hm1, true, wp);
-                    Taps t;
-                    make_taps(wp.p.u, wp.p.v, H, W, padding, t);
-                    if (t.valid) {
-                        const int xa = max(t.x0, 0), ya = max(t.y0, 0);
-                        const unsigned o00 = static_cast<unsigned>(ya * W + xa);
-                        const unsigned dxo = static_cast<unsigned>(min(t.x0 + 1, W - 1) - xa);
-                        const unsigned dyo = static_cast<unsigned>((min(t.y0 + 1, H - 1) - ya) * W);
-                        const float m0 = (t.valid & 1u) ? 1.f : 0.f, m1 = (t.valid & 2u) ? 1.f : 0.f;
-                        const float m2 = (t.valid & 4u) ? 1.f : 0.f, m3 = (t.valid & 8u) ? 1.f : 0.f;
-                        float gix = 0.0f, giy = 0.0f;
-                        const float bx = 1.0f - t.ax, by = 1.0f - t.ay;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const unsigned oc = o00 + static_cast<unsigned>(c * P);
-                            const float v0 = __ldg(src + oc) * m0, v1 = __ldg(src + (oc + dxo)) * m1;
-                            const float v2 = __ldg(src + (oc + dyo)) * m2, v3 = __ldg(src + (oc + dyo + dxo)) * m3;
-                            gix += g[k][c] * ((v1 - v0) * by + (v3 - v2) * t.ay);
-                            giy += g[k][c] * ((v2 - v0) * bx + (v3 - v1) * t.ax);
-                        }
-                        gd[k] += warp_pixel_adjoint(cam, wp, d, wm1, hm1, true, gix * t.mx, giy * t.my, gT);
-                    }
+                for (int c = 0; c < 3; ++c) {
+                    const unsigned oc = o00 + static_cast<unsigned>(c * P);
+                    const float v0 = __ldg(src + oc), v1 = __ldg(src + (oc + dxo));
+                    const float v2 = __ldg(src + (oc + dyo)), v3 = __ldg(src + (oc + dyo + dxo));
+                    gix += gc[c] * (v0 * kx0 + v1 * kx1 + v2 * kx2 + v3 * kx3);
+                    giy += gc[c] * (v0 * ky0 + v1 * ky1 + v2 * ky2 + v3 * ky3);
                 }
             }
-            if (pg.g_pose[v * n_preds + ip] != nullptr)
-                warp_accumulate<12>(gT, spread_acc(slot_at(ws, (v * n_preds + ip) * B + b)));
+            // lanes without a gradient (or outside the image) carry gix = giy = 0: every term below is then an exact zero
+            if (in && (gix != 0.0f || giy != 0.0f))
+                gd = warp_pixel_adjoint(cam, wp, d, nm.wm1, nm.hm1, true, gix * mx, giy * my, gT);
         }
-        if (gout != nullptr) {
-#pragma unroll
-            for (int k = 0; k < kHalf; ++k) {
-                if (in[k]) {
-                    float gg = gd[k];
-                    if (depth_kind == DROSFM_INV_DEPTH) gg = inv2depth_grad(dv[k], gg);
-                    gout[off[k]] = old[k] + gg;
-                }
-            }
+        if (gout != nullptr && in) {
+            const float gg = depth_kind == DROSFM_INV_DEPTH ? inv2depth_grad(dv[k], gd) : gd;
+            float* dst = gout + static_cast<unsigned>(y * W + x);
+            if constexpr (ADD) { if (gg != 0.0f) red_add1(dst, gg); }
+            else *dst = gg;
         }
     }
+    float* g_pose = pg.g_pose[v * n_preds + ip];
+    if (g_pose == nullptr) return;
+    Slot* slot_p = slot_at(ws, (v * n_preds + ip) * B + b);
+    warp_accumulate12(gT, spread_acc(slot_p));
     // one ticket per (view, prediction, sample): the last block turns the fp64 sums into the caller's encoding
-    __shared__ unsigned last_mask;
-    finish_last_slots(
-        V, static_cast<unsigned long long>(gridDim.x) * gridDim.y, &last_mask,
-        [&](int v) { return pg.g_pose[v * n_preds + ip] != nullptr ? slot_at(ws, (v * n_preds + ip) * B + b) : nullptr; },
-        [&](int v, Slot* slot) {
-            const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
-            finish_pose_grad_warp(slot, cams.pose_kind, eul ? pp.pose[v * n_preds + ip] + b * 6 : nullptr,
-                                  pg.g_pose[v * n_preds + ip] + b * (eul ? 6 : 16));
-        });
+    if (last_block(slot_p, gridDim.x * gridDim.y, &flag) && tid < 32) {
+        const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
+        finish_pose_grad_warp(slot_p, cams.pose_kind, eul ? pp.pose[v * n_preds + ip] + b * 6 : nullptr, g_pose + b * (eul ? 6 : 16));
+    }
+}
+
+// zero-fill of the depth-gradient maps the adjoint accumulates into (several views, nothing written before)
+__global__ void __launch_bounds__(256) zero_inv_grads_kernel(const __grid_constant__ PhotoGrads pg, size_t n) {
+    float* dst = pg.g_inv_depth[blockIdx.y];
+    if (dst == nullptr) return;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * 256) dst[i] = 0.0f;
+}
+
+// host side of the adjoint launch: accumulate == 0 -> the depth gradients are (over)written, else added to
+static int launch_adjoint(const PhotoPtrs& pp, const PhotoGrads& pg, int n_views, int depth_kind, int n_preds, const drosfm_cams_t* cams,
+                          int padding, const float* rgbx, const float* g_warped, Slot* ws, int accumulate, int B, int H, int W,
+                          cudaStream_t cs) {
+    dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds * n_views);
+    const bool add = accumulate != 0 || n_views > 1;
+    if (add && accumulate == 0) {
+        const size_t n = static_cast<size_t>(B) * H * W;
+        dim3 zgrid(static_cast<unsigned>(min(static_cast<size_t>(kNumSMs) * 4, (n + 255) / 256)), n_preds);
+        zero_inv_grads_kernel<<<zgrid, 256, 0, cs>>>(pg, n);
+        if (int e = launch_status("warp adjoint (zero fill)")) return e;
+    }
+#define ADJ(PK, AD) warp_sources_adjoint_kernel<PK, AD><<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, padding, rgbx, \
+                                                                                     g_warped, pg, ws, B, H, W)
+    if (rgbx != nullptr) { if (add) ADJ(true, true); else ADJ(true, false); }
+    else { if (add) ADJ(false, true); else ADJ(false, false); }
+#undef ADJ
+    return DROSFM_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1573,8 +1638,8 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
     if (warped_save != nullptr) {
         if (!(flags & DROSFM_PHOTO_WARPED_READY)) {
             dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds * n_views);
-            warp_sources_kernel<<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, opts->padding, warped_save, B, H,
-                                                               W);
+            warp_sources_kernel<false><<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, opts->padding, nullptr,
+                                                                      warped_save, B, H, W);
             if (int e = launch_status("photometric_fwd (warp_sources)")) return e;
         }
         if (n_views <= 2 && static_cast<long long>(n_views) * B * 3 * H * W < (1ll << 31)) {
@@ -1648,9 +1713,9 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
         DROSFM_REQUIRE(static_cast<long long>(n_views) * B * 3 * H * W < (1ll << 32), DROSFM_ERANGE,
                        "photometric_bwd: one prediction's warped views exceed 2^32 elements");
         if (int e = launch_status("photometric_bwd (window gradients)")) return e;
-        dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds);
-        warp_sources_adjoint_kernel<<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, opts->padding, g_warped,
-                                                                   pg, static_cast<Slot*>(ws), 0, B, H, W);
+        DROSFM_REQUIRE(static_cast<long long>(B) * n_preds * n_views <= 65535, DROSFM_ERANGE, "photometric_bwd: B * n_preds * n_views too large");
+        if (int e = launch_adjoint(pp, pg, n_views, depth_kind, n_preds, cams, opts->padding, nullptr, g_warped, static_cast<Slot*>(ws), 0,
+                                   B, H, W, cs)) return e;
     } else {
         photometric_bwd_kernel<false><<<grid, kBwdThreads, kBwdSmemBytes, cs>>>(
             g_loss, image, pp, n_views, depth_kind, n_preds, *cams, sel, *opts, l1_weight(opts), pg, static_cast<Slot*>(ws),
@@ -1660,8 +1725,8 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
 }
 
 int drosfm_warp_sources_fwd(const float* const* context, int n_views, const float* const* inv_depths, int depth_kind,
-                            int n_preds, const drosfm_cams_t* cams, const float* const* poses, int padding, float* warped,
-                            int B, int H, int W, drosfm_stream_t stream) {
+                            int n_preds, const drosfm_cams_t* cams, const float* const* poses, int padding, float* rgbx,
+                            float* warped, int B, int H, int W, drosfm_stream_t stream) {
     DROSFM_REQUIRE(B >= 0 && H >= 0 && W >= 0, DROSFM_EINVAL, "warp_sources_fwd: negative dimension");
     DROSFM_REQUIRE(n_views >= 1 && n_views <= DROSFM_MAX_VIEWS, DROSFM_ERANGE, "warp_sources_fwd: n_views=%d outside [1,%d]",
                    n_views, DROSFM_MAX_VIEWS);
@@ -1677,15 +1742,24 @@ int drosfm_warp_sources_fwd(const float* const* context, int n_views, const floa
     if (int e = fill_ptrs(pp, context, n_views, inv_depths, n_preds, poses, 1.0f)) return e;
     DROSFM_REQUIRE(static_cast<long long>(B) * n_preds * n_views <= 65535, DROSFM_ERANGE, "warp_sources_fwd: B * n_preds * n_views too large");
     dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds * n_views);
-    warp_sources_kernel<<<flat, kFlatThreads, 0, static_cast<cudaStream_t>(stream)>>>(pp, n_views, depth_kind, n_preds, *cams, padding,
-                                                                                      warped, B, H, W);
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    if (rgbx != nullptr) {
+        DROSFM_REQUIRE(aligned16(rgbx), DROSFM_EALIGN, "warp_sources_fwd: rgbx must be 16-byte aligned");
+        DROSFM_REQUIRE(B <= 65535, DROSFM_ERANGE, "warp_sources_fwd: B too large");
+        dim3 pgrid((H * W + 255) / 256, B, n_views);
+        pack_rgbx_kernel<<<pgrid, 256, 0, cs>>>(pp, B, H * W, rgbx);
+        if (int e = launch_status("warp_sources_fwd (rgbx)")) return e;
+        warp_sources_kernel<true><<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, padding, rgbx, warped, B, H, W);
+    } else {
+        warp_sources_kernel<false><<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, padding, nullptr, warped, B, H, W);
+    }
     return launch_status("warp_sources_fwd");
 }
 
 int drosfm_warp_sources_bwd(const float* g_warped, const float* const* context, int n_views, const float* const* inv_depths,
                             int depth_kind, int n_preds, const drosfm_cams_t* cams, const float* const* poses, int padding,
-                            float* const* g_inv_depths, float* const* g_poses, void* ws, int accumulate, int B, int H, int W,
-                            drosfm_stream_t stream) {
+                            const float* rgbx, float* const* g_inv_depths, float* const* g_poses, void* ws, int accumulate,
+                            int B, int H, int W, drosfm_stream_t stream) {
     DROSFM_REQUIRE(B >= 0 && H >= 0 && W >= 0, DROSFM_EINVAL, "warp_sources_bwd: negative dimension");
     DROSFM_REQUIRE(n_views >= 1 && n_views <= DROSFM_MAX_VIEWS, DROSFM_ERANGE, "warp_sources_bwd: n_views=%d outside [1,%d]",
                    n_views, DROSFM_MAX_VIEWS);
@@ -1710,9 +1784,10 @@ int drosfm_warp_sources_bwd(const float* g_warped, const float* const* context, 
     DROSFM_REQUIRE(static_cast<long long>(B) * n_preds <= 65535, DROSFM_ERANGE, "warp_sources_bwd: B * n_preds too large");
     DROSFM_REQUIRE(static_cast<long long>(n_views) * B * 3 * H * W < (1ll << 32), DROSFM_ERANGE,
                    "warp_sources_bwd: one prediction's warped views exceed 2^32 elements");
-    dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds);
-    warp_sources_adjoint_kernel<<<flat, kFlatThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        pp, n_views, depth_kind, n_preds, *cams, padding, g_warped, pg, static_cast<Slot*>(ws), accumulate ? 1 : 0, B, H, W);
+    DROSFM_REQUIRE(static_cast<long long>(B) * n_preds * n_views <= 65535, DROSFM_ERANGE, "warp_sources_bwd: B * n_preds * n_views too large");
+    DROSFM_REQUIRE(rgbx == nullptr || aligned16(rgbx), DROSFM_EALIGN, "warp_sources_bwd: rgbx must be 16-byte aligned");
+    if (int e = launch_adjoint(pp, pg, n_views, depth_kind, n_preds, cams, padding, rgbx, g_warped, static_cast<Slot*>(ws), accumulate, B, H, W,
+                               static_cast<cudaStream_t>(stream))) return e;
     return launch_status("warp_sources_bwd");
 }
 

@@ -631,6 +631,8 @@ SAVE_WARP = os.environ.get("DROSFM_PHOTO_SAVE_WARP", "1") != "0"
 # DROSFM_PHOTO_OVERLAP=0 keeps the whole loss on the caller's stream (no second stream for auto-mask / smoothness).
 # OVERLAP may also be set to "serial" (bench.py's per-kernel timing pass): the same split calls, on one stream.
 OVERLAP = os.environ.get("DROSFM_PHOTO_OVERLAP", "1") != "0"
+# DROSFM_PHOTO_RGBX=0 keeps the flat warp on the caller's planar pictures (no RGBx texel copy of the sources)
+RGBX = os.environ.get("DROSFM_PHOTO_RGBX", "1") != "0"
 
 
 def _reduce_op(name):
@@ -666,6 +668,8 @@ class _PhotoLoss(torch.autograd.Function):
         keep_warp = SAVE_WARP and any(ctx.needs_input_grad[6 + V:])
         wsave = torch.empty(n, V, B, 3, H, W, device=dev, dtype=torch.float32) if keep_warp else None
         stats = torch.empty(n, B, 4, device=dev, dtype=torch.float32) if smooth_w > 0.0 else None
+        # source pictures as RGBx texels for the flat warp and its adjoint (one 128-bit gather per tap)
+        rgbx = torch.empty(V, B, H, W, 4, device=dev, dtype=torch.float32) if keep_warp and RGBX else None
         lib = L.lib()
         staged = wsave is not None and bool(OVERLAP)        # split calls
         two_streams = staged and OVERLAP is True            # OVERLAP == "serial": split calls, one stream
@@ -698,7 +702,7 @@ class _PhotoLoss(torch.autograd.Function):
                         ev_mask = side_work()
                 else:
                     side_work()
-                L.check(lib.drosfm_warp_sources_fwd(pa, V, pi, depth_kind, n, cams, pp_, padding, L.ptr(wsave), B, H, W, st),
+                L.check(lib.drosfm_warp_sources_fwd(pa, V, pi, depth_kind, n, cams, pp_, padding, L.ptr(rgbx), L.ptr(wsave), B, H, W, st),
                         "warp_sources_fwd")
                 if two_streams:
                     main.wait_event(ev_mask)
@@ -711,7 +715,7 @@ class _PhotoLoss(torch.autograd.Function):
             if two_streams:
                 main.wait_stream(side)
         total = losses.sum().reshape(1)
-        ctx.save_for_backward(image, keep[0], keep[1], sel, stats, wsave, *context, *invs, *poses)
+        ctx.save_for_backward(image, keep[0], keep[1], sel, stats, wsave, rgbx if staged else None, *context, *invs, *poses)
         ctx.cfg, ctx.V, ctx.n, ctx.kind = cfg, V, n, kind
         ctx.mark_non_differentiable(losses)
         if sel is None:
@@ -723,8 +727,8 @@ class _PhotoLoss(torch.autograd.Function):
     def backward(ctx, g_total, *unused):
         ssim_w, C1, C2, padding, reduce_op, automask, gamma, smooth_w, depth_kind = ctx.cfg
         V, n, kind = ctx.V, ctx.n, ctx.kind
-        image, K, Kref, sel, stats, wsave = ctx.saved_tensors[:6]
-        rest = ctx.saved_tensors[6:]
+        image, K, Kref, sel, stats, wsave, rgbx = ctx.saved_tensors[:7]
+        rest = ctx.saved_tensors[7:]
         context, invs, poses = rest[:V], rest[V:V + n], rest[V + n:]
         B, _, H, W = image.shape
         dev = image.device
@@ -762,7 +766,7 @@ class _PhotoLoss(torch.autograd.Function):
                         "photometric_bwd")
                 if two_streams:
                     main.wait_stream(side)
-                L.check(lib.drosfm_warp_sources_bwd(L.ptr(g_warped), pa, V, pi, depth_kind, n, cams, pp_, padding,
+                L.check(lib.drosfm_warp_sources_bwd(L.ptr(g_warped), pa, V, pi, depth_kind, n, cams, pp_, padding, L.ptr(rgbx),
                                                     L.ptr_array(g_invs), L.ptr_array(g_poses), L.ptr(ws), 1, B, H, W, st),
                         "warp_sources_bwd")
             else:

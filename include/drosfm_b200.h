@@ -99,6 +99,11 @@ int drosfm_warp_coords_bwd(const float* g_uv, const float* depth, int depth_kind
                            float* g_depth, float* g_pose, void* ws, int B, int H, int W, int normalize,
                            drosfm_stream_t stream);
 
+/* Device self-test (used by the parity tests): counts the floats x with 2^-126 <= |x| < 2^126 -- all 4.2e9 of them -- for
+ * which the branch-free reciprocal of the fused kernels (MUFU.RCP + one Newton step) differs from rcp.rn.  `mismatches`
+ * is one zero-initialised uint64 on the device; expected result 0. */
+int drosfm_selftest_rcp(unsigned long long* mismatches, drosfm_stream_t stream);
+
 /* ---- F.grid_sample(bilinear, align_corners=True) (camera_utils.py:55, DepthPoseNet.py:92) ---
  * src [B,C,Hs,Ws], uv [B,H,W,2] -> out [B,C,H,W].  bwd: g_src accumulated; g_uv written. */
 int drosfm_grid_gather_fwd(const float* src, const float* uv, float* out, int B, int C, int Hs, int Ws,
@@ -215,14 +220,17 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
  * fwd: warped [n_preds,V,B,3,H,W] = view_synthesis(context_v; inv_depth_i, pose_{v,i}) for every (i, v); hand it to
  *      drosfm_photometric_fwd with DROSFM_PHOTO_WARPED_READY.
  * bwd: adjoint of that warp for the g_warped a DROSFM_PHOTO_NO_ADJOINT backward left behind: g_inv_depths[i] written
- *      (accumulate != 0: added to), g_poses[v*n_preds+i] written; ws of drosfm_ws_bytes(n_views*n_preds*B). */
+ *      (accumulate != 0: added to), g_poses[v*n_preds+i] written; ws of drosfm_ws_bytes(n_views*n_preds*B).
+ * rgbx (optional scratch, [V,B,H,W,4] floats, 16-byte aligned): when given, fwd first packs the source pictures into
+ *      RGBx texels there (one more launch) and both directions gather each bilinear tap with ONE 128-bit load instead
+ *      of three 32-bit ones; bwd expects the buffer fwd filled.  NULL: gathers from the caller's planes. */
 int drosfm_warp_sources_fwd(const float* const* context, int n_views, const float* const* inv_depths, int depth_kind,
-                            int n_preds, const drosfm_cams_t* cams, const float* const* poses, int padding, float* warped,
-                            int B, int H, int W, drosfm_stream_t stream);
+                            int n_preds, const drosfm_cams_t* cams, const float* const* poses, int padding, float* rgbx,
+                            float* warped, int B, int H, int W, drosfm_stream_t stream);
 int drosfm_warp_sources_bwd(const float* g_warped, const float* const* context, int n_views,
                             const float* const* inv_depths, int depth_kind, int n_preds, const drosfm_cams_t* cams,
-                            const float* const* poses, int padding, float* const* g_inv_depths, float* const* g_poses,
-                            void* ws, int accumulate, int B, int H, int W, drosfm_stream_t stream);
+                            const float* const* poses, int padding, const float* rgbx, float* const* g_inv_depths,
+                            float* const* g_poses, void* ws, int accumulate, int B, int H, int W, drosfm_stream_t stream);
 
 /* ---- smoothness loss (multiview_photometric_loss_mf.py:273-299, utils/depth.py:147-199) -------
  * loss = weight/n * sum_i (mean|dx(d_i/mean(d_i)) * wx| + mean|dy(..) * wy|) / 2^i.

@@ -186,9 +186,16 @@ def _check_photometric(dataset, B, H, W, V, n, min_depth, max_depth, padding="ze
     #     warp_sources_fwd + WARPED_READY, NO_ADJOINT + warp_sources_bwd(accumulate) == the single calls above
     wsave3 = torch.empty_like(wsave)
     pad = L.PAD_ZEROS if padding == "zeros" else L.PAD_BORDER
-    L.check(lib.drosfm_warp_sources_fwd(L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P), pad,
+    L.check(lib.drosfm_warp_sources_fwd(L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P), pad, None,
                                         L.ptr(wsave3), B, H, W, L.stream()))
     assert torch.equal(wsave3, wsave)
+    # the same warp through RGBx texels of the sources (one 128-bit gather per tap): bit-identical
+    rgbx = torch.full((V, B, H, W, 4), float("nan"), device=dev)
+    wsave4 = torch.empty_like(wsave)
+    L.check(lib.drosfm_warp_sources_fwd(L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P), pad, L.ptr(rgbx),
+                                        L.ptr(wsave4), B, H, W, L.stream()))
+    assert torch.equal(wsave4, wsave)
+    assert torch.equal(rgbx[..., :3], torch.stack(ctx).permute(0, 1, 3, 4, 2)) and not bool(rgbx[..., 3].any())
     loss3 = torch.zeros(1, device=dev)
     L.check(lib.drosfm_photometric_fwd(L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
                                        L.ptr(amask), opts, L.ptr(sel2), L.ptr(loss3), L.ptr(ws), L.ptr(wsave3),
@@ -200,9 +207,21 @@ def _check_photometric(dataset, B, H, W, V, n, min_depth, max_depth, padding="ze
                                        L.ptr_array(P), L.ptr(sel_forced), opts, None, None, L.ptr(ws), L.ptr(wsave3),
                                        L.ptr(g_warped), L.PHOTO_NO_ADJOINT, B, H, W, L.stream()))
     L.check(lib.drosfm_warp_sources_bwd(L.ptr(g_warped), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
-                                        pad, L.ptr_array(list(g_inv3)), L.ptr_array(list(g_pose3)), L.ptr(ws), 1, B, H, W, L.stream()))
+                                        pad, None, L.ptr_array(list(g_inv3)), L.ptr_array(list(g_pose3)), L.ptr(ws), 1, B, H, W,
+                                        L.stream()))
     assert_close((g_inv3 - base).cpu(), g_inv2.cpu(), rtol=1e-4, atol=2e-7 * float(base.abs().max()), what="g_inv (accumulated)")
     assert_close(g_pose3.cpu(), g_pose2.cpu(), rtol=1e-4, atol=1e-5 * float(g_pose.abs().max()), what="g_pose (split stages)")
+    # ... and through the RGBx texels, overwriting (accumulate = 0: the call zero-fills what several views add into)
+    g_inv4, g_pose4 = torch.full_like(g_inv, float("nan")), torch.empty_like(g_pose)
+    L.check(lib.drosfm_warp_sources_bwd(L.ptr(g_warped), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
+                                        pad, L.ptr(rgbx), L.ptr_array(list(g_inv4)), L.ptr_array(list(g_pose4)), L.ptr(ws), 0, B, H, W,
+                                        L.stream()))
+    assert_close(g_inv4.cpu(), g_inv2.cpu(), rtol=1e-4, atol=2e-7 * float(g_inv2.abs().max()), what="g_inv (RGBx texels)")
+    assert_close(g_pose4.cpu(), g_pose2.cpu(), rtol=1e-4, atol=1e-5 * float(g_pose.abs().max()), what="g_pose (RGBx texels)")
+    for i in range(n):
+        assert_close_or_better(g_inv4[i].cpu(), g32[i], g64[i], what=f"texel g_inv{i}")
+    for k in range(V * n):
+        assert_close_or_better(g_pose4[k].cpu(), g32[n + k], g64[n + k], what=f"texel g_pose{k}")
     # a half-specified staged call is refused
     rc = lib.drosfm_photometric_bwd(L.ptr(one), L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams,
                                     L.ptr_array(P), L.ptr(sel_forced), opts, L.ptr_array(list(g_inv2)), L.ptr_array(list(g_pose2)),
