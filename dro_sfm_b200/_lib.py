@@ -21,7 +21,7 @@ MAX_COST_JOBS = 9
 POSE_IDENTITY, POSE_MAT4, POSE_EULER6 = 0, 1, 2
 PAD_ZEROS, PAD_BORDER = 0, 1
 F32, F64 = 0, 1
-DEPTH, INV_DEPTH = 0, 1
+DEPTH, INV_DEPTH, DISP = 0, 1, 2
 REDUCE_MIN, REDUCE_MEAN = 0, 1
 NCHW, NHWC = 0, 1
 ACCUMULATE_FMAP = 1
@@ -48,8 +48,8 @@ class PhotoOpts(ctypes.Structure):
 
 class CostJob(ctypes.Structure):
     """drosfm_cost_job_t"""
-    _fields_ = [("fmap", _vp), ("fmap_ref", _pp), ("depth", _vp), ("depth_kind", ctypes.c_int32), ("poses", _pp),
-                ("n_views", ctypes.c_int32), ("cost", _vp)]
+    _fields_ = [("fmap", _vp), ("fmap_ref", _pp), ("depth", _vp), ("depth_kind", ctypes.c_int32), ("n_views", ctypes.c_int32),
+                ("poses", _pp), ("cost", _vp), ("disp_min", _f32), ("disp_range", _f32)]
 
 
 class CostJobGrads(ctypes.Structure):
@@ -102,8 +102,8 @@ SIGNATURES = {
     "drosfm_sup_depth_loss_bwd": ([_vp, _vp, _pp, _int, _f32, _f32, _f32, _pp, _int, _int, _int, _vp], _int),
     "drosfm_relayout": ([_vp, _vp, _int, _int, _int, _int, _int, _vp], _int),
     "drosfm_images_u8_to_f32": ([_vp, _vp, ctypes.c_size_t, _vp], _int),
-    "drosfm_upsample_depth_fwd": ([_vp, _vp, _vp, _int, _int, _int, _int, _vp], _int),
-    "drosfm_upsample_depth_bwd": ([_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp], _int),
+    "drosfm_upsample_depth_fwd": ([_vp, _vp, _vp, _int, _int, _int, _int, _f32, _f32, _vp], _int),
+    "drosfm_upsample_depth_bwd": ([_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _f32, _vp], _int),
     "drosfm_reproj_loss_fwd": ([_vp, _int, _cp, _pp, _pp, _int, _int, _f32, _f32, _f32, _vp, _vp,
                                 _int, _int, _int, _vp], _int),
     "drosfm_reproj_loss_bwd": ([_vp, _vp, _int, _cp, _pp, _pp, _int, _int, _f32, _f32, _f32, _pp, _vp,

@@ -307,7 +307,20 @@ struct CostJob {
     const float* ref[DROSFM_MAX_VIEWS];
     const float* pose[DROSFM_MAX_VIEWS];
     int V, depth_kind;
+    float disp_min, disp_range;      // DROSFM_DISP: inverse depth = disp_min + disp_range * raw (disp_to_depth, layers.py:11-20)
 };
+
+// depth of one pixel from what the job stores (depth | inverse depth | raw disparity)
+__device__ __forceinline__ float job_depth(const CostJob& job, float raw) {
+    if (job.depth_kind == DROSFM_DISP) return inv2depth_fast(__fadd_rn(job.disp_min, __fmul_rn(job.disp_range, raw)));
+    return to_depth_fast(raw, job.depth_kind);
+}
+// ... and the gradient back to the stored quantity
+__device__ __forceinline__ float job_depth_grad(const CostJob& job, float raw, float g_depth) {
+    if (job.depth_kind == DROSFM_DISP)
+        return inv2depth_grad(__fadd_rn(job.disp_min, __fmul_rn(job.disp_range, raw)), g_depth) * job.disp_range;
+    return job.depth_kind == DROSFM_INV_DEPTH ? inv2depth_grad(raw, g_depth) : g_depth;
+}
 struct CostJobGrad {
     const float* g_cost;
     float* g_fmap;
@@ -378,7 +391,7 @@ feat_cost_fwd_nhwc(const __grid_constant__ CostJobs jobs, drosfm_cams_t cams, in
     if (npix == 0) return;
     STap* wt = taps + static_cast<size_t>(wid) * ppw * VT;
     if (mine) {
-        const float d = to_depth_fast(draw, job.depth_kind);
+        const float d = job_depth(job, draw);
         const Norm nm = make_norm(w, h);
         int x, y;
         pix_xy(p, w, x, y);
@@ -457,7 +470,7 @@ feat_cost_bwd_nhwc(const __grid_constant__ CostJobs jobs, const __grid_constant_
     float2* gxy = reinterpret_cast<float2*>(taps + static_cast<size_t>(kWarpsPerBlock) * ppw * VT);   // [warp][ppw][VT]
     const CostJob& job = jobs.j[blockIdx.z];
     const CostJobGrad& jg = grads.j[blockIdx.z];
-    const int V = job.V, depth_kind = job.depth_kind, need_coord_grad = jg.need_coord, acc_fmap = jg.acc_fmap;
+    const int V = job.V, need_coord_grad = jg.need_coord, acc_fmap = jg.acc_fmap;
     const float* __restrict__ g_cost = jg.g_cost;
     const float* __restrict__ fmap = job.fmap;
     float* __restrict__ g_fmap = jg.g_fmap;
@@ -468,7 +481,7 @@ feat_cost_bwd_nhwc(const __grid_constant__ CostJobs jobs, const __grid_constant_
     const bool mine = lane < npix;
     const int p = pbase + lane;
     const float draw = mine ? __ldg(job.depth + static_cast<size_t>(b) * P + p) : 0.0f;
-    const float d = to_depth_fast(draw, depth_kind);
+    const float d = job_depth(job, draw);
     setup_cams_block<VT>(cams, job, b, cam);
     const Norm nm = make_norm(w, h);
     const float wm1 = nm.wm1, hm1 = nm.hm1;
@@ -587,7 +600,7 @@ feat_cost_bwd_nhwc(const __grid_constant__ CostJobs jobs, const __grid_constant_
         }
     }
     if (mine && jg.g_depth != nullptr)
-        jg.g_depth[static_cast<size_t>(b) * P + p] = depth_kind == DROSFM_INV_DEPTH ? inv2depth_grad(draw, gd) : gd;
+        jg.g_depth[static_cast<size_t>(b) * P + p] = job_depth_grad(job, draw, gd);
 #pragma unroll
     for (int v = 0; v < VT; ++v) {
         if (v < V && jg.g_pose[v] != nullptr) {
@@ -669,7 +682,10 @@ static int fill_jobs(const drosfm_cost_job_t* jobs, const drosfm_cost_job_grads_
         DROSFM_REQUIRE(in.fmap && in.depth && (grads != nullptr || in.cost), DROSFM_EINVAL, "%s: job %d has a NULL argument", who, k);
         DROSFM_REQUIRE(aligned16(in.fmap) && aligned16(in.cost), DROSFM_EALIGN, "%s: NHWC tensors must be 16-byte aligned", who);
         CostJob& o = cj.j[k];
+        DROSFM_REQUIRE(in.depth_kind == DROSFM_DEPTH || in.depth_kind == DROSFM_INV_DEPTH || in.depth_kind == DROSFM_DISP, DROSFM_EINVAL,
+                       "%s: job %d: bad depth_kind %d", who, k, in.depth_kind);
         o.fmap = in.fmap; o.depth = in.depth; o.cost = in.cost; o.V = in.n_views; o.depth_kind = in.depth_kind;
+        o.disp_min = in.disp_min; o.disp_range = in.disp_range;
         for (int v = 0; v < in.n_views; ++v) {
             DROSFM_REQUIRE(aligned16(in.fmap_ref[v]), DROSFM_EALIGN, "%s: NHWC tensors must be 16-byte aligned", who);
             o.ref[v] = in.fmap_ref[v];
@@ -769,7 +785,8 @@ int drosfm_feat_cost_fwd(const float* fmap, const float* const* fmap_ref, const 
     if (int e = check_cost_views(fmap_ref, poses, n_views)) return e;
     DROSFM_REQUIRE(fmap && depth && cost, DROSFM_EINVAL, "feat_cost_fwd: NULL argument");
     if (layout == DROSFM_NHWC) {
-        const drosfm_cost_job_t job{fmap, fmap_ref, depth, depth_kind, poses, n_views, cost};
+        DROSFM_REQUIRE(depth_kind != DROSFM_DISP, DROSFM_ENOTSUP, "feat_cost_fwd: DROSFM_DISP needs the batch entry (drosfm_cost_job_t carries the range)");
+        const drosfm_cost_job_t job{fmap, fmap_ref, depth, depth_kind, n_views, poses, cost, 0.0f, 1.0f};
         return drosfm_feat_cost_batch_fwd(&job, 1, cams, B, C, h, w, layout, stream);
     }
     ViewPtrs vp{};
@@ -798,7 +815,8 @@ int drosfm_feat_cost_bwd(const float* g_cost, const float* fmap, const float* co
     if (int e = check_cost_views(fmap_ref, poses, n_views)) return e;
     DROSFM_REQUIRE(g_cost && fmap && depth, DROSFM_EINVAL, "feat_cost_bwd: NULL argument");
     if (layout == DROSFM_NHWC) {
-        const drosfm_cost_job_t job{fmap, fmap_ref, depth, depth_kind, poses, n_views, nullptr};
+        DROSFM_REQUIRE(depth_kind != DROSFM_DISP, DROSFM_ENOTSUP, "feat_cost_bwd: DROSFM_DISP needs the batch entry");
+        const drosfm_cost_job_t job{fmap, fmap_ref, depth, depth_kind, n_views, poses, nullptr, 0.0f, 1.0f};
         const drosfm_cost_job_grads_t jg{g_cost, g_fmap, g_fmap_ref, g_depth, g_poses, flags};
         return drosfm_feat_cost_batch_bwd(&job, &jg, 1, cams, ws, B, C, h, w, layout, stream);
     }

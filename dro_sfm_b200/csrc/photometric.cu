@@ -717,15 +717,18 @@ warp_sources_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind,
         const int y = y0 + k * kStride;
         if (y < H) {
             const unsigned o = static_cast<unsigned>(y * W + x);
+            // one fixed evaluation order for both tap layouts (the compiler would otherwise contract them differently)
+            auto blend = [&](float a0, float a1, float a2, float a3) {
+                return __fmaf_rn(a3, cur.w11, __fmaf_rn(a2, cur.w10, __fmaf_rn(a1, cur.w01, __fmul_rn(a0, cur.w00))));
+            };
             if constexpr (PACKED) {
-                out[o] = tex4[0].x * cur.w00 + tex4[1].x * cur.w01 + tex4[2].x * cur.w10 + tex4[3].x * cur.w11;
-                out[o + P] = tex4[0].y * cur.w00 + tex4[1].y * cur.w01 + tex4[2].y * cur.w10 + tex4[3].y * cur.w11;
-                out[o + 2 * P] = tex4[0].z * cur.w00 + tex4[1].z * cur.w01 + tex4[2].z * cur.w10 + tex4[3].z * cur.w11;
+                out[o] = blend(tex4[0].x, tex4[1].x, tex4[2].x, tex4[3].x);
+                out[o + P] = blend(tex4[0].y, tex4[1].y, tex4[2].y, tex4[3].y);
+                out[o + 2 * P] = blend(tex4[0].z, tex4[1].z, tex4[2].z, tex4[3].z);
             } else {
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    out[o + static_cast<unsigned>(c * P)] = val[4 * c] * cur.w00 + val[4 * c + 1] * cur.w01 +
-                                                             val[4 * c + 2] * cur.w10 + val[4 * c + 3] * cur.w11;
+                    out[o + static_cast<unsigned>(c * P)] = blend(val[4 * c], val[4 * c + 1], val[4 * c + 2], val[4 * c + 3]);
             }
         }
         if (k + 1 < kFlatRows) {

@@ -27,7 +27,8 @@ __device__ __forceinline__ void load_neighbours(const float* __restrict__ depth,
 }
 
 __global__ void __launch_bounds__(kUpThreads)
-upsample_fwd_kernel(const float* __restrict__ depth, const float* __restrict__ mask, float* __restrict__ out, int H, int W) {
+upsample_fwd_kernel(const float* __restrict__ depth, const float* __restrict__ mask, float* __restrict__ out, int H, int W,
+                    float disp_min, float disp_range) {
     __shared__ float rows[8][32 * 8 + 4];
     const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
     const int x0 = blockIdx.x * 32, y = blockIdx.y, n = blockIdx.z;
@@ -52,7 +53,8 @@ upsample_fwd_kernel(const float* __restrict__ depth, const float* __restrict__ m
             den += e;
             num += e * d[k];
         }
-        rows[i][lane * 8 + j] = num / den;
+        // epilogue: disp_to_depth's scaling (layers.py:17; 0 + 1 * x for the plain operator)
+        rows[i][lane * 8 + j] = __fadd_rn(disp_min, __fmul_rn(disp_range, num / den));
     }
     __syncwarp();
     const int Wo = W * 8;
@@ -63,7 +65,7 @@ upsample_fwd_kernel(const float* __restrict__ depth, const float* __restrict__ m
 
 __global__ void __launch_bounds__(kUpThreads)
 upsample_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ depth, const float* __restrict__ mask,
-                    float* __restrict__ g_depth, float* __restrict__ g_mask, int H, int W) {
+                    float* __restrict__ g_depth, float* __restrict__ g_mask, int H, int W, float disp_range) {
     __shared__ float rows[8][32 * 8 + 4];
     __shared__ float part[8][9][32];
     const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
@@ -74,7 +76,7 @@ upsample_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ d
     const int Wo = W * 8;
     const float* g = g_out + (static_cast<size_t>(n) * H * 8 + y * 8 + i) * Wo + x0 * 8;
     const int valid = min(32, W - x0) * 8;
-    for (int c = lane; c < 256; c += 32) rows[i][c] = c < valid ? __ldg(g + c) : 0.0f;
+    for (int c = lane; c < 256; c += 32) rows[i][c] = c < valid ? __ldg(g + c) * disp_range : 0.0f;
     float d[9];
     load_neighbours(depth + n * P, y, x, H, W, on, d);
     __syncwarp();
@@ -134,22 +136,22 @@ using namespace drosfm;
 extern "C" {
 
 int drosfm_upsample_depth_fwd(const float* depth, const float* mask, float* out, int N, int H, int W, int ratio,
-                              drosfm_stream_t stream) {
+                              float disp_min, float disp_range, drosfm_stream_t stream) {
     if (int e = check_up(N, H, W, ratio)) return e;
     if (N == 0 || H * W == 0) return DROSFM_OK;
     DROSFM_REQUIRE(depth && mask && out, DROSFM_EINVAL, "upsample_depth_fwd: NULL argument");
     dim3 grid((W + 31) / 32, H, N);
-    upsample_fwd_kernel<<<grid, kUpThreads, 0, static_cast<cudaStream_t>(stream)>>>(depth, mask, out, H, W);
+    upsample_fwd_kernel<<<grid, kUpThreads, 0, static_cast<cudaStream_t>(stream)>>>(depth, mask, out, H, W, disp_min, disp_range);
     return launch_status("upsample_depth_fwd");
 }
 
 int drosfm_upsample_depth_bwd(const float* g_out, const float* depth, const float* mask, float* g_depth, float* g_mask,
-                              int N, int H, int W, int ratio, drosfm_stream_t stream) {
+                              int N, int H, int W, int ratio, float disp_range, drosfm_stream_t stream) {
     if (int e = check_up(N, H, W, ratio)) return e;
     if (N == 0 || H * W == 0) return DROSFM_OK;
     DROSFM_REQUIRE(g_out && depth && mask, DROSFM_EINVAL, "upsample_depth_bwd: NULL argument");
     dim3 grid((W + 31) / 32, H, N);
-    upsample_bwd_kernel<<<grid, kUpThreads, 0, static_cast<cudaStream_t>(stream)>>>(g_out, depth, mask, g_depth, g_mask, H, W);
+    upsample_bwd_kernel<<<grid, kUpThreads, 0, static_cast<cudaStream_t>(stream)>>>(g_out, depth, mask, g_depth, g_mask, H, W, disp_range);
     return launch_status("upsample_depth_bwd");
 }
 

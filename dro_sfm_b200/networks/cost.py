@@ -79,23 +79,26 @@ def depth_cost_calc(inv_depth, fmap, fmaps_ref, pose_list, K, ref_K, scale_facto
 def cost_batch(jobs, K, ref_K, scale_factor):
     """Several independent cost evaluations in ONE kernel launch (forward) and one more (backward).
 
-    jobs: (depth_or_inv_depth, fmap, fmaps_ref, pose_list, is_inverse_depth) tuples -- a depth_cost_calc call is
-    (inv_depth, fmap, fmaps_ref, pose_list, True), a get_cost_each call (depth, fmap, [fmap_ref], [pose], False).
+    jobs: (depth_or_inv_depth, fmap, fmaps_ref, pose_list, kind) tuples -- a depth_cost_calc call is
+    (inv_depth, fmap, fmaps_ref, pose_list, True), a get_cost_each call (depth, fmap, [fmap_ref], [pose], False);
+    kind = ("disp", min_depth, max_depth) hands over the network's raw disparity and lets the kernel apply
+    scale_inv_depth / disp_to_depth (DepthPoseNet.py:38-41, layers.py:11-20) itself.
     Used by the lock-step schedule (networks/lockstep.py); results equal the individual calls."""
     prepared = [(d, _channels_last(f), [_channels_last(r) for r in frs], list(ps), inv) for d, f, frs, ps, inv in jobs]
     return ops.feat_cost_batch(prepared, K, ref_K, scale_factor)
 
 
-def upsample_depth(depth, mask, ratio=8):
-    """Convex up-sampling of the low-resolution inverse depth (DepthPoseNet.py:63-74), one fused kernel."""
-    return ops.upsample_depth(depth, mask, ratio)
+def upsample_depth(depth, mask, ratio=8, disp_range=None):
+    """Convex up-sampling of the low-resolution inverse depth (DepthPoseNet.py:63-74), one fused kernel; with
+    disp_range = (min_depth, max_depth) the disp_to_depth scaling that follows it in DepthPoseNet.forward is its epilogue."""
+    return ops.upsample_depth(depth, mask, ratio, disp_range)
 
 
 class FeatureMetricCost:
     """Mixin with the reference's method names; ``patch.install`` grafts it onto DepthPoseNet."""
 
     def upsample_depth(self, depth, mask, ratio=8):
-        return upsample_depth(depth, mask, ratio)
+        return upsample_depth(depth, mask, ratio)        # the reference's signature (DepthPoseNet.py:63)
 
     def get_cost_each(self, pose, fmap, fmap_ref, depth, K, ref_K, scale_factor):
         return get_cost_each(pose, fmap, fmap_ref, depth, K, ref_K, scale_factor)

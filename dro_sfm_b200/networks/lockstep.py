@@ -28,10 +28,18 @@ def forward(self, target_image, ref_imgs, intrinsics):
     assert target_image.shape[2] / fmap.shape[2] == self.feat_ratio
     scale = 1.0 / self.feat_ratio
 
+    # scale_inv_depth (disp_to_depth, DepthPoseNet.py:38-41) is fused into its producers / consumers when the network
+    # normalises its output ('-out' versions): epilogue of the convex up-sampling, prologue of the depth cost
+    fused_scale = (self.min_depth, self.max_depth) if self.out_normalize else None
+
+    def upsampled_prediction(inv_lr, mask):
+        if fused_scale is not None:
+            return _cost.upsample_depth(inv_lr, mask, self.feat_ratio, disp_range=fused_scale)
+        return self.scale_inv_depth(self.upsample_depth(inv_lr, mask, ratio=self.feat_ratio))[0]
+
     poses = [self.pose_head(torch.cat([fmap, f], dim=1)) for f in fmaps_ref]
     inv_depth = self.depth_head(fmap, act_fn=torch.sigmoid)
-    first_up = self.upsample_depth(inv_depth, self.upmask_net(fmap), ratio=self.feat_ratio)
-    inv_depth_predictions = [self.scale_inv_depth(first_up)[0]]
+    inv_depth_predictions = [upsampled_prediction(inv_depth, self.upmask_net(fmap))]
     pose_predictions = [[p.clone() for p in poses]]
 
     if self.iters > 0:
@@ -52,7 +60,10 @@ def forward(self, target_image, ref_imgs, intrinsics):
         inv_seq, mask_seq, pose_seq = [], [], [[] for _ in range(n_views)]
         for _ in range(self.seq_len):
             # the 1 + V cost evaluations of this inner step: one launch
-            jobs = [(self.scale_inv_depth(inv_depth)[0], fmap, fmaps_ref, frozen_poses, True)]
+            if fused_scale is not None:
+                jobs = [(inv_depth, fmap, fmaps_ref, frozen_poses, ("disp",) + fused_scale)]
+            else:
+                jobs = [(self.scale_inv_depth(inv_depth)[0], fmap, fmaps_ref, frozen_poses, True)]
             jobs += [(frozen_depth, fmap, [fmaps_ref[v]], [poses[v]], False) for v in range(n_views)]
             costs = _cost.cost_batch(jobs, intrinsics, intrinsics, scale)
             # depth block, one inner step (update.py:159-171)
@@ -69,8 +80,7 @@ def forward(self, target_image, ref_imgs, intrinsics):
                 pose_seq[v].append(poses[v])
         keep = range(self.seq_len) if self.inter_sup else [self.seq_len - 1]
         for j in keep:
-            up = self.upsample_depth(inv_seq[j], mask_seq[j], ratio=self.feat_ratio)
-            inv_depth_predictions.append(self.scale_inv_depth(up)[0])
+            inv_depth_predictions.append(upsampled_prediction(inv_seq[j], mask_seq[j]))
             pose_predictions.append([pose_seq[v][j].clone() for v in range(n_views)])
 
     if not self.training:

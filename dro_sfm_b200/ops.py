@@ -501,8 +501,9 @@ class _FeatCostBatch(torch.autograd.Function):
     @staticmethod
     def _split(spec, tensors):
         jobs, pos = [], 0
-        for V, dk in spec:
-            jobs.append((tensors[pos], tensors[pos + 1], tensors[pos + 2:pos + 2 + V], tensors[pos + 2 + V:pos + 2 + 2 * V], dk))
+        for V, dk, dmin, drange in spec:
+            jobs.append((tensors[pos], tensors[pos + 1], tensors[pos + 2:pos + 2 + V], tensors[pos + 2 + V:pos + 2 + 2 * V],
+                         (dk, dmin, drange)))
             pos += 2 + 2 * V
         return jobs
 
@@ -524,8 +525,8 @@ class _FeatCostBatch(torch.autograd.Function):
             ra, pa = L.ptr_array(list(refs)), L.ptr_array(poses)
             hold += [ra, pa]
             j = table[k]
-            j.fmap, j.fmap_ref, j.depth, j.depth_kind = fmap.data_ptr(), ra, depth.data_ptr(), dk
-            j.poses, j.n_views, j.cost = pa, len(refs), cost.data_ptr()
+            j.fmap, j.fmap_ref, j.depth, j.depth_kind = fmap.data_ptr(), ra, depth.data_ptr(), dk[0]
+            j.poses, j.n_views, j.cost, j.disp_min, j.disp_range = pa, len(refs), cost.data_ptr(), dk[1], dk[2]
             saved += [depth, fmap, *refs, *poses]
             costs.append(cost)
         with torch.cuda.device(jobs[0][1].device):
@@ -551,7 +552,7 @@ class _FeatCostBatch(torch.autograd.Function):
             return (None, None, None, None, *rets)
         jt, gt = (L.CostJob * len(live))(), (L.CostJobGrads * len(live))()
         hold, pos_of, pos, slots = [], [], 0, 0
-        for V, _ in spec:
+        for V, *_ in spec:
             pos_of.append(pos)
             pos += 2 + 2 * V
         # every plain (non-sink) source-map gradient of the launch lives in one zero-filled slab: a single memset
@@ -589,7 +590,8 @@ class _FeatCostBatch(torch.autograd.Function):
             ra, pa, gra, gpa = L.ptr_array(list(refs)), L.ptr_array(list(poses)), L.ptr_array(g_refs), L.ptr_array(g_poses)
             hold += [ra, pa, gra, gpa, g]
             j, q = jt[row], gt[row]
-            j.fmap, j.fmap_ref, j.depth, j.depth_kind, j.poses, j.n_views, j.cost = fmap.data_ptr(), ra, depth.data_ptr(), dk, pa, V, None
+            j.fmap, j.fmap_ref, j.depth, j.depth_kind, j.poses, j.n_views, j.cost = fmap.data_ptr(), ra, depth.data_ptr(), dk[0], pa, V, None
+            j.disp_min, j.disp_range = dk[1], dk[2]
             q.g_cost, q.g_fmap, q.g_fmap_ref = g.data_ptr(), (None if g_fmap is None else g_fmap.data_ptr()), gra
             q.g_depth, q.g_poses, q.flags = (None if g_depth is None else g_depth.data_ptr()), gpa, flags
             slots += V * B
@@ -603,10 +605,19 @@ class _FeatCostBatch(torch.autograd.Function):
 def feat_cost_batch(jobs, K, Kref=None, scale=1.0):
     """Several independent feature-metric cost calls in ONE launch.
 
-    jobs: sequence of (depth, fmap, fmaps_ref, poses, inverse_depth) -- the arguments of `feat_cost` -- sharing K, Kref,
-    scale, the feature-map shape and the pose encoding.  Returns one cost map per job.  The batched kernels run on
-    channels_last maps; any other input falls back to one `feat_cost` call per job (same results)."""
-    jobs = [(d, f, list(fr), list(ps), bool(inv)) for d, f, fr, ps, inv in jobs]
+    jobs: sequence of (depth, fmap, fmaps_ref, poses, kind) -- the arguments of `feat_cost` -- sharing K, Kref, scale, the
+    feature-map shape and the pose encoding.  kind: False = depth, True = inverse depth, ("disp", min_depth, max_depth) =
+    the network's raw disparity, scaled by disp_to_depth (layers.py:11-20) inside the kernel, gradient w.r.t. the raw map.
+    Returns one cost map per job.  The batched kernels run on channels_last maps; any other input falls back to one
+    `feat_cost` call per job (same results; the disparity scaling then runs as torch ops)."""
+    def kind_of(k):
+        if isinstance(k, (tuple, list)):
+            if k[0] != "disp":
+                raise ValueError("unknown depth kind {!r}".format(k))
+            lo, hi = 1.0 / float(k[2]), 1.0 / float(k[1])                  # min_disp, max_disp as Python doubles (layers.py:14-15)
+            return (L.DISP, float(torch.tensor(lo, dtype=torch.float32)), float(torch.tensor(hi - lo, dtype=torch.float32)))
+        return (L.INV_DEPTH if k else L.DEPTH, 0.0, 1.0)
+    jobs = [(d, f, list(fr), list(ps), kind_of(k)) for d, f, fr, ps, k in jobs]
     Kref = K if Kref is None else Kref
     _no_grad_for("K", K)
 
@@ -615,9 +626,14 @@ def feat_cost_batch(jobs, K, Kref=None, scale=1.0):
 
     ok = 1 <= len(jobs) <= L.MAX_COST_JOBS and all(
         nhwc(f) and all(nhwc(r) for r in fr) and 1 <= len(fr) <= L.MAX_VIEWS and len(ps) == len(fr) for _, f, fr, ps, _ in jobs)
-    if not ok or len(jobs) == 1:
-        return [feat_cost(d, f, fr, ps, K, Kref, scale, inverse_depth=inv) for d, f, fr, ps, inv in jobs]
-    spec = tuple((len(fr), L.INV_DEPTH if inv else L.DEPTH) for _, _, fr, _, inv in jobs)
+    if not ok:
+        out = []
+        for d, f, fr, ps, (dk, dmin, drange) in jobs:
+            if dk == L.DISP:                                            # disp_to_depth with torch ops, as the reference
+                d, dk = dmin + drange * d, L.INV_DEPTH
+            out.append(feat_cost(d, f, fr, ps, K, Kref, scale, inverse_depth=(dk == L.INV_DEPTH)))
+        return out
+    spec = tuple((len(fr), dk, dmin, drange) for _, _, fr, _, (dk, dmin, drange) in jobs)
     flat = [t for d, f, fr, ps, _ in jobs for t in (d, f, *fr, *ps)]
     return list(_FeatCostBatch.apply(K, Kref, float(scale), spec, *flat))
 
@@ -949,16 +965,16 @@ def images_u8_to_f32(src, out=None):
 # ------------------------------------------------------------------------------------------------
 class _UpsampleDepth(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, depth, mask, ratio):
+    def forward(ctx, depth, mask, ratio, disp_min, disp_range):
         L.require_cuda(depth, mask)
         depth, mask = L.f32c(depth), L.f32c(mask)
         N, _, H, W = depth.shape
         out = torch.empty(N, 1, ratio * H, ratio * W, device=depth.device, dtype=torch.float32)
         with torch.cuda.device(depth.device):
-            L.check(L.lib().drosfm_upsample_depth_fwd(L.ptr(depth), L.ptr(mask), L.ptr(out), N, H, W, ratio, L.stream()),
-                    "upsample_depth_fwd")
+            L.check(L.lib().drosfm_upsample_depth_fwd(L.ptr(depth), L.ptr(mask), L.ptr(out), N, H, W, ratio, disp_min, disp_range,
+                                                      L.stream()), "upsample_depth_fwd")
         ctx.save_for_backward(depth, mask)
-        ctx.ratio = ratio
+        ctx.ratio, ctx.disp_range = ratio, disp_range
         return out
 
     @staticmethod
@@ -970,16 +986,22 @@ class _UpsampleDepth(torch.autograd.Function):
         gm = torch.empty_like(mask) if ctx.needs_input_grad[1] else None
         with torch.cuda.device(depth.device):
             L.check(L.lib().drosfm_upsample_depth_bwd(L.ptr(g), L.ptr(depth), L.ptr(mask), L.ptr(gd), L.ptr(gm), N, H, W,
-                                                      ctx.ratio, L.stream()), "upsample_depth_bwd")
-        return gd, gm, None
+                                                      ctx.ratio, ctx.disp_range, L.stream()), "upsample_depth_bwd")
+        return gd, gm, None, None, None
 
 
-def upsample_depth(depth, mask, ratio=8):
-    """DepthPoseNet.upsample_depth (DepthPoseNet.py:63-74): [N,1,H,W] x [N,9*ratio^2,H,W] -> [N,1,ratio*H,ratio*W]."""
+def upsample_depth(depth, mask, ratio=8, disp_range=None):
+    """DepthPoseNet.upsample_depth (DepthPoseNet.py:63-74): [N,1,H,W] x [N,9*ratio^2,H,W] -> [N,1,ratio*H,ratio*W].
+    disp_range = (min_depth, max_depth): additionally applies disp_to_depth's scaling (layers.py:11-20, what
+    DepthPoseNet.forward does to every up-sampled map) as the kernel's epilogue."""
     if depth.dim() != 4 or depth.shape[1] != 1:
         raise AssertionError("depth must be [N,1,H,W]")
     if ratio != 8:
         raise NotImplementedError("dro_sfm_b200: upsample_depth supports ratio 8 (DepthPoseNet.feat_ratio)")
     if tuple(mask.shape) != (depth.shape[0], 9 * ratio * ratio, depth.shape[2], depth.shape[3]):
         raise ValueError("mask must be [N,{},H,W], got {}".format(9 * ratio * ratio, tuple(mask.shape)))
-    return _UpsampleDepth.apply(depth, mask, int(ratio))
+    dmin, drange = 0.0, 1.0
+    if disp_range is not None:
+        lo, hi = 1.0 / float(disp_range[1]), 1.0 / float(disp_range[0])
+        dmin, drange = float(torch.tensor(lo, dtype=torch.float32)), float(torch.tensor(hi - lo, dtype=torch.float32))
+    return _UpsampleDepth.apply(depth, mask, int(ratio), dmin, drange)

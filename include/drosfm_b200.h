@@ -37,7 +37,7 @@ enum { DROSFM_OK = 0, DROSFM_EINVAL = -1, DROSFM_ERANGE = -2, DROSFM_EALIGN = -3
 enum { DROSFM_POSE_IDENTITY = 0, DROSFM_POSE_MAT4 = 1, DROSFM_POSE_EULER6 = 2 };
 enum { DROSFM_PAD_ZEROS = 0, DROSFM_PAD_BORDER = 1 };
 enum { DROSFM_F32 = 0, DROSFM_F64 = 1 };
-enum { DROSFM_DEPTH = 0, DROSFM_INV_DEPTH = 1 };
+enum { DROSFM_DEPTH = 0, DROSFM_INV_DEPTH = 1, DROSFM_DISP = 2 };   /* DISP: see drosfm_cost_job_t */
 enum { DROSFM_REDUCE_MIN = 0, DROSFM_REDUCE_MEAN = 1 };
 enum { DROSFM_NCHW = 0, DROSFM_NHWC = 1 };
 enum { DROSFM_ACCUMULATE_FMAP = 1 };   /* feat_cost_bwd flags */
@@ -150,11 +150,16 @@ int drosfm_feat_cost_bwd(const float* g_cost, const float* fmap, const float* co
 typedef struct {
     const float* fmap;               /* [B,C,h,w] target features (NHWC storage)                   */
     const float* const* fmap_ref;    /* n_views source maps                                         */
-    const float* depth;              /* [B,1,h,w] depth or inverse depth                            */
-    int32_t depth_kind;              /* DROSFM_DEPTH | DROSFM_INV_DEPTH                             */
-    const float* const* poses;       /* n_views poses in cams->pose_kind encoding                   */
+    const float* depth;              /* [B,1,h,w] depth, inverse depth or raw disparity             */
+    int32_t depth_kind;              /* DROSFM_DEPTH | DROSFM_INV_DEPTH | DROSFM_DISP               */
     int32_t n_views;                 /* 1 = get_cost_each, V = depth_cost_calc (mean over views)    */
+    const float* const* poses;       /* n_views poses in cams->pose_kind encoding                   */
     float* cost;                     /* [B,C,h,w] output (ignored by the backward)                  */
+    /* DROSFM_DISP: `depth` is the network's disparity in [0,1]; the kernel evaluates disp_to_depth as the reference does
+     * (networks/layers/resnet/layers.py:11-20, DepthPoseNet.py:38-41: inverse depth = disp_min + disp_range * disp with
+     * disp_min = 1/max_depth, disp_range = 1/min_depth - 1/max_depth, both rounded to float32) and then inv2depth;
+     * g_depth is the gradient w.r.t. the raw disparity. */
+    float disp_min, disp_range;
 } drosfm_cost_job_t;
 typedef struct {
     const float* g_cost;             /* upstream gradient of the job's cost map                     */
@@ -272,11 +277,14 @@ int drosfm_sup_depth_loss_bwd(const float* g_loss, const float* gt_inv_depth, co
 /* ---- convex up-sampling (DepthPoseNet.upsample_depth, DepthPoseNet.py:63-74) ------
  * depth [N,1,H,W], mask [N,9*ratio*ratio,H,W] -> out [N,1,ratio*H,ratio*W]:
  * out[8y+i,8x+j] = sum_k softmax_k(mask[k*64+i*8+j, y, x]) * depth_zero_padded[y+k/3-1, x+k%3-1].  ratio must be 8.
- * bwd: g_mask written, g_depth accumulated (either may be NULL). */
+ * bwd: g_mask written, g_depth accumulated (either may be NULL).
+ * disp_min / disp_range: the disp_to_depth scaling that follows every up-sampling in DepthPoseNet.forward
+ * (scale_inv_depth, DepthPoseNet.py:38-41,128,180; layers.py:11-20) as an epilogue: out = disp_min + disp_range * up
+ * (0, 1 = plain up-sampling). */
 int drosfm_upsample_depth_fwd(const float* depth, const float* mask, float* out, int N, int H, int W, int ratio,
-                              drosfm_stream_t stream);
+                              float disp_min, float disp_range, drosfm_stream_t stream);
 int drosfm_upsample_depth_bwd(const float* g_out, const float* depth, const float* mask, float* g_depth, float* g_mask,
-                              int N, int H, int W, int ratio, drosfm_stream_t stream);
+                              int N, int H, int W, int ratio, float disp_range, drosfm_stream_t stream);
 
 /* ---- feature-map storage layout (the encoder's maps are NCHW, DepthPoseNet.py:113-115) -----------
  * Copies a [B,C,H,W] tensor from NCHW storage to NHWC storage (to_layout = DROSFM_NHWC) or back (DROSFM_NCHW);

@@ -40,7 +40,7 @@ def test_structs_match_header_layout():
     assert ctypes.sizeof(_lib.Cams) == 56
     assert _lib.Cams.Twc.offset == 32 and _lib.Cams.pose_kind.offset == 48
     assert ctypes.sizeof(_lib.PhotoOpts) == 28
-    assert ctypes.sizeof(_lib.CostJob) == 56 and _lib.CostJob.cost.offset == 48
+    assert ctypes.sizeof(_lib.CostJob) == 56 and _lib.CostJob.cost.offset == 40 and _lib.CostJob.disp_range.offset == 52
     assert ctypes.sizeof(_lib.CostJobGrads) == 48 and _lib.CostJobGrads.flags.offset == 40
 
 
