@@ -11,7 +11,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libdrosfm_b200.so")
+SO_PATH = os.environ.get("DROSFM_SO") or os.path.join(_HERE, "libdrosfm_b200.so")     # DROSFM_SO: alternative build (experiments)
 
 ABI_VERSION = 3
 MAX_VIEWS = 8

@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SO = os.path.join(HERE, "libdrosfm_b200.so")
+SO = os.environ.get("DROSFM_SO") or os.path.join(HERE, "libdrosfm_b200.so")     # DROSFM_SO: an alternative build (experiments)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 FLAGS = [
@@ -19,7 +19,7 @@ FLAGS = [
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
     "-cudart", "static",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("DROSFM_NVCC_FLAGS", "").split()
 
 
 def sources():
@@ -38,7 +38,7 @@ def build(force=False, verbose=False):
     """Compile every .cu under csrc/ into one shared library; returns its path."""
     if not force and not stale():
         return SO
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build") if not os.environ.get("DROSFM_SO") else SO + ".objs"
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []

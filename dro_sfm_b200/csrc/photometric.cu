@@ -187,8 +187,9 @@ __device__ __forceinline__ void fill_source_tile(float* __restrict__ xs, const f
             if (sidx[k] < N) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float o = WARP ? v[k][4 * c] * w00[k] + v[k][4 * c + 1] * w01[k] + v[k][4 * c + 2] * w10[k] +
-                                               v[k][4 * c + 3] * w11[k]
+                    // the evaluation order of the flat warp (warp_sources_kernel): both paths produce the same bits
+                    const float o = WARP ? __fmaf_rn(v[k][4 * c + 3], w11[k], __fmaf_rn(v[k][4 * c + 2], w10[k],
+                                               __fmaf_rn(v[k][4 * c + 1], w01[k], __fmul_rn(v[k][4 * c], w00[k]))))
                                          : v[k][c];
                     xs[c * N + sidx[k]] = o;
                 }
@@ -621,7 +622,20 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
 // The SSIM stages then carry no camera state (fewer registers, more resident warps) and the geometry runs
 // once per pixel instead of once per pixel of every tile + halo.
 constexpr int kFlatThreads = 256, kFlatRows = 8;
-constexpr int kFlatTileH = (kFlatThreads / 32) * kFlatRows;       // a block covers 32 columns x 64 rows
+constexpr int kFlatTileH = (kFlatThreads / 32) * kFlatRows;       // one tile: 32 columns x 64 rows
+#ifndef DROSFM_FLAT_TILES
+#define DROSFM_FLAT_TILES 2
+#endif
+#ifndef DROSFM_FWD_MINBLOCKS
+#define DROSFM_FWD_MINBLOCKS 3
+#endif
+#ifndef DROSFM_ADJ_MINBLOCKS
+#define DROSFM_ADJ_MINBLOCKS 3
+#endif
+#ifndef DROSFM_ADJ_UNROLL
+#define DROSFM_ADJ_UNROLL 1
+#endif
+constexpr int kFlatTiles = DROSFM_FLAT_TILES;                     // tiles a block walks down (amortises its camera set-up)
 
 // Source pictures as RGBx texels ([V][B][H][W][4] floats, x = 0): every bilinear tap of the flat warp and of its adjoint
 // is ONE 128-bit gather instead of three 32-bit ones from three planes (a third of the load instructions and address
@@ -655,7 +669,7 @@ __device__ __forceinline__ FlatTap flat_taps(float u, float v, int H, int W, int
 
 // PACKED: the sources are read as RGBx texels (`rgbx`), otherwise as the caller's three planes.
 template <bool PACKED>
-__global__ void __launch_bounds__(kFlatThreads, 3)
+__global__ void __launch_bounds__(kFlatThreads, DROSFM_FWD_MINBLOCKS)
 warp_sources_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind, int n_preds, drosfm_cams_t cams, int padding,
                     const float* __restrict__ rgbx, float* __restrict__ warped, int B, int H, int W) {
     __shared__ Cam cam_s;
@@ -667,73 +681,78 @@ warp_sources_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind,
     const int P = H * W;
     const Norm nm = make_norm(W, H);
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y0 = blockIdx.y * kFlatTileH + (threadIdx.x >> 5);
     const float* __restrict__ invd = pp.inv_depth[ip] + static_cast<size_t>(b) * P;
     const float* __restrict__ src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
     const float4* __restrict__ tex = reinterpret_cast<const float4*>(rgbx) + (static_cast<size_t>(v) * B + b) * P;
     float* __restrict__ out = warped + static_cast<size_t>(slot) * 3 * P;
     if (x >= W) return;
     constexpr int kStride = kFlatThreads / 32;
-    // Software pipeline over the thread's rows: the depths are all requested up front; the gathers of row k
-    // are in flight while the coordinate chain of row k+1 runs.
-    float d[kFlatRows];
+    // a block walks down kFlatTiles tiles of 64 rows: the camera set-up (one thread, a barrier) is paid once for all of them
+#pragma unroll 1
+    for (int tile = 0; tile < kFlatTiles; ++tile) {
+        const int y0 = (blockIdx.y * kFlatTiles + tile) * kFlatTileH + (threadIdx.x >> 5);
+        if (y0 - static_cast<int>(threadIdx.x >> 5) >= H) break;
+        // Software pipeline over the thread's rows: the depths are all requested up front; the gathers of row k
+        // are in flight while the coordinate chain of row k+1 runs.
+        float d[kFlatRows];
 #pragma unroll
-    for (int k = 0; k < kFlatRows; ++k) {
-        const int y = y0 + k * kStride;
-        d[k] = y < H ? __ldg(invd + y * W + x) : 0.0f;
-    }
-    auto taps_of = [&](int k) {
-        // rows beyond the image run the chain on depth 0 (in-range addresses, results discarded): no divergence
-        Warp wp;
-        warp_pixel_fast(cam, x, y0 + k * kStride, to_depth_fast(d[k], depth_kind), nm, true, wp);
-        return flat_taps(wp.p.u, wp.p.v, H, W, padding);
-    };
-    float val[12];
-    float4 tex4[4];
-    auto gather = [&](const FlatTap& tp) {
-        if constexpr (PACKED) {
-            const float4* r0 = tex + tp.o00;
-            tex4[0] = __ldg(r0);
-            tex4[1] = __ldg(r0 + tp.dxo);
-            tex4[2] = __ldg(r0 + tp.dyo);
-            tex4[3] = __ldg(r0 + tp.dyo + tp.dxo);
-        } else {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float* r0 = src + (static_cast<unsigned>(c * P) + static_cast<unsigned>(tp.o00));
-                val[4 * c + 0] = __ldg(r0);
-                val[4 * c + 1] = __ldg(r0 + tp.dxo);
-                val[4 * c + 2] = __ldg(r0 + tp.dyo);
-                val[4 * c + 3] = __ldg(r0 + tp.dyo + tp.dxo);
-            }
+        for (int k = 0; k < kFlatRows; ++k) {
+            const int y = y0 + k * kStride;
+            d[k] = y < H ? __ldg(invd + y * W + x) : 0.0f;
         }
-    };
-    FlatTap cur = taps_of(0);
-    gather(cur);
-#pragma unroll
-    for (int k = 0; k < kFlatRows; ++k) {
-        FlatTap nxt = cur;
-        if (k + 1 < kFlatRows) nxt = taps_of(k + 1);
-        const int y = y0 + k * kStride;
-        if (y < H) {
-            const unsigned o = static_cast<unsigned>(y * W + x);
-            // one fixed evaluation order for both tap layouts (the compiler would otherwise contract them differently)
-            auto blend = [&](float a0, float a1, float a2, float a3) {
-                return __fmaf_rn(a3, cur.w11, __fmaf_rn(a2, cur.w10, __fmaf_rn(a1, cur.w01, __fmul_rn(a0, cur.w00))));
-            };
+        auto taps_of = [&](int k) {
+            // rows beyond the image run the chain on depth 0 (in-range addresses, results discarded): no divergence
+            Warp wp;
+            warp_pixel_fast(cam, x, y0 + k * kStride, to_depth_fast(d[k], depth_kind), nm, true, wp);
+            return flat_taps(wp.p.u, wp.p.v, H, W, padding);
+        };
+        float val[12];
+        float4 tex4[4];
+        auto gather = [&](const FlatTap& tp) {
             if constexpr (PACKED) {
-                out[o] = blend(tex4[0].x, tex4[1].x, tex4[2].x, tex4[3].x);
-                out[o + P] = blend(tex4[0].y, tex4[1].y, tex4[2].y, tex4[3].y);
-                out[o + 2 * P] = blend(tex4[0].z, tex4[1].z, tex4[2].z, tex4[3].z);
+                const float4* r0 = tex + tp.o00;
+                tex4[0] = __ldg(r0);
+                tex4[1] = __ldg(r0 + tp.dxo);
+                tex4[2] = __ldg(r0 + tp.dyo);
+                tex4[3] = __ldg(r0 + tp.dyo + tp.dxo);
             } else {
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    out[o + static_cast<unsigned>(c * P)] = blend(val[4 * c], val[4 * c + 1], val[4 * c + 2], val[4 * c + 3]);
+                for (int c = 0; c < 3; ++c) {
+                    const float* r0 = src + (static_cast<unsigned>(c * P) + static_cast<unsigned>(tp.o00));
+                    val[4 * c + 0] = __ldg(r0);
+                    val[4 * c + 1] = __ldg(r0 + tp.dxo);
+                    val[4 * c + 2] = __ldg(r0 + tp.dyo);
+                    val[4 * c + 3] = __ldg(r0 + tp.dyo + tp.dxo);
+                }
             }
-        }
-        if (k + 1 < kFlatRows) {
-            cur = nxt;
-            gather(cur);
+        };
+        FlatTap cur = taps_of(0);
+        gather(cur);
+#pragma unroll
+        for (int k = 0; k < kFlatRows; ++k) {
+            FlatTap nxt = cur;
+            if (k + 1 < kFlatRows) nxt = taps_of(k + 1);
+            const int y = y0 + k * kStride;
+            if (y < H) {
+                const unsigned o = static_cast<unsigned>(y * W + x);
+                // one fixed evaluation order for both tap layouts (the compiler would otherwise contract them differently)
+                auto blend = [&](float a0, float a1, float a2, float a3) {
+                    return __fmaf_rn(a3, cur.w11, __fmaf_rn(a2, cur.w10, __fmaf_rn(a1, cur.w01, __fmul_rn(a0, cur.w00))));
+                };
+                if constexpr (PACKED) {
+                    out[o] = blend(tex4[0].x, tex4[1].x, tex4[2].x, tex4[3].x);
+                    out[o + P] = blend(tex4[0].y, tex4[1].y, tex4[2].y, tex4[3].y);
+                    out[o + 2 * P] = blend(tex4[0].z, tex4[1].z, tex4[2].z, tex4[3].z);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        out[o + static_cast<unsigned>(c * P)] = blend(val[4 * c], val[4 * c + 1], val[4 * c + 2], val[4 * c + 3]);
+                }
+            }
+            if (k + 1 < kFlatRows) {
+                cur = nxt;
+                gather(cur);
+            }
         }
     }
 }
@@ -748,7 +767,7 @@ __device__ __forceinline__ void red_add1(float* p, float v) { asm volatile("red.
 // meet in g_inv_depth through red.global.add (ADD) or are stored (V == 1, nothing to add to).
 // A row is skipped when no lane of the warp has a non-zero upstream gradient (un-selected view / auto-masked region).
 template <bool PACKED, bool ADD>
-__global__ void __launch_bounds__(kFlatThreads, 3)
+__global__ void __launch_bounds__(kFlatThreads, DROSFM_ADJ_MINBLOCKS)
 warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind, int n_preds, drosfm_cams_t cams,
                             int padding, const float* __restrict__ rgbx, const float* __restrict__ g_warped,
                             const __grid_constant__ PhotoGrads pg, Slot* ws, int B, int H, int W) {
@@ -763,9 +782,10 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
     const int P = H * W;
     const Norm nm = make_norm(W, H);
     const int x = blockIdx.x * 32 + (tid & 31);
-    const int y0 = blockIdx.y * kFlatTileH + (tid >> 5);
+    const int row0 = blockIdx.y * kFlatTiles * kFlatTileH + (tid >> 5);       // first row of this thread; then every 8th
     const bool col_ok = x < W;
     constexpr int kStride = kFlatThreads / 32;
+    constexpr int kRows = kFlatTiles * kFlatRows;
     const float* __restrict__ invd = pp.inv_depth[ip] + static_cast<size_t>(b) * P;
     float* __restrict__ gout = pg.g_inv_depth[ip] != nullptr ? pg.g_inv_depth[ip] + static_cast<size_t>(b) * P : nullptr;
     const float* __restrict__ gw = g_warped + static_cast<size_t>(slot) * 3 * P;
@@ -774,31 +794,29 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
     float gT[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) gT[i] = 0.0f;
-    // the depths of all rows are requested up front, the upstream gradients one row ahead
-    float dv[kFlatRows];
-#pragma unroll
-    for (int k = 0; k < kFlatRows; ++k) {
-        const int y = y0 + k * kStride;
-        dv[k] = (col_ok && y < H) ? __ldg(invd + y * W + x) : 0.0f;
-    }
-    float gn[3];
-    auto fetch_g = [&](int k) {
-        const int y = y0 + k * kStride;
+    // the upstream gradients and the depth of a row are requested one row ahead; the row loop is NOT unrolled (the body
+    // is ~400 instructions: eight copies of it thrash the instruction cache)
+    float gn[3], dn;
+    auto fetch = [&](int k) {
+        const int y = row0 + k * kStride;
         const bool in = col_ok && y < H;
         const unsigned o = in ? static_cast<unsigned>(y * W + x) : 0u;
 #pragma unroll
         for (int c = 0; c < 3; ++c) gn[c] = in ? __ldg(gw + (o + static_cast<unsigned>(c * P))) : 0.0f;
+        dn = in ? __ldg(invd + o) : 0.0f;
     };
-    fetch_g(0);
-#pragma unroll
-    for (int k = 0; k < kFlatRows; ++k) {
-        const float g0 = gn[0], g1 = gn[1], g2 = gn[2];
-        if (k + 1 < kFlatRows) fetch_g(k + 1);
-        const int y = y0 + k * kStride;
+    fetch(0);
+    constexpr int kAdjUnroll = DROSFM_ADJ_UNROLL;
+#pragma unroll kAdjUnroll
+    for (int k = 0; k < kRows; ++k) {
+        const int y = row0 + k * kStride;
+        if (y - static_cast<int>(tid >> 5) >= H) break;                         // block-uniform: rows beyond the image
+        const float g0 = gn[0], g1 = gn[1], g2 = gn[2], draw = dn;
+        if (k + 1 < kRows) fetch(k + 1);
         const bool in = col_ok && y < H;
         float gd = 0.0f;
         if (__any_sync(0xffffffffu, g0 != 0.0f || g1 != 0.0f || g2 != 0.0f)) {
-            const float d = to_depth_fast(dv[k], depth_kind);
+            const float d = to_depth_fast(draw, depth_kind);
             Warp wp;
             warp_pixel_fast(cam, x, y, d, nm, true, wp);
             float mx, my;
@@ -835,7 +853,7 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
                 gd = warp_pixel_adjoint(cam, wp, d, nm.wm1, nm.hm1, true, gix * mx, giy * my, gT);
         }
         if (gout != nullptr && in) {
-            const float gg = depth_kind == DROSFM_INV_DEPTH ? inv2depth_grad(dv[k], gd) : gd;
+            const float gg = depth_kind == DROSFM_INV_DEPTH ? inv2depth_grad(draw, gd) : gd;
             float* dst = gout + static_cast<unsigned>(y * W + x);
             if constexpr (ADD) { if (gg != 0.0f) red_add1(dst, gg); }
             else *dst = gg;
@@ -863,7 +881,7 @@ __global__ void __launch_bounds__(256) zero_inv_grads_kernel(const __grid_consta
 static int launch_adjoint(const PhotoPtrs& pp, const PhotoGrads& pg, int n_views, int depth_kind, int n_preds, const drosfm_cams_t* cams,
                           int padding, const float* rgbx, const float* g_warped, Slot* ws, int accumulate, int B, int H, int W,
                           cudaStream_t cs) {
-    dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds * n_views);
+    dim3 flat((W + 31) / 32, (H + kFlatTiles * kFlatTileH - 1) / (kFlatTiles * kFlatTileH), B * n_preds * n_views);
     const bool add = accumulate != 0 || n_views > 1;
     if (add && accumulate == 0) {
         const size_t n = static_cast<size_t>(B) * H * W;
@@ -1640,7 +1658,7 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
     if (warped_save != nullptr) {
         if (!(flags & DROSFM_PHOTO_WARPED_READY)) {
-            dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds * n_views);
+            dim3 flat((W + 31) / 32, (H + kFlatTiles * kFlatTileH - 1) / (kFlatTiles * kFlatTileH), B * n_preds * n_views);
             warp_sources_kernel<false><<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, opts->padding, nullptr,
                                                                       warped_save, B, H, W);
             if (int e = launch_status("photometric_fwd (warp_sources)")) return e;
@@ -1744,7 +1762,7 @@ int drosfm_warp_sources_fwd(const float* const* context, int n_views, const floa
     PhotoPtrs pp{};
     if (int e = fill_ptrs(pp, context, n_views, inv_depths, n_preds, poses, 1.0f)) return e;
     DROSFM_REQUIRE(static_cast<long long>(B) * n_preds * n_views <= 65535, DROSFM_ERANGE, "warp_sources_fwd: B * n_preds * n_views too large");
-    dim3 flat((W + 31) / 32, (H + kFlatTileH - 1) / kFlatTileH, B * n_preds * n_views);
+    dim3 flat((W + 31) / 32, (H + kFlatTiles * kFlatTileH - 1) / (kFlatTiles * kFlatTileH), B * n_preds * n_views);
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
     if (rgbx != nullptr) {
         DROSFM_REQUIRE(aligned16(rgbx), DROSFM_EALIGN, "warp_sources_fwd: rgbx must be 16-byte aligned");
