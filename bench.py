@@ -461,9 +461,124 @@ def run_gpu(args, wl):
             "gpu_launches_per_step": launches_per_step,
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity, "gpu_aten_reference": aten,
         }
-        print(json.dumps(out))
-    if world > 1:
+    else:
+        out = None
+    if world > 1 and not getattr(args, "keep_group", False):
         dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: isolated warp / feature-cost / SSIM-photometric sweep, GB/s against the HBM roofline
+# ------------------------------------------------------------------------------------------------
+def run_microbench(args):
+    """Per-operator sweep over resolution (192x640 -> 384x1280) and source views (2, 4, 8) with batches sized so that the
+    algorithmic bytes of ONE launch are >= 4x the 126 MB L2 -- the regime in which the HBM roofline applies.  Algorithmic
+    bytes: SURVEY.md section 8(d).  One JSON line; `sweep` holds every measurement."""
+    from dro_sfm_b200 import ops, synthetic as syn
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    peak, peak_src = measured_peaks()
+    L2 = 126e6
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    rows = []
+
+    def timed(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    def add(op, H, W, V, B, ms, nbytes, launches):
+        gbps = nbytes / (ms * 1e-3) / 1e9
+        rows.append({"op": op, "H": H, "W": W, "views": V, "batch": B, "ms": round(ms, 4), "algorithmic_MB": round(nbytes / 1e6, 1),
+                     "GBps": round(gbps, 1), "frac": round(gbps / peak, 4), "launches": launches})
+
+    shapes = [(192, 640), (256, 832), (320, 1024), (384, 1280)]
+    views = [2, 4, 8]
+    if args.quick:
+        shapes, views = [(192, 640), (384, 1280)], [2, 8]
+    g = syn.gen(5)
+    for H, W in shapes:
+        K = syn.intrinsics("kitti", 1, H, W)
+        P, h, w = H * W, H // 8, W // 8
+        # ---- warp: view_synthesis of one source view (kernels 1 + 2 fused), 28 B/px forward, 32 B/px backward
+        B = min(512, max(1, int(4 * L2 / (28 * P)) + 1))
+        img = syn.images(g, 2, H, W).repeat((B + 1) // 2, 1, 1, 1)[:B].to(dev)
+        inv = syn.inv_depth(g, 2, H, W, 0.5, 80.0).repeat((B + 1) // 2, 1, 1, 1)[:B].to(dev).requires_grad_(True)
+        pose = syn.pose_vec(g, B, "kitti").to(dev).requires_grad_(True)
+        Kb = K.repeat(B, 1, 1).to(dev)
+        out = [None]
+
+        def f_warp():
+            out[0] = ops.view_synthesis(img, inv, pose, Kb, None, 1.0, "zeros", inverse_depth=True)
+        gout = torch.randn(B, 3, H, W, device=dev)
+        add("warp_fwd", H, W, 1, B, timed(f_warp), 28 * P * B, 1)
+        add("warp_bwd", H, W, 1, B, timed(lambda: torch.autograd.grad(out[0], (inv, pose), gout, retain_graph=True)), 32 * P * B, 1)
+        del img, inv, gout, out
+        for V in views:
+            # ---- feature-metric cost (depth_cost_calc: V views, mean), C = 128 at 1/8 resolution
+            C, p = 128, h * w
+            fwd_b, bwd_b = (V + 2) * 4 * C + 4, (2 * V + 3) * 4 * C + 8
+            B = min(1024, max(1, int(4 * L2 / (fwd_b * p)) + 1))
+            cl = torch.channels_last
+            fmap = syn.features(g, 2, C, h, w).repeat((B + 1) // 2, 1, 1, 1)[:B].to(dev).contiguous(memory_format=cl).requires_grad_(True)
+            frefs = [syn.features(g, 2, C, h, w).repeat((B + 1) // 2, 1, 1, 1)[:B].to(dev).contiguous(memory_format=cl).requires_grad_(True)
+                     for _ in range(V)]
+            invl = syn.inv_depth(g, 2, h, w, 0.5, 80.0).repeat((B + 1) // 2, 1, 1, 1)[:B].to(dev).requires_grad_(True)
+            poses = [syn.pose_vec(g, B, "kitti", 1.0 if v % 2 == 0 else -1.0).to(dev).requires_grad_(True) for v in range(V)]
+            Kb = K.repeat(B, 1, 1).to(dev)
+            gc = torch.randn(B, C, h, w, device=dev).contiguous(memory_format=cl)
+            res = [None]
+
+            def f_cost():
+                res[0] = ops.feat_cost(invl, fmap, frefs, poses, Kb, None, 0.125, inverse_depth=True)
+            add("feat_cost_fwd", H, W, V, B, timed(f_cost), fwd_b * p * B, 1)
+            add("feat_cost_bwd", H, W, V, B, timed(lambda: torch.autograd.grad(res[0], [invl, fmap] + frefs + poses, gc, retain_graph=True)),
+                bwd_b * p * B, 1)
+            del fmap, frefs, gc, res
+            # ---- photometric loss of one prediction (SSIM + L1, auto-mask, per-pixel min), V source views
+            fwd_b, bwd_b = 16 + 12 * V, 20 + 12 * V
+            B = min(256, max(1, int(4 * L2 / (fwd_b * P)) + 1))
+            image = syn.images(g, 2, H, W).repeat((B + 1) // 2, 1, 1, 1)[:B].to(dev)
+            ctx = [syn.images(g, 2, H, W).repeat((B + 1) // 2, 1, 1, 1)[:B].to(dev) for _ in range(V)]
+            invs = [syn.inv_depth(g, 2, H, W, 0.5, 80.0).repeat((B + 1) // 2, 1, 1, 1)[:B].to(dev).requires_grad_(True)]
+            pv = [[(syn.pose_vec(g, B, "kitti", 1.0 if v % 2 == 0 else -1.0) * 0.3).to(dev).requires_grad_(True)] for v in range(V)]
+            Kb = K.repeat(B, 1, 1).to(dev)
+            tot = [None]
+            before = ops.L.lib().drosfm_launch_count()
+
+            def f_photo():
+                tot[0] = ops.photometric_loss(image, ctx, invs, Kb, Kb, pv, smooth_w=0.0)[0]
+            f_photo()
+            n_f = int(ops.L.lib().drosfm_launch_count() - before)
+            leaves = invs + [x for row in pv for x in row]
+            before = ops.L.lib().drosfm_launch_count()
+            torch.autograd.grad(tot[0].sum(), leaves, retain_graph=True)
+            n_b = int(ops.L.lib().drosfm_launch_count() - before)
+            add("photometric_fwd", H, W, V, B, timed(f_photo), fwd_b * P * B, n_f)
+            add("photometric_bwd", H, W, V, B, timed(lambda: torch.autograd.grad(tot[0].sum(), leaves, retain_graph=True)), bwd_b * P * B, n_b)
+            del image, ctx, invs, pv, tot
+            torch.cuda.empty_cache()
+    best = {}
+    for r in rows:
+        if (r["H"], r["W"]) == shapes[-1]:
+            best[r["op"]] = max(best.get(r["op"], 0.0), r["frac"])
+    out = {"metric": "isolated warp / feature-cost / SSIM-photometric GB/s vs HBM roofline", "unit": "GB/s", "workload": "microbench",
+           "config": {"workload": "microbench (BASELINE.json configs[4])", "shapes": shapes, "views": views,
+                      "batch": "per row: algorithmic bytes of one launch >= 4 x 126 MB L2", "l2": "flushed between timed iterations"},
+           "peak": peak, "peak_source": peak_src, "dtype": "f32", "data": "synthetic", "n_gpus": 1,
+           "best_frac_at_%dx%d" % shapes[-1]: best, "sweep": rows}
+    print(json.dumps(out))
 
 
 def main():
@@ -478,13 +593,35 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--log-every", type=int, default=10, help="all-reduce the logged loss every k steps (multi-GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="microbench: corner points of the sweep only")
     args = ap.parse_args()
     from dro_sfm_b200 import synthetic as syn
+    if args.workload == "microbench":
+        return run_microbench(args)
+    if args.workload == "all":
+        # every BASELINE.json training configuration through the same step; the headline line stays configs[1]
+        args.keep_group = True
+        results = {}
+        for name in syn.WORKLOADS:
+            args.no_cpu_baseline = name != "train_kitti_mf_selfsup"
+            out = run_gpu(args, syn.WORKLOADS[name]) if args.impl != "reference" else None
+            if out is not None:
+                results[name] = out
+        if results:
+            head = dict(results["train_kitti_mf_selfsup"])
+            head["other_workloads"] = {k: {"value": v["value"], "e2e": v["e2e"]["value"], "ms_per_step": v["ms_per_step"],
+                                           "gpu_launches_per_step": v["gpu_launches_per_step"], "config": v["config"],
+                                           "step_frac": v["roofline"]["step_frac"], "dominant": v["roofline"]["kernel"],
+                                           "dominant_frac": v["roofline"]["frac"]} for k, v in results.items() if k != "train_kitti_mf_selfsup"}
+            print(json.dumps(head))
+        return
     wl = syn.WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
     else:
-        run_gpu(args, wl)
+        out = run_gpu(args, wl)
+        if out is not None:
+            print(json.dumps(out))
 
 
 if __name__ == "__main__":

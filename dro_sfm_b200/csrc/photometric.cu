@@ -623,19 +623,29 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
 // once per pixel instead of once per pixel of every tile + halo.
 constexpr int kFlatThreads = 256, kFlatRows = 8;
 constexpr int kFlatTileH = (kFlatThreads / 32) * kFlatRows;       // one tile: 32 columns x 64 rows
-#ifndef DROSFM_FLAT_TILES
-#define DROSFM_FLAT_TILES 2
+// Tuning (B200, 320x960, B=2, n=9, V=2; loss graph replay, scratch/loss_bench.py):
+//   forward : 4 blocks/SM (64 registers) 130 us, 3 blocks 142 us, 2 blocks 152 us; tiles per block 1 / 2 / 5: 136 / 142 / 130 us
+//   adjoint : 2 blocks/SM (128 registers, no spills) 202 us, 3 blocks (80 registers, 120 B spilled) 219 us;
+//             tiles per block 1 / 2 / 5: 229 / 219 / 236 us; row loop unrolled: 317 us (instruction cache)
+#ifndef DROSFM_FWD_TILES
+#define DROSFM_FWD_TILES 1
+#endif
+#ifndef DROSFM_ADJ_TILES
+#define DROSFM_ADJ_TILES 2
 #endif
 #ifndef DROSFM_FWD_MINBLOCKS
-#define DROSFM_FWD_MINBLOCKS 3
+#define DROSFM_FWD_MINBLOCKS 4
 #endif
 #ifndef DROSFM_ADJ_MINBLOCKS
-#define DROSFM_ADJ_MINBLOCKS 3
+#define DROSFM_ADJ_MINBLOCKS 2
 #endif
 #ifndef DROSFM_ADJ_UNROLL
 #define DROSFM_ADJ_UNROLL 1
 #endif
-constexpr int kFlatTiles = DROSFM_FLAT_TILES;                     // tiles a block walks down (amortises its camera set-up)
+#ifndef DROSFM_ADJ_ILP
+#define DROSFM_ADJ_ILP 2
+#endif
+constexpr int kFwdTiles = DROSFM_FWD_TILES, kAdjTiles = DROSFM_ADJ_TILES;   // tiles a block walks down (amortises its camera set-up)
 
 // Source pictures as RGBx texels ([V][B][H][W][4] floats, x = 0): every bilinear tap of the flat warp and of its adjoint
 // is ONE 128-bit gather instead of three 32-bit ones from three planes (a third of the load instructions and address
@@ -687,10 +697,10 @@ warp_sources_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind,
     float* __restrict__ out = warped + static_cast<size_t>(slot) * 3 * P;
     if (x >= W) return;
     constexpr int kStride = kFlatThreads / 32;
-    // a block walks down kFlatTiles tiles of 64 rows: the camera set-up (one thread, a barrier) is paid once for all of them
+    // a block walks down kFwdTiles tiles of 64 rows: the camera set-up (one thread, a barrier) is paid once for all of them
 #pragma unroll 1
-    for (int tile = 0; tile < kFlatTiles; ++tile) {
-        const int y0 = (blockIdx.y * kFlatTiles + tile) * kFlatTileH + (threadIdx.x >> 5);
+    for (int tile = 0; tile < kFwdTiles; ++tile) {
+        const int y0 = (blockIdx.y * kFwdTiles + tile) * kFlatTileH + (threadIdx.x >> 5);
         if (y0 - static_cast<int>(threadIdx.x >> 5) >= H) break;
         // Software pipeline over the thread's rows: the depths are all requested up front; the gathers of row k
         // are in flight while the coordinate chain of row k+1 runs.
@@ -782,10 +792,10 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
     const int P = H * W;
     const Norm nm = make_norm(W, H);
     const int x = blockIdx.x * 32 + (tid & 31);
-    const int row0 = blockIdx.y * kFlatTiles * kFlatTileH + (tid >> 5);       // first row of this thread; then every 8th
+    const int row0 = blockIdx.y * kAdjTiles * kFlatTileH + (tid >> 5);       // first row of this thread; then every 8th
     const bool col_ok = x < W;
     constexpr int kStride = kFlatThreads / 32;
-    constexpr int kRows = kFlatTiles * kFlatRows;
+    constexpr int kRows = kAdjTiles * kFlatRows;
     const float* __restrict__ invd = pp.inv_depth[ip] + static_cast<size_t>(b) * P;
     float* __restrict__ gout = pg.g_inv_depth[ip] != nullptr ? pg.g_inv_depth[ip] + static_cast<size_t>(b) * P : nullptr;
     const float* __restrict__ gw = g_warped + static_cast<size_t>(slot) * 3 * P;
@@ -794,69 +804,93 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
     float gT[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) gT[i] = 0.0f;
-    // the upstream gradients and the depth of a row are requested one row ahead; the row loop is NOT unrolled (the body
-    // is ~400 instructions: eight copies of it thrash the instruction cache)
-    float gn[3], dn;
-    auto fetch = [&](int k) {
-        const int y = row0 + k * kStride;
-        const bool in = col_ok && y < H;
-        const unsigned o = in ? static_cast<unsigned>(y * W + x) : 0u;
+    // The upstream gradients and the depths of the next kIlp rows are requested while the current ones are processed; the
+    // row loop is NOT unrolled beyond that (the body is ~400 instructions per row: eight copies thrash the instruction
+    // cache).  kIlp rows are processed side by side in one basic block so that their chains and gathers overlap.
+    constexpr int kIlp = DROSFM_ADJ_ILP;
+    static_assert(kRows % kIlp == 0, "rows per block must be a multiple of the interleave");
+    float gn[kIlp][3], dn[kIlp];
+    auto fetch = [&](int k0) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) gn[c] = in ? __ldg(gw + (o + static_cast<unsigned>(c * P))) : 0.0f;
-        dn = in ? __ldg(invd + o) : 0.0f;
+        for (int r = 0; r < kIlp; ++r) {
+            const int y = row0 + (k0 + r) * kStride;
+            const bool in = col_ok && y < H;
+            const unsigned o = in ? static_cast<unsigned>(y * W + x) : 0u;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gn[r][c] = in ? __ldg(gw + (o + static_cast<unsigned>(c * P))) : 0.0f;
+            dn[r] = in ? __ldg(invd + o) : 0.0f;
+        }
     };
     fetch(0);
     constexpr int kAdjUnroll = DROSFM_ADJ_UNROLL;
 #pragma unroll kAdjUnroll
-    for (int k = 0; k < kRows; ++k) {
-        const int y = row0 + k * kStride;
-        if (y - static_cast<int>(tid >> 5) >= H) break;                         // block-uniform: rows beyond the image
-        const float g0 = gn[0], g1 = gn[1], g2 = gn[2], draw = dn;
-        if (k + 1 < kRows) fetch(k + 1);
-        const bool in = col_ok && y < H;
-        float gd = 0.0f;
-        if (__any_sync(0xffffffffu, g0 != 0.0f || g1 != 0.0f || g2 != 0.0f)) {
-            const float d = to_depth_fast(draw, depth_kind);
-            Warp wp;
-            warp_pixel_fast(cam, x, y, d, nm, true, wp);
-            float mx, my;
-            const ATap tx = axis_taps(unnormalize(wp.p.u, W, padding, mx), W);
-            const ATap ty = axis_taps(unnormalize(wp.p.v, H, padding, my), H);
-            const unsigned o00 = static_cast<unsigned>(ty.i0 * W + tx.i0);
-            const unsigned dxo = static_cast<unsigned>(tx.step), dyo = static_cast<unsigned>(ty.step * W);
-            // d(sample)/d(ix) = (ne - nw) wy0 + (se - sw) wy1 and d(sample)/d(iy) = (sw - nw) wx0 + (se - ne) wx1, a tap
-            // outside the source counting as zero: four coefficients per direction, shared by the channels
-            const float kx0 = -tx.f0 * ty.w0, kx1 = tx.f1 * ty.w0, kx2 = -tx.f0 * ty.w1, kx3 = tx.f1 * ty.w1;
-            const float ky0 = -ty.f0 * tx.w0, ky1 = -ty.f0 * tx.w1, ky2 = ty.f1 * tx.w0, ky3 = ty.f1 * tx.w1;
-            float gix, giy;
-            if constexpr (PACKED) {
-                const float4 t0 = __ldg(tex + o00), t1 = __ldg(tex + (o00 + dxo));
-                const float4 t2 = __ldg(tex + (o00 + dyo)), t3 = __ldg(tex + (o00 + dyo + dxo));
-                gix = g0 * (t0.x * kx0 + t1.x * kx1 + t2.x * kx2 + t3.x * kx3) + g1 * (t0.y * kx0 + t1.y * kx1 + t2.y * kx2 + t3.y * kx3) +
-                      g2 * (t0.z * kx0 + t1.z * kx1 + t2.z * kx2 + t3.z * kx3);
-                giy = g0 * (t0.x * ky0 + t1.x * ky1 + t2.x * ky2 + t3.x * ky3) + g1 * (t0.y * ky0 + t1.y * ky1 + t2.y * ky2 + t3.y * ky3) +
-                      g2 * (t0.z * ky0 + t1.z * ky1 + t2.z * ky2 + t3.z * ky3);
-            } else {
-                gix = giy = 0.0f;
-                const float gc[3] = {g0, g1, g2};
+    for (int k = 0; k < kRows; k += kIlp) {
+        if (row0 + k * kStride - static_cast<int>(tid >> 5) >= H) break;        // block-uniform: rows beyond the image
+        float g[kIlp][3], draw[kIlp];
+        bool any = false;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const unsigned oc = o00 + static_cast<unsigned>(c * P);
-                    const float v0 = __ldg(src + oc), v1 = __ldg(src + (oc + dxo));
-                    const float v2 = __ldg(src + (oc + dyo)), v3 = __ldg(src + (oc + dyo + dxo));
-                    gix += gc[c] * (v0 * kx0 + v1 * kx1 + v2 * kx2 + v3 * kx3);
-                    giy += gc[c] * (v0 * ky0 + v1 * ky1 + v2 * ky2 + v3 * ky3);
+        for (int r = 0; r < kIlp; ++r) {
+            g[r][0] = gn[r][0]; g[r][1] = gn[r][1]; g[r][2] = gn[r][2];
+            draw[r] = dn[r];
+            any |= g[r][0] != 0.0f || g[r][1] != 0.0f || g[r][2] != 0.0f;
+        }
+        if (k + kIlp < kRows) fetch(k + kIlp);
+        float gd[kIlp];
+#pragma unroll
+        for (int r = 0; r < kIlp; ++r) gd[r] = 0.0f;
+        if (__any_sync(0xffffffffu, any)) {
+            Warp wp[kIlp];
+            float d[kIlp], mx[kIlp], my[kIlp], gix[kIlp], giy[kIlp];
+#pragma unroll
+            for (int r = 0; r < kIlp; ++r) {
+                const int y = row0 + (k + r) * kStride;
+                d[r] = to_depth_fast(draw[r], depth_kind);
+                warp_pixel_fast(cam, x, y, d[r], nm, true, wp[r]);
+                const ATap tx = axis_taps(unnormalize(wp[r].p.u, W, padding, mx[r]), W);
+                const ATap ty = axis_taps(unnormalize(wp[r].p.v, H, padding, my[r]), H);
+                const unsigned o00 = static_cast<unsigned>(ty.i0 * W + tx.i0);
+                const unsigned dxo = static_cast<unsigned>(tx.step), dyo = static_cast<unsigned>(ty.step * W);
+                // d(sample)/d(ix) = (ne - nw) wy0 + (se - sw) wy1 and d(sample)/d(iy) = (sw - nw) wx0 + (se - ne) wx1, a tap
+                // outside the source counting as zero: four coefficients per direction, shared by the channels
+                const float kx0 = -tx.f0 * ty.w0, kx1 = tx.f1 * ty.w0, kx2 = -tx.f0 * ty.w1, kx3 = tx.f1 * ty.w1;
+                const float ky0 = -ty.f0 * tx.w0, ky1 = -ty.f0 * tx.w1, ky2 = ty.f1 * tx.w0, ky3 = ty.f1 * tx.w1;
+                const float g0 = g[r][0], g1 = g[r][1], g2 = g[r][2];
+                if constexpr (PACKED) {
+                    const float4 t0 = __ldg(tex + o00), t1 = __ldg(tex + (o00 + dxo));
+                    const float4 t2 = __ldg(tex + (o00 + dyo)), t3 = __ldg(tex + (o00 + dyo + dxo));
+                    gix[r] = g0 * (t0.x * kx0 + t1.x * kx1 + t2.x * kx2 + t3.x * kx3) + g1 * (t0.y * kx0 + t1.y * kx1 + t2.y * kx2 + t3.y * kx3) +
+                             g2 * (t0.z * kx0 + t1.z * kx1 + t2.z * kx2 + t3.z * kx3);
+                    giy[r] = g0 * (t0.x * ky0 + t1.x * ky1 + t2.x * ky2 + t3.x * ky3) + g1 * (t0.y * ky0 + t1.y * ky1 + t2.y * ky2 + t3.y * ky3) +
+                             g2 * (t0.z * ky0 + t1.z * ky1 + t2.z * ky2 + t3.z * ky3);
+                } else {
+                    gix[r] = giy[r] = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const unsigned oc = o00 + static_cast<unsigned>(c * P);
+                        const float v0 = __ldg(src + oc), v1 = __ldg(src + (oc + dxo));
+                        const float v2 = __ldg(src + (oc + dyo)), v3 = __ldg(src + (oc + dyo + dxo));
+                        gix[r] += g[r][c] * (v0 * kx0 + v1 * kx1 + v2 * kx2 + v3 * kx3);
+                        giy[r] += g[r][c] * (v0 * ky0 + v1 * ky1 + v2 * ky2 + v3 * ky3);
+                    }
                 }
             }
-            // lanes without a gradient (or outside the image) carry gix = giy = 0: every term below is then an exact zero
-            if (in && (gix != 0.0f || giy != 0.0f))
-                gd = warp_pixel_adjoint(cam, wp, d, nm.wm1, nm.hm1, true, gix * mx, giy * my, gT);
+#pragma unroll
+            for (int r = 0; r < kIlp; ++r) {
+                const bool in = col_ok && row0 + (k + r) * kStride < H;
+                // lanes without a gradient (or outside the image) carry gix = giy = 0: every term is then an exact zero
+                if (in && (gix[r] != 0.0f || giy[r] != 0.0f))
+                    gd[r] = warp_pixel_adjoint(cam, wp[r], d[r], nm.wm1, nm.hm1, true, gix[r] * mx[r], giy[r] * my[r], gT);
+            }
         }
-        if (gout != nullptr && in) {
-            const float gg = depth_kind == DROSFM_INV_DEPTH ? inv2depth_grad(draw, gd) : gd;
-            float* dst = gout + static_cast<unsigned>(y * W + x);
-            if constexpr (ADD) { if (gg != 0.0f) red_add1(dst, gg); }
-            else *dst = gg;
+#pragma unroll
+        for (int r = 0; r < kIlp; ++r) {
+            const int y = row0 + (k + r) * kStride;
+            if (gout != nullptr && col_ok && y < H) {
+                const float gg = depth_kind == DROSFM_INV_DEPTH ? inv2depth_grad(draw[r], gd[r]) : gd[r];
+                float* dst = gout + static_cast<unsigned>(y * W + x);
+                if constexpr (ADD) { if (gg != 0.0f) red_add1(dst, gg); }
+                else *dst = gg;
+            }
         }
     }
     float* g_pose = pg.g_pose[v * n_preds + ip];
@@ -881,7 +915,7 @@ __global__ void __launch_bounds__(256) zero_inv_grads_kernel(const __grid_consta
 static int launch_adjoint(const PhotoPtrs& pp, const PhotoGrads& pg, int n_views, int depth_kind, int n_preds, const drosfm_cams_t* cams,
                           int padding, const float* rgbx, const float* g_warped, Slot* ws, int accumulate, int B, int H, int W,
                           cudaStream_t cs) {
-    dim3 flat((W + 31) / 32, (H + kFlatTiles * kFlatTileH - 1) / (kFlatTiles * kFlatTileH), B * n_preds * n_views);
+    dim3 flat((W + 31) / 32, (H + kAdjTiles * kFlatTileH - 1) / (kAdjTiles * kFlatTileH), B * n_preds * n_views);
     const bool add = accumulate != 0 || n_views > 1;
     if (add && accumulate == 0) {
         const size_t n = static_cast<size_t>(B) * H * W;
@@ -1658,7 +1692,7 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
     if (warped_save != nullptr) {
         if (!(flags & DROSFM_PHOTO_WARPED_READY)) {
-            dim3 flat((W + 31) / 32, (H + kFlatTiles * kFlatTileH - 1) / (kFlatTiles * kFlatTileH), B * n_preds * n_views);
+            dim3 flat((W + 31) / 32, (H + kFwdTiles * kFlatTileH - 1) / (kFwdTiles * kFlatTileH), B * n_preds * n_views);
             warp_sources_kernel<false><<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, opts->padding, nullptr,
                                                                       warped_save, B, H, W);
             if (int e = launch_status("photometric_fwd (warp_sources)")) return e;
@@ -1762,7 +1796,7 @@ int drosfm_warp_sources_fwd(const float* const* context, int n_views, const floa
     PhotoPtrs pp{};
     if (int e = fill_ptrs(pp, context, n_views, inv_depths, n_preds, poses, 1.0f)) return e;
     DROSFM_REQUIRE(static_cast<long long>(B) * n_preds * n_views <= 65535, DROSFM_ERANGE, "warp_sources_fwd: B * n_preds * n_views too large");
-    dim3 flat((W + 31) / 32, (H + kFlatTiles * kFlatTileH - 1) / (kFlatTiles * kFlatTileH), B * n_preds * n_views);
+    dim3 flat((W + 31) / 32, (H + kFwdTiles * kFlatTileH - 1) / (kFwdTiles * kFlatTileH), B * n_preds * n_views);
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
     if (rgbx != nullptr) {
         DROSFM_REQUIRE(aligned16(rgbx), DROSFM_EALIGN, "warp_sources_fwd: rgbx must be 16-byte aligned");
