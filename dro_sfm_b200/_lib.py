@@ -43,7 +43,8 @@ class Cams(ctypes.Structure):
 class PhotoOpts(ctypes.Structure):
     """drosfm_photo_opts_t"""
     _fields_ = [("ssim_w", _f32), ("C1", _f32), ("C2", _f32), ("padding", ctypes.c_int32),
-                ("reduce_op", ctypes.c_int32), ("automask", ctypes.c_int32), ("gamma", _f32)]
+                ("reduce_op", ctypes.c_int32), ("automask", ctypes.c_int32), ("gamma", _f32), ("clip_loss", _f32),
+                ("clip_scratch", _vp)]
 
 
 class CostJob(ctypes.Structure):

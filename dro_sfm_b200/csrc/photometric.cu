@@ -224,18 +224,39 @@ constexpr int kFwdThreads = 512, kFwdGroups = kFwdThreads / 32;
 constexpr int FW = 32, FH = 64, FSW = FW + 2, FSH = FH + 2, FRPT = FH / kFwdGroups;
 constexpr int kFwdSmemBytes = 2 * 3 * FSH * FSW * static_cast<int>(sizeof(float));
 
+// clip_loss > 0 (calc_photometric_loss, multiview_photometric_loss_mf.py:220-227): every photometric map -- one per
+// (prediction, view), plus the V un-warped maps of the auto-mask -- is clamped at mean + clip * std of that map.  One slot
+// of the caller's scratch per map: the sums of the statistics pass, then the threshold.
+struct alignas(8) ClipSlot {
+    double s1, s2;       // sum and sum of squares of the map (statistics pass)
+    float thr, pad_;     // min(map, thr) afterwards
+    double pad2_;
+};
+static_assert(sizeof(ClipSlot) == 32, "ClipSlot is 8 floats of drosfm_photo_opts_t.clip_scratch");
+
+__global__ void clip_threshold_kernel(ClipSlot* slots, int count, double n_elems, float clip) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const double mean = slots[i].s1 / n_elems;
+    const double var = n_elems > 1.0 ? (slots[i].s2 - n_elems * mean * mean) / (n_elems - 1.0) : 0.0;     // torch.std: unbiased
+    // the reference forms mean + clip * std from float32 tensors (and then takes float())
+    slots[i].thr = __fadd_rn(static_cast<float>(mean), __fmul_rn(clip, static_cast<float>(sqrt(var > 0.0 ? var : 0.0))));
+}
+
 // SAVED: the warped sources come from warp_sources_kernel's output instead of being sampled here.
-template <int MODE, bool SAVED>
+// STATS: statistics pass of the clipped loss -- only the sums of every map are produced (into `clip`).
+template <int MODE, bool SAVED, bool STATS = false>
 __global__ void __launch_bounds__(kFwdThreads, (SAVED || MODE == 1) ? 2 : 1)
 photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ PhotoPtrs pp, int V, int depth_kind, int n_preds,
                        drosfm_cams_t cams, const float* __restrict__ automask_in, drosfm_photo_opts_t opts,
                        float l1_w, uint8_t* __restrict__ sel_out, float* __restrict__ automask_out,
-                       float* __restrict__ loss, Slot* ws, const float* __restrict__ warped_save, int B, int H, int W) {
+                       float* __restrict__ loss, Slot* ws, const float* __restrict__ warped_save, ClipSlot* clip,
+                       int B, int H, int W) {
     extern __shared__ float smem[];
     float* ys = smem;                        // [3][FSH][FSW]
     float* xs = smem + 3 * FSH * FSW;        // [3][FSH][FSW]
     __shared__ Cam cam_s[(MODE == 0 && !SAVED) ? DROSFM_MAX_VIEWS : 1];
-    __shared__ double red[kFwdGroups];
+    __shared__ double red[2 * kFwdGroups];
     __shared__ int flag;
     constexpr int PLANE = FSH * FSW;
     const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
@@ -306,18 +327,32 @@ photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ 
                 xcb = xc; ycb = yc;
             }
         }
+        // the map's slot in the clip scratch: the V un-warped maps first, then (prediction, view)
+        ClipSlot* cslot = clip != nullptr ? clip + (MODE == 1 ? v : V + ip * V + v) : nullptr;
+        const float thr = (!STATS && cslot != nullptr) ? cslot->thr : __int_as_float(0x7f800000);
+        float st[2] = {0.0f, 0.0f};
 #pragma unroll
         for (int k = 0; k < FRPT; ++k) {
-            const float pm = __fadd_rn(__fmul_rn(opts.ssim_w, __fdiv_rn(ssim_acc[k], 3.0f)),
-                                       __fmul_rn(l1_w, __fdiv_rn(l1_acc[k], 3.0f)));
+            float pm = __fadd_rn(__fmul_rn(opts.ssim_w, __fdiv_rn(ssim_acc[k], 3.0f)),
+                                 __fmul_rn(l1_w, __fdiv_rn(l1_acc[k], 3.0f)));
+            if (STATS) {
+                if (gy0 + k < H && gx < W) { st[0] += pm; st[1] += pm * pm; }
+                continue;
+            }
+            const bool clipped = pm > thr;           // torch.clamp(max=thr): the value becomes thr, its gradient zero
+            pm = clipped ? thr : pm;
             if (use_min) {
-                if (pm < best[k]) { best[k] = pm; sel[k] = v; }
+                if (pm < best[k]) { best[k] = pm; sel[k] = clipped ? 254 : v; }
             } else {
                 best[k] += pm;
+                if (v == 0) sel[k] = 0;
+                if (!clipped) sel[k] |= 1 << v;      // 'mean': bit v = view v carries a gradient at this pixel
             }
         }
+        if (STATS) block_accumulate<2>(st, red, &cslot->s1);
         __syncthreads();
     }
+    if (STATS) return;
 
     // epilogue
     float local = 0.0f;
@@ -341,6 +376,7 @@ photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ 
         }
     }
     if (MODE == 1) return;
+    __syncthreads();
     double part = warp_sum(static_cast<double>(local));
     if (lane == 0) red[grp] = part;
     __syncthreads();
@@ -396,6 +432,7 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
     const int P = H * W;
     const float wm1 = static_cast<float>(W - 1), hm1 = static_cast<float>(H - 1);
     const bool use_min = opts.reduce_op == DROSFM_REDUCE_MIN;
+    const bool mask_mode = !use_min && opts.clip_loss > 0.0f;
     const float G = __ldg(g_loss) * pp.weight[ip] /
                     (static_cast<float>(B) * static_cast<float>(P) * (use_min ? 1.0f : static_cast<float>(V)));
     const float kp = G * opts.ssim_w * (-1.0f / 6.0f) * (2.0f / 9.0f);   // d loss / d ssim  x  2/9 of the window derivative
@@ -411,9 +448,12 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
             const int ry = idx / CW, rx = idx - ry * CW;
             const int gy = cy0 + ry, gx = cx0 + rx;
             const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
-            const int sv = in ? (use_min ? sel_in[(static_cast<size_t>(ip) * B + b) * P + gy * W + gx] : 253) : 254;
+            // min: the winning view (254 none, 255 auto-mask); mean: 253 = every view; mean with a clipped loss: bit v =
+            // view v was not clipped at this pixel (mask_mode)
+            const int raw = in && (use_min || mask_mode) ? sel_in[(static_cast<size_t>(ip) * B + b) * P + gy * W + gx] : 0;
+            const int sv = mask_mode ? (in ? raw : 0) : (in ? (use_min ? raw : 253) : 254);
             selt[idx] = static_cast<uint8_t>(sv);
-            seen |= sv == 253 ? 0xffffffffu : (sv < 32 ? 1u << sv : 0u);
+            seen |= mask_mode ? static_cast<unsigned>(sv) : (sv == 253 ? 0xffffffffu : (sv < 32 ? 1u << sv : 0u));
         }
         seen = __reduce_or_sync(0xffffffffu, seen);
         if (lane == 0 && seen) atomicOr(&present, seen);
@@ -484,7 +524,7 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
                         const int r = prow0 + j - 2;
                         float a = 0.0f, bb = 0.0f, cq = 0.0f;
                         const int sv = selt[r * CW + lane];
-                        if (sv == v || sv == 253) {
+                        if (mask_mode ? ((sv >> v) & 1) != 0 : (sv == v || sv == 253)) {
                             const Ssim s = ssim_from(add3(ra, rb, rc), opts.C1, opts.C2);
                             const float l = (1.0f - s.s) * 0.5f;
                             if (l >= 0.0f && l <= 1.0f) {
@@ -531,7 +571,7 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
                         const float xq = xs[c * SPLANE + (r + 1) * BSW + lane + 1], yq = ys[c * SPLANE + (r + 1) * BSW + lane + 1];
                         float gxv = ga + gb * xq + gc * yq;
                         const int sv = selt[r * CW + lane];
-                        if (sv == v || sv == 253) {
+                        if (mask_mode ? ((sv >> v) & 1) != 0 : (sv == v || sv == 253)) {
                             const float df = xq - yq;
                             gxv += df > 0.0f ? kl1 : (df < 0.0f ? -kl1 : 0.0f);
                         }
@@ -643,7 +683,7 @@ constexpr int kFlatTileH = (kFlatThreads / 32) * kFlatRows;       // one tile: 3
 #define DROSFM_ADJ_UNROLL 1
 #endif
 #ifndef DROSFM_ADJ_ILP
-#define DROSFM_ADJ_ILP 2
+#define DROSFM_ADJ_ILP 1      // rows interleaved per iteration: 1 -> 203 us, 2 -> 205 us, 4 -> 323 us (registers)
 #endif
 constexpr int kFwdTiles = DROSFM_FWD_TILES, kAdjTiles = DROSFM_ADJ_TILES;   // tiles a block walks down (amortises its camera set-up)
 
@@ -1603,6 +1643,10 @@ static int allow_big_smem() {
     if (e == cudaSuccess && dev != done_for_device) {
         e = cudaFuncSetAttribute(photometric_fwd_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
         if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(photometric_fwd_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(photometric_fwd_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
+        if (e == cudaSuccess)
             e = cudaFuncSetAttribute(photometric_fwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(photometric_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
@@ -1642,8 +1686,20 @@ int drosfm_automask_fwd(const float* image, const float* const* context, int n_v
     drosfm_cams_t none{};
     dim3 grid((W + FW - 1) / FW, (H + FH - 1) / FH, B);
     if (int e = allow_big_smem()) return e;
-    photometric_fwd_kernel<1, false><<<grid, kFwdThreads, kFwdSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-        image, pp, n_views, DROSFM_DEPTH, 1, none, nullptr, o, l1_weight(opts), nullptr, automask, nullptr, nullptr, nullptr, B, H, W);
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    ClipSlot* clip = nullptr;
+    if (opts->clip_loss > 0.0f) {
+        // statistics pass over the V un-warped maps, then their thresholds (slots 0..V-1 of the zero-filled scratch)
+        DROSFM_REQUIRE(opts->clip_scratch != nullptr, DROSFM_EINVAL, "automask_fwd: clip_loss > 0 needs opts->clip_scratch");
+        clip = reinterpret_cast<ClipSlot*>(opts->clip_scratch);
+        photometric_fwd_kernel<1, false, true><<<grid, kFwdThreads, kFwdSmemBytes, cs>>>(
+            image, pp, n_views, DROSFM_DEPTH, 1, none, nullptr, o, l1_weight(opts), nullptr, nullptr, nullptr, nullptr, nullptr, clip, B, H, W);
+        if (int e = launch_status("automask_fwd (statistics)")) return e;
+        clip_threshold_kernel<<<1, 64, 0, cs>>>(clip, n_views, static_cast<double>(B) * H * W, opts->clip_loss);
+        if (int e = launch_status("automask_fwd (thresholds)")) return e;
+    }
+    photometric_fwd_kernel<1, false><<<grid, kFwdThreads, kFwdSmemBytes, cs>>>(
+        image, pp, n_views, DROSFM_DEPTH, 1, none, nullptr, o, l1_weight(opts), nullptr, automask, nullptr, nullptr, nullptr, clip, B, H, W);
     return launch_status("automask_fwd");
 }
 
@@ -1681,6 +1737,8 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
                    "photometric_fwd: pose_kind must be MAT4 or EULER6");
     DROSFM_REQUIRE(loss != nullptr && ws != nullptr, DROSFM_EINVAL, "photometric_fwd: NULL loss/ws");
     DROSFM_REQUIRE(opts->reduce_op == DROSFM_REDUCE_MEAN || sel != nullptr, DROSFM_EINVAL, "photometric_fwd: min needs sel");
+    DROSFM_REQUIRE(!(opts->clip_loss > 0.0f) || (warped_save == nullptr && opts->clip_scratch != nullptr && sel != nullptr), DROSFM_ENOTSUP,
+                   "photometric_fwd: clip_loss > 0 runs on the fused path (warped_save == NULL) and needs opts->clip_scratch and sel");
     DROSFM_REQUIRE(!(opts->automask && opts->reduce_op != DROSFM_REDUCE_MIN), DROSFM_EINVAL,
                    "photometric_fwd: auto-masking needs the min reduce op");
     DROSFM_REQUIRE(!opts->automask || automask != nullptr, DROSFM_EINVAL, "photometric_fwd: automask map is NULL");
@@ -1711,12 +1769,25 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
         } else {
             photometric_fwd_kernel<0, true><<<grid, kFwdThreads, kFwdSmemBytes, cs>>>(
                 image, pp, n_views, depth_kind, n_preds, *cams, opts->automask ? automask : nullptr, *opts, l1_weight(opts), sel,
-                nullptr, loss, static_cast<Slot*>(ws), warped_save, B, H, W);
+                nullptr, loss, static_cast<Slot*>(ws), warped_save, nullptr, B, H, W);
         }
     } else {
+        ClipSlot* clip = nullptr;
+        if (opts->clip_loss > 0.0f) {
+            // statistics pass over the n_preds x V warped maps, then their thresholds (slots V.. of the scratch; the first V
+            // belong to the un-warped maps of drosfm_automask_fwd)
+            clip = reinterpret_cast<ClipSlot*>(opts->clip_scratch);
+            photometric_fwd_kernel<0, false, true><<<grid, kFwdThreads, kFwdSmemBytes, cs>>>(
+                image, pp, n_views, depth_kind, n_preds, *cams, nullptr, *opts, l1_weight(opts), nullptr, nullptr, nullptr, nullptr,
+                nullptr, clip, B, H, W);
+            if (int e = launch_status("photometric_fwd (statistics)")) return e;
+            clip_threshold_kernel<<<(n_preds * n_views + 63) / 64, 64, 0, cs>>>(clip + n_views, n_preds * n_views,
+                                                                                static_cast<double>(B) * H * W, opts->clip_loss);
+            if (int e = launch_status("photometric_fwd (thresholds)")) return e;
+        }
         photometric_fwd_kernel<0, false><<<grid, kFwdThreads, kFwdSmemBytes, cs>>>(
             image, pp, n_views, depth_kind, n_preds, *cams, opts->automask ? automask : nullptr, *opts, l1_weight(opts), sel,
-            nullptr, loss, static_cast<Slot*>(ws), nullptr, B, H, W);
+            nullptr, loss, static_cast<Slot*>(ws), nullptr, clip, B, H, W);
     }
     return launch_status("photometric_fwd");
 }
@@ -1735,6 +1806,8 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
                    "photometric_bwd: pose_kind must be MAT4 or EULER6");
     DROSFM_REQUIRE(g_loss != nullptr, DROSFM_EINVAL, "photometric_bwd: NULL g_loss");
     DROSFM_REQUIRE(opts->reduce_op == DROSFM_REDUCE_MEAN || sel != nullptr, DROSFM_EINVAL, "photometric_bwd: min needs sel");
+    DROSFM_REQUIRE(!(opts->clip_loss > 0.0f) || (warped_save == nullptr && sel != nullptr), DROSFM_ENOTSUP,
+                   "photometric_bwd: clip_loss > 0 runs on the fused path (warped_save == NULL) and needs the forward's sel");
     DROSFM_REQUIRE((warped_save == nullptr) == (g_warped == nullptr), DROSFM_EINVAL,
                    "photometric_bwd: warped_save and g_warped go together (both NULL: fused path)");
     PhotoPtrs pp{};

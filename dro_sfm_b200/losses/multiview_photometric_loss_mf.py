@@ -57,10 +57,6 @@ class MultiViewPhotometricDecayLoss(LossBase):
                 'For automasking only the min photometric_reduce_op is supported.'
         if self.photometric_reduce_op not in ('min', 'mean'):
             raise NotImplementedError('Unknown photometric_reduce_op: {}'.format(self.photometric_reduce_op))
-        if self.clip_loss > 0.0:
-            # The reference clips each map at mean + clip*std with a host sync per map (lines 223-227);
-            # every shipped config sets clip_loss: 0.0 (configs/default_config.py:103).
-            raise NotImplementedError("dro_sfm_b200: clip_loss > 0 is not implemented; the configs use clip_loss=0.0")
 
     @property
     def logs(self):
@@ -87,7 +83,7 @@ class MultiViewPhotometricDecayLoss(LossBase):
             image, list(context), list(inv_depths), K, ref_K, self._pose_mats(poses, self.n),
             ssim_w=self.ssim_loss_weight, C1=self.C1, C2=self.C2, reduce_op=self.photometric_reduce_op,
             padding_mode=self.padding_mode, automask=self.automask_loss, smooth_w=self.smooth_loss_weight,
-            gamma=0.85, inverse_depth=True, want_selection=True)
+            gamma=0.85, inverse_depth=True, want_selection=True, clip=self.clip_loss)
         if self.smooth_loss_weight > 0.0:
             self.add_metric('smoothness_loss', terms[1])
             # reference quirk: 'photometric_loss' aliases the tensor that `loss += smoothness` then

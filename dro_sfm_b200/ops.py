@@ -665,7 +665,7 @@ class _PhotoLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, image, K, Kref, cfg, V, n, *tensors):
-        ssim_w, C1, C2, padding, reduce_op, automask, gamma, smooth_w, depth_kind = cfg
+        ssim_w, C1, C2, padding, reduce_op, automask, gamma, smooth_w, depth_kind, clip = cfg
         context = [L.f32c(x) for x in tensors[:V]]
         invs = [L.f32c(x) for x in tensors[V:V + n]]
         poses = [L.f32c(x) for x in tensors[V + n:]]
@@ -675,13 +675,17 @@ class _PhotoLoss(torch.autograd.Function):
         dev = image.device
         kind = _pose_kind(poses[0])
         cams, keep = L.make_cams(K, Kref, 1.0, None, None, None, kind)
-        opts = L.PhotoOpts(ssim_w, C1, C2, padding, reduce_op, int(automask), gamma)
+        # clip_loss > 0: per-map thresholds from a statistics pass (fused path only); the scratch holds one 8-float slot
+        # per photometric map and must be zero on entry
+        clip_scratch = torch.zeros(8 * (V + n * V), device=dev, dtype=torch.float32) if clip > 0.0 else None
+        opts = L.PhotoOpts(ssim_w, C1, C2, padding, reduce_op, int(automask), gamma, clip,
+                           None if clip_scratch is None else clip_scratch.data_ptr())
         # [photometric, smoothness]: each written by its kernel's finisher (zero only if there is no smoothness term)
         losses = (torch.empty if smooth_w > 0.0 else torch.zeros)(2, device=dev, dtype=torch.float32)
-        sel = torch.empty(n, B, H, W, device=dev, dtype=torch.uint8) if reduce_op == L.REDUCE_MIN else None
+        sel = torch.empty(n, B, H, W, device=dev, dtype=torch.uint8) if (reduce_op == L.REDUCE_MIN or clip > 0.0) else None
         # staged path (12 bytes per pixel, view and prediction): the sources are warped once by a flat kernel and
         # the SSIM kernels of both passes read the result; without it everything runs fused and keeps nothing
-        keep_warp = SAVE_WARP and any(ctx.needs_input_grad[6 + V:])
+        keep_warp = SAVE_WARP and any(ctx.needs_input_grad[6 + V:]) and not clip > 0.0
         wsave = torch.empty(n, V, B, 3, H, W, device=dev, dtype=torch.float32) if keep_warp else None
         stats = torch.empty(n, B, 4, device=dev, dtype=torch.float32) if smooth_w > 0.0 else None
         # source pictures as RGBx texels for the flat warp and its adjoint (one 128-bit gather per tap)
@@ -741,7 +745,7 @@ class _PhotoLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_total, *unused):
-        ssim_w, C1, C2, padding, reduce_op, automask, gamma, smooth_w, depth_kind = ctx.cfg
+        ssim_w, C1, C2, padding, reduce_op, automask, gamma, smooth_w, depth_kind, clip = ctx.cfg
         V, n, kind = ctx.V, ctx.n, ctx.kind
         image, K, Kref, sel, stats, wsave, rgbx = ctx.saved_tensors[:7]
         rest = ctx.saved_tensors[7:]
@@ -755,7 +759,7 @@ class _PhotoLoss(torch.autograd.Function):
         need_pose = [need[6 + V + n + k] for k in range(V * n)]
         g = L.f32c(g_total.reshape(1))
         cams, _ = L.make_cams(K, Kref, 1.0, None, None, None, kind)
-        opts = L.PhotoOpts(ssim_w, C1, C2, padding, reduce_op, int(automask), gamma)
+        opts = L.PhotoOpts(ssim_w, C1, C2, padding, reduce_op, int(automask), gamma, clip, None)
         g_inv_slab = torch.empty(n, *invs[0].shape, device=dev, dtype=torch.float32) if any(need_inv) else None
         g_invs = [g_inv_slab[i] if need_inv[i] else None for i in range(n)]
         g_pose_slab = torch.empty(V * n, *poses[0].shape, device=dev, dtype=torch.float32) if any(need_pose) else None
@@ -796,13 +800,16 @@ class _PhotoLoss(torch.autograd.Function):
 
 
 def photometric_loss(image, context, inv_depths, K, ref_K, poses, ssim_w=0.85, C1=1e-4, C2=9e-4, reduce_op="min",
-                     padding_mode="zeros", automask=True, smooth_w=0.001, gamma=0.85, inverse_depth=True, want_selection=False):
+                     padding_mode="zeros", automask=True, smooth_w=0.001, gamma=0.85, inverse_depth=True, want_selection=False,
+                     clip=0.0):
     """MultiViewPhotometricDecayLoss.forward (multiview_photometric_loss_mf.py:303-361), fused.
 
     context: V source images; inv_depths: n predictions [B,1,H,W]; poses[v][i]: [B,4,4] or [B,6].
     Returns (total [1], terms [2]) with terms = detached [photometric, smoothness] values; with want_selection also
     the arg-min view per pixel of every prediction ([n,B,H,W] uint8; 255 = an un-warped / auto-mask map won; None for the
-    'mean' reduce op)."""
+    'mean' reduce op).  clip > 0: every photometric map is clamped at its mean + clip * std (lines 220-227 of the
+    reference; thresholds from a statistics pass on the device, no host synchronisation; the selection then reads 254
+    where the winning map was clipped, and for 'mean' it is the bit mask of the un-clipped views)."""
     V, n = len(context), len(inv_depths)
     if not (1 <= V <= L.MAX_VIEWS and 1 <= n <= L.MAX_PREDS):
         raise ValueError("photometric_loss supports 1..{} views and 1..{} predictions".format(L.MAX_VIEWS, L.MAX_PREDS))
@@ -817,7 +824,7 @@ def photometric_loss(image, context, inv_depths, K, ref_K, poses, ssim_w=0.85, C
             raise NotImplementedError("dro_sfm_b200: predictions must be at the image resolution")
     _no_grad_for("K", K)
     cfg = (float(ssim_w), float(C1), float(C2), _padding(padding_mode), _reduce_op(reduce_op), bool(automask), float(gamma),
-           float(smooth_w), L.INV_DEPTH if inverse_depth else L.DEPTH)
+           float(smooth_w), L.INV_DEPTH if inverse_depth else L.DEPTH, float(clip))
     flat = [p for pv in poses for p in pv]
     out = _PhotoLoss.apply(image, K, ref_K, cfg, V, n, *context, *inv_depths, *flat)
     if want_selection:

@@ -184,6 +184,14 @@ typedef struct {
     int32_t reduce_op;   /* DROSFM_REDUCE_MIN | DROSFM_REDUCE_MEAN */
     int32_t automask;    /* 1: un-warped source maps compete in the per-pixel min (min only) */
     float gamma;         /* decay over predictions: weight_i = gamma^(n-1-i) (0.85) */
+    /* clip_loss > 0 (calc_photometric_loss, multiview_photometric_loss_mf.py:220-227): every photometric map is clamped at
+     * mean + clip_loss * std of that map (unbiased std over B*H*W).  Costs one extra statistics pass per call; runs on the
+     * fused path only (warped_save == NULL).  clip_scratch: 8 * (n_views + n_preds * n_views) floats of device memory,
+     * 8-byte aligned, ZERO-FILLED by the caller before drosfm_automask_fwd / drosfm_photometric_fwd of a step (the first
+     * n_views slots belong to the un-warped maps).  With clip_loss > 0, sel is required for both reduce ops: for 'mean' it
+     * receives the bit mask of the views that were NOT clipped at the pixel (their gradient survives). */
+    float clip_loss;
+    float* clip_scratch;
 } drosfm_photo_opts_t;
 
 /* flags of drosfm_photometric_fwd / _bwd (staged path only) */

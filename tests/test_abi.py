@@ -39,7 +39,7 @@ def test_structs_match_header_layout():
     # drosfm_cams_t: 2 pointers, int32, 2 floats, (pad), 2 pointers, int32 (+pad) on LP64
     assert ctypes.sizeof(_lib.Cams) == 56
     assert _lib.Cams.Twc.offset == 32 and _lib.Cams.pose_kind.offset == 48
-    assert ctypes.sizeof(_lib.PhotoOpts) == 28
+    assert ctypes.sizeof(_lib.PhotoOpts) == 40 and _lib.PhotoOpts.clip_scratch.offset == 32
     assert ctypes.sizeof(_lib.CostJob) == 56 and _lib.CostJob.cost.offset == 40 and _lib.CostJob.disp_range.offset == 52
     assert ctypes.sizeof(_lib.CostJobGrads) == 48 and _lib.CostJobGrads.flags.offset == 40
 
