@@ -148,7 +148,7 @@ view_synthesis_fwd_kernel(const float* __restrict__ src, const float* __restrict
                           int padding) {
     __shared__ Cam cam;
     const int b = blockIdx.y, P = H * W;
-    const float wm1 = static_cast<float>(W - 1), hm1 = static_cast<float>(H - 1);
+    const Norm nm = make_norm(W, H);
     constexpr int PX = VEC ? 4 : 1;
     const int p0 = (blockIdx.x * kThreads + threadIdx.x) * PX;
     float d[PX];
@@ -170,7 +170,7 @@ view_synthesis_fwd_kernel(const float* __restrict__ src, const float* __restrict
         int x, y;
         pix_xy(p0 + k, W, x, y);
         Warp wp;
-        warp_pixel<true>(cam, x, y, to_depth(d[k], depth_kind), wm1, hm1, true, wp);
+        warp_pixel_fast(cam, x, y, to_depth_fast(d[k], depth_kind), nm, true, wp);
         make_taps(wp.p.u, wp.p.v, Hs, Ws, padding, t[k]);
         w[k] = tap_weights(t[k]);
     }
@@ -195,7 +195,8 @@ view_synthesis_bwd_kernel(const float* __restrict__ g_out, const float* __restri
     __shared__ double red[12 * (kThreads / 32)];
     __shared__ int flag;
     const int b = blockIdx.y, P = H * W;
-    const float wm1 = static_cast<float>(W - 1), hm1 = static_cast<float>(H - 1);
+    const Norm nm = make_norm(W, H);
+    const float wm1 = nm.wm1, hm1 = nm.hm1;
     if (threadIdx.x == 0) setup_cam(cams, cams.pose, b, cam);
     __syncthreads();
     float gT[12];
@@ -217,7 +218,7 @@ view_synthesis_bwd_kernel(const float* __restrict__ g_out, const float* __restri
             int x, y;
             pix_xy(p, W, x, y);
             dv = __ldg(depth + static_cast<size_t>(b) * P + p);
-            warp_pixel<true>(cam, x, y, to_depth(dv, depth_kind), wm1, hm1, true, wp);
+            warp_pixel_fast(cam, x, y, to_depth_fast(dv, depth_kind), nm, true, wp);
             make_taps(wp.p.u, wp.p.v, Hs, Ws, padding, t);
         }
         const Weights w = tap_weights(t);
@@ -237,7 +238,7 @@ view_synthesis_bwd_kernel(const float* __restrict__ g_out, const float* __restri
             if (g_src != nullptr) scatter_taps(g_src + (static_cast<size_t>(b) * C + ch) * sp, Ws, t, w, m, g);
         }
         if (active) {
-            const float gd = warp_pixel_adjoint(cam, wp, to_depth(dv, depth_kind), wm1, hm1, true, gx * t.mx, gy * t.my, gT);
+            const float gd = warp_pixel_adjoint(cam, wp, to_depth_fast(dv, depth_kind), wm1, hm1, true, gx * t.mx, gy * t.my, gT);
             if (g_depth != nullptr)
                 g_depth[static_cast<size_t>(b) * P + p] = depth_kind == DROSFM_INV_DEPTH ? inv2depth_grad(dv, gd) : gd;
         }
