@@ -532,7 +532,6 @@ feat_cost_bwd_nhwc(const __grid_constant__ CostJobs jobs, const __grid_constant_
             };
             STap t = wt[v];
             PixLoad cur = fetch(0, t);
-            const float2 frac = mine ? wg[lane * VT + v] : make_float2(0.f, 0.f);
             for (int j = 0; j < npix; ++j) {
                 STap tn = t;
                 PixLoad nxt = cur;
@@ -567,14 +566,24 @@ feat_cost_bwd_nhwc(const __grid_constant__ CostJobs jobs, const __grid_constant_
                     const float4 bq = make_float4(cur.b.x * m1, cur.b.y * m1, cur.b.z * m1, cur.b.w * m1);
                     const float4 c4 = make_float4(cur.c.x * m2, cur.c.y * m2, cur.c.z * m2, cur.c.w * m2);
                     const float4 e = make_float4(cur.e.x * m3, cur.e.y * m3, cur.e.z * m3, cur.e.w * m3);
-                    float s01 = co.x * (bq.x - a.x) + co.y * (bq.y - a.y) + co.z * (bq.z - a.z) + co.w * (bq.w - a.w);
-                    float s23 = co.x * (e.x - c4.x) + co.y * (e.y - c4.y) + co.z * (e.z - c4.z) + co.w * (e.w - c4.w);
-                    float s02 = co.x * (c4.x - a.x) + co.y * (c4.y - a.y) + co.z * (c4.z - a.z) + co.w * (c4.w - a.w);
-                    float s13 = co.x * (e.x - bq.x) + co.y * (e.y - bq.y) + co.z * (e.z - bq.z) + co.w * (e.w - bq.w);
-                    s01 = warp_sum(s01); s23 = warp_sum(s23); s02 = warp_sum(s02); s13 = warp_sum(s13);
+                    const float s01 = co.x * (bq.x - a.x) + co.y * (bq.y - a.y) + co.z * (bq.z - a.z) + co.w * (bq.w - a.w);
+                    const float s23 = co.x * (e.x - c4.x) + co.y * (e.y - c4.y) + co.z * (e.z - c4.z) + co.w * (e.w - c4.w);
+                    const float s02 = co.x * (c4.x - a.x) + co.y * (c4.y - a.y) + co.z * (c4.z - a.z) + co.w * (c4.w - a.w);
+                    const float s13 = co.x * (e.x - bq.x) + co.y * (e.y - bq.y) + co.z * (e.z - bq.z) + co.w * (e.w - bq.w);
+                    // this lane's share of d cost / d (ix, iy) of pixel j (its fractional offsets are broadcast from shared
+                    // memory), then ONE reduce-scatter over the warp: 6 shuffles instead of 4 butterflies of 5
+                    const float2 fr = wg[j * VT + v];
+                    const float px_ = s01 * (1.0f - fr.y) + s23 * fr.y, py_ = s02 * (1.0f - fr.x) + s13 * fr.x;
+                    const bool hi = lane & 16;
+                    float r = xchg_add(hi ? py_ : px_, hi ? px_ : py_, 16);      // lanes 0-15: x share, lanes 16-31: y share
+                    r += __shfl_xor_sync(0xffffffffu, r, 8);
+                    r += __shfl_xor_sync(0xffffffffu, r, 4);
+                    r += __shfl_xor_sync(0xffffffffu, r, 2);
+                    r += __shfl_xor_sync(0xffffffffu, r, 1);
+                    const float other = __shfl_xor_sync(0xffffffffu, r, 16);
                     if (lane == j) {
-                        acc_g[v].x -= s01 * (1.0f - frac.y) + s23 * frac.y;
-                        acc_g[v].y -= s02 * (1.0f - frac.x) + s13 * frac.x;
+                        acc_g[v].x -= hi ? other : r;
+                        acc_g[v].y -= hi ? r : other;
                     }
                 }
                 cur = nxt;
