@@ -327,7 +327,8 @@ def run_gpu(args, wl):
         clocks.start()                                           # sampled from the warm-up through both timed regions
     for _ in range(max(args.warmup, 3)):
         one_step(False)
-        one_step(True)
+        warm_loss = one_step(True)
+    du.average_loss(warm_loss.detach().clone())          # NCCL sets its channels up on the first collective: not in the timed region
     if launches_per_step is None:
         before = L.lib().drosfm_launch_count()
         one_step(False)

@@ -283,6 +283,7 @@ photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ 
     float best[FRPT];
     int sel[FRPT];
     const bool use_min = opts.reduce_op == DROSFM_REDUCE_MIN;
+    const bool l1_only = !(opts.ssim_w > 0.0f);
 #pragma unroll
     for (int k = 0; k < FRPT; ++k) {
         best[k] = use_min ? __int_as_float(0x7f800000) : 0.0f;
@@ -304,6 +305,30 @@ photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ 
         __syncthreads();
 
         // phase B: SSIM + L1 with a vertical sliding window
+        // the map's slot in the clip scratch: the V un-warped maps first, then (prediction, view)
+        ClipSlot* cslot = clip != nullptr ? clip + (MODE == 1 ? v : V + ip * V + v) : nullptr;
+        const float thr = (!STATS && cslot != nullptr) ? cslot->thr : __int_as_float(0x7f800000);
+        float st[2] = {0.0f, 0.0f};
+        // one value of one photometric map at row k of this thread's column: statistics, clip, min / sum.  `code` is what
+        // the selection records when the value wins (the view; for the per-channel L1 maps view + 8 * channel).
+        auto consume = [&](int k, float pm, int code) {
+            if (STATS) {
+                if (gy0 + k < H && gx < W) { st[0] += pm; st[1] += pm * pm; }
+                return;
+            }
+            const bool clipped = pm > thr;           // torch.clamp(max=thr): the value becomes thr, its gradient zero
+            pm = clipped ? thr : pm;
+            if (use_min) {
+                if (pm < best[k]) { best[k] = pm; sel[k] = clipped ? 254 : code; }
+            } else {
+                best[k] += pm;
+                if (!clipped) sel[k] |= 1 << v;      // 'mean': bit v = view v carries a gradient at this pixel
+            }
+        };
+        if (!use_min && v == 0) {
+#pragma unroll
+            for (int k = 0; k < FRPT; ++k) sel[k] = 0;
+        }
         float ssim_acc[FRPT], l1_acc[FRPT];
 #pragma unroll
         for (int k = 0; k < FRPT; ++k) ssim_acc[k] = l1_acc[k] = 0.0f;
@@ -318,36 +343,25 @@ photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ 
                 float xc, yc;
                 const Win rc = row_sums(xc_ + roff[j], yc_ + roff[j], cm, c0, cp, xc, yc);
                 if (j >= 2) {
-                    const Ssim s = ssim_from(add3(ra, rb, rc), opts.C1, opts.C2);
-                    const float l = (1.0f - s.s) * 0.5f;
-                    ssim_acc[j - 2] += fminf(fmaxf(l, 0.0f), 1.0f);
-                    l1_acc[j - 2] += fabsf(xcb - ycb);
+                    if (l1_only) {
+                        // ssim_loss_weight == 0: the map IS the per-channel |a - b| (three channels per view,
+                        // multiview_photometric_loss_mf.py:217-218), every channel competes in the min on its own
+                        consume(j - 2, fabsf(xcb - ycb), v + 8 * c);
+                    } else {
+                        const Ssim s = ssim_from(add3(ra, rb, rc), opts.C1, opts.C2);
+                        const float l = (1.0f - s.s) * 0.5f;
+                        ssim_acc[j - 2] += fminf(fmaxf(l, 0.0f), 1.0f);
+                        l1_acc[j - 2] += fabsf(xcb - ycb);
+                    }
                 }
                 ra = rb; rb = rc;
                 xcb = xc; ycb = yc;
             }
         }
-        // the map's slot in the clip scratch: the V un-warped maps first, then (prediction, view)
-        ClipSlot* cslot = clip != nullptr ? clip + (MODE == 1 ? v : V + ip * V + v) : nullptr;
-        const float thr = (!STATS && cslot != nullptr) ? cslot->thr : __int_as_float(0x7f800000);
-        float st[2] = {0.0f, 0.0f};
+        if (!l1_only) {
 #pragma unroll
-        for (int k = 0; k < FRPT; ++k) {
-            float pm = __fadd_rn(__fmul_rn(opts.ssim_w, __fdiv_rn(ssim_acc[k], 3.0f)),
-                                 __fmul_rn(l1_w, __fdiv_rn(l1_acc[k], 3.0f)));
-            if (STATS) {
-                if (gy0 + k < H && gx < W) { st[0] += pm; st[1] += pm * pm; }
-                continue;
-            }
-            const bool clipped = pm > thr;           // torch.clamp(max=thr): the value becomes thr, its gradient zero
-            pm = clipped ? thr : pm;
-            if (use_min) {
-                if (pm < best[k]) { best[k] = pm; sel[k] = clipped ? 254 : v; }
-            } else {
-                best[k] += pm;
-                if (v == 0) sel[k] = 0;
-                if (!clipped) sel[k] |= 1 << v;      // 'mean': bit v = view v carries a gradient at this pixel
-            }
+            for (int k = 0; k < FRPT; ++k)
+                consume(k, __fadd_rn(__fmul_rn(opts.ssim_w, __fdiv_rn(ssim_acc[k], 3.0f)), __fmul_rn(l1_w, __fdiv_rn(l1_acc[k], 3.0f))), v);
         }
         if (STATS) block_accumulate<2>(st, red, &cslot->s1);
         __syncthreads();
@@ -386,9 +400,10 @@ photometric_fwd_kernel(const float* __restrict__ image, const __grid_constant__ 
         atomicAdd(spread_acc(slot_at(ws, ip)), s);
     }
     Slot* ticket = slot_at(ws, n_preds);
+    // 'mean': every map is averaged over its own elements -- B*P of them, or B*3*P for the per-channel L1 maps
     if (last_block(ticket, gridDim.x * gridDim.y * gridDim.z, &flag) && tid < 32)
-        finish_weighted_means(ws, n_preds, pp.weight, static_cast<double>(B) * P * (use_min ? 1.0 : static_cast<double>(V)), ticket,
-                              loss);
+        finish_weighted_means(ws, n_preds, pp.weight,
+                              static_cast<double>(B) * P * (use_min ? 1.0 : static_cast<double>(V) * (l1_only ? 3.0 : 1.0)), ticket, loss);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -433,10 +448,12 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
     const float wm1 = static_cast<float>(W - 1), hm1 = static_cast<float>(H - 1);
     const bool use_min = opts.reduce_op == DROSFM_REDUCE_MIN;
     const bool mask_mode = !use_min && opts.clip_loss > 0.0f;
+    const bool l1_only = !(opts.ssim_w > 0.0f);        // per-channel L1 maps: the selection is view + 8 * channel
     const float G = __ldg(g_loss) * pp.weight[ip] /
                     (static_cast<float>(B) * static_cast<float>(P) * (use_min ? 1.0f : static_cast<float>(V)));
     const float kp = G * opts.ssim_w * (-1.0f / 6.0f) * (2.0f / 9.0f);   // d loss / d ssim  x  2/9 of the window derivative
-    const float kl1 = G * l1_w * (1.0f / 3.0f);
+    // L1 term: l1_w * mean over the channels; a per-channel L1 map that won the min carries the whole gradient
+    const float kl1 = (l1_only && use_min) ? G : G * l1_w * (1.0f / 3.0f);
 
     if (!SAVED && tid < V) setup_cam(cams, pp.pose[tid * n_preds + ip], b, cam_s[tid]);
     if (tid == 0) present = 0u;
@@ -453,7 +470,7 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
             const int raw = in && (use_min || mask_mode) ? sel_in[(static_cast<size_t>(ip) * B + b) * P + gy * W + gx] : 0;
             const int sv = mask_mode ? (in ? raw : 0) : (in ? (use_min ? raw : 253) : 254);
             selt[idx] = static_cast<uint8_t>(sv);
-            seen |= mask_mode ? static_cast<unsigned>(sv) : (sv == 253 ? 0xffffffffu : (sv < 32 ? 1u << sv : 0u));
+            seen |= mask_mode ? static_cast<unsigned>(sv) : (sv == 253 ? 0xffffffffu : (sv < 32 ? 1u << (sv & 7) : 0u));
         }
         seen = __reduce_or_sync(0xffffffffu, seen);
         if (lane == 0 && seen) atomicOr(&present, seen);
@@ -571,7 +588,7 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
                         const float xq = xs[c * SPLANE + (r + 1) * BSW + lane + 1], yq = ys[c * SPLANE + (r + 1) * BSW + lane + 1];
                         float gxv = ga + gb * xq + gc * yq;
                         const int sv = selt[r * CW + lane];
-                        if (mask_mode ? ((sv >> v) & 1) != 0 : (sv == v || sv == 253)) {
+                        if (mask_mode ? ((sv >> v) & 1) != 0 : (sv == (l1_only ? v + 8 * c : v) || sv == 253)) {
                             const float df = xq - yq;
                             gxv += df > 0.0f ? kl1 : (df < 0.0f ? -kl1 : 0.0f);
                         }
@@ -1625,8 +1642,9 @@ static int check_photo(const float* image, const float* const* context, int n_vi
     DROSFM_REQUIRE(opts->padding == DROSFM_PAD_ZEROS || opts->padding == DROSFM_PAD_BORDER, DROSFM_EINVAL, "photometric: bad padding");
     DROSFM_REQUIRE(opts->reduce_op == DROSFM_REDUCE_MIN || opts->reduce_op == DROSFM_REDUCE_MEAN, DROSFM_EINVAL,
                    "photometric: bad reduce_op");
-    DROSFM_REQUIRE(opts->ssim_w > 0.0f, DROSFM_ENOTSUP,
-                   "photometric: ssim_loss_weight == 0 (per-channel L1 maps) is not supported by the fused kernel");
+    DROSFM_REQUIRE(opts->ssim_w >= 0.0f, DROSFM_EINVAL, "photometric: negative ssim_loss_weight");
+    DROSFM_REQUIRE(opts->ssim_w > 0.0f || !(opts->clip_loss > 0.0f && opts->reduce_op == DROSFM_REDUCE_MEAN), DROSFM_ENOTSUP,
+                   "photometric: per-channel L1 maps (ssim_loss_weight == 0) with clip_loss > 0 need the 'min' reduce op");
     if (B == 0 || H * W == 0) return DROSFM_OK;
     DROSFM_REQUIRE(H >= 2 && W >= 2, DROSFM_ENOTSUP, "photometric: reflection padding needs H, W >= 2");
     DROSFM_REQUIRE(static_cast<long long>(H) * W < (1ll << 28) && B <= 4096, DROSFM_ERANGE, "photometric: dimension out of range");
@@ -1695,7 +1713,7 @@ int drosfm_automask_fwd(const float* image, const float* const* context, int n_v
         photometric_fwd_kernel<1, false, true><<<grid, kFwdThreads, kFwdSmemBytes, cs>>>(
             image, pp, n_views, DROSFM_DEPTH, 1, none, nullptr, o, l1_weight(opts), nullptr, nullptr, nullptr, nullptr, nullptr, clip, B, H, W);
         if (int e = launch_status("automask_fwd (statistics)")) return e;
-        clip_threshold_kernel<<<1, 64, 0, cs>>>(clip, n_views, static_cast<double>(B) * H * W, opts->clip_loss);
+        clip_threshold_kernel<<<1, 64, 0, cs>>>(clip, n_views, static_cast<double>(B) * H * W * (opts->ssim_w > 0.0f ? 1.0 : 3.0), opts->clip_loss);
         if (int e = launch_status("automask_fwd (thresholds)")) return e;
     }
     photometric_fwd_kernel<1, false><<<grid, kFwdThreads, kFwdSmemBytes, cs>>>(
@@ -1739,6 +1757,8 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
     DROSFM_REQUIRE(opts->reduce_op == DROSFM_REDUCE_MEAN || sel != nullptr, DROSFM_EINVAL, "photometric_fwd: min needs sel");
     DROSFM_REQUIRE(!(opts->clip_loss > 0.0f) || (warped_save == nullptr && opts->clip_scratch != nullptr && sel != nullptr), DROSFM_ENOTSUP,
                    "photometric_fwd: clip_loss > 0 runs on the fused path (warped_save == NULL) and needs opts->clip_scratch and sel");
+    DROSFM_REQUIRE(opts->ssim_w > 0.0f || warped_save == nullptr, DROSFM_ENOTSUP,
+                   "photometric_fwd: ssim_loss_weight == 0 runs on the fused path (warped_save == NULL)");
     DROSFM_REQUIRE(!(opts->automask && opts->reduce_op != DROSFM_REDUCE_MIN), DROSFM_EINVAL,
                    "photometric_fwd: auto-masking needs the min reduce op");
     DROSFM_REQUIRE(!opts->automask || automask != nullptr, DROSFM_EINVAL, "photometric_fwd: automask map is NULL");
@@ -1782,7 +1802,7 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
                 nullptr, clip, B, H, W);
             if (int e = launch_status("photometric_fwd (statistics)")) return e;
             clip_threshold_kernel<<<(n_preds * n_views + 63) / 64, 64, 0, cs>>>(clip + n_views, n_preds * n_views,
-                                                                                static_cast<double>(B) * H * W, opts->clip_loss);
+                                                                                static_cast<double>(B) * H * W * (opts->ssim_w > 0.0f ? 1.0 : 3.0), opts->clip_loss);
             if (int e = launch_status("photometric_fwd (thresholds)")) return e;
         }
         photometric_fwd_kernel<0, false><<<grid, kFwdThreads, kFwdSmemBytes, cs>>>(
@@ -1808,6 +1828,8 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
     DROSFM_REQUIRE(opts->reduce_op == DROSFM_REDUCE_MEAN || sel != nullptr, DROSFM_EINVAL, "photometric_bwd: min needs sel");
     DROSFM_REQUIRE(!(opts->clip_loss > 0.0f) || (warped_save == nullptr && sel != nullptr), DROSFM_ENOTSUP,
                    "photometric_bwd: clip_loss > 0 runs on the fused path (warped_save == NULL) and needs the forward's sel");
+    DROSFM_REQUIRE(opts->ssim_w > 0.0f || warped_save == nullptr, DROSFM_ENOTSUP,
+                   "photometric_bwd: ssim_loss_weight == 0 runs on the fused path (warped_save == NULL)");
     DROSFM_REQUIRE((warped_save == nullptr) == (g_warped == nullptr), DROSFM_EINVAL,
                    "photometric_bwd: warped_save and g_warped go together (both NULL: fused path)");
     PhotoPtrs pp{};

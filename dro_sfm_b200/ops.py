@@ -685,7 +685,7 @@ class _PhotoLoss(torch.autograd.Function):
         sel = torch.empty(n, B, H, W, device=dev, dtype=torch.uint8) if (reduce_op == L.REDUCE_MIN or clip > 0.0) else None
         # staged path (12 bytes per pixel, view and prediction): the sources are warped once by a flat kernel and
         # the SSIM kernels of both passes read the result; without it everything runs fused and keeps nothing
-        keep_warp = SAVE_WARP and any(ctx.needs_input_grad[6 + V:]) and not clip > 0.0
+        keep_warp = SAVE_WARP and any(ctx.needs_input_grad[6 + V:]) and not clip > 0.0 and ssim_w > 0.0
         wsave = torch.empty(n, V, B, 3, H, W, device=dev, dtype=torch.float32) if keep_warp else None
         stats = torch.empty(n, B, 4, device=dev, dtype=torch.float32) if smooth_w > 0.0 else None
         # source pictures as RGBx texels for the flat warp and its adjoint (one 128-bit gather per tap)
@@ -817,8 +817,10 @@ def photometric_loss(image, context, inv_depths, K, ref_K, poses, ssim_w=0.85, C
         raise ValueError("poses must be a list of V lists of n transforms")
     if automask and reduce_op != "min":
         raise AssertionError("For automasking only the min photometric_reduce_op is supported.")
-    if ssim_w <= 0.0:
-        raise NotImplementedError("dro_sfm_b200: ssim_loss_weight == 0 is not supported by the fused photometric kernel")
+    if ssim_w < 0.0:
+        raise ValueError("ssim_loss_weight must be >= 0")
+    if ssim_w == 0.0 and clip > 0.0 and reduce_op != "min":
+        raise NotImplementedError("dro_sfm_b200: ssim_loss_weight == 0 with clip_loss > 0 needs photometric_reduce_op='min'")
     for d in inv_depths:
         if tuple(d.shape[-2:]) != tuple(image.shape[-2:]):
             raise NotImplementedError("dro_sfm_b200: predictions must be at the image resolution")

@@ -26,6 +26,8 @@ PHOTO_VARIANTS = {
                                padding_mode="border", ssim_loss_weight=0.85),
     "min_nomask_clip": dict(automask_loss=False, photometric_reduce_op="min", clip_loss=0.5, smooth_loss_weight=0.0,
                             padding_mode="zeros", ssim_loss_weight=0.85),
+    "l1only": dict(automask_loss=True, photometric_reduce_op="min", clip_loss=0.0, smooth_loss_weight=0.0,
+                   padding_mode="zeros", ssim_loss_weight=0.0),
 }
 
 
@@ -234,7 +236,9 @@ def _check_photometric(dataset, B, H, W, V, n, min_depth, max_depth, padding="ze
     assert rc < 0 and b"g_warped" in lib.drosfm_last_error()
 
 
-@pytest.mark.parametrize("kwargs", [dict(), dict(automask_loss=True, photometric_reduce_op="min", clip_loss=0.7)])
+@pytest.mark.parametrize("kwargs", [dict(), dict(automask_loss=True, photometric_reduce_op="min", clip_loss=0.7),
+                                    dict(ssim_loss_weight=0.0, clip_loss=0.0, photometric_reduce_op="mean"),
+                                    dict(ssim_loss_weight=0.0, clip_loss=0.6, photometric_reduce_op="min", automask_loss=True)])
 def test_clipped_photometric_loss_vs_oracle(kwargs):
     """clip_loss > 0 (the CLASS DEFAULT is clip_loss=0.5 with the 'mean' reduce op, multiview_photometric_loss_mf.py:92-95):
     the default-constructed module and a clipped auto-masked 'min' loss against the oracle -- loss, and gradients for the
