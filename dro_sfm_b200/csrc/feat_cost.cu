@@ -296,7 +296,10 @@ feat_cost_bwd_nchw(const float* __restrict__ g_cost, const float* __restrict__ f
 // the update blocks in lock-step submits them together.  At the training shapes a single call is a one-wave launch
 // bound by the latency of one warp's chain; three or more jobs per launch overlap each other's phases.
 // ------------------------------------------------------------------------------------------
-constexpr int kWarpsPerBlock = 4;
+#ifndef DROSFM_COST_WARPS
+#define DROSFM_COST_WARPS 4
+#endif
+constexpr int kWarpsPerBlock = DROSFM_COST_WARPS;      // >= 3 (camera set-up of multi-view jobs uses three warps)
 constexpr int kMaxPpw = 32;
 constexpr int kMaxJobs = DROSFM_MAX_COST_JOBS;
 
@@ -454,10 +457,13 @@ struct PixLoad {
     float4 g, f, a, b, c, e;
 };
 
-// Register budget per template: one and two views fit 5 blocks per SM (<= 102 registers; the 40x120x2 maps of the
-// KITTI configuration launch 600 blocks per job, 4 per SM left a tail wave); four and eight views keep per-view state
-// (fractional offsets, validity) for every view and get 4 / 3 blocks per SM instead of spilling.
-template <int VT> struct BwdBlocks { static constexpr int value = VT <= 2 ? 5 : (VT <= 4 ? 4 : 3); };
+// Register budget per template: four and eight views keep per-view state for every view and get 4 / 3 blocks per SM
+// instead of spilling (round 1's 5 blocks/SM spilled 104 / 256 local-memory accesses in the V = 4 / 8 kernels).
+// one / two views: 4 blocks per SM (128 registers): cost phase of the benchmark step 360 us; 5 blocks 371, 6 blocks 371
+#ifndef DROSFM_COST_BWD_BLOCKS
+#define DROSFM_COST_BWD_BLOCKS 4
+#endif
+template <int VT> struct BwdBlocks { static constexpr int value = (VT <= 2 ? DROSFM_COST_BWD_BLOCKS : (VT <= 4 ? 4 : 3)) * 4 / kWarpsPerBlock; };
 
 template <int VT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, BwdBlocks<VT>::value)

@@ -1200,7 +1200,11 @@ struct FwdRow2 {
     float2 xc[3];
 };
 
-__global__ void __launch_bounds__(kSsimThreads, 2)
+// blocks per SM (B200, benchmark workload): 1 -> 202 us, 2 -> 138, 3 -> 231, 4 -> 326 (spills)
+#ifndef DROSFM_SSIMF_MINBLOCKS
+#define DROSFM_SSIMF_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(kSsimThreads, DROSFM_SSIMF_MINBLOCKS)
 ssim_fwd_stream2_kernel(const float* __restrict__ image, const float* __restrict__ warped, const __grid_constant__ PhotoPtrs pp,
                         int n_preds, const float* __restrict__ automask_in, drosfm_photo_opts_t opts, float l1_w,
                         uint8_t* __restrict__ sel_out, float* __restrict__ loss, Slot* ws, int B, int H, int W, int nstrips,
@@ -1479,10 +1483,14 @@ struct BwdRow2 {
     float2 ha, hb, hc;
 };
 
-// 128-thread blocks, 5 per SM: 102 registers hold the packed state without spills at 20 resident warps
+// 128-thread blocks
 constexpr int kBwd2Threads = 128, kBwd2Warps = kBwd2Threads / 32;
 
-__global__ void __launch_bounds__(kBwd2Threads, 5)
+// blocks per SM (B200, benchmark workload): 3 -> 203.5 us, 4 -> 207, 5 -> 213, 6 -> 270 (spills)
+#ifndef DROSFM_SSIMB_MINBLOCKS
+#define DROSFM_SSIMB_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(kBwd2Threads, DROSFM_SSIMB_MINBLOCKS)
 ssim_bwd_stream2_kernel(const float* __restrict__ g_loss, const float* __restrict__ image, const float* __restrict__ warped,
                         const __grid_constant__ PhotoPtrs pp, int V, const uint8_t* __restrict__ sel_in,
                         drosfm_photo_opts_t opts, float l1_w, float* __restrict__ g_warped, int B, int H, int W, int nstrips,
