@@ -663,12 +663,19 @@ static int channel_group(int P, int B, int C) {
 // NHWC: pixels per warp.  Enough warps to fill the chip several times over wins at small maps (each warp
 // keeps ~5 * ppw 128-bit loads in flight); large maps amortise the per-warp coordinate work over 32 pixels.
 // `units` = pixel-views of the whole launch (all jobs).
-static int pixels_per_warp(long long units) {
+static int pixels_per_warp(long long units, bool backward) {
+    // the forward holds 44-48 registers (all warps of a training-shape launch are resident at once: the more the better);
+    // the backward 90-150 (fewer, longer warps).  Measured on the cost phase of the benchmark steps (fwd / bwd pixels per
+    // warp): KITTI 4/8 = 8/8 = 360 us, 8/4 = 414, 16/16 = 410; ScanNet 5 views 4/8 = 567, 8/8 = 629, 16/16 = 889
+    const long long want = static_cast<long long>(kNumSMs) * (backward ? 32 : 64);
     int ppw = kMaxPpw;
-    while (ppw > 4 && units / ppw < static_cast<long long>(kNumSMs) * 32) ppw /= 2;
-    if (const char* e = std::getenv("DROSFM_PPW")) {        // tuning knob; anything but a supported value is ignored
-        const int v = atoi(e);
-        if (v == 4 || v == 8 || v == 16 || v == 32) ppw = v;
+    while (ppw > 4 && units / ppw < want) ppw /= 2;
+    // tuning knobs (DROSFM_PPW for both directions, DROSFM_PPW_FWD / _BWD for one); anything but a supported value is ignored
+    for (const char* name : {"DROSFM_PPW", backward ? "DROSFM_PPW_BWD" : "DROSFM_PPW_FWD"}) {
+        if (const char* e = std::getenv(name)) {
+            const int v = atoi(e);
+            if (v == 4 || v == 8 || v == 16 || v == 32) ppw = v;
+        }
     }
     return ppw;
 }
@@ -735,7 +742,7 @@ static int fill_jobs(const drosfm_cost_job_t* jobs, const drosfm_cost_job_grads_
 static int launch_cost_fwd_nhwc(const CostJobs& cj, int n_jobs, int max_v, long long units, const drosfm_cams_t* cams,
                                 int B, int C, int h, int w, cudaStream_t s) {
     const int P = h * w, VT = vt_of(max_v);
-    const int ppw = pixels_per_warp(static_cast<long long>(P) * B * units);
+    const int ppw = pixels_per_warp(static_cast<long long>(P) * B * units, false);
     const int per_block = kWarpsPerBlock * ppw;
     dim3 grid((P + per_block - 1) / per_block, B, n_jobs);
     const size_t smem = static_cast<size_t>(kWarpsPerBlock) * ppw * VT * sizeof(STap);
@@ -748,7 +755,7 @@ static int launch_cost_fwd_nhwc(const CostJobs& cj, int n_jobs, int max_v, long 
 static int launch_cost_bwd_nhwc(const CostJobs& cj, const CostJobGrads& cg, int n_jobs, int max_v, long long units,
                                 const drosfm_cams_t* cams, void* ws, int B, int C, int h, int w, cudaStream_t s) {
     const int P = h * w, VT = vt_of(max_v);
-    const int ppw = pixels_per_warp(static_cast<long long>(P) * B * units);
+    const int ppw = pixels_per_warp(static_cast<long long>(P) * B * units, true);
     const int per_block = kWarpsPerBlock * ppw;
     dim3 grid((P + per_block - 1) / per_block, B, n_jobs);
     const size_t smem = static_cast<size_t>(kWarpsPerBlock) * ppw * VT * (sizeof(STap) + sizeof(float2));
