@@ -25,7 +25,7 @@ DEPTH, INV_DEPTH, DISP = 0, 1, 2
 REDUCE_MIN, REDUCE_MEAN = 0, 1
 NCHW, NHWC = 0, 1
 ACCUMULATE_FMAP = 1
-PHOTO_WARPED_READY, PHOTO_NO_ADJOINT = 1, 2
+PHOTO_WARPED_READY, PHOTO_NO_ADJOINT, PHOTO_FUSE_BWD = 1, 2, 4
 SLOT_BYTES = 128
 
 _vp = ctypes.c_void_p
@@ -90,12 +90,12 @@ SIGNATURES = {
     "drosfm_feat_cost_batch_fwd": ([_jp, _int, _cp, _int, _int, _int, _int, _int, _vp], _int),
     "drosfm_feat_cost_batch_bwd": ([_jp, _gp, _int, _cp, _vp, _int, _int, _int, _int, _int, _vp], _int),
     "drosfm_automask_fwd": ([_vp, _pp, _int, _op, _vp, _int, _int, _int, _vp], _int),
-    "drosfm_photometric_fwd": ([_vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _vp, _vp, _vp, _vp,
+    "drosfm_photometric_fwd": ([_vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _vp, _vp, _vp, _vp, _vp,
                                 _int, _int, _int, _int, _vp], _int),
     "drosfm_photometric_bwd": ([_vp, _vp, _pp, _int, _pp, _int, _int, _cp, _pp, _vp, _op, _pp, _pp, _vp, _vp, _vp,
                                 _int, _int, _int, _int, _vp], _int),
     "drosfm_warp_sources_fwd": ([_pp, _int, _pp, _int, _int, _cp, _pp, _int, _vp, _vp, _int, _int, _int, _vp], _int),
-    "drosfm_warp_sources_bwd": ([_vp, _pp, _int, _pp, _int, _int, _cp, _pp, _int, _vp, _pp, _pp, _vp, _int,
+    "drosfm_warp_sources_bwd": ([_vp, _pp, _int, _pp, _int, _int, _cp, _pp, _int, _vp, _vp, _pp, _pp, _vp, _int,
                                  _int, _int, _int, _vp], _int),
     "drosfm_smoothness_fwd": ([_vp, _pp, _int, _f32, _vp, _vp, _vp, _int, _int, _int, _vp], _int),
     "drosfm_smoothness_bwd": ([_vp, _vp, _pp, _int, _f32, _vp, _pp, _int, _int, _int, _int, _vp], _int),

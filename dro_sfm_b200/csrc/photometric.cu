@@ -837,7 +837,7 @@ template <bool PACKED, bool ADD>
 __global__ void __launch_bounds__(kFlatThreads, DROSFM_ADJ_MINBLOCKS)
 warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind, int n_preds, drosfm_cams_t cams,
                             int padding, const float* __restrict__ rgbx, const float* __restrict__ g_warped,
-                            const __grid_constant__ PhotoGrads pg, Slot* ws, int B, int H, int W) {
+                            const float* __restrict__ g_scale, const __grid_constant__ PhotoGrads pg, Slot* ws, int B, int H, int W) {
     __shared__ Cam cam_s;
     __shared__ int flag;
     const int tid = threadIdx.x;
@@ -848,6 +848,8 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
     const Cam& cam = cam_s;                                    // read from shared memory on use: the registers go to occupancy
     const int P = H * W;
     const Norm nm = make_norm(W, H);
+    // g_warped may come unscaled from the training forward (ssim_train_stream2_kernel): times the loss's upstream gradient
+    const float gs = g_scale != nullptr ? __ldg(g_scale) : 1.0f;
     const int x = blockIdx.x * 32 + (tid & 31);
     const int row0 = blockIdx.y * kAdjTiles * kFlatTileH + (tid >> 5);       // first row of this thread; then every 8th
     const bool col_ok = x < W;
@@ -874,7 +876,7 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
             const bool in = col_ok && y < H;
             const unsigned o = in ? static_cast<unsigned>(y * W + x) : 0u;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) gn[r][c] = in ? __ldg(gw + (o + static_cast<unsigned>(c * P))) : 0.0f;
+            for (int c = 0; c < 3; ++c) gn[r][c] = in ? __ldg(gw + (o + static_cast<unsigned>(c * P))) * gs : 0.0f;
             dn[r] = in ? __ldg(invd + o) : 0.0f;
         }
     };
@@ -970,8 +972,8 @@ __global__ void __launch_bounds__(256) zero_inv_grads_kernel(const __grid_consta
 
 // host side of the adjoint launch: accumulate == 0 -> the depth gradients are (over)written, else added to
 static int launch_adjoint(const PhotoPtrs& pp, const PhotoGrads& pg, int n_views, int depth_kind, int n_preds, const drosfm_cams_t* cams,
-                          int padding, const float* rgbx, const float* g_warped, Slot* ws, int accumulate, int B, int H, int W,
-                          cudaStream_t cs) {
+                          int padding, const float* rgbx, const float* g_warped, const float* g_scale, Slot* ws, int accumulate,
+                          int B, int H, int W, cudaStream_t cs) {
     dim3 flat((W + 31) / 32, (H + kAdjTiles * kFlatTileH - 1) / (kAdjTiles * kFlatTileH), B * n_preds * n_views);
     const bool add = accumulate != 0 || n_views > 1;
     if (add && accumulate == 0) {
@@ -981,7 +983,7 @@ static int launch_adjoint(const PhotoPtrs& pp, const PhotoGrads& pg, int n_views
         if (int e = launch_status("warp adjoint (zero fill)")) return e;
     }
 #define ADJ(PK, AD) warp_sources_adjoint_kernel<PK, AD><<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, padding, rgbx, \
-                                                                                     g_warped, pg, ws, B, H, W)
+                                                                                     g_warped, g_scale, pg, ws, B, H, W)
     if (rgbx != nullptr) { if (add) ADJ(true, true); else ADJ(true, false); }
     else { if (add) ADJ(false, true); else ADJ(false, false); }
 #undef ADJ
@@ -1641,6 +1643,203 @@ ssim_bwd_stream2_kernel(const float* __restrict__ g_loss, const float* __restric
     }
 }
 
+// ---- training forward, two views: SSIM forward AND the window gradients in one pass -----------------------------
+// The backward SSIM stage recomputes every window statistic the forward stage had: with the upstream gradient being
+// a scalar factor, d loss / d warped can be produced by the forward itself (unscaled: the warp adjoint multiplies by the
+// upstream gradient of the loss), and the backward pass of the loss shrinks to the warp adjoint.
+//
+// Block = 3 warps: the three colour channels of one 28-column strip x 32-row band of one (prediction, sample), both views
+// packed as float2 (the walk of ssim_bwd_stream2_kernel).  Per row step each channel warp computes its SSIM / L1 terms of
+// the window just completed; the three warps exchange them through shared memory (double-buffered, ONE named barrier per
+// step), every warp forms the photometric values of both views, the min / auto-mask selection and from it the
+// coefficients of its own channel.  Channel 0 accumulates the loss and writes the selection.
+constexpr int kTrainThreads = 96;
+
+#ifndef DROSFM_SSIMT_MINBLOCKS
+#define DROSFM_SSIMT_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(kTrainThreads, DROSFM_SSIMT_MINBLOCKS)
+ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restrict__ warped, const __grid_constant__ PhotoPtrs pp,
+                          int n_preds, const float* __restrict__ automask_in, drosfm_photo_opts_t opts, float l1_w,
+                          uint8_t* __restrict__ sel_out, float* __restrict__ loss, Slot* ws, float* __restrict__ g_warped,
+                          int B, int H, int W, int nstrips, int nbands) {
+    __shared__ float4 xchg[2][3][32];
+    __shared__ int flag;
+    const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+    const int wg = blockIdx.x;
+    const int strip = wg % nstrips, band = wg / nstrips;
+    const int b = static_cast<int>(blockIdx.y) % B, ip = static_cast<int>(blockIdx.y) / B;
+    const int P = H * W;
+    const int gx = strip * kBwdStripW - 2 + lane, gy0 = band * kBwdBandH;
+    const bool col_in = gx >= 0 && gx < W;
+    const bool out_lane = lane >= 2 && lane <= kBwdStripW + 1 && gx < W;
+    const Lanes nb = neighbour_lanes(lane, gx == 0, gx == W - 1);
+    const int gxc = clampi(gx, 0, W - 1);
+    const bool use_min = opts.reduce_op == DROSFM_REDUCE_MIN;
+    // unscaled by the upstream gradient (see above)
+    const float G = pp.weight[ip] / (static_cast<float>(B) * static_cast<float>(P) * (use_min ? 1.0f : 2.0f));
+    const float kp = G * opts.ssim_w * (-1.0f / 6.0f) * (2.0f / 9.0f);
+    const float kl1 = G * l1_w * (1.0f / 3.0f);
+    const size_t slot0 = (static_cast<size_t>(ip) * 2) * B + b;
+    const unsigned vstride = static_cast<unsigned>(B) * 3u * static_cast<unsigned>(P);     // view 1 relative to view 0
+    const float* __restrict__ ypl = image + (static_cast<size_t>(b) * 3 + c) * P + gxc;
+    const float* __restrict__ xpl = warped + (slot0 * 3 + c) * P + gxc;
+    float* __restrict__ gpl = g_warped + (slot0 * 3 + c) * P + gxc;
+    const float* __restrict__ apl = automask_in != nullptr ? automask_in + static_cast<size_t>(b) * P + gxc : nullptr;
+    uint8_t* __restrict__ spl = sel_out != nullptr ? sel_out + (static_cast<size_t>(ip) * B + b) * P + gxc : nullptr;
+    const float2 wx0 = bc2(gx <= 0 ? 0.0f : (gx == 1 ? 2.0f : 1.0f));
+    const float2 wx2 = bc2(gx >= W - 1 ? 0.0f : (gx == W - 2 ? 2.0f : 1.0f));
+    const float2 inv9 = bc2(1.0f / 9.0f), ninv9 = bc2(-1.0f / 9.0f), two = bc2(2.0f);
+    const float2 C1 = bc2(opts.C1), C2 = bc2(opts.C2);
+
+    struct Pre {
+        float2 x;
+        float y, am;
+    };
+    Pre f0, f1, f2;
+    auto fetch = [&](int gy, Pre& f) {
+        const unsigned off = static_cast<unsigned>(padded_row(gy, H) * W);
+        f.x.x = col_in ? __ldg(xpl + off) : 0.0f;
+        f.x.y = col_in ? __ldg(xpl + (off + vstride)) : 0.0f;
+        f.y = col_in ? __ldg(ypl + off) : 0.0f;
+        // the auto-mask value of a row travels with it (consumed one step later, when the row is a window centre)
+        f.am = (apl != nullptr && col_in && gy >= 0 && gy < H) ? __ldg(apl + static_cast<unsigned>(gy * W)) : __int_as_float(0x7f800000);
+    };
+    float am_row = __int_as_float(0x7f800000);      // auto-mask of the row loaded in the previous step = this step's window centre
+    int sv_prev = 254;
+    float local = 0.0f;
+    auto step = [&](BwdRow2& p2, BwdRow2& p1, BwdRow2& cur, Pre& mine, Pre& refill, int j) {
+        const int gy = gy0 - 2 + j;          // row loaded in this step; windows centred on gy-1; gradients of row gy-2
+        const int gc = gy - 1;
+        cur.x = mine.x;
+        cur.y = mine.y;
+        const float am = am_row;
+        am_row = mine.am;
+        fetch(gy + 2, refill);
+        const float2 xl = shfl2(cur.x, nb.l), xr = shfl2(cur.x, nb.r);
+        float yl, yr;
+        neighbours(cur.y, nb, yl, yr);
+        const float2 yl2 = bc2(yl), yc2 = bc2(cur.y), yr2 = bc2(yr);
+        cur.sy = yl + cur.y + yr;
+        cur.syy = yl * yl + cur.y * cur.y + yr * yr;
+        cur.sx = add2(add2(xl, cur.x), xr);
+        cur.sxx = fma2(xr, xr, fma2(cur.x, cur.x, mul2(xl, xl)));
+        cur.sxy = fma2(xr, yr2, fma2(cur.x, yc2, mul2(xl, yl2)));
+        int sv = 254;
+        if (j >= 2) {
+            // statistics of the window centred on (gc, gx), this channel, both views
+            const float2 wsx = add2(add2(p2.sx, p1.sx), cur.sx);
+            const float2 wsxx = add2(add2(p2.sxx, p1.sxx), cur.sxx);
+            const float2 wsxy = add2(add2(p2.sxy, p1.sxy), cur.sxy);
+            const float wsy = p2.sy + p1.sy + cur.sy, wsyy = p2.syy + p1.syy + cur.syy;
+            const float mu_y = wsy * (1.0f / 9.0f);
+            const float mu_yy = mu_y * mu_y;
+            const float sig_y = wsyy * (1.0f / 9.0f) - mu_yy;
+            const float2 mu_y2 = bc2(mu_y);
+            const float2 mu_x = mul2(wsx, inv9), nmu_x = mul2(wsx, ninv9);
+            const float2 mu_xy = mul2(mu_x, mu_y2), mu_xx = mul2(mu_x, mu_x);
+            const float2 sig_x = fma2(nmu_x, mu_x, mul2(wsxx, inv9));
+            const float2 sig_xy = fma2(nmu_x, mu_y2, mul2(wsxy, inv9));
+            const float2 A1 = fma2(two, mu_xy, C1), A2 = fma2(two, sig_xy, C2);
+            const float2 B1 = add2(mu_xx, bc2(mu_yy + opts.C1)), B2 = add2(sig_x, bc2(sig_y + opts.C2));
+            const float2 num = mul2(A1, A2), den = mul2(B1, B2);
+            const float2 rden = make_float2(__fdividef(1.0f, den.x), __fdividef(1.0f, den.y));
+            const float2 sm = mul2(num, rden);
+            const float l0 = (1.0f - sm.x) * 0.5f, l1 = (1.0f - sm.y) * 0.5f;
+            // this channel's terms of the photometric value of the window centre (row p1)
+            const float4 mineq = make_float4(fminf(fmaxf(l0, 0.0f), 1.0f), fminf(fmaxf(l1, 0.0f), 1.0f),
+                                             fabsf(p1.x.x - p1.y), fabsf(p1.x.y - p1.y));
+            xchg[j & 1][c][lane] = mineq;
+            asm volatile("bar.sync 1, 96;" ::: "memory");
+            const float4 q0 = xchg[j & 1][0][lane], q1 = xchg[j & 1][1][lane], q2 = xchg[j & 1][2][lane];
+            const float pm0 = __fadd_rn(__fmul_rn(opts.ssim_w, third(q0.x + q1.x + q2.x)), __fmul_rn(l1_w, third(q0.z + q1.z + q2.z)));
+            const float pm1 = __fadd_rn(__fmul_rn(opts.ssim_w, third(q0.y + q1.y + q2.y)), __fmul_rn(l1_w, third(q0.w + q1.w + q2.w)));
+            float best;
+            if (use_min) {
+                best = __int_as_float(0x7f800000);
+                if (pm0 < best) { best = pm0; sv = 0; }
+                if (pm1 < best) { best = pm1; sv = 1; }
+                if (am < best) { best = am; sv = 255; }
+            } else {
+                best = pm0 + pm1;
+                sv = 253;
+            }
+            const bool centre_in = col_in && gc >= 0 && gc < H;
+            if (!centre_in) sv = 254;
+            if (c == 0 && out_lane && gc >= gy0 && gc < gy0 + kBwdBandH && gc < H) {
+                local += best;
+                if (spl != nullptr) spl[static_cast<unsigned>(gc * W)] = static_cast<uint8_t>(use_min ? sv : 254);
+            }
+            // coefficients of the windows that carry a gradient
+            float2 a = bc2(0.0f), bb = a, cq = a;
+            const bool on0 = sv == 0 || sv == 253, on1 = sv == 1 || sv == 253;
+            if (on0 || on1) {
+                const float2 q = mul2(bc2(kp), rden);
+                const float2 neg1 = bc2(-1.0f);
+                const float2 dA = fma2(neg1, A1, A2), dB = fma2(neg1, B1, B2);
+                const float2 inner = fma2(mul2(sm, nmu_x), dB, mul2(mu_y2, dA));
+                const float2 a_ = mul2(q, inner);
+                const float2 b_ = mul2(mul2(mul2(bc2(-kp), rden), sm), B1);
+                const float2 c_ = mul2(q, A1);
+                const bool k0 = on0 && l0 >= 0.0f && l0 <= 1.0f, k1 = on1 && l1 >= 0.0f && l1 <= 1.0f;
+                a = make_float2(k0 ? a_.x : 0.0f, k1 ? a_.y : 0.0f);
+                bb = make_float2(k0 ? b_.x : 0.0f, k1 ? b_.y : 0.0f);
+                cq = make_float2(k0 ? c_.x : 0.0f, k1 ? c_.y : 0.0f);
+            }
+            const int ll = (lane - 1) & 31, lr = (lane + 1) & 31;      // the outermost lanes' sums are never used
+            p1.ha = fma2(wx2, shfl2(a, lr), fma2(wx0, shfl2(a, ll), a));
+            p1.hb = fma2(wx2, shfl2(bb, lr), fma2(wx0, shfl2(bb, ll), bb));
+            p1.hc = fma2(wx2, shfl2(cq, lr), fma2(wx0, shfl2(cq, ll), cq));
+        }
+        if (j >= 4) {
+            const int gq = gy - 2;
+            if (out_lane && gq < gy0 + kBwdBandH && gq < H) {
+                const float2 wy0 = bc2(gq <= 0 ? 0.0f : (gq == 1 ? 2.0f : 1.0f));
+                const float2 wy2 = bc2(gq >= H - 1 ? 0.0f : (gq == H - 2 ? 2.0f : 1.0f));
+                const float2 ga = fma2(wy2, p1.ha, fma2(wy0, cur.ha, p2.ha));
+                const float2 gb = fma2(wy2, p1.hb, fma2(wy0, cur.hb, p2.hb));
+                const float2 gc_ = fma2(wy2, p1.hc, fma2(wy0, cur.hc, p2.hc));
+                float2 gxv = fma2(gc_, bc2(p2.y), fma2(gb, p2.x, ga));
+                const bool q0 = sv_prev == 0 || sv_prev == 253, q1 = sv_prev == 1 || sv_prev == 253;
+                if (q0) {
+                    const float df = p2.x.x - p2.y;
+                    gxv.x += df == 0.0f ? 0.0f : __int_as_float(__float_as_int(kl1) ^ (__float_as_int(df) & 0x80000000));
+                }
+                if (q1) {
+                    const float df = p2.x.y - p2.y;
+                    gxv.y += df == 0.0f ? 0.0f : __int_as_float(__float_as_int(kl1) ^ (__float_as_int(df) & 0x80000000));
+                }
+                const unsigned o = static_cast<unsigned>(gq * W);
+                gpl[o] = gxv.x;
+                gpl[o + vstride] = gxv.y;
+            }
+        }
+        sv_prev = sv;
+    };
+    BwdRow2 r0, r1, r2;
+    r0.ha = r0.hb = r0.hc = r1.ha = r1.hb = r1.hc = r2.ha = r2.hb = r2.hc = bc2(0.0f);
+    r0.sx = r0.sxx = r0.sxy = r1.sx = r1.sxx = r1.sxy = bc2(0.0f);
+    r0.sy = r0.syy = r1.sy = r1.syy = 0.0f;
+    r0.x = r1.x = bc2(0.0f);
+    r0.y = r1.y = 0.0f;
+    fetch(gy0 - 2, f0);
+    fetch(gy0 - 1, f1);
+#pragma unroll 1
+    for (int j = 0; j < kBwdBandH + 4; j += 3) {
+        step(r1, r2, r0, f0, f2, j);
+        step(r2, r0, r1, f1, f0, j + 1);
+        step(r0, r1, r2, f2, f1, j + 2);
+    }
+    // loss: channel 0's lanes hold the per-pixel values of the band
+    if (c == 0) {
+        const double part = warp_sum(static_cast<double>(local));
+        if (lane == 0 && part != 0.0) atomicAdd(spread_acc(slot_at(ws, ip)), part);
+    }
+    Slot* ticket = slot_at(ws, n_preds);
+    if (last_block(ticket, gridDim.x * gridDim.y, &flag) && threadIdx.x < 32)
+        finish_weighted_means(ws, n_preds, pp.weight, static_cast<double>(B) * P * (use_min ? 1.0 : 2.0), ticket, loss);
+}
+
 static int check_photo(const float* image, const float* const* context, int n_views, const drosfm_photo_opts_t* opts,
                        int B, int H, int W) {
     DROSFM_REQUIRE(B >= 0 && H >= 0 && W >= 0, DROSFM_EINVAL, "photometric: negative dimension");
@@ -1753,7 +1952,7 @@ static int fill_ptrs(PhotoPtrs& pp, const float* const* context, int n_views, co
 int drosfm_photometric_fwd(const float* image, const float* const* context, int n_views, const float* const* inv_depths,
                            int depth_kind, int n_preds, const drosfm_cams_t* cams, const float* const* poses,
                            const float* automask, const drosfm_photo_opts_t* opts, uint8_t* sel, float* loss, void* ws,
-                           float* warped_save, int flags, int B, int H, int W, drosfm_stream_t stream) {
+                           float* warped_save, float* g_warped, int flags, int B, int H, int W, drosfm_stream_t stream) {
     if (int e = check_photo(image, context, n_views, opts, B, H, W)) return e;
     DROSFM_REQUIRE(B > 0 && H * W > 0, DROSFM_EINVAL, "photometric_fwd: empty batch (the mean over zero pixels is undefined)");
     DROSFM_REQUIRE(!(flags & DROSFM_PHOTO_WARPED_READY) || warped_save != nullptr, DROSFM_EINVAL,
@@ -1767,6 +1966,10 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
                    "photometric_fwd: clip_loss > 0 runs on the fused path (warped_save == NULL) and needs opts->clip_scratch and sel");
     DROSFM_REQUIRE(opts->ssim_w > 0.0f || warped_save == nullptr, DROSFM_ENOTSUP,
                    "photometric_fwd: ssim_loss_weight == 0 runs on the fused path (warped_save == NULL)");
+    DROSFM_REQUIRE(!(flags & DROSFM_PHOTO_FUSE_BWD) ||
+                       (warped_save != nullptr && g_warped != nullptr && n_views == 2 && !(opts->clip_loss > 0.0f) &&
+                        static_cast<long long>(B) * 3 * H * W < (1ll << 31) && static_cast<long long>(B) * n_preds <= 65535),
+                   DROSFM_ENOTSUP, "photometric_fwd: DROSFM_PHOTO_FUSE_BWD needs the staged path (warped_save, g_warped), two views, no clip");
     DROSFM_REQUIRE(!(opts->automask && opts->reduce_op != DROSFM_REDUCE_MIN), DROSFM_EINVAL,
                    "photometric_fwd: auto-masking needs the min reduce op");
     DROSFM_REQUIRE(!opts->automask || automask != nullptr, DROSFM_EINVAL, "photometric_fwd: automask map is NULL");
@@ -1783,7 +1986,14 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
                                                                       warped_save, B, H, W);
             if (int e = launch_status("photometric_fwd (warp_sources)")) return e;
         }
-        if (n_views <= 2 && static_cast<long long>(n_views) * B * 3 * H * W < (1ll << 31)) {
+        if (flags & DROSFM_PHOTO_FUSE_BWD) {
+            // training forward: loss, selection AND d loss / d warped (unscaled) in one pass over the warped copy
+            const int nstrips = (W + kBwdStripW - 1) / kBwdStripW, nbands = (H + kBwdBandH - 1) / kBwdBandH;
+            dim3 tgrid(nstrips * nbands, B * n_preds);
+            ssim_train_stream2_kernel<<<tgrid, kTrainThreads, 0, cs>>>(image, warped_save, pp, n_preds, opts->automask ? automask : nullptr,
+                                                                      *opts, l1_weight(opts), sel, loss, static_cast<Slot*>(ws), g_warped,
+                                                                      B, H, W, nstrips, nbands);
+        } else if (n_views <= 2 && static_cast<long long>(n_views) * B * 3 * H * W < (1ll << 31)) {
             const int nstrips = (W + kFwdStripW - 1) / kFwdStripW, nbands = (H + kFwdBandH - 1) / kFwdBandH;
             dim3 sgrid((nstrips * nbands + kSsimWarps - 1) / kSsimWarps, B * n_preds);
             if (n_views == 1)
@@ -1872,8 +2082,8 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
                        "photometric_bwd: one prediction's warped views exceed 2^32 elements");
         if (int e = launch_status("photometric_bwd (window gradients)")) return e;
         DROSFM_REQUIRE(static_cast<long long>(B) * n_preds * n_views <= 65535, DROSFM_ERANGE, "photometric_bwd: B * n_preds * n_views too large");
-        if (int e = launch_adjoint(pp, pg, n_views, depth_kind, n_preds, cams, opts->padding, nullptr, g_warped, static_cast<Slot*>(ws), 0,
-                                   B, H, W, cs)) return e;
+        if (int e = launch_adjoint(pp, pg, n_views, depth_kind, n_preds, cams, opts->padding, nullptr, g_warped, nullptr,
+                                   static_cast<Slot*>(ws), 0, B, H, W, cs)) return e;
     } else {
         photometric_bwd_kernel<false><<<grid, kBwdThreads, kBwdSmemBytes, cs>>>(
             g_loss, image, pp, n_views, depth_kind, n_preds, *cams, sel, *opts, l1_weight(opts), pg, static_cast<Slot*>(ws),
@@ -1916,8 +2126,8 @@ int drosfm_warp_sources_fwd(const float* const* context, int n_views, const floa
 
 int drosfm_warp_sources_bwd(const float* g_warped, const float* const* context, int n_views, const float* const* inv_depths,
                             int depth_kind, int n_preds, const drosfm_cams_t* cams, const float* const* poses, int padding,
-                            const float* rgbx, float* const* g_inv_depths, float* const* g_poses, void* ws, int accumulate,
-                            int B, int H, int W, drosfm_stream_t stream) {
+                            const float* rgbx, const float* g_scale, float* const* g_inv_depths, float* const* g_poses, void* ws,
+                            int accumulate, int B, int H, int W, drosfm_stream_t stream) {
     DROSFM_REQUIRE(B >= 0 && H >= 0 && W >= 0, DROSFM_EINVAL, "warp_sources_bwd: negative dimension");
     DROSFM_REQUIRE(n_views >= 1 && n_views <= DROSFM_MAX_VIEWS, DROSFM_ERANGE, "warp_sources_bwd: n_views=%d outside [1,%d]",
                    n_views, DROSFM_MAX_VIEWS);
@@ -1944,8 +2154,8 @@ int drosfm_warp_sources_bwd(const float* g_warped, const float* const* context, 
                    "warp_sources_bwd: one prediction's warped views exceed 2^32 elements");
     DROSFM_REQUIRE(static_cast<long long>(B) * n_preds * n_views <= 65535, DROSFM_ERANGE, "warp_sources_bwd: B * n_preds * n_views too large");
     DROSFM_REQUIRE(rgbx == nullptr || aligned16(rgbx), DROSFM_EALIGN, "warp_sources_bwd: rgbx must be 16-byte aligned");
-    if (int e = launch_adjoint(pp, pg, n_views, depth_kind, n_preds, cams, padding, rgbx, g_warped, static_cast<Slot*>(ws), accumulate, B, H, W,
-                               static_cast<cudaStream_t>(stream))) return e;
+    if (int e = launch_adjoint(pp, pg, n_views, depth_kind, n_preds, cams, padding, rgbx, g_warped, g_scale, static_cast<Slot*>(ws), accumulate,
+                               B, H, W, static_cast<cudaStream_t>(stream))) return e;
     return launch_status("warp_sources_bwd");
 }
 

@@ -647,6 +647,9 @@ SAVE_WARP = os.environ.get("DROSFM_PHOTO_SAVE_WARP", "1") != "0"
 # DROSFM_PHOTO_OVERLAP=0 keeps the whole loss on the caller's stream (no second stream for auto-mask / smoothness).
 # OVERLAP may also be set to "serial" (bench.py's per-kernel timing pass): the same split calls, on one stream.
 OVERLAP = os.environ.get("DROSFM_PHOTO_OVERLAP", "1") != "0"
+# DROSFM_PHOTO_FUSE_BWD=0: the window gradients of the photometric loss are computed in the backward pass (their own
+# kernel) instead of by the training forward (two-view losses on the staged path)
+FUSE_BWD = os.environ.get("DROSFM_PHOTO_FUSE_BWD", "1") != "0"
 # DROSFM_PHOTO_RGBX=0 keeps the flat warp on the caller's planar pictures (no RGBx texel copy of the sources)
 RGBX = os.environ.get("DROSFM_PHOTO_RGBX", "1") != "0"
 
@@ -693,6 +696,10 @@ class _PhotoLoss(torch.autograd.Function):
         lib = L.lib()
         staged = wsave is not None and bool(OVERLAP)        # split calls
         two_streams = staged and OVERLAP is True            # OVERLAP == "serial": split calls, one stream
+        # two views in training: the forward's SSIM pass also produces d loss / d warped (unscaled); the backward of the
+        # loss is then the warp adjoint alone, and the warped copy is not kept
+        fused_bwd = staged and FUSE_BWD and V == 2 and B * 3 * H * W < 2 ** 31 and B * n <= 65535
+        g_warped = torch.empty_like(wsave) if fused_bwd else None
         with torch.cuda.device(dev):
             ws = L.workspace(dev, max(n * B + 1, V * n * B))
             st = L.stream()
@@ -726,16 +733,18 @@ class _PhotoLoss(torch.autograd.Function):
                         "warp_sources_fwd")
                 if two_streams:
                     main.wait_event(ev_mask)
-                flags = L.PHOTO_WARPED_READY
+                flags = L.PHOTO_WARPED_READY | (L.PHOTO_FUSE_BWD if fused_bwd else 0)
             else:
                 side_work()
                 flags = 0
             L.check(lib.drosfm_photometric_fwd(pc, pa, V, pi, depth_kind, n, cams, pp_, L.ptr(amask), opts, L.ptr(sel),
-                                               L.ptr(losses), L.ptr(ws), L.ptr(wsave), flags, B, H, W, st), "photometric_fwd")
+                                               L.ptr(losses), L.ptr(ws), L.ptr(wsave), L.ptr(g_warped), flags, B, H, W, st),
+                    "photometric_fwd")
             if two_streams:
                 main.wait_stream(side)
         total = losses.sum().reshape(1)
-        ctx.save_for_backward(image, keep[0], keep[1], sel, stats, wsave, rgbx if staged else None, *context, *invs, *poses)
+        ctx.save_for_backward(image, keep[0], keep[1], sel, stats, None if fused_bwd else wsave, rgbx if staged else None, g_warped,
+                              *context, *invs, *poses)
         ctx.cfg, ctx.V, ctx.n, ctx.kind = cfg, V, n, kind
         ctx.mark_non_differentiable(losses)
         if sel is None:
@@ -747,8 +756,8 @@ class _PhotoLoss(torch.autograd.Function):
     def backward(ctx, g_total, *unused):
         ssim_w, C1, C2, padding, reduce_op, automask, gamma, smooth_w, depth_kind, clip = ctx.cfg
         V, n, kind = ctx.V, ctx.n, ctx.kind
-        image, K, Kref, sel, stats, wsave, rgbx = ctx.saved_tensors[:7]
-        rest = ctx.saved_tensors[7:]
+        image, K, Kref, sel, stats, wsave, rgbx, g_fused = ctx.saved_tensors[:8]
+        rest = ctx.saved_tensors[8:]
         context, invs, poses = rest[:V], rest[V:V + n], rest[V + n:]
         B, _, H, W = image.shape
         dev = image.device
@@ -767,6 +776,27 @@ class _PhotoLoss(torch.autograd.Function):
         g_warped = torch.empty_like(wsave) if wsave is not None else None     # scratch between the two backward stages
         lib = L.lib()
         smooth = smooth_w > 0.0 and any(need_inv)
+        if g_fused is not None:
+            # the forward left d loss / d warped behind (unscaled): the backward is the warp adjoint, scaled by g
+            with torch.cuda.device(dev):
+                ws = L.workspace(dev, max(n * B + 1, V * n * B))
+                st = L.stream()
+                pa, pi, pp_ = L.ptr_array(context), L.ptr_array(invs), L.ptr_array(poses)
+                two_streams = OVERLAP is True and smooth
+                main = torch.cuda.current_stream(dev)
+                side = L.side_stream(dev) if two_streams else main
+                if smooth:
+                    if two_streams:
+                        side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        L.check(lib.drosfm_smoothness_bwd(L.ptr(g), L.ptr(image), pi, n, smooth_w, L.ptr(stats), L.ptr_array(g_invs), 0,
+                                                          B, H, W, L.stream()), "smoothness_bwd")
+                    if two_streams:
+                        main.wait_stream(side)
+                L.check(lib.drosfm_warp_sources_bwd(L.ptr(g_fused), pa, V, pi, depth_kind, n, cams, pp_, padding, L.ptr(rgbx), L.ptr(g),
+                                                    L.ptr_array(g_invs), L.ptr_array(g_poses), L.ptr(ws), 1 if smooth else 0, B, H, W, st),
+                        "warp_sources_bwd")
+            return (None, None, None, None, None, None, *([None] * V), *g_invs, *g_poses)
         with torch.cuda.device(dev):
             ws = L.workspace(dev, max(n * B + 1, V * n * B))
             st = L.stream()
@@ -786,7 +816,7 @@ class _PhotoLoss(torch.autograd.Function):
                         "photometric_bwd")
                 if two_streams:
                     main.wait_stream(side)
-                L.check(lib.drosfm_warp_sources_bwd(L.ptr(g_warped), pa, V, pi, depth_kind, n, cams, pp_, padding, L.ptr(rgbx),
+                L.check(lib.drosfm_warp_sources_bwd(L.ptr(g_warped), pa, V, pi, depth_kind, n, cams, pp_, padding, L.ptr(rgbx), None,
                                                     L.ptr_array(g_invs), L.ptr_array(g_poses), L.ptr(ws), 1, B, H, W, st),
                         "warp_sources_bwd")
             else:

@@ -197,6 +197,9 @@ typedef struct {
 /* flags of drosfm_photometric_fwd / _bwd (staged path only) */
 #define DROSFM_PHOTO_WARPED_READY 1 /* fwd: warped_save already holds drosfm_warp_sources_fwd's output */
 #define DROSFM_PHOTO_NO_ADJOINT 2   /* bwd: stop after g_warped; the caller runs drosfm_warp_sources_bwd itself */
+#define DROSFM_PHOTO_FUSE_BWD 4     /* fwd (training, two views): also write g_warped = d loss / d warped, UNSCALED by the
+                                     * loss's upstream gradient -- the backward of the loss is then drosfm_warp_sources_bwd alone
+                                     * (with g_scale = that upstream gradient); drosfm_photometric_bwd is not called */
 
 /* Un-warped (auto-mask) pass: automask[b,y,x] = min_v photometric(context_v, image), computed once
  * per step instead of once per prediction (lines 346-351 recompute it n times). */
@@ -215,7 +218,7 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
                            const float* const* inv_depths, int depth_kind, int n_preds,
                            const drosfm_cams_t* cams, const float* const* poses, const float* automask,
                            const drosfm_photo_opts_t* opts, uint8_t* sel, float* loss, void* ws,
-                           float* warped_save, int flags, int B, int H, int W, drosfm_stream_t stream);
+                           float* warped_save, float* g_warped, int flags, int B, int H, int W, drosfm_stream_t stream);
 /* g_loss: 1 float on the device (upstream gradient).  g_inv_depths[i] [B,1,H,W] written;
  * g_poses[v*n_preds+i] written ([B,4,4] or [B,6]); ws of drosfm_ws_bytes(n_views*n_preds*B).
  * warped_save (the forward's) and g_warped (scratch of the same size, contents undefined on return) go together:
@@ -234,6 +237,8 @@ int drosfm_photometric_bwd(const float* g_loss, const float* image, const float*
  *      drosfm_photometric_fwd with DROSFM_PHOTO_WARPED_READY.
  * bwd: adjoint of that warp for the g_warped a DROSFM_PHOTO_NO_ADJOINT backward left behind: g_inv_depths[i] written
  *      (accumulate != 0: added to), g_poses[v*n_preds+i] written; ws of drosfm_ws_bytes(n_views*n_preds*B).
+ * g_scale (bwd, optional): one float on the device that multiplies g_warped (the loss's upstream gradient when g_warped
+ *      came from a DROSFM_PHOTO_FUSE_BWD forward); NULL = 1.
  * rgbx (optional scratch, [V,B,H,W,4] floats, 16-byte aligned): when given, fwd first packs the source pictures into
  *      RGBx texels there (one more launch) and both directions gather each bilinear tap with ONE 128-bit load instead
  *      of three 32-bit ones; bwd expects the buffer fwd filled.  NULL: gathers from the caller's planes. */
@@ -242,8 +247,9 @@ int drosfm_warp_sources_fwd(const float* const* context, int n_views, const floa
                             float* warped, int B, int H, int W, drosfm_stream_t stream);
 int drosfm_warp_sources_bwd(const float* g_warped, const float* const* context, int n_views,
                             const float* const* inv_depths, int depth_kind, int n_preds, const drosfm_cams_t* cams,
-                            const float* const* poses, int padding, const float* rgbx, float* const* g_inv_depths,
-                            float* const* g_poses, void* ws, int accumulate, int B, int H, int W, drosfm_stream_t stream);
+                            const float* const* poses, int padding, const float* rgbx, const float* g_scale,
+                            float* const* g_inv_depths, float* const* g_poses, void* ws, int accumulate, int B, int H, int W,
+                            drosfm_stream_t stream);
 
 /* ---- smoothness loss (multiview_photometric_loss_mf.py:273-299, utils/depth.py:147-199) -------
  * loss = weight/n * sum_i (mean|dx(d_i/mean(d_i)) * wx| + mean|dy(..) * wy|) / 2^i.

@@ -136,7 +136,7 @@ def _check_photometric(dataset, B, H, W, V, n, min_depth, max_depth, padding="ze
     lib = L.lib()
     L.check(lib.drosfm_automask_fwd(L.ptr(img), L.ptr_array(ctx), V, opts, L.ptr(amask), B, H, W, L.stream()))
     L.check(lib.drosfm_photometric_fwd(L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
-                                       L.ptr(amask), opts, L.ptr(sel), L.ptr(loss), L.ptr(ws), None, 0, B, H, W, L.stream()))
+                                       L.ptr(amask), opts, L.ptr(sel), L.ptr(loss), L.ptr(ws), None, None, 0, B, H, W, L.stream()))
     assert_close(loss.cpu()[0], loss32, what="loss")
     # (2) selection: identical except at near-ties
     flips = near_ties = 0
@@ -169,7 +169,7 @@ def _check_photometric(dataset, B, H, W, V, n, min_depth, max_depth, padding="ze
     loss2 = torch.zeros(1, device=dev)
     sel2 = torch.empty_like(sel)
     L.check(lib.drosfm_photometric_fwd(L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
-                                       L.ptr(amask), opts, L.ptr(sel2), L.ptr(loss2), L.ptr(ws), L.ptr(wsave), 0, B, H, W, L.stream()))
+                                       L.ptr(amask), opts, L.ptr(sel2), L.ptr(loss2), L.ptr(ws), L.ptr(wsave), None, 0, B, H, W, L.stream()))
     assert_close(loss2.cpu(), loss.cpu(), rtol=RTOL_SELF, atol=0, what="loss (staged vs fused)")
     assert int((sel2 != sel).sum()) <= max(2, int(1e-4 * sel.numel()))      # near-ties only (see the docstring)
     for i in range(n):
@@ -205,7 +205,7 @@ def _check_photometric(dataset, B, H, W, V, n, min_depth, max_depth, padding="ze
     assert torch.equal(rgbx[..., :3], torch.stack(ctx).permute(0, 1, 3, 4, 2)) and not bool(rgbx[..., 3].any())
     loss3 = torch.zeros(1, device=dev)
     L.check(lib.drosfm_photometric_fwd(L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
-                                       L.ptr(amask), opts, L.ptr(sel2), L.ptr(loss3), L.ptr(ws), L.ptr(wsave3),
+                                       L.ptr(amask), opts, L.ptr(sel2), L.ptr(loss3), L.ptr(ws), L.ptr(wsave3), None,
                                        L.PHOTO_WARPED_READY, B, H, W, L.stream()))
     assert_close(loss3.cpu(), loss2.cpu(), rtol=RTOL_SELF, atol=0, what="loss (split stages)")
     base = torch.randn_like(g_inv)
@@ -214,14 +214,14 @@ def _check_photometric(dataset, B, H, W, V, n, min_depth, max_depth, padding="ze
                                        L.ptr_array(P), L.ptr(sel_forced), opts, None, None, L.ptr(ws), L.ptr(wsave3),
                                        L.ptr(g_warped), L.PHOTO_NO_ADJOINT, B, H, W, L.stream()))
     L.check(lib.drosfm_warp_sources_bwd(L.ptr(g_warped), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
-                                        pad, None, L.ptr_array(list(g_inv3)), L.ptr_array(list(g_pose3)), L.ptr(ws), 1, B, H, W,
+                                        pad, None, None, L.ptr_array(list(g_inv3)), L.ptr_array(list(g_pose3)), L.ptr(ws), 1, B, H, W,
                                         L.stream()))
     assert_close((g_inv3 - base).cpu(), g_inv2.cpu(), rtol=1e-4, atol=2e-7 * float(base.abs().max()), what="g_inv (accumulated)")
     assert_close(g_pose3.cpu(), g_pose2.cpu(), rtol=1e-4, atol=1e-5 * float(g_pose.abs().max()), what="g_pose (split stages)")
     # ... and through the RGBx texels, overwriting (accumulate = 0: the call zero-fills what several views add into)
     g_inv4, g_pose4 = torch.full_like(g_inv, float("nan")), torch.empty_like(g_pose)
     L.check(lib.drosfm_warp_sources_bwd(L.ptr(g_warped), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
-                                        pad, L.ptr(rgbx), L.ptr_array(list(g_inv4)), L.ptr_array(list(g_pose4)), L.ptr(ws), 0, B, H, W,
+                                        pad, L.ptr(rgbx), None, L.ptr_array(list(g_inv4)), L.ptr_array(list(g_pose4)), L.ptr(ws), 0, B, H, W,
                                         L.stream()))
     assert_close(g_inv4.cpu(), g_inv2.cpu(), rtol=1e-4, atol=2e-7 * float(g_inv2.abs().max()), what="g_inv (RGBx texels)")
     assert_close(g_pose4.cpu(), g_pose2.cpu(), rtol=1e-4, atol=1e-5 * float(g_pose.abs().max()), what="g_pose (RGBx texels)")
@@ -229,6 +229,37 @@ def _check_photometric(dataset, B, H, W, V, n, min_depth, max_depth, padding="ze
         assert_close_or_better(g_inv4[i].cpu(), g32[i], g64[i], what=f"texel g_inv{i}")
     for k in range(V * n):
         assert_close_or_better(g_pose4[k].cpu(), g32[n + k], g64[n + k], what=f"texel g_pose{k}")
+    # (6) two views: the training forward that also emits d loss / d warped (DROSFM_PHOTO_FUSE_BWD) == the forward stage +
+    #     the window-gradient stage run on that forward's own selection; its adjoint (scaled by g_scale) gives the gradients
+    if V == 2:
+        loss4, sel4 = torch.zeros(1, device=dev), torch.empty_like(sel)
+        g_w4 = torch.full_like(wsave, float("nan"))
+        L.check(lib.drosfm_photometric_fwd(L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
+                                           L.ptr(amask), opts, L.ptr(sel4), L.ptr(loss4), L.ptr(ws), L.ptr(wsave3), L.ptr(g_w4),
+                                           L.PHOTO_WARPED_READY | L.PHOTO_FUSE_BWD, B, H, W, L.stream()))
+        assert_close(loss4.cpu(), loss2.cpu(), rtol=RTOL_SELF, atol=0, what="loss (training forward)")
+        assert int((sel4 != sel2).sum()) <= max(2, int(1e-4 * sel.numel()))
+        g_w5 = torch.full_like(wsave, float("nan"))
+        L.check(lib.drosfm_photometric_bwd(L.ptr(one), L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams,
+                                           L.ptr_array(P), L.ptr(sel4), opts, None, None, L.ptr(ws), L.ptr(wsave3),
+                                           L.ptr(g_w5), L.PHOTO_NO_ADJOINT, B, H, W, L.stream()))
+        assert not bool(torch.isnan(g_w4).any())
+        assert_close(g_w4.cpu(), g_w5.cpu(), rtol=1e-5, atol=1e-6 * float(g_w5.abs().max()), what="d loss / d warped (training forward)")
+        # gradients through the adjoint with an upstream gradient of 0.5, against the oracle's (selection forced to the oracle's)
+        L.check(lib.drosfm_photometric_fwd(L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
+                                           L.ptr(amask), opts, L.ptr(sel4), L.ptr(loss4), L.ptr(ws), L.ptr(wsave3), L.ptr(g_w4),
+                                           L.PHOTO_WARPED_READY | L.PHOTO_FUSE_BWD, B, H, W, L.stream()))
+        half = torch.full((1,), 0.5, device=dev)
+        g_inv6, g_pose6 = torch.full_like(g_inv, float("nan")), torch.empty_like(g_pose)
+        L.check(lib.drosfm_warp_sources_bwd(L.ptr(g_w5), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
+                                            pad, L.ptr(rgbx), L.ptr(half), L.ptr_array(list(g_inv6)), L.ptr_array(list(g_pose6)), L.ptr(ws),
+                                            0, B, H, W, L.stream()))
+        g_inv7, g_pose7 = torch.full_like(g_inv, float("nan")), torch.empty_like(g_pose)
+        L.check(lib.drosfm_warp_sources_bwd(L.ptr(g_w5), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams, L.ptr_array(P),
+                                            pad, L.ptr(rgbx), None, L.ptr_array(list(g_inv7)), L.ptr_array(list(g_pose7)), L.ptr(ws),
+                                            0, B, H, W, L.stream()))
+        assert_close(2.0 * g_inv6.cpu(), g_inv7.cpu(), rtol=1e-6, atol=1e-7 * float(g_inv7.abs().max()), what="g_scale")
+        assert_close(2.0 * g_pose6.cpu(), g_pose7.cpu(), rtol=1e-5, atol=1e-6 * float(g_pose7.abs().max()), what="g_scale (poses)")
     # a half-specified staged call is refused
     rc = lib.drosfm_photometric_bwd(L.ptr(one), L.ptr(img), L.ptr_array(ctx), V, L.ptr_array(inv), L.INV_DEPTH, n, cams,
                                     L.ptr_array(P), L.ptr(sel_forced), opts, L.ptr_array(list(g_inv2)), L.ptr_array(list(g_pose2)),
