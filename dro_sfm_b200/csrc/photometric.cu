@@ -848,8 +848,14 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
     const Cam& cam = cam_s;                                    // read from shared memory on use: the registers go to occupancy
     const int P = H * W;
     const Norm nm = make_norm(W, H);
-    // g_warped may come unscaled from the training forward (ssim_train_stream2_kernel): times the loss's upstream gradient
-    const float gs = g_scale != nullptr ? __ldg(g_scale) : 1.0f;
+    // g_warped may come unscaled from the training forward (ssim_train_stream2_kernel).  Everything below is linear in it, so
+    // the loss's upstream gradient multiplies the OUTPUTS (depth gradient per row, pose sums once); it is re-read where it is
+    // used instead of being carried in a register through the row loop (the kernel sits at its register cap)
+    auto load_scale = [&]() {
+        float v = 1.0f;
+        if (g_scale != nullptr) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(g_scale));
+        return v;
+    };
     const int x = blockIdx.x * 32 + (tid & 31);
     const int row0 = blockIdx.y * kAdjTiles * kFlatTileH + (tid >> 5);       // first row of this thread; then every 8th
     const bool col_ok = x < W;
@@ -876,7 +882,7 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
             const bool in = col_ok && y < H;
             const unsigned o = in ? static_cast<unsigned>(y * W + x) : 0u;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) gn[r][c] = in ? __ldg(gw + (o + static_cast<unsigned>(c * P))) * gs : 0.0f;
+            for (int c = 0; c < 3; ++c) gn[r][c] = in ? __ldg(gw + (o + static_cast<unsigned>(c * P))) : 0.0f;      // consumed one row later
             dn[r] = in ? __ldg(invd + o) : 0.0f;
         }
     };
@@ -945,7 +951,7 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
         for (int r = 0; r < kIlp; ++r) {
             const int y = row0 + (k + r) * kStride;
             if (gout != nullptr && col_ok && y < H) {
-                const float gg = depth_kind == DROSFM_INV_DEPTH ? inv2depth_grad(draw[r], gd[r]) : gd[r];
+                const float gg = (depth_kind == DROSFM_INV_DEPTH ? inv2depth_grad(draw[r], gd[r]) : gd[r]) * load_scale();
                 float* dst = gout + static_cast<unsigned>(y * W + x);
                 if constexpr (ADD) { if (gg != 0.0f) red_add1(dst, gg); }
                 else *dst = gg;
@@ -955,6 +961,11 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
     float* g_pose = pg.g_pose[v * n_preds + ip];
     if (g_pose == nullptr) return;
     Slot* slot_p = slot_at(ws, (v * n_preds + ip) * B + b);
+    {
+        const float gs = load_scale();
+#pragma unroll
+        for (int i = 0; i < 12; ++i) gT[i] *= gs;
+    }
     warp_accumulate12(gT, spread_acc(slot_p));
     // one ticket per (view, prediction, sample): the last block turns the fp64 sums into the caller's encoding
     if (last_block(slot_p, gridDim.x * gridDim.y, &flag) && tid < 32) {
@@ -1656,7 +1667,7 @@ ssim_bwd_stream2_kernel(const float* __restrict__ g_loss, const float* __restric
 constexpr int kTrainThreads = 96;
 
 #ifndef DROSFM_SSIMT_MINBLOCKS
-#define DROSFM_SSIMT_MINBLOCKS 4
+#define DROSFM_SSIMT_MINBLOCKS 5      // blocks per SM: 2-4 -> 337 us, 5 -> 310 us
 #endif
 __global__ void __launch_bounds__(kTrainThreads, DROSFM_SSIMT_MINBLOCKS)
 ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restrict__ warped, const __grid_constant__ PhotoPtrs pp,
