@@ -102,6 +102,9 @@ SIGNATURES = {
     "drosfm_sup_depth_loss_fwd": ([_vp, _pp, _int, _f32, _f32, _f32, _vp, _vp, _int, _int, _int, _vp], _int),
     "drosfm_sup_depth_loss_bwd": ([_vp, _vp, _pp, _int, _f32, _f32, _f32, _pp, _int, _int, _int, _vp], _int),
     "drosfm_relayout": ([_vp, _vp, _int, _int, _int, _int, _int, _vp], _int),
+    "drosfm_post_process_inv_depth": ([_vp, _vp, _vp, _int, _int, _int, _int, _vp], _int),
+    "drosfm_eval_ws_bytes": ([_int], ctypes.c_size_t),
+    "drosfm_depth_metrics": ([_vp, _vp, _int, _int, _int, _int, _int, _f32, _f32, _int, _int, _vp, _vp, _vp], _int),
     "drosfm_images_u8_to_f32": ([_vp, _vp, ctypes.c_size_t, _vp], _int),
     "drosfm_upsample_depth_fwd": ([_vp, _vp, _vp, _int, _int, _int, _int, _f32, _f32, _vp], _int),
     "drosfm_upsample_depth_bwd": ([_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _f32, _vp], _int),
@@ -263,6 +266,19 @@ def side_stream(device):
     if st is None:
         st = _side_streams[idx] = torch.cuda.Stream(device)
     return st
+
+
+_eval_ws = {}
+
+
+def eval_workspace(device, B):
+    """Zero-initialised, self-cleaning workspace of drosfm_depth_metrics, one per (device, stream)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    need = int(lib().drosfm_eval_ws_bytes(int(B)))
+    ws = _eval_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _eval_ws[key] = torch.zeros(need, dtype=torch.uint8, device=device)
+    return ws
 
 
 def workspace(device, slots):

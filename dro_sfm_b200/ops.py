@@ -12,7 +12,7 @@ import torch
 from . import _lib as L
 
 __all__ = ["pose_vec2mat", "reconstruct", "project", "warp_coords", "grid_gather", "view_synthesis", "feat_cost", "feat_cost_batch",
-           "photometric_loss", "reproj_pose_loss", "sup_depth_loss", "upsample_depth", "images_u8_to_f32"]
+           "photometric_loss", "reproj_pose_loss", "sup_depth_loss", "upsample_depth", "images_u8_to_f32", "post_process_inv_depth", "depth_metrics"]
 
 
 def _pose_kind(pose):
@@ -978,6 +978,43 @@ def sup_depth_loss(inv_depths, gt_inv_depth, min_depth, max_depth, gamma=0.85):
         if tuple(d.shape) != tuple(gt_inv_depth.shape):
             raise NotImplementedError("dro_sfm_b200: predictions must be at the ground-truth resolution")
     return _SupDepthLoss.apply(gt_inv_depth, (float(min_depth), float(max_depth), float(gamma)), n, *inv_depths)
+
+
+# ------------------------------------------------------------------------------------------------
+# evaluation path
+# ------------------------------------------------------------------------------------------------
+def post_process_inv_depth(inv_depth, inv_depth_flipped, method="mean"):
+    """post_process_inv_depth (utils/depth.py:230-258), one launch.  No gradient (evaluation only)."""
+    methods = {"mean": 0, "max": 1, "min": 2}
+    if method not in methods:
+        raise ValueError("Unknown post-process method {}".format(method))
+    L.require_cuda(inv_depth, inv_depth_flipped)
+    a, b = L.f32c(inv_depth.detach()), L.f32c(inv_depth_flipped.detach())
+    if a.shape != b.shape or a.dim() != 4:
+        raise ValueError("inverse depth maps must be [B,C,H,W] tensors of the same shape")
+    B, C, H, W = a.shape
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        L.check(L.lib().drosfm_post_process_inv_depth(L.ptr(a), L.ptr(b), L.ptr(out), B * C, H, W, methods[method], L.stream()),
+                "post_process_inv_depth")
+    return out
+
+
+def depth_metrics(gt, pred, min_depth, max_depth, crop="", use_gt_scale=True):
+    """compute_depth_metrics (utils/depth.py:261-340) -> float32 [9] on the device: abs_rel, sq_rel, rmse, rmse_log, a1,
+    a2, a3, SILog, iabs_diff.  gt [B,1,H,W]; pred [B,1,h,w] (interpolated to the ground-truth resolution inside)."""
+    L.require_cuda(gt, pred)
+    g, p = L.f32c(gt.detach()), L.f32c(pred.detach())
+    if g.dim() != 4 or p.dim() != 4 or g.shape[1] != 1 or p.shape[1] != 1 or g.shape[0] != p.shape[0]:
+        raise ValueError("gt and pred must be [B,1,H,W] / [B,1,h,w]")
+    B, _, H, W = g.shape
+    code = {"garg": 1, "eigen_nyu": 2}.get(crop, 0)
+    out = torch.empty(9, device=g.device, dtype=torch.float32)
+    with torch.cuda.device(g.device):
+        ws = L.eval_workspace(g.device, B)
+        L.check(L.lib().drosfm_depth_metrics(L.ptr(g), L.ptr(p), B, H, W, p.shape[2], p.shape[3], float(min_depth), float(max_depth),
+                                             code, int(bool(use_gt_scale)), L.ptr(out), L.ptr(ws), L.stream()), "depth_metrics")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -8,6 +8,7 @@ Replaces (by name, keeping signatures) the hot-path symbols of the reference:
   dro_sfm.geometry.camera_utils.view_synthesis,
   dro_sfm.losses.multiview_photometric_loss_mf.MultiViewPhotometricDecayLoss,
   dro_sfm.losses.supervised_loss.SupervisedDepthPoseLoss,
+  dro_sfm.utils.depth.post_process_inv_depth / compute_depth_metrics (evaluation path),
   DepthPoseNet.get_cost_each / depth_cost_calc / upsample_depth, and (lockstep=True, the default) DepthPoseNet.forward
   by the lock-step schedule of networks/lockstep.py: the same sub-modules and arithmetic, with the 1 + V cost
   evaluations of every inner step of the recurrent optimiser submitted as one kernel launch.
@@ -36,6 +37,7 @@ def install(lockstep=True):
     from .geometry import Camera, Pose, view_synthesis
     from .losses import MultiViewPhotometricDecayLoss, SupervisedDepthPoseLoss
     from .networks.cost import FeatureMetricCost
+    from .utils.depth import post_process_inv_depth, compute_depth_metrics
 
     patched = []
     table = [
@@ -51,6 +53,11 @@ def install(lockstep=True):
                                               MultiViewPhotometricDecayLoss=MultiViewPhotometricDecayLoss)),
         ("dro_sfm.models.SfmModelMF", dict(Pose=Pose)),
         ("dro_sfm.networks.depth_pose.DepthPoseNet", dict(Camera=Camera, Pose=Pose)),
+        # evaluation path (model_wrapper.py:355-399): CUDA tensors only -- the reference's own functions stay in place for
+        # CPU evaluation because these wrappers refuse non-CUDA tensors
+        ("dro_sfm.utils.depth", dict(post_process_inv_depth=post_process_inv_depth, compute_depth_metrics=compute_depth_metrics)),
+        ("dro_sfm.models.model_wrapper", dict(post_process_inv_depth=post_process_inv_depth,
+                                              compute_depth_metrics=compute_depth_metrics)),
     ]
     for module_name, symbols in table:
         if _rebind(module_name, **symbols):

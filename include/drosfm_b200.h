@@ -300,6 +300,21 @@ int drosfm_upsample_depth_fwd(const float* depth, const float* mask, float* out,
 int drosfm_upsample_depth_bwd(const float* g_out, const float* depth, const float* mask, float* g_depth, float* g_mask,
                               int N, int H, int W, int ratio, float disp_range, drosfm_stream_t stream);
 
+/* ---- evaluation path (ModelWrapper.evaluate_depth, models/model_wrapper.py:355-399) -------
+ * post_process_inv_depth (dro_sfm/utils/depth.py:230-258): out = mask_hat * inv + mask * flip(inv_flipped) +
+ * (1 - mask - mask_hat) * fuse(inv, flip(inv_flipped)); inv, inv_flipped, out: [B,1,H,W]; method 0 mean, 1 max, 2 min. */
+int drosfm_post_process_inv_depth(const float* inv_depth, const float* inv_depth_flipped, float* out, int B, int H, int W,
+                                  int method, drosfm_stream_t stream);
+/* compute_depth_metrics (dro_sfm/utils/depth.py:261-340): gt [B,1,H,W], pred [B,1,Hp,Wp] (interpolated to H x W inside:
+ * bilinear, align_corners=True; clamped at 1e-6) -> metrics[9] = abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3, SILog,
+ * iabs_diff, each the batch average of the per-sample value over its valid pixels (min_depth < gt < max_depth inside the
+ * crop: 0 none, 1 'garg', 2 'eigen_nyu').  use_gt_scale: every sample's prediction is scaled by the median of gt / pred
+ * over its valid pixels -- the exact lower median torch.median returns, found by a three-pass radix selection.
+ * ws: drosfm_eval_ws_bytes(B) bytes, zero-filled once (left zeroed). */
+size_t drosfm_eval_ws_bytes(int B);
+int drosfm_depth_metrics(const float* gt, const float* pred, int B, int H, int W, int Hp, int Wp, float min_depth, float max_depth,
+                         int crop, int use_gt_scale, float* metrics, void* ws, drosfm_stream_t stream);
+
 /* ---- feature-map storage layout (the encoder's maps are NCHW, DepthPoseNet.py:113-115) -----------
  * Copies a [B,C,H,W] tensor from NCHW storage to NHWC storage (to_layout = DROSFM_NHWC) or back (DROSFM_NCHW);
  * what `.contiguous(memory_format=torch.channels_last)` / `.contiguous()` do, as a coalesced tiled transpose. */

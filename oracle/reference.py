@@ -102,6 +102,7 @@ def load():
     from dro_sfm.geometry.pose import Pose
     from dro_sfm.geometry.camera_utils import view_synthesis, scale_intrinsics
     from dro_sfm.utils.depth import inv2depth, calc_smoothness
+    from dro_sfm.utils import depth as _depth_utils
     from dro_sfm.losses.multiview_photometric_loss_mf import MultiViewPhotometricDecayLoss, SSIM
     from dro_sfm.losses.supervised_loss import SupervisedDepthPoseLoss
     from dro_sfm.networks.depth_pose.DepthPoseNet import DepthPoseNet
@@ -110,7 +111,8 @@ def load():
     # the stock functions are captured HERE, before any patch.install(): callers that want the stock behaviour after
     # the reference tree has been patched keep using these
     stock = dict(get_cost_each=DepthPoseNet.get_cost_each, depth_cost_calc=DepthPoseNet.depth_cost_calc,
-                 upsample_depth=DepthPoseNet.upsample_depth)
+                 upsample_depth=DepthPoseNet.upsample_depth, post_process_inv_depth=_depth_utils.post_process_inv_depth,
+                 compute_depth_metrics=_depth_utils.compute_depth_metrics)
     _loaded = types.SimpleNamespace(
         root=ref_root, Camera=Camera, Pose=Pose, view_synthesis=view_synthesis, scale_intrinsics=scale_intrinsics,
         inv2depth=inv2depth, calc_smoothness=calc_smoothness, SSIM=SSIM,
@@ -119,6 +121,7 @@ def load():
         get_cost_each=lambda *a, **k: stock["get_cost_each"](net, *a, **k),
         depth_cost_calc=lambda *a, **k: stock["depth_cost_calc"](net, *a, **k),
         upsample_depth=lambda *a, **k: stock["upsample_depth"](net, *a, **k),
+        post_process_inv_depth=stock["post_process_inv_depth"], compute_depth_metrics=stock["compute_depth_metrics"],
     )
     return _loaded
 

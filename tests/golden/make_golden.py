@@ -288,16 +288,51 @@ def case_upsample(ref):
     save("upsample", **out)
 
 
+def case_eval(ref):
+    """Evaluation path (model_wrapper.py:355-399): post_process_inv_depth (utils/depth.py:230-258) and
+    compute_depth_metrics (utils/depth.py:261-340), the reference's own functions on the CPU."""
+    import types
+    g = syn.gen(707)
+    out = {}
+    # post-processing: odd and even widths (the linspace mask is built from both ends)
+    for tag, (B, H, W) in (("pp_a", (2, 6, 41)), ("pp_b", (1, 5, 64))):
+        a = syn.inv_depth(g, B, H, W, 0.5, 80.0)
+        b = syn.inv_depth(g, B, H, W, 0.5, 80.0)
+        out[tag + "_inv"], out[tag + "_inv_flipped"] = a, b
+        for method in ("mean", "max", "min"):
+            out["%s_%s" % (tag, method)] = ref.post_process_inv_depth(a, b, method=method)
+    # metrics: sparse ground truth with out-of-range values, a prediction at another resolution, one sample without a
+    # single valid pixel, every crop mode, with and without median scaling
+    cases = {"m_garg": ("garg", 0.1, 80.0, (3, 48, 160), (24, 80)), "m_none": ("", 0.5, 10.0, (2, 30, 50), (30, 50)),
+             "m_nyu": ("eigen_nyu", 0.1, 10.0, (1, 480, 640), (60, 80))}
+    for tag, (crop, lo, hi, (B, H, W), (h, w)) in cases.items():
+        gt = lo * 0.5 + torch.rand(B, 1, H, W, generator=g) * (hi * 1.2 - lo * 0.5)
+        gt = gt * (torch.rand(B, 1, H, W, generator=g) < (0.4 if H < 400 else 0.08))  # sparse (LiDAR-like)
+        pred = lo + torch.rand(B, 1, h, w, generator=g) * (hi - lo) * 0.7
+        pred[0, 0, 0, :3] = 0.0                                                        # exercised by clamp(min=1e-6)
+        if B > 2:
+            gt[1] = 0.0                                                                # sample without valid pixels
+        cfg = types.SimpleNamespace(crop=crop, min_depth=lo, max_depth=hi)
+        out[tag + "_gt"], out[tag + "_pred"] = gt, pred
+        out[tag + "_cfg"] = np.array([lo, hi, {"": 0, "garg": 1, "eigen_nyu": 2}[crop]], np.float64)
+        for scale in (True, False):
+            out["%s_scale%d" % (tag, int(scale))] = ref.compute_depth_metrics(cfg, gt, pred, use_gt_scale=scale)
+    save("eval", **out)
+
+
 def main():
     ref = ref_import.load()
     if len(sys.argv) > 1 and sys.argv[1] == "upsample":
         return case_upsample(ref)
+    if len(sys.argv) > 1 and sys.argv[1] == "eval":
+        return case_eval(ref)
     case_coords(ref)
     case_view_synthesis(ref)
     case_feat_cost(ref)
     case_photometric(ref)
     case_supervised(ref)
     case_upsample(ref)
+    case_eval(ref)
 
 
 if __name__ == "__main__":
