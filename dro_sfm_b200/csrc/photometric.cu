@@ -21,6 +21,7 @@
 //
 // Algorithmic bytes per pixel and prediction: fwd 16 + 12 V (target 12 + depth 4 + V sources 12),
 // bwd 20 + 12 V.
+#include <type_traits>
 #include "common.cuh"
 
 namespace drosfm {
@@ -1665,10 +1666,23 @@ ssim_bwd_stream2_kernel(const float* __restrict__ g_loss, const float* __restric
 // step), every warp forms the photometric values of both views, the min / auto-mask selection and from it the
 // coefficients of its own channel.  Channel 0 accumulates the loss and writes the selection.
 constexpr int kTrainThreads = 96;
+#ifndef DROSFM_SSIMT_INNER
+#define DROSFM_SSIMT_INNER 1      // bands away from the top / bottom edge run a copy of the walk without the row tests
+#endif
+#ifndef DROSFM_SSIMT_BAND
+#define DROSFM_SSIMT_BAND 32
+#endif
+constexpr int kTrainBandH = DROSFM_SSIMT_BAND;      // rows written per block (4 more are loaded)
 
 #ifndef DROSFM_SSIMT_MINBLOCKS
 #define DROSFM_SSIMT_MINBLOCKS 5      // blocks per SM: 2-4 -> 337 us, 5 -> 310 us
 #endif
+__device__ __forceinline__ float2 third2(float2 x) {      // third() of both halves
+    const float2 r = bc2(1.0f / 3.0f);
+    const float2 q = mul2(x, r);
+    return fma2(fma2(bc2(-3.0f), q, x), r, q);
+}
+
 __global__ void __launch_bounds__(kTrainThreads, DROSFM_SSIMT_MINBLOCKS)
 ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restrict__ warped, const __grid_constant__ PhotoPtrs pp,
                           int n_preds, const float* __restrict__ automask_in, drosfm_photo_opts_t opts, float l1_w,
@@ -1681,7 +1695,7 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
     const int strip = wg % nstrips, band = wg / nstrips;
     const int b = static_cast<int>(blockIdx.y) % B, ip = static_cast<int>(blockIdx.y) / B;
     const int P = H * W;
-    const int gx = strip * kBwdStripW - 2 + lane, gy0 = band * kBwdBandH;
+    const int gx = strip * kBwdStripW - 2 + lane, gy0 = band * kTrainBandH;
     const bool col_in = gx >= 0 && gx < W;
     const bool out_lane = lane >= 2 && lane <= kBwdStripW + 1 && gx < W;
     const Lanes nb = neighbour_lanes(lane, gx == 0, gx == W - 1);
@@ -1708,25 +1722,43 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
         float y, am;
     };
     Pre f0, f1, f2;
-    auto fetch = [&](int gy, Pre& f) {
-        const unsigned off = static_cast<unsigned>(padded_row(gy, H) * W);
-        f.x.x = col_in ? __ldg(xpl + off) : 0.0f;
-        f.x.y = col_in ? __ldg(xpl + (off + vstride)) : 0.0f;
-        f.y = col_in ? __ldg(ypl + off) : 0.0f;
-        // the auto-mask value of a row travels with it (consumed one step later, when the row is a window centre)
-        f.am = (apl != nullptr && col_in && gy >= 0 && gy < H) ? __ldg(apl + static_cast<unsigned>(gy * W)) : __int_as_float(0x7f800000);
+    // INNER (a block-uniform compile-time tag): every row the band touches lies inside the picture, at least two rows away
+    // from its top and bottom edge -- no reflection, no row tests, unit vertical window weights
+    // (the INNER walk reads and writes consecutive rows: running row pointers instead of row * W products)
+    const float *xrow = nullptr, *yrow = nullptr, *arow = nullptr;
+    float* grow = nullptr;
+    uint8_t* srow = nullptr;
+    auto fetch = [&](auto inner, int gy, Pre& f) {
+        constexpr bool INNER = decltype(inner)::value;
+        if constexpr (INNER) {
+            f.x.x = col_in ? __ldg(xrow) : 0.0f;
+            f.x.y = col_in ? __ldg(xrow + vstride) : 0.0f;
+            f.y = col_in ? __ldg(yrow) : 0.0f;
+            f.am = (apl != nullptr && col_in) ? __ldg(arow) : __int_as_float(0x7f800000);
+            xrow += W;
+            yrow += W;
+            arow += W;
+        } else {
+            const unsigned off = static_cast<unsigned>(padded_row(gy, H) * W);
+            f.x.x = col_in ? __ldg(xpl + off) : 0.0f;
+            f.x.y = col_in ? __ldg(xpl + (off + vstride)) : 0.0f;
+            f.y = col_in ? __ldg(ypl + off) : 0.0f;
+            // the auto-mask value of a row travels with it (consumed one step later, when the row is a window centre)
+            f.am = (apl != nullptr && col_in && gy >= 0 && gy < H) ? __ldg(apl + static_cast<unsigned>(gy * W)) : __int_as_float(0x7f800000);
+        }
     };
     float am_row = __int_as_float(0x7f800000);      // auto-mask of the row loaded in the previous step = this step's window centre
     int sv_prev = 254;
     float local = 0.0f;
-    auto step = [&](BwdRow2& p2, BwdRow2& p1, BwdRow2& cur, Pre& mine, Pre& refill, int j) {
+    auto step = [&](auto inner, BwdRow2& p2, BwdRow2& p1, BwdRow2& cur, Pre& mine, Pre& refill, int j) {
+        constexpr bool INNER = decltype(inner)::value;
         const int gy = gy0 - 2 + j;          // row loaded in this step; windows centred on gy-1; gradients of row gy-2
         const int gc = gy - 1;
         cur.x = mine.x;
         cur.y = mine.y;
         const float am = am_row;
         am_row = mine.am;
-        fetch(gy + 2, refill);
+        fetch(inner, gy + 2, refill);
         const float2 xl = shfl2(cur.x, nb.l), xr = shfl2(cur.x, nb.r);
         float yl, yr;
         neighbours(cur.y, nb, yl, yr);
@@ -1756,15 +1788,19 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
             const float2 num = mul2(A1, A2), den = mul2(B1, B2);
             const float2 rden = make_float2(__fdividef(1.0f, den.x), __fdividef(1.0f, den.y));
             const float2 sm = mul2(num, rden);
-            const float l0 = (1.0f - sm.x) * 0.5f, l1 = (1.0f - sm.y) * 0.5f;
+            const float2 l01 = mul2(fma2(bc2(-1.0f), sm, bc2(1.0f)), bc2(0.5f));      // (1 - ssim) / 2, both views
+            const float l0 = l01.x, l1 = l01.y;
             // this channel's terms of the photometric value of the window centre (row p1)
-            const float4 mineq = make_float4(fminf(fmaxf(l0, 0.0f), 1.0f), fminf(fmaxf(l1, 0.0f), 1.0f),
-                                             fabsf(p1.x.x - p1.y), fabsf(p1.x.y - p1.y));
+            const float2 dxy = fma2(bc2(-1.0f), bc2(p1.y), p1.x);                     // x - y, exact as a difference
+            const float4 mineq = make_float4(fminf(fmaxf(l0, 0.0f), 1.0f), fminf(fmaxf(l1, 0.0f), 1.0f), fabsf(dxy.x), fabsf(dxy.y));
             xchg[j & 1][c][lane] = mineq;
             asm volatile("bar.sync 1, 96;" ::: "memory");
             const float4 q0 = xchg[j & 1][0][lane], q1 = xchg[j & 1][1][lane], q2 = xchg[j & 1][2][lane];
-            const float pm0 = __fadd_rn(__fmul_rn(opts.ssim_w, third(q0.x + q1.x + q2.x)), __fmul_rn(l1_w, third(q0.z + q1.z + q2.z)));
-            const float pm1 = __fadd_rn(__fmul_rn(opts.ssim_w, third(q0.y + q1.y + q2.y)), __fmul_rn(l1_w, third(q0.w + q1.w + q2.w)));
+            // channel means and the weighted sum, both views at once (same operations, same order as the scalar form)
+            const float2 ssum = add2(add2(make_float2(q0.x, q0.y), make_float2(q1.x, q1.y)), make_float2(q2.x, q2.y));
+            const float2 lsum = add2(add2(make_float2(q0.z, q0.w), make_float2(q1.z, q1.w)), make_float2(q2.z, q2.w));
+            const float2 pm = add2(mul2(bc2(opts.ssim_w), third2(ssum)), mul2(bc2(l1_w), third2(lsum)));
+            const float pm0 = pm.x, pm1 = pm.y;
             float best;
             if (use_min) {
                 best = __int_as_float(0x7f800000);
@@ -1775,12 +1811,16 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
                 best = pm0 + pm1;
                 sv = 253;
             }
-            const bool centre_in = col_in && gc >= 0 && gc < H;
+            const bool centre_in = col_in && (INNER || (gc >= 0 && gc < H));
             if (!centre_in) sv = 254;
-            if (c == 0 && out_lane && gc >= gy0 && gc < gy0 + kBwdBandH && gc < H) {
+            if (c == 0 && out_lane && j >= 3 && j < kTrainBandH + 3 && (INNER || gc < H)) {
                 local += best;
-                if (spl != nullptr) spl[static_cast<unsigned>(gc * W)] = static_cast<uint8_t>(use_min ? sv : 254);
+                if (spl != nullptr) {
+                    if constexpr (INNER) *srow = static_cast<uint8_t>(use_min ? sv : 254);
+                    else spl[static_cast<unsigned>(gc * W)] = static_cast<uint8_t>(use_min ? sv : 254);
+                }
             }
+            if (INNER && j >= 3) srow += W;
             // coefficients of the windows that carry a gradient
             float2 a = bc2(0.0f), bb = a, cq = a;
             const bool on0 = sv == 0 || sv == 253, on1 = sv == 1 || sv == 253;
@@ -1804,12 +1844,19 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
         }
         if (j >= 4) {
             const int gq = gy - 2;
-            if (out_lane && gq < gy0 + kBwdBandH && gq < H) {
-                const float2 wy0 = bc2(gq <= 0 ? 0.0f : (gq == 1 ? 2.0f : 1.0f));
-                const float2 wy2 = bc2(gq >= H - 1 ? 0.0f : (gq == H - 2 ? 2.0f : 1.0f));
-                const float2 ga = fma2(wy2, p1.ha, fma2(wy0, cur.ha, p2.ha));
-                const float2 gb = fma2(wy2, p1.hb, fma2(wy0, cur.hb, p2.hb));
-                const float2 gc_ = fma2(wy2, p1.hc, fma2(wy0, cur.hc, p2.hc));
+            if (out_lane && j < kTrainBandH + 4 && (INNER || gq < H)) {
+                float2 ga, gb, gc_;
+                if constexpr (INNER) {      // unit weights: the same sums, bit for bit
+                    ga = add2(p1.ha, add2(cur.ha, p2.ha));
+                    gb = add2(p1.hb, add2(cur.hb, p2.hb));
+                    gc_ = add2(p1.hc, add2(cur.hc, p2.hc));
+                } else {
+                    const float2 wy0 = bc2(gq <= 0 ? 0.0f : (gq == 1 ? 2.0f : 1.0f));
+                    const float2 wy2 = bc2(gq >= H - 1 ? 0.0f : (gq == H - 2 ? 2.0f : 1.0f));
+                    ga = fma2(wy2, p1.ha, fma2(wy0, cur.ha, p2.ha));
+                    gb = fma2(wy2, p1.hb, fma2(wy0, cur.hb, p2.hb));
+                    gc_ = fma2(wy2, p1.hc, fma2(wy0, cur.hc, p2.hc));
+                }
                 float2 gxv = fma2(gc_, bc2(p2.y), fma2(gb, p2.x, ga));
                 const bool q0 = sv_prev == 0 || sv_prev == 253, q1 = sv_prev == 1 || sv_prev == 253;
                 if (q0) {
@@ -1820,10 +1867,16 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
                     const float df = p2.x.y - p2.y;
                     gxv.y += df == 0.0f ? 0.0f : __int_as_float(__float_as_int(kl1) ^ (__float_as_int(df) & 0x80000000));
                 }
-                const unsigned o = static_cast<unsigned>(gq * W);
-                gpl[o] = gxv.x;
-                gpl[o + vstride] = gxv.y;
+                if constexpr (INNER) {
+                    grow[0] = gxv.x;
+                    grow[vstride] = gxv.y;
+                } else {
+                    const unsigned o = static_cast<unsigned>(gq * W);
+                    gpl[o] = gxv.x;
+                    gpl[o + vstride] = gxv.y;
+                }
             }
+            if constexpr (INNER) grow += W;
         }
         sv_prev = sv;
     };
@@ -1833,14 +1886,30 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
     r0.sy = r0.syy = r1.sy = r1.syy = 0.0f;
     r0.x = r1.x = bc2(0.0f);
     r0.y = r1.y = 0.0f;
-    fetch(gy0 - 2, f0);
-    fetch(gy0 - 1, f1);
+    auto walk = [&](auto inner) {
+        if constexpr (decltype(inner)::value) {
+            const unsigned first = static_cast<unsigned>((gy0 - 2) * W), out0 = static_cast<unsigned>(gy0 * W);
+            xrow = xpl + first;
+            yrow = ypl + first;
+            arow = apl != nullptr ? apl + first : nullptr;
+            grow = gpl + out0;
+            srow = spl != nullptr ? spl + out0 : nullptr;
+        }
+        fetch(inner, gy0 - 2, f0);
+        fetch(inner, gy0 - 1, f1);
 #pragma unroll 1
-    for (int j = 0; j < kBwdBandH + 4; j += 3) {
-        step(r1, r2, r0, f0, f2, j);
-        step(r2, r0, r1, f1, f0, j + 1);
-        step(r0, r1, r2, f2, f1, j + 2);
-    }
+        for (int j = 0; j < kTrainBandH + 4; j += 3) {
+            step(inner, r1, r2, r0, f0, f2, j);
+            step(inner, r2, r0, r1, f1, f0, j + 1);
+            step(inner, r0, r1, r2, f2, f1, j + 2);
+        }
+    };
+    constexpr int kSteps = (kTrainBandH + 4 + 2) / 3 * 3;      // the last row fetched is gy0 + kSteps - 1
+#if DROSFM_SSIMT_INNER
+    if (gy0 >= 2 && gy0 + kSteps - 1 <= H - 1) walk(std::true_type{});
+    else
+#endif
+        walk(std::false_type{});
     // loss: channel 0's lanes hold the per-pixel values of the band
     if (c == 0) {
         const double part = warp_sum(static_cast<double>(local));
@@ -1999,7 +2068,7 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
         }
         if (flags & DROSFM_PHOTO_FUSE_BWD) {
             // training forward: loss, selection AND d loss / d warped (unscaled) in one pass over the warped copy
-            const int nstrips = (W + kBwdStripW - 1) / kBwdStripW, nbands = (H + kBwdBandH - 1) / kBwdBandH;
+            const int nstrips = (W + kBwdStripW - 1) / kBwdStripW, nbands = (H + kTrainBandH - 1) / kTrainBandH;
             dim3 tgrid(nstrips * nbands, B * n_preds);
             ssim_train_stream2_kernel<<<tgrid, kTrainThreads, 0, cs>>>(image, warped_save, pp, n_preds, opts->automask ? automask : nullptr,
                                                                       *opts, l1_weight(opts), sel, loss, static_cast<Slot*>(ws), g_warped,
