@@ -354,22 +354,12 @@ __device__ __forceinline__ float4 blend4(const float4& a, const float4& b, const
                        a.z * wa + b.z * wb + c.z * wc + d.z * wd, a.w * wa + b.w * wb + c.w * wc + d.w * wd);
 }
 
-// Camera set-up of a block for the V views of its job.  Several views: the three parts of every view's set-up run in
-// three warps (measured: -0.3 / -1.2 us per call); one view: a second barrier costs more than the split saves.
+// Camera set-up of a block for the V views of its job: the three parts of every view's set-up run in three warps
+// (lane = view), one barrier.
 template <int VT>
 __device__ __forceinline__ void setup_cams_block(const drosfm_cams_t& cams, const CostJob& job, int b, Cam* cam) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, V = job.V;
-    if constexpr (VT >= 2) {
-        if (V >= 2) {
-            if (wid < 3 && lane < V) setup_cam_part(cams, job.pose[lane], b, cam[lane], wid);      // kWarpsPerBlock >= 3
-            __syncthreads();
-            if (threadIdx.x < V) setup_cam_finish(cam[threadIdx.x]);
-        } else if (threadIdx.x == 0) {
-            setup_cam(cams, job.pose[0], b, cam[0]);
-        }
-    } else {
-        if (threadIdx.x == 0) setup_cam(cams, job.pose[0], b, cam[0]);
-    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (wid < 3 && lane < job.V) setup_cam_part(cams, job.pose[lane], b, cam[lane], wid);      // kWarpsPerBlock >= 3
     __syncthreads();
 }
 
@@ -460,6 +450,9 @@ struct PixLoad {
 // Register budget per template: four and eight views keep per-view state for every view and get 4 / 3 blocks per SM
 // instead of spilling (round 1's 5 blocks/SM spilled 104 / 256 local-memory accesses in the V = 4 / 8 kernels).
 // one / two views: 4 blocks per SM (128 registers): cost phase of the benchmark step 360 us; 5 blocks 371, 6 blocks 371
+#ifndef DROSFM_COST_BWD_ALLVALID
+#define DROSFM_COST_BWD_ALLVALID 1
+#endif
 #ifndef DROSFM_COST_BWD_BLOCKS
 #define DROSFM_COST_BWD_BLOCKS 4
 #endif
@@ -566,12 +559,18 @@ feat_cost_bwd_nhwc(const __grid_constant__ CostJobs jobs, const __grid_constant_
                 }
                 if (need_coord_grad) {
                     // taps outside the source count as zeros in the coordinate gradient
-                    const float m0 = (t.valid & 1u) ? 1.f : 0.f, m1 = (t.valid & 2u) ? 1.f : 0.f;
-                    const float m2 = (t.valid & 4u) ? 1.f : 0.f, m3 = (t.valid & 8u) ? 1.f : 0.f;
-                    const float4 a = make_float4(cur.a.x * m0, cur.a.y * m0, cur.a.z * m0, cur.a.w * m0);
-                    const float4 bq = make_float4(cur.b.x * m1, cur.b.y * m1, cur.b.z * m1, cur.b.w * m1);
-                    const float4 c4 = make_float4(cur.c.x * m2, cur.c.y * m2, cur.c.z * m2, cur.c.w * m2);
-                    const float4 e = make_float4(cur.e.x * m3, cur.e.y * m3, cur.e.z * m3, cur.e.w * m3);
+                    float4 a = cur.a, bq = cur.b, c4 = cur.c, e = cur.e;
+#if DROSFM_COST_BWD_ALLVALID
+                    if (t.valid != 15u)      // warp-uniform (the tap record is a shared-memory broadcast); rare: image border
+#endif
+                    {
+                        const float m0 = (t.valid & 1u) ? 1.f : 0.f, m1 = (t.valid & 2u) ? 1.f : 0.f;
+                        const float m2 = (t.valid & 4u) ? 1.f : 0.f, m3 = (t.valid & 8u) ? 1.f : 0.f;
+                        a = make_float4(a.x * m0, a.y * m0, a.z * m0, a.w * m0);
+                        bq = make_float4(bq.x * m1, bq.y * m1, bq.z * m1, bq.w * m1);
+                        c4 = make_float4(c4.x * m2, c4.y * m2, c4.z * m2, c4.w * m2);
+                        e = make_float4(e.x * m3, e.y * m3, e.z * m3, e.w * m3);
+                    }
                     const float s01 = co.x * (bq.x - a.x) + co.y * (bq.y - a.y) + co.z * (bq.z - a.z) + co.w * (bq.w - a.w);
                     const float s23 = co.x * (e.x - c4.x) + co.y * (e.y - c4.y) + co.z * (e.z - c4.z) + co.w * (e.w - c4.w);
                     const float s02 = co.x * (c4.x - a.x) + co.y * (c4.y - a.y) + co.z * (c4.z - a.z) + co.w * (c4.w - a.w);

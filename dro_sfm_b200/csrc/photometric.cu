@@ -743,9 +743,7 @@ warp_sources_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind,
     __shared__ Cam cam_s;
     const int slot = blockIdx.z;                               // (ip * V + v) * B + b
     const int b = slot % B, v = (slot / B) % V, ip = slot / (B * V);
-    if (threadIdx.x == 0) setup_cam(cams, pp.pose[v * n_preds + ip], b, cam_s);
-    __syncthreads();
-    const Cam cam = cam_s;
+    setup_cam_split(cams, pp.pose[v * n_preds + ip], b, cam_s);
     const int P = H * W;
     const Norm nm = make_norm(W, H);
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -753,21 +751,30 @@ warp_sources_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind,
     const float* __restrict__ src = pp.context[v] + static_cast<size_t>(b) * 3 * P;
     const float4* __restrict__ tex = reinterpret_cast<const float4*>(rgbx) + (static_cast<size_t>(v) * B + b) * P;
     float* __restrict__ out = warped + static_cast<size_t>(slot) * 3 * P;
-    if (x >= W) return;
     constexpr int kStride = kFlatThreads / 32;
-    // a block walks down kFwdTiles tiles of 64 rows: the camera set-up (one thread, a barrier) is paid once for all of them
+    // the depths of a tile are all requested up front -- those of the first tile before the barrier of the camera set-up,
+    // whose latency they share
+    float d[kFlatRows];
+    auto load_depths = [&](int tile) {
+        const int y0 = (blockIdx.y * kFwdTiles + tile) * kFlatTileH + (threadIdx.x >> 5);
+#pragma unroll
+        for (int k = 0; k < kFlatRows; ++k) {
+            const int y = y0 + k * kStride;
+            d[k] = (x < W && y < H) ? __ldg(invd + y * W + x) : 0.0f;
+        }
+    };
+    load_depths(0);
+    __syncthreads();
+    const Cam cam = cam_s;
+    if (x >= W) return;
+    // a block walks down kFwdTiles tiles of 64 rows: the camera set-up (three threads, a barrier) is paid once for all of them
 #pragma unroll 1
     for (int tile = 0; tile < kFwdTiles; ++tile) {
         const int y0 = (blockIdx.y * kFwdTiles + tile) * kFlatTileH + (threadIdx.x >> 5);
         if (y0 - static_cast<int>(threadIdx.x >> 5) >= H) break;
-        // Software pipeline over the thread's rows: the depths are all requested up front; the gathers of row k
-        // are in flight while the coordinate chain of row k+1 runs.
-        float d[kFlatRows];
-#pragma unroll
-        for (int k = 0; k < kFlatRows; ++k) {
-            const int y = y0 + k * kStride;
-            d[k] = y < H ? __ldg(invd + y * W + x) : 0.0f;
-        }
+        // Software pipeline over the thread's rows: the gathers of row k are in flight while the coordinate chain of
+        // row k+1 runs.
+        if (tile > 0) load_depths(tile);
         auto taps_of = [&](int k) {
             // rows beyond the image run the chain on depth 0 (in-range addresses, results discarded): no divergence
             Warp wp;
@@ -844,8 +851,7 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
     const int tid = threadIdx.x;
     const int slot = blockIdx.z;                               // (ip * V + v) * B + b
     const int b = slot % B, v = (slot / B) % V, ip = slot / (B * V);
-    if (tid == 0) setup_cam(cams, pp.pose[v * n_preds + ip], b, cam_s);
-    __syncthreads();
+    setup_cam_split(cams, pp.pose[v * n_preds + ip], b, cam_s);      // the barrier follows the first loads (below)
     const Cam& cam = cam_s;                                    // read from shared memory on use: the registers go to occupancy
     const int P = H * W;
     const Norm nm = make_norm(W, H);
@@ -888,6 +894,7 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
         }
     };
     fetch(0);
+    __syncthreads();                                           // camera set-up done (its latency shared with the loads above)
     constexpr int kAdjUnroll = DROSFM_ADJ_UNROLL;
 #pragma unroll kAdjUnroll
     for (int k = 0; k < kRows; k += kIlp) {
