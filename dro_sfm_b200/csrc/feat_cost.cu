@@ -248,7 +248,7 @@ feat_cost_bwd_nchw(const float* __restrict__ g_cost, const float* __restrict__ f
                     const float mx = 0.5f * static_cast<float>(w - 1), my = 0.5f * static_cast<float>(h - 1);
                     gd += warp_pixel_adjoint(cam[v], wp, d, wm1, hm1, true, gx * mx, gy * my, gT);
                 }
-                if (vg.g_pose[v] != nullptr) warp_accumulate<12>(gT, spread_acc(slot_at(ws, v * B + b)));
+                if (vg.g_pose[v] != nullptr) warp_accumulate12(gT, spread_acc(slot_at(ws, v * B + b)));
             }
         }
     }
@@ -610,7 +610,7 @@ feat_cost_bwd_nhwc(const __grid_constant__ CostJobs jobs, const __grid_constant_
                 const float mx = 0.5f * static_cast<float>(w - 1), my = 0.5f * static_cast<float>(h - 1);
                 gd += warp_pixel_adjoint(cam[v], wp, d, wm1, hm1, true, acc_g[v].x * mx, acc_g[v].y * my, gT);
             }
-            if (jg.g_pose[v] != nullptr) warp_accumulate<12>(gT, spread_acc(slot_at(ws, jg.slot0 + v * B + b)));
+            if (jg.g_pose[v] != nullptr) warp_accumulate12(gT, spread_acc(slot_at(ws, jg.slot0 + v * B + b)));
         }
     }
     if (mine && jg.g_depth != nullptr)

@@ -638,7 +638,7 @@ photometric_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict
             }
         }
         if (pg.g_pose[v * n_preds + ip] != nullptr)
-            warp_accumulate<12>(gT, spread_acc(slot_at(ws, (v * n_preds + ip) * B + b)));
+            warp_accumulate12(gT, spread_acc(slot_at(ws, (v * n_preds + ip) * B + b)));
         __syncthreads();      // gxs / xs are rewritten by the next view
     }
     if (SAVED) return;

@@ -182,6 +182,76 @@ def test_reference_model_stock_vs_patched(kind, wl_name, B, flip, lockstep):
         assert d_grad <= 5e-3, d_grad
 
 
+@pytest.mark.parametrize("kind,wl_name,B", [("selfsup", "train_kitti_mf_selfsup", 2), ("sup", "train_scannet_mf_gt_view3", 2)])
+def test_reference_model_training_step_as_cuda_graph(kind, wl_name, B):
+    """the patched reference model's whole training step (encoder, GRU iterations, cost calls, loss, backward)
+    recorded in ONE CUDA graph (dro_sfm_b200.graphs.GraphedStep) -- same loss and gradients as the eager step, on a second
+    batch as well (the graph must read the static buffers, not constants baked in at capture)."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    from dro_sfm_b200.graphs import GraphedStep
+    wl = syn.WORKLOADS[wl_name]
+    reference.load()
+    version = "it8-seq4-inter-out" if kind == "selfsup" else "it12-h-out"
+    net = reference.build_depth_pose_net(version, wl.min_depth, wl.max_depth, seed=3).to(DEV).train()
+    batch = _batch(wl, B, kind == "sup")
+    batch2 = dict(batch, rgb=torch.roll(batch["rgb"], 5, 2), rgb_original=torch.roll(batch["rgb"], 5, 2))
+    mod_name, cls_name = ("dro_sfm.models.SelfSupModelMF", "SelfSupModelMF") if kind == "selfsup" else \
+        ("dro_sfm.models.SupModelMF", "SupModelMF")
+    kwargs = dict(LOSS_CFG, flip_lr_prob=0.0, min_depth=wl.min_depth, max_depth=wl.max_depth)
+    state = _install(True)
+    try:
+        model = getattr(importlib.import_module(mod_name), cls_name)(**kwargs)
+        model.add_depth_net(net)
+        model = model.to(DEV).train()
+        for m in model.modules():                      # BatchNorm running statistics would differ between the two arms
+            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+                m.momentum = 0.0
+        eager = [_step(model, b) for b in (batch, batch2)]
+        ms_eager = _timed(model, batch)
+        step = GraphedStep(lambda b: model(b), batch, model.parameters())
+        got = []
+        for b in (batch, batch2, batch):
+            out = step(b)
+            torch.cuda.synchronize()
+            got.append((out["loss"].detach().clone(), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            step(batch)
+        torch.cuda.synchronize()
+        ms_graph = (time.perf_counter() - t0) / 5 * 1e3
+        # the same pair with PyTorch's default convolution precision (TF32 allowed), as a user trains: timing only
+        torch.backends.cudnn.allow_tf32 = True
+        ms_eager_tf32 = _timed(model, batch)
+        step_tf32 = GraphedStep(lambda b: model(b), batch, model.parameters())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            step_tf32(batch)
+        torch.cuda.synchronize()
+        ms_graph_tf32 = (time.perf_counter() - t0) / 5 * 1e3
+    finally:
+        torch.backends.cudnn.allow_tf32 = False
+        _uninstall(state)
+    for i, j in ((0, 0), (1, 1), (2, 0)):
+        loss_e, _, _, grads_e = eager[j]
+        loss_g, grads_g = got[i]
+        d_loss = abs(float(loss_g.sum()) - float(loss_e.sum())) / abs(float(loss_e.sum()))
+        ge = torch.cat([grads_e[k].flatten() for k in sorted(grads_e)])
+        gg = torch.cat([grads_g[k].flatten() for k in sorted(grads_e)])
+        d_grad = _rel(gg, ge)
+        _log("%s %s B=%d CUDA-graph replay %d vs eager: loss %.2e, parameter gradients %.2e" % (cls_name, wl_name, B, i, d_loss, d_grad))
+        # same kernels, same inputs: only the order of the atomic accumulations differs between two runs
+        assert d_loss <= 1e-5 and d_grad <= 2e-3, (i, d_loss, d_grad)
+    assert float((got[0][0] - got[1][0]).abs().sum()) > 0.0, "the second batch did not reach the graph"
+    _log("%s %s B=%d whole training step fwd+bwd: eager (patched) %.1f ms, one CUDA graph %.1f ms (x%.2f)"
+         % (cls_name, wl_name, B, ms_eager, ms_graph, ms_eager / ms_graph))
+    _log("   with cuDNN TF32 convolutions (PyTorch default): eager %.1f ms, one CUDA graph %.1f ms (x%.2f)"
+         % (ms_eager_tf32, ms_graph_tf32, ms_eager_tf32 / ms_graph_tf32))
+
+
 def _install(lockstep=True):
     """patch.install() with a record of what it replaced, so that the next parametrisation starts from the stock tree."""
     import sys
@@ -189,7 +259,7 @@ def _install(lockstep=True):
     names = ["dro_sfm.geometry.pose", "dro_sfm.geometry.camera", "dro_sfm.geometry.camera_utils",
              "dro_sfm.losses.multiview_photometric_loss_mf", "dro_sfm.losses.supervised_loss", "dro_sfm.models.SelfSupModelMF",
              "dro_sfm.models.SupModelMF", "dro_sfm.models.SemiSupModelMF", "dro_sfm.models.SfmModelMF",
-             "dro_sfm.networks.depth_pose.DepthPoseNet"]
+             "dro_sfm.networks.depth_pose.DepthPoseNet", "dro_sfm.utils.depth"]
     saved = {}
     for n in names:
         try:
