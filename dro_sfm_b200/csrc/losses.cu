@@ -72,44 +72,69 @@ smooth_mean_kernel(const __grid_constant__ DepthList dl, float* __restrict__ sta
 __device__ __forceinline__ float edge_weight(const float* __restrict__ img, int P, int p, int q) {
     const float a = fabsf(__ldg(img + p) - __ldg(img + q)) + fabsf(__ldg(img + P + p) - __ldg(img + P + q)) +
                     fabsf(__ldg(img + 2 * P + p) - __ldg(img + 2 * P + q));
-    return expf(-(a / 3.0f));
+    // a / 3, correctly rounded, without the division's ~15 instructions (q = RN(a/3) from one Newton-style correction)
+    const float r = 1.0f / 3.0f, t = __fmul_rn(a, r);
+    return expf(-__fmaf_rn(__fmaf_rn(-3.0f, t, a), r, t));
 }
 
 // pass 2: sums of |dx|*wx and |dy|*wy per (prediction, sample); the last block folds them into the loss.
 // One thread per pixel (grid-stride), the normalisation d / mean is a multiplication by the reciprocal mean
 // (computed once per thread; 1 ulp from the reference's division, far inside the loss tolerance).
+// NP: n_preds rounded up to a multiple of four (the per-prediction code is unrolled NP times; slots beyond n_preds are
+// predicated off but still issue)
+template <int NP>
 __global__ void __launch_bounds__(kLossThreads)
 smooth_fwd_kernel(const float* __restrict__ image, const __grid_constant__ DepthList dl, int n_preds, float weight,
                   float* __restrict__ stats, float* __restrict__ loss, Slot* ws, int B, int H, int W) {
-    __shared__ float red[2 * DROSFM_MAX_PREDS][kLossThreads / 32];
+    __shared__ float red[2 * NP][kLossThreads / 32];
+    __shared__ float rm_s[NP];
     __shared__ int flag;
     const int b = blockIdx.y, P = H * W;
     const float* img = image + static_cast<size_t>(b) * 3 * P;
-    float sx[DROSFM_MAX_PREDS], sy[DROSFM_MAX_PREDS], rm[DROSFM_MAX_PREDS];
+    // reciprocal means: one division per prediction and BLOCK
+    if (threadIdx.x < NP) rm_s[threadIdx.x] = threadIdx.x < n_preds ? 1.0f / fmaxf(stats[(threadIdx.x * B + b) * 4], 1e-6f) : 0.0f;
+    __syncthreads();
+    float sx[NP], sy[NP], rm[NP];
 #pragma unroll
-    for (int i = 0; i < DROSFM_MAX_PREDS; ++i) {
+    for (int i = 0; i < NP; ++i) {
         sx[i] = sy[i] = 0.0f;
-        rm[i] = i < n_preds ? 1.0f / fmaxf(stats[(i * B + b) * 4], 1e-6f) : 0.0f;
+        rm[i] = rm_s[i];
     }
-    for (int p = blockIdx.x * kLossThreads + threadIdx.x; p < P; p += gridDim.x * kLossThreads) {
-        const int y = p / W, x = p - y * W;
+    const int p0 = blockIdx.x * kLossThreads + threadIdx.x;
+    int y = p0 / W, x = p0 - y * W;
+    const int stride = gridDim.x * kLossThreads, sy_ = stride / W, sx_ = stride - sy_ * W;
+    for (int p = p0; p < P; p += stride) {
         const bool hx = x + 1 < W, hy = y + 1 < H;
         const int px = hx ? p + 1 : p, py = hy ? p + W : p;
+        // all 3 n depth loads of the pixel are requested before the first is consumed
+        float dc[NP], dx[NP], dy[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            if (i < n_preds) {
+                const float* d = dl.d[i] + static_cast<size_t>(b) * P;
+                dc[i] = __ldg(d + p);
+                dx[i] = __ldg(d + px);
+                dy[i] = __ldg(d + py);
+            }
+        }
         const float wx = hx ? edge_weight(img, P, p, px) : 0.0f;
         const float wy = hy ? edge_weight(img, P, p, py) : 0.0f;
 #pragma unroll
-        for (int i = 0; i < DROSFM_MAX_PREDS; ++i) {
+        for (int i = 0; i < NP; ++i) {
             if (i < n_preds) {
-                const float* d = dl.d[i] + static_cast<size_t>(b) * P;
-                const float dc = __ldg(d + p) * rm[i];
-                sx[i] += fabsf((dc - __ldg(d + px) * rm[i]) * wx);
-                sy[i] += fabsf((dc - __ldg(d + py) * rm[i]) * wy);
+                const float c = dc[i] * rm[i];
+                sx[i] += fabsf((c - dx[i] * rm[i]) * wx);
+                sy[i] += fabsf((c - dy[i] * rm[i]) * wy);
             }
         }
+        // next pixel of this thread: (x, y) advance without a division
+        x += sx_;
+        y += sy_;
+        if (x >= W) { x -= W; ++y; }
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < DROSFM_MAX_PREDS; ++i) {
+    for (int i = 0; i < NP; ++i) {
         if (i < n_preds) {
             const float a = warp_sum(sx[i]), c = warp_sum(sy[i]);
             if (lane == 0) { red[2 * i][wid] = a; red[2 * i + 1][wid] = c; }
@@ -158,39 +183,68 @@ __global__ void __launch_bounds__(kLossThreads)
 smooth_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict__ image, const __grid_constant__ DepthList dl,
                   int n_preds, float weight, const float* __restrict__ stats, const __grid_constant__ DepthGrads dg,
                   int accumulate, int B, int H, int W) {
+    // per (prediction, sample) constants, computed once per BLOCK (they hold all the divisions of the formula):
+    // 1/mean, kx/mean, ky/mean and the gradient through the mean
+    __shared__ float4 cst[DROSFM_MAX_PREDS];
     const int b = blockIdx.y, P = H * W;
+    if (threadIdx.x < n_preds) {
+        const int i = threadIdx.x;
+        const float* st = stats + (i * B + b) * 4;
+        const float g0 = __ldg(g_loss) * weight / static_cast<float>(n_preds);
+        const float nx = static_cast<float>(B) * H * (W - 1), ny = static_cast<float>(B) * (H - 1) * W;
+        const float pw = static_cast<float>(1u << i);
+        const float mean = st[0], rm = 1.0f / fmaxf(mean, 1e-6f);
+        const float kx = nx > 0.0f ? g0 / (pw * nx) : 0.0f, ky = ny > 0.0f ? g0 / (pw * ny) : 0.0f;
+        const float corr = mean >= 1e-6f ? (kx * st[1] + ky * st[2]) * rm * (1.0f / static_cast<float>(P)) : 0.0f;
+        cst[i] = make_float4(rm, kx, ky, corr);
+    }
+    __syncthreads();
     const int p = blockIdx.x * kLossThreads + threadIdx.x;
     if (p >= P) return;
     const float* img = image + static_cast<size_t>(b) * 3 * P;
     const int y = p / W, x = p - y * W;
     const bool xr = x + 1 < W, xl = x > 0, yd = y + 1 < H, yu = y > 0;
     const int pr = xr ? p + 1 : p, pl = xl ? p - 1 : p, pd = yd ? p + W : p, pu = yu ? p - W : p;
+    const size_t o = static_cast<size_t>(b) * P + p;
+    // predictions in groups of four: the 5 (+1) loads of every prediction of a group are requested before any is consumed
+    constexpr int kGroup = 4;
+    float vc[kGroup], vr[kGroup], vl[kGroup], vd[kGroup], vu[kGroup], vo[kGroup];
+    auto fetch = [&](int i0) {
+#pragma unroll
+        for (int k = 0; k < kGroup; ++k) {
+            const int i = i0 + k;
+            vo[k] = 0.0f;
+            if (i < n_preds && dg.g[i] != nullptr) {
+                const float* d = dl.d[i] + static_cast<size_t>(b) * P;
+                vc[k] = __ldg(d + p); vr[k] = __ldg(d + pr); vl[k] = __ldg(d + pl); vd[k] = __ldg(d + pd); vu[k] = __ldg(d + pu);
+                if (accumulate) vo[k] = dg.g[i][o];
+            }
+        }
+    };
+    fetch(0);
     const float w_r = xr ? edge_weight(img, P, p, pr) : 0.0f;
     const float w_l = xl ? edge_weight(img, P, pl, p) : 0.0f;
     const float w_d = yd ? edge_weight(img, P, p, pd) : 0.0f;
     const float w_u = yu ? edge_weight(img, P, pu, p) : 0.0f;
-    const float g0 = __ldg(g_loss) * weight / static_cast<float>(n_preds);
-    const float nx = static_cast<float>(B) * H * (W - 1), ny = static_cast<float>(B) * (H - 1) * W;
-    const float invP = 1.0f / static_cast<float>(P);
-    float pw = 1.0f;
-    for (int i = 0; i < n_preds; ++i, pw *= 2.0f) {
-        float* go = dg.g[i];
-        if (go == nullptr) continue;
-        const float* d = dl.d[i] + static_cast<size_t>(b) * P;
-        const float* st = stats + (i * B + b) * 4;
-        const float mean = st[0], rm = 1.0f / fmaxf(mean, 1e-6f);
-        const float kx = nx > 0.0f ? g0 / (pw * nx) : 0.0f, ky = ny > 0.0f ? g0 / (pw * ny) : 0.0f;
-        const float dc = __ldg(d + p) * rm;
-        // d L / d dn[p], dn = d * (1/mean) (the normalised values are formed exactly as in the forward pass)
-        float h = 0.0f;
-        h += kx * w_r * sgn(dc - __ldg(d + pr) * rm);
-        h -= kx * w_l * sgn(__ldg(d + pl) * rm - dc);
-        h += ky * w_d * sgn(dc - __ldg(d + pd) * rm);
-        h -= ky * w_u * sgn(__ldg(d + pu) * rm - dc);
-        float g = h * rm;
-        if (mean >= 1e-6f) g -= (kx * st[1] + ky * st[2]) * rm * invP;
-        const size_t o = static_cast<size_t>(b) * P + p;
-        go[o] = accumulate ? go[o] + g : g;
+    for (int i0 = 0; i0 < n_preds; i0 += kGroup) {
+#pragma unroll
+        for (int k = 0; k < kGroup; ++k) {
+            const int i = i0 + k;
+            if (i < n_preds && dg.g[i] != nullptr) {
+                const float4 c = cst[i];
+                const float rm = c.x, kx = c.y, ky = c.z;
+                const float dc = vc[k] * rm;
+                // d L / d dn[p], dn = d * (1/mean) (the normalised values are formed exactly as in the forward pass)
+                float h = 0.0f;
+                h += kx * w_r * sgn(dc - vr[k] * rm);
+                h -= kx * w_l * sgn(vl[k] * rm - dc);
+                h += ky * w_d * sgn(dc - vd[k] * rm);
+                h -= ky * w_u * sgn(vu[k] * rm - dc);
+                const float g = h * rm - c.w;
+                dg.g[i][o] = accumulate ? vo[k] + g : g;
+            }
+        }
+        if (i0 + kGroup < n_preds) fetch(i0 + kGroup);
     }
 }
 
@@ -439,10 +493,15 @@ int drosfm_smoothness_fwd(const float* image, const float* const* inv_depths, in
     if (mb > 64) mb = 64;
     smooth_mean_kernel<<<dim3(mb, n_preds * B), kLossThreads, 0, s>>>(dl, stats, static_cast<Slot*>(ws), B, P);
     if (int e = launch_status("smoothness_fwd (mean)")) return e;
-    int fb = (P + kLossThreads * 8 - 1) / (kLossThreads * 8);     // eight pixels per thread: the 2 n shuffle reductions + atomics of the epilogue are per thread
+    int fb = (P + kLossThreads * 4 - 1) / (kLossThreads * 4);     // four pixels per thread: the 2 n shuffle reductions + atomics of the epilogue are per thread
     if (fb < 1) fb = 1;
-    smooth_fwd_kernel<<<dim3(fb, B), kLossThreads, 0, s>>>(image, dl, n_preds, weight, stats, loss,
-                                                                           static_cast<Slot*>(ws), B, H, W);
+#define SMOOTH_FWD(NP_) smooth_fwd_kernel<NP_><<<dim3(fb, B), kLossThreads, 0, s>>>(image, dl, n_preds, weight, stats, loss, \
+                                                                                  static_cast<Slot*>(ws), B, H, W)
+    if (n_preds <= 4) SMOOTH_FWD(4);
+    else if (n_preds <= 8) SMOOTH_FWD(8);
+    else if (n_preds <= 12) SMOOTH_FWD(12);
+    else SMOOTH_FWD(16);
+#undef SMOOTH_FWD
     return launch_status("smoothness_fwd");
 }
 
