@@ -102,11 +102,16 @@ class HotPathStep:
 
         self.image = next(it)
         self.context = take(V)
-        self.fmap = next(it).requires_grad_(True)
-        self.frefs = [f.requires_grad_(True) for f in take(V)]
+        # the feature maps of [target, source_1..V] are ONE tensor, as the encoder delivers them (DepthPoseNet.py:113-118:
+        # fnet(torch.cat([target] + refs)) followed by torch.split); they are adjacent in the flat buffer
+        parts = [next(it)] + take(V)
+        o0 = offs[1 + V]
+        with torch.no_grad():
+            stacked = self.flat[o0:o0 + sum(p.numel() for p in parts)].view((1 + V) * self.B, *parts[0].shape[1:])
+        assert stacked.data_ptr() == parts[0].data_ptr() and parts[0].shape[0] == self.B
         if self.channels_last:                               # a network that already runs channels_last
-            self.fmap = self.fmap.detach().contiguous(memory_format=torch.channels_last).requires_grad_(True)
-            self.frefs = [f.detach().contiguous(memory_format=torch.channels_last).requires_grad_(True) for f in self.frefs]
+            stacked = stacked.detach().contiguous(memory_format=torch.channels_last)
+        self.fmaps_all = stacked.requires_grad_(True)
         self.inv_lr = [x.requires_grad_(True) for x in take(T)]
         self.inv_depths = [x.requires_grad_(True) for x in take(n)]
         flat_pose_lr = take(T * V)
@@ -131,8 +136,21 @@ class HotPathStep:
         self.h2d_bytes = self.host_u8.numel() + self.host_extra.numel() * 4 + self.host_K.numel() * 8
 
     def leaves(self):
-        out = [self.fmap] + self.frefs + self.inv_lr + [p for r in self.pose_lr for p in r]
+        out = [self.fmaps_all] + self.inv_lr + [p for r in self.pose_lr for p in r]
         return out + self.inv_depths + [p for r in self.poses for p in r]
+
+    def grads(self):
+        """Gradients in the order bench.cpu_step returns them: fmap, fmaps_ref[0..V-1], inv_depth_lr, pose_lr, inv_depths,
+        poses (the stacked feature-map gradient split per map)."""
+        ls = self.leaves()
+        return list(torch.split(ls[0].grad, self.B, dim=0)) + [t.grad for t in ls[1:]]
+
+    def feature_maps(self):
+        """(fmap, fmaps_ref) of this step: batch slices of the stacked tensor -- converted to channels_last once when the
+        cost kernels want that layout (networks/cost.py: split_feature_maps)."""
+        from .networks import cost as _cost_mod
+        pieces = _cost_mod.split_feature_maps(self.fmaps_all, [self.B] * (1 + self.wl.V))
+        return pieces[0], list(pieces[1:])
 
     def prefetch(self, stream):
         """Host -> device copy of the NEXT step's batch (uint8 pictures, intrinsics, GT tensors; pinned memory) into the
@@ -160,17 +178,18 @@ class HotPathStep:
     def forward_backward(self):
         wl = self.wl
         costs = []
+        fmap, frefs = self.feature_maps()
         for t in range(wl.T):
             poses_t = [p.detach() for p in self.pose_lr[t]]          # DepthPoseNet.py:156
             depth = self.depth_lr[t // wl.seq_len]
             if self.lockstep:
-                jobs = [(self.inv_lr[t], self.fmap, self.frefs, poses_t, True)]
-                jobs += [(depth, self.fmap, [self.frefs[v]], [self.pose_lr[t][v]], False) for v in range(wl.V)]
+                jobs = [(self.inv_lr[t], fmap, frefs, poses_t, True)]
+                jobs += [(depth, fmap, [frefs[v]], [self.pose_lr[t][v]], False) for v in range(wl.V)]
                 costs += cost_batch(jobs, self.K, self.K, 1.0 / 8)
                 continue
-            costs.append(depth_cost_calc(self.inv_lr[t], self.fmap, self.frefs, poses_t, self.K, self.K, 1.0 / 8))
+            costs.append(depth_cost_calc(self.inv_lr[t], fmap, frefs, poses_t, self.K, self.K, 1.0 / 8))
             for v in range(wl.V):
-                costs.append(get_cost_each(self.pose_lr[t][v], self.fmap, self.frefs[v], depth, self.K, self.K, 1.0 / 8))
+                costs.append(get_cost_each(self.pose_lr[t][v], fmap, frefs[v], depth, self.K, self.K, 1.0 / 8))
         poses = [[Pose.from_vec(p, 'euler') for p in row] for row in self.poses]   # SfmModelMF.py:169-182
         if wl.supervised:
             out = self.loss_mod(self.image, self.context, self.inv_depths, self.gt_inv_depth,

@@ -49,6 +49,18 @@ def _channels_last(t):
     return converted
 
 
+def split_feature_maps(stacked, sizes):
+    """torch.split(stacked, sizes, dim=0) of the encoder's output for [target, source_1..V] (DepthPoseNet.py:113-118), with
+    the channels_last conversion the cost kernels want done ONCE for the stacked tensor: one conversion launch, one
+    zero-filled gradient buffer and one back-conversion per step instead of one per map (ops.split_channels_last_sink)."""
+    t = stacked
+    usable = (_LAYOUT == "nhwc" and t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.shape[1] % 4 == 0
+              and t.shape[1] >= 32 and t.is_contiguous())
+    if not usable:
+        return list(torch.split(stacked, list(sizes), dim=0))
+    return ops.split_channels_last_sink(stacked, sizes)
+
+
 def _cost(pose_list, fmap, fmaps_ref, depth, K, ref_K, scale_factor, inverse_depth):
     # poses arrive as [B,6] euler vectors (Pose.from_vec(pose, "euler") in the reference)
     fmap = _channels_last(fmap)

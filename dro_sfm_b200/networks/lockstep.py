@@ -23,7 +23,8 @@ def forward(self, target_image, ref_imgs, intrinsics):
     from dro_sfm.utils.depth import inv2depth          # the patched tree is importable by construction
 
     n_views, B = len(ref_imgs), target_image.shape[0]
-    fmaps = torch.split(self.fnet(torch.cat([target_image] + list(ref_imgs), dim=0)), [B] * (1 + n_views), dim=0)
+    # one channels_last conversion (and one gradient buffer) for the stacked encoder output, then batch slices
+    fmaps = _cost.split_feature_maps(self.fnet(torch.cat([target_image] + list(ref_imgs), dim=0)), [B] * (1 + n_views))
     fmap, fmaps_ref = fmaps[0], list(fmaps[1:])
     assert target_image.shape[2] / fmap.shape[2] == self.feat_ratio
     scale = 1.0 / self.feat_ratio

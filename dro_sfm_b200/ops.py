@@ -12,7 +12,7 @@ import torch
 from . import _lib as L
 
 __all__ = ["pose_vec2mat", "reconstruct", "project", "warp_coords", "grid_gather", "view_synthesis", "feat_cost", "feat_cost_batch",
-           "photometric_loss", "reproj_pose_loss", "sup_depth_loss", "upsample_depth", "images_u8_to_f32", "post_process_inv_depth", "depth_metrics"]
+           "photometric_loss", "reproj_pose_loss", "sup_depth_loss", "upsample_depth", "images_u8_to_f32", "post_process_inv_depth", "depth_metrics", "split_channels_last_sink"]
 
 
 def _pose_kind(pose):
@@ -319,12 +319,13 @@ class GradSink:
     contribution into ``buffer`` inside the kernel (the scatter into the source maps is atomic anyway, the
     target-map gradient becomes a read-modify-write), instead of returning 2*V*T separate tensors that
     autograd would have to sum with as many element-wise kernels."""
-    __slots__ = ("buffer", "dummy", "consumed")
+    __slots__ = ("buffer", "dummy", "consumed", "subs")
 
     def __init__(self):
         self.buffer = None
         self.dummy = None
         self.consumed = False        # set once the backward pass went through: the copy belongs to a finished step
+        self.subs = []               # SubSinks of a stacked map (split_channels_last_sink)
 
 
 def relayout(t, layout):
@@ -375,11 +376,97 @@ def to_channels_last_sink(t):
     return out
 
 
+class SubSink:
+    """The part of a GradSink that belongs to one batch-slice of a stacked map (see split_channels_last_sink)."""
+    __slots__ = ("parent", "start", "stop", "shape", "device", "asked")
+
+    def __init__(self, parent, start, stop, like):
+        # shape and device only: a reference to the stacked tensor would close a cycle through its autograd graph and
+        # keep a finished step's AccumulateGrad nodes (and their streams) alive until the garbage collector runs
+        self.parent, self.start, self.stop, self.asked = parent, start, stop, False
+        self.shape, self.device = tuple(like.shape), like.device
+
+    @property
+    def consumed(self):
+        return self.parent.consumed
+
+
+class _SplitSink(torch.autograd.Function):
+    """torch.split along the batch axis of a stacked channels_last map whose pieces carry sub-sinks: the backward hands
+    ONE placeholder to the stacked tensor's sink node instead of materialising a full-size gradient per piece."""
+
+    @staticmethod
+    def forward(ctx, stacked, sink, sizes):
+        ctx.sink, ctx.sizes = sink, sizes
+        ctx.meta = (stacked.shape, stacked.device)
+        return tuple(torch.split(stacked.detach(), sizes, dim=0))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        sink, (shape, device) = ctx.sink, ctx.meta
+        dummy = sink.dummy
+        real = []
+        start = 0
+        for g, n in zip(gs, ctx.sizes):
+            if g is not None and not (dummy is not None and g.data_ptr() == dummy.data_ptr() and all(st == 0 for st in g.stride())):
+                real.append((start, n, g))
+            start += n
+        if real:                                       # an ordinary consumer of a piece: its gradient joins the sums
+            if sink.buffer is None:
+                sink.buffer = torch.empty(shape, device=device, dtype=torch.float32, memory_format=torch.channels_last).zero_()
+            for start, n, g in real:
+                sink.buffer[start:start + n].add_(g)
+        for sub in sink.subs:
+            sub.asked = False
+        if sink.buffer is None:
+            return None, None, None
+        if sink.dummy is None:
+            sink.dummy = _zero_scalar(device)
+        return sink.dummy.expand(shape), None, None
+
+
+def split_channels_last_sink(stacked, sizes):
+    """Converts a stacked NCHW map (e.g. the encoder's output for [target, source_1..V]) to channels_last ONCE and splits
+    it along the batch axis; every piece adds its cost gradients into its slice of ONE buffer, which returns to NCHW
+    through one launch (instead of one conversion, one zero-fill and one back-conversion per piece)."""
+    sizes = [int(n) for n in sizes]
+    conv = to_channels_last_sink(stacked)
+    sink = conv._drosfm_sink_state
+    pieces = _SplitSink.apply(conv, sink, sizes)
+    start = 0
+    for piece, n in zip(pieces, sizes):
+        sub = SubSink(sink, start, start + n, conv)
+        sink.subs.append(sub)
+        piece._drosfm_sink = sub if conv._drosfm_sink is not None else None
+        piece._drosfm_sink_state = sub
+        start += n
+    return list(pieces)
+
+
 def sink_buffer(sink, like):
     """(buffer, value to return to autograd): the first consumer of a backward pass allocates the zeroed
     buffer and returns a zero placeholder so that the sink node runs; later ones return None.  The buffer
     belongs to ONE backward pass: a callback at the end of the pass drops it if the sink node was not reached
     (torch.autograd.grad(cost, inputs=[pose]) or an aborted pass), so partial sums never leak into the next."""
+    if isinstance(sink, SubSink):
+        parent = sink.parent
+        if parent.buffer is None:
+            parent.buffer = torch.empty(sink.shape, device=sink.device, dtype=torch.float32, memory_format=torch.channels_last).zero_()
+            buf = parent.buffer
+
+            def end_of_pass(parent=parent, buf=buf):
+                if parent.buffer is buf:
+                    parent.buffer = None
+                for sub in parent.subs:
+                    sub.asked = False
+            torch.autograd.Variable._execution_engine.queue_callback(end_of_pass)
+        if parent.dummy is None:
+            parent.dummy = _zero_scalar(like.device)
+        piece = parent.buffer[sink.start:sink.stop]
+        # as for a plain sink: only the first consumer of a piece returns the placeholder (autograd would otherwise
+        # materialise the sum of two stride-0 tensors)
+        first, sink.asked = not sink.asked, True
+        return piece, (parent.dummy.expand(like.shape) if first else None)
     if sink.buffer is None:
         sink.buffer = torch.zeros_like(like)
         if sink.dummy is None or sink.dummy.shape != like.shape:

@@ -38,7 +38,7 @@ def test_full_step_matches_the_cpu_arm(wl_name, B):
     step = HotPathStep(wl, DEV, B=B, seed=1234)
     loss_eager = step.step()
     torch.cuda.synchronize()
-    grads_eager = [t.grad.detach().cpu().clone() for t in step.leaves()]
+    grads_eager = [g.detach().cpu().clone() for g in step.grads()]
     sel = getattr(step.loss_mod, "last_selection", None)
 
     # (1) the loss against the CPU arm as bench.py runs it (its own per-pixel arg-min)
@@ -84,4 +84,4 @@ def test_full_step_matches_the_cpu_arm(wl_name, B):
         assert abs(float(loss.detach()) - float(loss_eager.detach())) <= 1e-6 * abs(float(loss_eager.detach())), tag
         if sel is not None:
             assert torch.equal(step2.loss_mod.last_selection.cpu(), sel), tag
-        check([t.grad.detach().cpu() for t in step2.leaves()], tag)
+        check([g.detach().cpu() for g in step2.grads()], tag)
