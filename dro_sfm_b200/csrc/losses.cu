@@ -217,7 +217,7 @@ smooth_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict__ im
             if (i < n_preds && dg.g[i] != nullptr) {
                 const float* d = dl.d[i] + static_cast<size_t>(b) * P;
                 vc[k] = __ldg(d + p); vr[k] = __ldg(d + pr); vl[k] = __ldg(d + pl); vd[k] = __ldg(d + pd); vu[k] = __ldg(d + pu);
-                if (accumulate) vo[k] = dg.g[i][o];
+                if (accumulate == 1) vo[k] = dg.g[i][o];
             }
         }
     };
@@ -241,7 +241,11 @@ smooth_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict__ im
                 h += ky * w_d * sgn(dc - vd[k] * rm);
                 h -= ky * w_u * sgn(vu[k] * rm - dc);
                 const float g = h * rm - c.w;
-                dg.g[i][o] = accumulate ? vo[k] + g : g;
+                if (accumulate == 2) {      // another kernel may be adding into the same maps right now: fire-and-forget atomic
+                    if (g != 0.0f) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dg.g[i] + o), "f"(g) : "memory");
+                } else {
+                    dg.g[i][o] = accumulate ? vo[k] + g : g;
+                }
             }
         }
         if (i0 + kGroup < n_preds) fetch(i0 + kGroup);

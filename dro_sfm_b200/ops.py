@@ -856,13 +856,16 @@ class _PhotoLoss(torch.autograd.Function):
         g = L.f32c(g_total.reshape(1))
         cams, _ = L.make_cams(K, Kref, 1.0, None, None, None, kind)
         opts = L.PhotoOpts(ssim_w, C1, C2, padding, reduce_op, int(automask), gamma, clip, None)
-        g_inv_slab = torch.empty(n, *invs[0].shape, device=dev, dtype=torch.float32) if any(need_inv) else None
+        smooth = smooth_w > 0.0 and any(need_inv)
+        # fused backward with a smoothness term on a second stream: both kernels ADD into the same (zero-filled) maps with
+        # atomic reductions, so neither waits for the other
+        concurrent = g_fused is not None and smooth and OVERLAP is True
+        g_inv_slab = (torch.zeros if concurrent else torch.empty)(n, *invs[0].shape, device=dev, dtype=torch.float32) if any(need_inv) else None
         g_invs = [g_inv_slab[i] if need_inv[i] else None for i in range(n)]
         g_pose_slab = torch.empty(V * n, *poses[0].shape, device=dev, dtype=torch.float32) if any(need_pose) else None
         g_poses = [g_pose_slab[k] if need_pose[k] else None for k in range(V * n)]
         g_warped = torch.empty_like(wsave) if wsave is not None else None     # scratch between the two backward stages
         lib = L.lib()
-        smooth = smooth_w > 0.0 and any(need_inv)
         if g_fused is not None:
             # the forward left d loss / d warped behind (unscaled): the backward is the warp adjoint, scaled by g
             with torch.cuda.device(dev):
@@ -876,13 +879,13 @@ class _PhotoLoss(torch.autograd.Function):
                     if two_streams:
                         side.wait_stream(main)
                     with torch.cuda.stream(side):
-                        L.check(lib.drosfm_smoothness_bwd(L.ptr(g), L.ptr(image), pi, n, smooth_w, L.ptr(stats), L.ptr_array(g_invs), 0,
-                                                          B, H, W, L.stream()), "smoothness_bwd")
-                    if two_streams:
-                        main.wait_stream(side)
+                        L.check(lib.drosfm_smoothness_bwd(L.ptr(g), L.ptr(image), pi, n, smooth_w, L.ptr(stats), L.ptr_array(g_invs),
+                                                          2 if concurrent else 0, B, H, W, L.stream()), "smoothness_bwd")
                 L.check(lib.drosfm_warp_sources_bwd(L.ptr(g_fused), pa, V, pi, depth_kind, n, cams, pp_, padding, L.ptr(rgbx), L.ptr(g),
                                                     L.ptr_array(g_invs), L.ptr_array(g_poses), L.ptr(ws), 1 if smooth else 0, B, H, W, st),
                         "warp_sources_bwd")
+                if smooth and two_streams:
+                    main.wait_stream(side)
             return (None, None, None, None, None, None, *([None] * V), *g_invs, *g_poses)
         with torch.cuda.device(dev):
             ws = L.workspace(dev, max(n * B + 1, V * n * B))

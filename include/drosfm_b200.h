@@ -255,7 +255,8 @@ int drosfm_warp_sources_bwd(const float* g_warped, const float* const* context, 
  * loss = weight/n * sum_i (mean|dx(d_i/mean(d_i)) * wx| + mean|dy(..) * wy|) / 2^i.
  * stats [n_preds,B,4] float scratch written by fwd and read by bwd (per-sample mean inverse depth
  * and the two per-sample edge sums); ws of drosfm_ws_bytes(n_preds*B + 1).
- * bwd: g_inv_depths[i] [B,1,H,W] written, or added to when accumulate != 0 (entries may be NULL). */
+ * bwd: g_inv_depths[i] [B,1,H,W] written (accumulate 0), added to (1), or added to with atomic reductions (2: another kernel
+ * -- the warp adjoint of the photometric term -- may add into the same maps concurrently on a second stream); entries may be NULL. */
 int drosfm_smoothness_fwd(const float* image, const float* const* inv_depths, int n_preds, float weight,
                           float* stats, float* loss, void* ws, int B, int H, int W, drosfm_stream_t stream);
 int drosfm_smoothness_bwd(const float* g_loss, const float* image, const float* const* inv_depths, int n_preds,
