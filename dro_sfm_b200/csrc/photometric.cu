@@ -1225,11 +1225,14 @@ struct FwdRow2 {
 #ifndef DROSFM_SSIMF_MINBLOCKS
 #define DROSFM_SSIMF_MINBLOCKS 2
 #endif
+// MASK: the auto-mask pass -- the two "warped" pictures are the UN-warped sources pp.context[0..1], the per-pixel minimum of
+// their photometric maps is written to mask_out [B,H,W]; no loss, no selection, no finisher.
+template <bool MASK>
 __global__ void __launch_bounds__(kSsimThreads, DROSFM_SSIMF_MINBLOCKS)
 ssim_fwd_stream2_kernel(const float* __restrict__ image, const float* __restrict__ warped, const __grid_constant__ PhotoPtrs pp,
                         int n_preds, const float* __restrict__ automask_in, drosfm_photo_opts_t opts, float l1_w,
-                        uint8_t* __restrict__ sel_out, float* __restrict__ loss, Slot* ws, int B, int H, int W, int nstrips,
-                        int nbands) {
+                        uint8_t* __restrict__ sel_out, float* __restrict__ loss, Slot* ws, float* __restrict__ mask_out, int B, int H,
+                        int W, int nstrips, int nbands) {
     __shared__ double red[kSsimWarps];
     __shared__ int flag;
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -1245,8 +1248,10 @@ ssim_fwd_stream2_kernel(const float* __restrict__ image, const float* __restrict
     const int gxc = clampi(gx, 0, W - 1);
     const bool use_min = opts.reduce_op == DROSFM_REDUCE_MIN;
     const float* __restrict__ ybase = image + static_cast<size_t>(b) * 3 * P + gxc;
-    const float* __restrict__ xbase = warped + (static_cast<size_t>(ip) * 2 * B + b) * 3 * P + gxc;
-    const unsigned vstride = static_cast<unsigned>(B) * 3u * static_cast<unsigned>(P);
+    const float* __restrict__ xbase = MASK ? pp.context[0] + static_cast<size_t>(b) * 3 * P + gxc
+                                           : warped + (static_cast<size_t>(ip) * 2 * B + b) * 3 * P + gxc;
+    const float* __restrict__ xbase1 = MASK ? pp.context[1] + static_cast<size_t>(b) * 3 * P + gxc
+                                            : xbase + static_cast<size_t>(B) * 3u * static_cast<unsigned>(P);
     const float2 inv9 = bc2(1.0f / 9.0f), ninv9 = bc2(-1.0f / 9.0f), two = bc2(2.0f);
     const float2 C1 = bc2(opts.C1), C2 = bc2(opts.C2);
 
@@ -1258,7 +1263,7 @@ ssim_fwd_stream2_kernel(const float* __restrict__ image, const float* __restrict
         for (int c = 0; c < 3; ++c) {
             ry[c] = col_in ? __ldg(ybase + (off + c * P)) : 0.0f;
             rx[c].x = col_in ? __ldg(xbase + (off + c * P)) : 0.0f;
-            rx[c].y = col_in ? __ldg(xbase + (off + c * P + vstride)) : 0.0f;
+            rx[c].y = col_in ? __ldg(xbase1 + (off + c * P)) : 0.0f;
         }
     };
     float local = 0.0f;
@@ -1328,12 +1333,16 @@ ssim_fwd_stream2_kernel(const float* __restrict__ image, const float* __restrict
             const int gyo = gy - 1;
             if (out_lane && gyo < gy0 + kFwdBandH && gyo < H) {
                 const size_t o = static_cast<size_t>(b) * P + gyo * W + gx;
-                if (automask_in != nullptr) {
-                    const float a = __ldg(automask_in + o);
-                    if (a < best) { best = a; sel = 255; }
+                if constexpr (MASK) {
+                    mask_out[o] = best;
+                } else {
+                    if (automask_in != nullptr) {
+                        const float a = __ldg(automask_in + o);
+                        if (a < best) { best = a; sel = 255; }
+                    }
+                    if (sel_out != nullptr) sel_out[static_cast<size_t>(ip) * B * P + o] = static_cast<uint8_t>(sel);
+                    local += best;
                 }
-                if (sel_out != nullptr) sel_out[static_cast<size_t>(ip) * B * P + o] = static_cast<uint8_t>(sel);
-                local += best;
             }
         }
 #pragma unroll
@@ -1359,6 +1368,7 @@ ssim_fwd_stream2_kernel(const float* __restrict__ image, const float* __restrict
         }
     }
 
+    if constexpr (MASK) return;
     double part = warp_sum(static_cast<double>(local));
     if (lane == 0) red[wib] = part;
     __syncthreads();
@@ -1995,10 +2005,19 @@ int drosfm_automask_fwd(const float* image, const float* const* context, int n_v
     for (int v = 0; v < n_views; ++v) pp.context[v] = context[v];
     drosfm_photo_opts_t o = *opts;
     o.reduce_op = DROSFM_REDUCE_MIN;
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    if (n_views == 2 && !(opts->clip_loss > 0.0f) && opts->ssim_w > 0.0f && static_cast<long long>(B) * 3 * H * W < (1ll << 31)) {
+        // two views: the streaming SSIM walk of the loss forward on the un-warped sources (the tile kernel below executes
+        // three times its instructions)
+        const int nstrips = (W + kFwdStripW - 1) / kFwdStripW, nbands = (H + kFwdBandH - 1) / kFwdBandH;
+        dim3 sgrid((nstrips * nbands + kSsimWarps - 1) / kSsimWarps, B);
+        ssim_fwd_stream2_kernel<true><<<sgrid, kSsimThreads, 0, cs>>>(image, nullptr, pp, 1, nullptr, o, l1_weight(opts), nullptr, nullptr,
+                                                                      nullptr, automask, B, H, W, nstrips, nbands);
+        return launch_status("automask_fwd");
+    }
     drosfm_cams_t none{};
     dim3 grid((W + FW - 1) / FW, (H + FH - 1) / FH, B);
     if (int e = allow_big_smem()) return e;
-    cudaStream_t cs = static_cast<cudaStream_t>(stream);
     ClipSlot* clip = nullptr;
     if (opts->clip_loss > 0.0f) {
         // statistics pass over the V un-warped maps, then their thresholds (slots 0..V-1 of the zero-filled scratch)
@@ -2088,9 +2107,9 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
                                                                           *opts, l1_weight(opts), sel, loss, static_cast<Slot*>(ws), B, H,
                                                                           W, nstrips, nbands);
             else
-                ssim_fwd_stream2_kernel<<<sgrid, kSsimThreads, 0, cs>>>(image, warped_save, pp, n_preds, opts->automask ? automask : nullptr,
-                                                                        *opts, l1_weight(opts), sel, loss, static_cast<Slot*>(ws), B, H, W,
-                                                                        nstrips, nbands);
+                ssim_fwd_stream2_kernel<false><<<sgrid, kSsimThreads, 0, cs>>>(image, warped_save, pp, n_preds, opts->automask ? automask : nullptr,
+                                                                               *opts, l1_weight(opts), sel, loss, static_cast<Slot*>(ws), nullptr,
+                                                                               B, H, W, nstrips, nbands);
         } else {
             photometric_fwd_kernel<0, true><<<grid, kFwdThreads, kFwdSmemBytes, cs>>>(
                 image, pp, n_views, depth_kind, n_preds, *cams, opts->automask ? automask : nullptr, *opts, l1_weight(opts), sel,
