@@ -613,7 +613,8 @@ def main():
             head = dict(results["train_kitti_mf_selfsup"])
             head["other_workloads"] = {k: {"value": v["value"], "e2e": v["e2e"]["value"], "ms_per_step": v["ms_per_step"],
                                            "gpu_launches_per_step": v["gpu_launches_per_step"], "config": v["config"],
-                                           "step_frac": v["roofline"]["step_frac"], "dominant": v["roofline"]["kernel"],
+                                           "step_frac": v["roofline"]["step_frac"], "kernel_ms_per_step": v["roofline"]["kernel_ms_per_step"],
+                                           "dominant": v["roofline"]["kernel"],
                                            "dominant_frac": v["roofline"]["frac"]} for k, v in results.items() if k != "train_kitti_mf_selfsup"}
             print(json.dumps(head))
         return

@@ -34,6 +34,20 @@ class Pose:
         # to() / repeat() restore the flag themselves because they keep the values
         self._mat, self._vec, self._is_identity = value, None, False
 
+    @staticmethod
+    def materialize(poses):
+        """[B,4,4] matrices of a list of poses (Pose objects or tensors).  Poses that still are un-converted euler vectors
+        (from_vec) of one shape are converted by ONE launch for the whole list instead of one each -- the supervised loss
+        needs the matrices of all V x n predicted poses at once."""
+        lazy = [k for k, p in enumerate(poses) if isinstance(p, Pose) and p._mat is None and p._vec is not None]
+        if len(lazy) > 1 and len({tuple(poses[k]._vec.shape) for k in lazy}) == 1 \
+                and len({(poses[k]._vec.dtype, poses[k]._vec.device) for k in lazy}) == 1:
+            vecs = torch.stack([poses[k]._vec for k in lazy], dim=0)                  # [m, B, 6]
+            mats = ops.pose_vec2mat(vecs.reshape(-1, 6)).reshape(len(lazy), -1, 4, 4)
+            for k, m in zip(lazy, mats.unbind(0)):
+                poses[k]._mat = m
+        return [p.mat if hasattr(p, "mat") else p for p in poses]
+
     def kernel_arg(self):
         """What the fused kernels consume: the [B,6] euler vector when known (the conversion then runs in
         the kernel prologue and the gradient lands on the vector directly), else the [B,4,4] matrix."""

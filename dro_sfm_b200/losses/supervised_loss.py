@@ -11,6 +11,16 @@ from ..geometry.pose import Pose
 from .loss_base import LossBase, ProgressiveScaling
 
 
+def _materialize_rows(rows):
+    """[B,4,4] matrices of rows of poses, same nesting; one conversion launch for all lazy euler vectors."""
+    flat = Pose.materialize([p for row in rows for p in row])
+    out, k = [], 0
+    for row in rows:
+        out.append(flat[k:k + len(row)])
+        k += len(row)
+    return out
+
+
 class SupervisedDepthPoseLoss(LossBase):
     def __init__(self, supervised_method='sparse-l1', supervised_num_scales=4, progressive_scaling=0.0,
                  min_depth=0.1, max_depth=100, **kwargs):
@@ -41,8 +51,7 @@ class SupervisedDepthPoseLoss(LossBase):
 
     def calc_pose_loss(self, pred_poses, gt_pose_context, gt_depth, K, ref_K):
         """Reprojection loss of the predicted poses on GT depth (supervised_loss.py:293-325)."""
-        preds = [[p.mat if hasattr(p, "mat") else p for p in pv] for pv in pred_poses]
-        preds = [pv[:self.n] for pv in preds]
+        preds = _materialize_rows([pv[:self.n] for pv in pred_poses])
         gts = [g.mat if hasattr(g, "mat") else g for g in gt_pose_context]
         return ops.reproj_pose_loss(preds, gts, gt_depth, K, ref_K, self.min_depth, self.max_depth, 0.85)
 
@@ -55,7 +64,8 @@ class SupervisedDepthPoseLoss(LossBase):
                 raise NotImplementedError("dro_sfm_b200: predictions must be at the ground-truth resolution")
         loss_depth = self.calculate_loss(inv_depths, [gt_inv_depth] * self.n)
         # calc_pose_loss (and the reference, supervised_loss.py:306-312) use the first self.n predictions of every view
-        preds = [[p.mat if hasattr(p, "mat") else p for p in pv[:self.n]] for pv in poses]
+        # (one conversion launch for all V x n euler vectors that are still lazy, see Pose.materialize)
+        preds = _materialize_rows([pv[:self.n] for pv in poses])
         gts = [g.mat if hasattr(g, "mat") else g for g in gt_pose_context]
         # inv2depth of the GT map is fused into the kernel
         loss_pose = ops.reproj_pose_loss(preds, gts, gt_inv_depth, K, ref_K, self.min_depth, self.max_depth, 0.85,
