@@ -1692,8 +1692,13 @@ constexpr int kTrainThreads = 96;
 constexpr int kTrainBandH = DROSFM_SSIMT_BAND;      // rows written per block (4 more are loaded)
 
 #ifndef DROSFM_SSIMT_MINBLOCKS
-#define DROSFM_SSIMT_MINBLOCKS 5      // blocks per SM: 2-4 -> 337 us, 5 -> 310 us
+#define DROSFM_SSIMT_MINBLOCKS 5      // blocks per SM (15 warps, 124 registers, no spill); any spill costs > 10 %
 #endif
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float2 third2(float2 x) {      // third() of both halves
     const float2 r = bc2(1.0f / 3.0f);
     const float2 q = mul2(x, r);
@@ -1705,7 +1710,7 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
                           int n_preds, const float* __restrict__ automask_in, drosfm_photo_opts_t opts, float l1_w,
                           uint8_t* __restrict__ sel_out, float* __restrict__ loss, Slot* ws, float* __restrict__ g_warped,
                           int B, int H, int W, int nstrips, int nbands) {
-    __shared__ float4 xchg[2][3][32];
+    __shared__ float4 xchg[3][3][32];      // [row step within the unrolled triple][channel][lane]: static offsets
     __shared__ int flag;
     const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
     const int wg = blockIdx.x;
@@ -1767,8 +1772,9 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
     float am_row = __int_as_float(0x7f800000);      // auto-mask of the row loaded in the previous step = this step's window centre
     int sv_prev = 254;
     float local = 0.0f;
-    auto step = [&](auto inner, BwdRow2& p2, BwdRow2& p1, BwdRow2& cur, Pre& mine, Pre& refill, int j) {
+    auto step = [&](auto inner, auto kbuf, BwdRow2& p2, BwdRow2& p1, BwdRow2& cur, Pre& mine, Pre& refill, int j) {
         constexpr bool INNER = decltype(inner)::value;
+        constexpr int KB = decltype(kbuf)::value;       // exchange buffer of this step (a buffer is reused three steps later)
         const int gy = gy0 - 2 + j;          // row loaded in this step; windows centred on gy-1; gradients of row gy-2
         const int gc = gy - 1;
         cur.x = mine.x;
@@ -1803,16 +1809,18 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
             const float2 A1 = fma2(two, mu_xy, C1), A2 = fma2(two, sig_xy, C2);
             const float2 B1 = add2(mu_xx, bc2(mu_yy + opts.C1)), B2 = add2(sig_x, bc2(sig_y + opts.C2));
             const float2 num = mul2(A1, A2), den = mul2(B1, B2);
-            const float2 rden = make_float2(__fdividef(1.0f, den.x), __fdividef(1.0f, den.y));
+            // den >= C1 * C2 > 0, far inside the normal range: the bare reciprocal approximation (what __fdividef(1, x) uses,
+            // without its range scaling)
+            const float2 rden = make_float2(rcp_approx(den.x), rcp_approx(den.y));
             const float2 sm = mul2(num, rden);
             const float2 l01 = mul2(fma2(bc2(-1.0f), sm, bc2(1.0f)), bc2(0.5f));      // (1 - ssim) / 2, both views
             const float l0 = l01.x, l1 = l01.y;
             // this channel's terms of the photometric value of the window centre (row p1)
             const float2 dxy = fma2(bc2(-1.0f), bc2(p1.y), p1.x);                     // x - y, exact as a difference
             const float4 mineq = make_float4(fminf(fmaxf(l0, 0.0f), 1.0f), fminf(fmaxf(l1, 0.0f), 1.0f), fabsf(dxy.x), fabsf(dxy.y));
-            xchg[j & 1][c][lane] = mineq;
+            xchg[KB][c][lane] = mineq;
             asm volatile("bar.sync 1, 96;" ::: "memory");
-            const float4 q0 = xchg[j & 1][0][lane], q1 = xchg[j & 1][1][lane], q2 = xchg[j & 1][2][lane];
+            const float4 q0 = xchg[KB][0][lane], q1 = xchg[KB][1][lane], q2 = xchg[KB][2][lane];
             // channel means and the weighted sum, both views at once (same operations, same order as the scalar form)
             const float2 ssum = add2(add2(make_float2(q0.x, q0.y), make_float2(q1.x, q1.y)), make_float2(q2.x, q2.y));
             const float2 lsum = add2(add2(make_float2(q0.z, q0.w), make_float2(q1.z, q1.w)), make_float2(q2.z, q2.w));
@@ -1837,23 +1845,18 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
                     else spl[static_cast<unsigned>(gc * W)] = static_cast<uint8_t>(use_min ? sv : 254);
                 }
             }
-            if (INNER && j >= 3) srow += W;
             // coefficients of the windows that carry a gradient
-            float2 a = bc2(0.0f), bb = a, cq = a;
+            // (branch-free: every quantity is finite -- den >= C1 * C2 -- so a window without a gradient is masked by a
+            // multiplication with zero instead of a divergent branch around the block)
             const bool on0 = sv == 0 || sv == 253, on1 = sv == 1 || sv == 253;
-            if (on0 || on1) {
-                const float2 q = mul2(bc2(kp), rden);
-                const float2 neg1 = bc2(-1.0f);
-                const float2 dA = fma2(neg1, A1, A2), dB = fma2(neg1, B1, B2);
-                const float2 inner = fma2(mul2(sm, nmu_x), dB, mul2(mu_y2, dA));
-                const float2 a_ = mul2(q, inner);
-                const float2 b_ = mul2(mul2(mul2(bc2(-kp), rden), sm), B1);
-                const float2 c_ = mul2(q, A1);
-                const bool k0 = on0 && l0 >= 0.0f && l0 <= 1.0f, k1 = on1 && l1 >= 0.0f && l1 <= 1.0f;
-                a = make_float2(k0 ? a_.x : 0.0f, k1 ? a_.y : 0.0f);
-                bb = make_float2(k0 ? b_.x : 0.0f, k1 ? b_.y : 0.0f);
-                cq = make_float2(k0 ? c_.x : 0.0f, k1 ? c_.y : 0.0f);
-            }
+            const bool k0 = on0 && l0 >= 0.0f && l0 <= 1.0f, k1 = on1 && l1 >= 0.0f && l1 <= 1.0f;
+            const float2 q = mul2(mul2(bc2(kp), rden), make_float2(k0 ? 1.0f : 0.0f, k1 ? 1.0f : 0.0f));
+            const float2 neg1 = bc2(-1.0f);
+            const float2 dA = fma2(neg1, A1, A2), dB = fma2(neg1, B1, B2);
+            const float2 inner = fma2(mul2(sm, nmu_x), dB, mul2(mu_y2, dA));
+            const float2 a = mul2(q, inner);
+            const float2 bb = mul2(mul2(mul2(q, neg1), sm), B1);
+            const float2 cq = mul2(q, A1);
             const int ll = (lane - 1) & 31, lr = (lane + 1) & 31;      // the outermost lanes' sums are never used
             p1.ha = fma2(wx2, shfl2(a, lr), fma2(wx0, shfl2(a, ll), a));
             p1.hb = fma2(wx2, shfl2(bb, lr), fma2(wx0, shfl2(bb, ll), bb));
@@ -1893,7 +1896,10 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
                     gpl[o + vstride] = gxv.y;
                 }
             }
-            if constexpr (INNER) grow += W;
+        }
+        if constexpr (INNER) {       // the output rows advance with the walk (written from step 3 / 4 on)
+            srow += W;
+            grow += W;
         }
         sv_prev = sv;
     };
@@ -1905,20 +1911,21 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
     r0.y = r1.y = 0.0f;
     auto walk = [&](auto inner) {
         if constexpr (decltype(inner)::value) {
-            const unsigned first = static_cast<unsigned>((gy0 - 2) * W), out0 = static_cast<unsigned>(gy0 * W);
+            // step j loads row gy0 - 2 + j (+2 ahead), selects for row gy0 - 3 + j, writes gradients of row gy0 - 4 + j
+            const unsigned first = static_cast<unsigned>((gy0 - 2) * W);
             xrow = xpl + first;
             yrow = ypl + first;
             arow = apl != nullptr ? apl + first : nullptr;
-            grow = gpl + out0;
-            srow = spl != nullptr ? spl + out0 : nullptr;
+            grow = gpl + static_cast<unsigned>((gy0 - 4) * W);
+            srow = spl != nullptr ? spl + static_cast<unsigned>((gy0 - 3) * W) : nullptr;
         }
         fetch(inner, gy0 - 2, f0);
         fetch(inner, gy0 - 1, f1);
 #pragma unroll 1
         for (int j = 0; j < kTrainBandH + 4; j += 3) {
-            step(inner, r1, r2, r0, f0, f2, j);
-            step(inner, r2, r0, r1, f1, f0, j + 1);
-            step(inner, r0, r1, r2, f2, f1, j + 2);
+            step(inner, std::integral_constant<int, 0>{}, r1, r2, r0, f0, f2, j);
+            step(inner, std::integral_constant<int, 1>{}, r2, r0, r1, f1, f0, j + 1);
+            step(inner, std::integral_constant<int, 2>{}, r0, r1, r2, f2, f1, j + 2);
         }
     };
     constexpr int kSteps = (kTrainBandH + 4 + 2) / 3 * 3;      // the last row fetched is gy0 + kSteps - 1
