@@ -127,7 +127,7 @@ warp_coords_bwd_kernel(const float* __restrict__ g_uv, const float* __restrict__
     }
     if (g_pose == nullptr) return;
     Slot* slot = slot_at(ws, b);
-    block_accumulate<12>(gT, red, spread_acc(slot));
+    block_accumulate12(gT, red, spread_acc(slot));
     if (last_block(slot, gridDim.x, &flag) && threadIdx.x < 32) {
         const int stride = cams.pose_kind == DROSFM_POSE_EULER6 ? 6 : 16;
         finish_pose_grad_warp(slot, cams.pose_kind, cams.pose_kind == DROSFM_POSE_EULER6 ? cams.pose + b * 6 : nullptr,
@@ -270,7 +270,7 @@ project_bwd_kernel(const float* __restrict__ g_uv, const float* __restrict__ poi
     }
     if (g_Tcw == nullptr) return;
     Slot* slot = slot_at(ws, b);
-    block_accumulate<12>(gT, red, spread_acc(slot));
+    block_accumulate12(gT, red, spread_acc(slot));
     if (last_block(slot, gridDim.x, &flag) && threadIdx.x < 32)
         finish_pose_grad_warp(slot, DROSFM_POSE_MAT4, nullptr, g_Tcw + b * 16);
 }

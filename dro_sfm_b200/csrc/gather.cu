@@ -245,7 +245,7 @@ view_synthesis_bwd_kernel(const float* __restrict__ g_out, const float* __restri
     }
     if (g_pose == nullptr) return;
     Slot* slot = slot_at(ws, b);
-    block_accumulate<12>(gT, red, spread_acc(slot));
+    block_accumulate12(gT, red, spread_acc(slot));
     if (last_block(slot, gridDim.x, &flag) && threadIdx.x < 32) {
         const int st = cams.pose_kind == DROSFM_POSE_EULER6 ? 6 : 16;
         finish_pose_grad_warp(slot, cams.pose_kind, cams.pose_kind == DROSFM_POSE_EULER6 ? cams.pose + b * 6 : nullptr,

@@ -271,14 +271,22 @@ __device__ __forceinline__ void setup_src(const drosfm_cams_t& c, const float* p
         out.c[k] = out.T[4 * k] * out.Rt[3] + out.T[4 * k + 1] * out.Rt[7] + out.T[4 * k + 2] * out.Rt[11] + out.T[4 * k + 3];
 }
 
-// One block = a strip of pixels of one sample; loops over all (view, prediction) pairs.
+// One block = a strip of pixels of one sample.  The predictions of a view are processed in groups of four: one pass over
+// the block's pixels evaluates the GT projection once and the four predicted projections next to it (the GT chain, the
+// camera set-up barrier and the block reductions are paid per group, not per prediction).
 // MODE 0: forward sums per prediction.  MODE 1: backward, pose gradients per (view, prediction).
+#ifndef DROSFM_REPROJ_BWD_GROUP
+#define DROSFM_REPROJ_BWD_GROUP 2      // the backward keeps 12 pose-gradient sums per prediction of the group in registers
+#endif
+constexpr int kReprojGroupMax = 4;
+
 template <int MODE>
 __global__ void __launch_bounds__(kLossThreads)
 reproj_kernel(const float* __restrict__ g_loss, const float* __restrict__ depth, int depth_kind, drosfm_cams_t cams,
               const __grid_constant__ ReprojPtrs rp, int V, int n_preds, float min_depth, float max_depth, float wsum,
               float* __restrict__ loss, Slot* ws, int B, int H, int W) {
-    __shared__ Cam base, cgt, cpr;
+    constexpr int kReprojGroup = MODE == 0 ? kReprojGroupMax : DROSFM_REPROJ_BWD_GROUP;
+    __shared__ Cam base, cgt, cpr[kReprojGroup];
     __shared__ double red[12 * (kLossThreads / 32)];
     __shared__ int flag;
     const int b = blockIdx.y, P = H * W;
@@ -287,52 +295,74 @@ reproj_kernel(const float* __restrict__ g_loss, const float* __restrict__ depth,
     __syncthreads();
     const float dmax = max_depth / 4.0f;
     const int stride = gridDim.x * kLossThreads;
+    const float gl = MODE == 1 ? __ldg(g_loss) : 0.0f;
     for (int v = 0; v < V; ++v) {
-        if (threadIdx.x == 0) setup_src(cams, rp.gt[v], b, base, cgt);
-        for (int i = 0; i < n_preds; ++i) {
+        for (int i0 = 0; i0 < n_preds; i0 += kReprojGroup) {
+            const int ng = min(kReprojGroup, n_preds - i0);
             __syncthreads();
-            if (threadIdx.x == 0) setup_src(cams, rp.pred[v * n_preds + i], b, base, cpr);
+            // lane 0 of warps 0..ng sets up the GT camera / one predicted camera each
+            if ((threadIdx.x & 31) == 0) {
+                const int k = threadIdx.x >> 5;
+                if (k == 0) setup_src(cams, rp.gt[v], b, base, cgt);
+                else if (k <= ng) setup_src(cams, rp.pred[v * n_preds + i0 + k - 1], b, base, cpr[k - 1]);
+            }
             __syncthreads();
-            float acc = 0.0f;
-            float gT[12];
+            float acc[kReprojGroup];
+            float gT[kReprojGroup][12];
+            float kscale[kReprojGroup];
 #pragma unroll
-            for (int k = 0; k < 12; ++k) gT[k] = 0.0f;
-            // d loss / d |diff| for this (view, prediction): w_i / (V * wsum * numel)
-            const float kscale = MODE == 1 ? __ldg(g_loss) * rp.weight[i] /
-                                                 (static_cast<float>(V) * wsum * 2.0f * static_cast<float>(B) * static_cast<float>(P))
-                                           : 0.0f;
+            for (int k = 0; k < kReprojGroup; ++k) {
+                acc[k] = 0.0f;
+#pragma unroll
+                for (int q = 0; q < 12; ++q) gT[k][q] = 0.0f;
+                // d loss / d |diff| for this (view, prediction): w_i / (V * wsum * numel)
+                kscale[k] = (MODE == 1 && k < ng) ? gl * rp.weight[i0 + k] /
+                                                        (static_cast<float>(V) * wsum * 2.0f * static_cast<float>(B) * static_cast<float>(P))
+                                                  : 0.0f;
+            }
             for (int p = blockIdx.x * kLossThreads + threadIdx.x; p < P; p += stride) {
                 const int y = p / W, x = p - y * W;
                 const float d = to_depth(__ldg(depth + static_cast<size_t>(b) * P + p), depth_kind);
                 if (!(d > min_depth && d < dmax)) continue;
-                Warp wg, wp;
+                Warp wg;
                 warp_pixel<true>(cgt, x, y, d, wm1, hm1, true, wg);
-                warp_pixel<true>(cpr, x, y, d, wm1, hm1, true, wp);
-                const bool vu = wg.p.u >= -1.0f && wg.p.u <= 1.0f && wp.p.u >= -1.0f && wp.p.u <= 1.0f;
-                const bool vv = wg.p.v >= -1.0f && wg.p.v <= 1.0f && wp.p.v >= -1.0f && wp.p.v <= 1.0f;
-                const float du = wp.p.u - wg.p.u, dv = wp.p.v - wg.p.v;
-                if (MODE == 0) {
-                    if (vu) acc += fminf(fabsf(du), 1.0f);
-                    if (vv) acc += fminf(fabsf(dv), 1.0f);
-                } else {
-                    const float gu = (vu && fabsf(du) <= 1.0f) ? kscale * sgn(du) : 0.0f;
-                    const float gv = (vv && fabsf(dv) <= 1.0f) ? kscale * sgn(dv) : 0.0f;
-                    if (gu != 0.0f || gv != 0.0f) warp_pixel_adjoint(cpr, wp, d, wm1, hm1, true, gu, gv, gT);
+                const bool gu_in = wg.p.u >= -1.0f && wg.p.u <= 1.0f, gv_in = wg.p.v >= -1.0f && wg.p.v <= 1.0f;
+#pragma unroll
+                for (int k = 0; k < kReprojGroup; ++k) {
+                    if (k < ng) {
+                        Warp wp;
+                        warp_pixel<true>(cpr[k], x, y, d, wm1, hm1, true, wp);
+                        const bool vu = gu_in && wp.p.u >= -1.0f && wp.p.u <= 1.0f;
+                        const bool vv = gv_in && wp.p.v >= -1.0f && wp.p.v <= 1.0f;
+                        const float du = wp.p.u - wg.p.u, dv = wp.p.v - wg.p.v;
+                        if (MODE == 0) {
+                            if (vu) acc[k] += fminf(fabsf(du), 1.0f);
+                            if (vv) acc[k] += fminf(fabsf(dv), 1.0f);
+                        } else {
+                            const float gu = (vu && fabsf(du) <= 1.0f) ? kscale[k] * sgn(du) : 0.0f;
+                            const float gv = (vv && fabsf(dv) <= 1.0f) ? kscale[k] * sgn(dv) : 0.0f;
+                            if (gu != 0.0f || gv != 0.0f) warp_pixel_adjoint(cpr[k], wp, d, wm1, hm1, true, gu, gv, gT[k]);
+                        }
+                    }
                 }
             }
-            if (MODE == 0) {
-                block_accumulate<1>(&acc, red, spread_acc(slot_at(ws, i)));
-            } else if (rp.g_pred[v * n_preds + i] != nullptr) {
-                Slot* slot = slot_at(ws, (v * n_preds + i) * B + b);
-                block_accumulate<12>(gT, red, spread_acc(slot));
-                if (last_block(slot, gridDim.x, &flag) && threadIdx.x < 32) {
-                    const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
-                    finish_pose_grad_warp(slot, cams.pose_kind, eul ? rp.pred[v * n_preds + i] + b * 6 : nullptr,
-                                          rp.g_pred[v * n_preds + i] + b * (eul ? 6 : 16));
+#pragma unroll
+            for (int k = 0; k < kReprojGroup; ++k) {
+                if (k >= ng) continue;                                  // block-uniform
+                const int i = i0 + k;
+                if (MODE == 0) {
+                    block_accumulate<1>(&acc[k], red, spread_acc(slot_at(ws, i)));
+                } else if (rp.g_pred[v * n_preds + i] != nullptr) {
+                    Slot* slot = slot_at(ws, (v * n_preds + i) * B + b);
+                    block_accumulate12(gT[k], red, spread_acc(slot));
+                    if (last_block(slot, gridDim.x, &flag) && threadIdx.x < 32) {
+                        const bool eul = cams.pose_kind == DROSFM_POSE_EULER6;
+                        finish_pose_grad_warp(slot, cams.pose_kind, eul ? rp.pred[v * n_preds + i] + b * 6 : nullptr,
+                                              rp.g_pred[v * n_preds + i] + b * (eul ? 6 : 16));
+                    }
                 }
             }
         }
-        __syncthreads();
     }
     if (MODE == 0) {
         Slot* ticket = slot_at(ws, n_preds);
