@@ -71,3 +71,20 @@ def test_relayout_of_host_tensors_is_torchs_copy():
     assert ops.relayout(cl, _lib.NHWC) is cl
     back = ops.relayout(cl, _lib.NCHW)
     assert back.is_contiguous() and torch.equal(back, x)
+
+
+def test_graphed_step_tree_helpers_and_plain_split():
+    """Host logic that needs no GPU: the batch-pytree helpers of graphs.GraphedStep; split_feature_maps is a plain
+    torch.split (no layout conversion, no kernel) for tensors that are not CUDA float32 NCHW maps."""
+    import torch
+    from dro_sfm_b200 import graphs
+    from dro_sfm_b200.networks import cost as cost_mod
+    batch = {"rgb": torch.zeros(2, 3), "ctx": [torch.zeros(2), torch.ones(2)], "idx": 7, "t": (torch.zeros(1),)}
+    clone = graphs._tree_map(lambda t: t.clone(), batch)
+    assert clone["idx"] == 7 and clone["ctx"][1] is not batch["ctx"][1] and isinstance(clone["t"], tuple)
+    new = {"rgb": torch.full((2, 3), 5.0), "ctx": [torch.full((2,), 2.0), torch.full((2,), 3.0)], "idx": 8, "t": (torch.ones(1),)}
+    graphs._tree_copy_(clone, new)
+    assert float(clone["rgb"].sum()) == 30.0 and float(clone["ctx"][1][0]) == 3.0 and float(clone["t"][0]) == 1.0
+    stacked = torch.randn(6, 8, 4, 5)
+    parts = cost_mod.split_feature_maps(stacked, [2, 2, 2])
+    assert len(parts) == 3 and all(torch.equal(p, q) for p, q in zip(parts, torch.split(stacked, 2)))

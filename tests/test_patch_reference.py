@@ -30,6 +30,13 @@ def test_install_rebinds_the_hot_path_symbols():
     assert rn.DepthPoseNet.get_cost_each is FeatureMetricCost.get_cost_each
     assert rn.DepthPoseNet.depth_cost_calc is FeatureMetricCost.depth_cost_calc
     assert rn.DepthPoseNet.upsample_depth is FeatureMetricCost.upsample_depth
+    # evaluation path (model_wrapper.py:355-399 imports these two names from dro_sfm.utils.depth)
+    import dro_sfm.utils.depth as rd
+    from dro_sfm_b200.utils.depth import post_process_inv_depth, compute_depth_metrics
+    assert rd.post_process_inv_depth is post_process_inv_depth and rd.compute_depth_metrics is compute_depth_metrics
+    # the lock-step schedule is grafted onto the network's forward
+    from dro_sfm_b200.networks import lockstep
+    assert rn.DepthPoseNet.forward is lockstep.forward
 
 
 def test_dropin_signatures_match_the_reference():
@@ -58,4 +65,10 @@ def test_dropin_signatures_match_the_reference():
     assert params(FeatureMetricCost.depth_cost_calc) == ["self", "inv_depth", "fmap", "fmaps_ref", "pose_list", "K", "ref_K",
                                                          "scale_factor"]
     assert params(FeatureMetricCost.upsample_depth) == ["self", "depth", "mask", "ratio"]
+    from dro_sfm_b200.utils import depth as my_depth
+    src = open(os.path.join(ref_import.REF_ROOT, "dro_sfm/utils/depth.py")).read()
+    assert "def post_process_inv_depth(inv_depth, inv_depth_flipped, method='mean')" in src
+    assert params(my_depth.post_process_inv_depth) == ["inv_depth", "inv_depth_flipped", "method"]
+    assert "def compute_depth_metrics(config, gt, pred, use_gt_scale=True)" in src
+    assert params(my_depth.compute_depth_metrics) == ["config", "gt", "pred", "use_gt_scale"]
     assert orig_cam is not None and ref is not None
