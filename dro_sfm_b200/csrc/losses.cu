@@ -392,29 +392,57 @@ struct SupPtrs {
 };
 
 // MODE 0: loss = sum_i w_i * mean(valid * |gt - d_i|) / sum_i w_i;  MODE 1: gradients w.r.t. every d_i.
-template <int MODE>
+// NP: n_preds rounded up to a multiple of four (unrolled).  VEC: elements per thread and step (4: 128-bit accesses).  All
+// loads of a step are requested before anything is stored (a store between them would serialise the memory round trips).
+template <int MODE, int NP, int VEC>
 __global__ void __launch_bounds__(kLossThreads)
 sup_depth_kernel(const float* __restrict__ g_loss, const float* __restrict__ gt, const __grid_constant__ SupPtrs sp, int n_preds,
                  float lo, float hi, float wsum, float* __restrict__ loss, Slot* ws, long long N) {
-    __shared__ double red[DROSFM_MAX_PREDS][kLossThreads / 32];
+    __shared__ double red[NP][kLossThreads / 32];
     __shared__ int flag;
-    float acc[DROSFM_MAX_PREDS];
+    float acc[NP];
 #pragma unroll
-    for (int i = 0; i < DROSFM_MAX_PREDS; ++i) acc[i] = 0.0f;
+    for (int i = 0; i < NP; ++i) acc[i] = 0.0f;
     const float gscale = MODE == 1 ? __ldg(g_loss) / (wsum * static_cast<float>(N)) : 0.0f;
-    for (long long p = static_cast<long long>(blockIdx.x) * kLossThreads + threadIdx.x; p < N;
-         p += static_cast<long long>(gridDim.x) * kLossThreads) {
-        const float t = __ldg(gt + p);
-        const bool valid = t > lo && t < hi;
+    const long long steps = N / VEC;                 // the host picks VEC = 4 only when N is a multiple of four
+    for (long long q = static_cast<long long>(blockIdx.x) * kLossThreads + threadIdx.x; q < steps;
+         q += static_cast<long long>(gridDim.x) * kLossThreads) {
+        float t[VEC], d[NP][VEC];
+        if constexpr (VEC == 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(gt) + q);
+            t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+        } else {
+            t[0] = __ldg(gt + q);
+        }
 #pragma unroll
-        for (int i = 0; i < DROSFM_MAX_PREDS; ++i) {
+        for (int i = 0; i < NP; ++i) {
             if (i < n_preds) {
-                const float df = t - __ldg(sp.d[i] + p);
-                if (MODE == 0) {
-                    if (valid) acc[i] += fabsf(df);
-                } else if (sp.g[i] != nullptr) {
-                    // d|gt - d|/dd = -sign(gt - d)
-                    sp.g[i][p] = valid ? -gscale * sp.weight[i] * (df > 0.0f ? 1.0f : (df < 0.0f ? -1.0f : 0.0f)) : 0.0f;
+                if constexpr (VEC == 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(sp.d[i]) + q);
+                    d[i][0] = v.x; d[i][1] = v.y; d[i][2] = v.z; d[i][3] = v.w;
+                } else {
+                    d[i][0] = __ldg(sp.d[i] + q);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            if (i < n_preds) {
+                float g[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    const bool valid = t[e] > lo && t[e] < hi;
+                    const float df = t[e] - d[i][e];
+                    if (MODE == 0) {
+                        if (valid) acc[i] += fabsf(df);
+                    } else {
+                        // d|gt - d|/dd = -sign(gt - d)
+                        g[e] = valid ? -gscale * sp.weight[i] * (df > 0.0f ? 1.0f : (df < 0.0f ? -1.0f : 0.0f)) : 0.0f;
+                    }
+                }
+                if (MODE == 1 && sp.g[i] != nullptr) {
+                    if constexpr (VEC == 4) reinterpret_cast<float4*>(sp.g[i])[q] = make_float4(g[0], g[1], g[2], g[3]);
+                    else sp.g[i][q] = g[0];
                 }
             }
         }
@@ -422,7 +450,7 @@ sup_depth_kernel(const float* __restrict__ g_loss, const float* __restrict__ gt,
     if (MODE == 1) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < DROSFM_MAX_PREDS; ++i) {
+    for (int i = 0; i < NP; ++i) {
         if (i < n_preds) {
             const double s = warp_sum(static_cast<double>(acc[i]));
             if (lane == 0) red[i][wid] = s;
@@ -449,6 +477,30 @@ sup_depth_kernel(const float* __restrict__ g_loss, const float* __restrict__ gt,
             *loss = static_cast<float>(total / static_cast<double>(wsum));
         }
     }
+}
+
+// launches sup_depth_kernel<MODE, NP, VEC> for the prediction count and the alignment of the maps
+template <int MODE>
+static void launch_sup_depth(unsigned blocks, cudaStream_t cs, bool vec4, const float* g_loss, const float* gt, const SupPtrs& sp,
+                             int n_preds, float lo, float hi, float wsum, float* loss, Slot* ws, long long N) {
+#define SUP(NP_, VEC_) sup_depth_kernel<MODE, NP_, VEC_><<<blocks, kLossThreads, 0, cs>>>(g_loss, gt, sp, n_preds, lo, hi, wsum, loss, ws, N)
+#define SUP_NP(VEC_)                                  \
+    do {                                              \
+        if (n_preds <= 4) SUP(4, VEC_);               \
+        else if (n_preds <= 8) SUP(8, VEC_);          \
+        else if (n_preds <= 12) SUP(12, VEC_);        \
+        else SUP(16, VEC_);                           \
+    } while (0)
+    if (vec4) SUP_NP(4);
+    else SUP_NP(1);
+#undef SUP_NP
+#undef SUP
+}
+
+static bool sup_vec4(const float* gt, const SupPtrs& sp, int n_preds, long long N) {
+    bool ok = (N % 4) == 0 && aligned16(gt);
+    for (int i = 0; i < n_preds; ++i) ok = ok && aligned16(sp.d[i]) && (sp.g[i] == nullptr || aligned16(sp.g[i]));
+    return ok;
 }
 
 static int fill_sup(SupPtrs& sp, float& wsum, const float* const* inv_depths, float* const* g, int n_preds, float gamma) {
@@ -568,10 +620,12 @@ int drosfm_sup_depth_loss_fwd(const float* gt_inv_depth, const float* const* inv
     float wsum = 1.0f;
     if (int e = fill_sup(sp, wsum, inv_depths, nullptr, n_preds, gamma)) return e;
     const long long N = static_cast<long long>(B) * H * W;
-    long long blocks = (N + kLossThreads * 4 - 1) / (kLossThreads * 4);
-    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    sup_depth_kernel<0><<<static_cast<unsigned>(blocks), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        nullptr, gt_inv_depth, sp, n_preds, 1.0f / max_depth, 1.0f / min_depth, wsum, loss, static_cast<Slot*>(ws), N);
+    const bool vec4 = sup_vec4(gt_inv_depth, sp, n_preds, N);
+    const long long steps = vec4 ? N / 4 : N;
+    long long blocks = (steps + kLossThreads - 1) / kLossThreads;       // one step per thread up to 16 blocks per SM
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    launch_sup_depth<0>(static_cast<unsigned>(blocks), static_cast<cudaStream_t>(stream), vec4, nullptr, gt_inv_depth, sp, n_preds,
+                        1.0f / max_depth, 1.0f / min_depth, wsum, loss, static_cast<Slot*>(ws), N);
     return launch_status("sup_depth_loss_fwd");
 }
 
@@ -584,9 +638,12 @@ int drosfm_sup_depth_loss_bwd(const float* g_loss, const float* gt_inv_depth, co
     float wsum = 1.0f;
     if (int e = fill_sup(sp, wsum, inv_depths, g_inv_depths, n_preds, gamma)) return e;
     const long long N = static_cast<long long>(B) * H * W;
-    const long long blocks = (N + kLossThreads - 1) / kLossThreads;
-    sup_depth_kernel<1><<<static_cast<unsigned>(blocks), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        g_loss, gt_inv_depth, sp, n_preds, 1.0f / max_depth, 1.0f / min_depth, wsum, nullptr, nullptr, N);
+    const bool vec4 = sup_vec4(gt_inv_depth, sp, n_preds, N);
+    const long long steps = vec4 ? N / 4 : N;
+    const long long blocks = (steps + kLossThreads - 1) / kLossThreads;
+    DROSFM_REQUIRE(blocks < (1ll << 31), DROSFM_ERANGE, "sup_depth_loss_bwd: too large");
+    launch_sup_depth<1>(static_cast<unsigned>(blocks), static_cast<cudaStream_t>(stream), vec4, g_loss, gt_inv_depth, sp, n_preds,
+                        1.0f / max_depth, 1.0f / min_depth, wsum, nullptr, nullptr, N);
     return launch_status("sup_depth_loss_bwd");
 }
 
