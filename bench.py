@@ -39,13 +39,13 @@ def measured_peaks():
 # C-ABI call -> the CUDA kernels it launches (names as in the ncu reports); the staged photometric calls are two each
 NCU_NAMES = {"photometric_bwd": ["ssim_bwd_stream"], "photometric_fwd": ["ssim_train_stream2_kernel"],
              "feat_cost_batch_fwd": ["feat_cost_fwd_nhwc<2>"], "feat_cost_batch_bwd": ["feat_cost_bwd_nhwc<2>"],
-             "photometric_loss_fwd": ["photometric_fwd_kernel<1, 0, 0>", "pack_rgbx_kernel", "warp_sources_kernel<1>",
+             "photometric_loss_fwd": ["ssim_fwd_stream2_kernel<1>", "pack_rgbx_kernel", "warp_sources_kernel<1>",
                                       "ssim_train_stream2_kernel"],
              "photometric_loss_bwd": ["warp_sources_adjoint_kernel<1, 1>"],
              "warp_sources_fwd": ["pack_rgbx_kernel", "warp_sources_kernel<1>"], "warp_sources_bwd": ["warp_sources_adjoint_kernel<1, 1>"],
              "feat_cost_fwd_v1": ["feat_cost_fwd_nhwc<1>"], "feat_cost_bwd_v1": ["feat_cost_bwd_nhwc<1>"],
              "feat_cost_fwd_vN": ["feat_cost_fwd_nhwc<2>"], "feat_cost_bwd_vN": ["feat_cost_bwd_nhwc<2>"],
-             "automask_fwd": ["photometric_fwd_kernel<1, 0, 0>"], "smoothness_fwd": ["smooth_mean_kernel", "smooth_fwd_kernel"],
+             "automask_fwd": ["ssim_fwd_stream2_kernel<1>"], "smoothness_fwd": ["smooth_mean_kernel", "smooth_fwd_kernel"],
              "smoothness_bwd": ["smooth_bwd_kernel"]}
 
 
