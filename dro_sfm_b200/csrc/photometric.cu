@@ -1682,7 +1682,7 @@ ssim_bwd_stream2_kernel(const float* __restrict__ g_loss, const float* __restric
 // the window just completed; the three warps exchange them through shared memory (double-buffered, ONE named barrier per
 // step), every warp forms the photometric values of both views, the min / auto-mask selection and from it the
 // coefficients of its own channel.  Channel 0 accumulates the loss and writes the selection.
-constexpr int kTrainThreads = 96;
+constexpr int kTrainThreads = 96;      // per view PAIR: three channel warps
 #ifndef DROSFM_SSIMT_INNER
 #define DROSFM_SSIMT_INNER 1      // bands away from the top / bottom edge run a copy of the walk without the row tests
 #endif
@@ -1705,14 +1705,19 @@ __device__ __forceinline__ float2 third2(float2 x) {      // third() of both hal
     return fma2(fma2(bc2(-3.0f), q, x), r, q);
 }
 
-__global__ void __launch_bounds__(kTrainThreads, DROSFM_SSIMT_MINBLOCKS)
+// PAIRS = V / 2 view pairs per block (3 * PAIRS warps): every pair's warps exchange their terms, every warp forms the
+// photometric values of ALL views and the selection, and keeps the coefficients of its own pair and channel.
+template <int PAIRS>
+__global__ void __launch_bounds__(kTrainThreads * PAIRS, PAIRS == 1 ? DROSFM_SSIMT_MINBLOCKS : (PAIRS == 2 ? 2 : 1))
 ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restrict__ warped, const __grid_constant__ PhotoPtrs pp,
                           int n_preds, const float* __restrict__ automask_in, drosfm_photo_opts_t opts, float l1_w,
                           uint8_t* __restrict__ sel_out, float* __restrict__ loss, Slot* ws, float* __restrict__ g_warped,
                           int B, int H, int W, int nstrips, int nbands) {
-    __shared__ float4 xchg[3][3][32];      // [row step within the unrolled triple][channel][lane]: static offsets
+    __shared__ float4 xchg[3][PAIRS][3][32];      // [row step within the unrolled triple][pair][channel][lane]: static offsets
     __shared__ int flag;
-    const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+    constexpr int V = 2 * PAIRS;
+    const int pr = PAIRS == 1 ? 0 : static_cast<int>(threadIdx.x) / kTrainThreads;
+    const int lane = threadIdx.x & 31, c = (static_cast<int>(threadIdx.x) - pr * kTrainThreads) >> 5;
     const int wg = blockIdx.x;
     const int strip = wg % nstrips, band = wg / nstrips;
     const int b = static_cast<int>(blockIdx.y) % B, ip = static_cast<int>(blockIdx.y) / B;
@@ -1724,10 +1729,10 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
     const int gxc = clampi(gx, 0, W - 1);
     const bool use_min = opts.reduce_op == DROSFM_REDUCE_MIN;
     // unscaled by the upstream gradient (see above)
-    const float G = pp.weight[ip] / (static_cast<float>(B) * static_cast<float>(P) * (use_min ? 1.0f : 2.0f));
+    const float G = pp.weight[ip] / (static_cast<float>(B) * static_cast<float>(P) * (use_min ? 1.0f : static_cast<float>(V)));
     const float kp = G * opts.ssim_w * (-1.0f / 6.0f) * (2.0f / 9.0f);
     const float kl1 = G * l1_w * (1.0f / 3.0f);
-    const size_t slot0 = (static_cast<size_t>(ip) * 2) * B + b;
+    const size_t slot0 = (static_cast<size_t>(ip) * V + 2 * pr) * B + b;
     const unsigned vstride = static_cast<unsigned>(B) * 3u * static_cast<unsigned>(P);     // view 1 relative to view 0
     const float* __restrict__ ypl = image + (static_cast<size_t>(b) * 3 + c) * P + gxc;
     const float* __restrict__ xpl = warped + (slot0 * 3 + c) * P + gxc;
@@ -1818,27 +1823,29 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
             // this channel's terms of the photometric value of the window centre (row p1)
             const float2 dxy = fma2(bc2(-1.0f), bc2(p1.y), p1.x);                     // x - y, exact as a difference
             const float4 mineq = make_float4(fminf(fmaxf(l0, 0.0f), 1.0f), fminf(fmaxf(l1, 0.0f), 1.0f), fabsf(dxy.x), fabsf(dxy.y));
-            xchg[KB][c][lane] = mineq;
-            asm volatile("bar.sync 1, 96;" ::: "memory");
-            const float4 q0 = xchg[KB][0][lane], q1 = xchg[KB][1][lane], q2 = xchg[KB][2][lane];
-            // channel means and the weighted sum, both views at once (same operations, same order as the scalar form)
-            const float2 ssum = add2(add2(make_float2(q0.x, q0.y), make_float2(q1.x, q1.y)), make_float2(q2.x, q2.y));
-            const float2 lsum = add2(add2(make_float2(q0.z, q0.w), make_float2(q1.z, q1.w)), make_float2(q2.z, q2.w));
-            const float2 pm = add2(mul2(bc2(opts.ssim_w), third2(ssum)), mul2(bc2(l1_w), third2(lsum)));
-            const float pm0 = pm.x, pm1 = pm.y;
-            float best;
-            if (use_min) {
-                best = __int_as_float(0x7f800000);
-                if (pm0 < best) { best = pm0; sv = 0; }
-                if (pm1 < best) { best = pm1; sv = 1; }
-                if (am < best) { best = am; sv = 255; }
-            } else {
-                best = pm0 + pm1;
-                sv = 253;
+            xchg[KB][pr][c][lane] = mineq;
+            asm volatile("bar.sync 1, %0;" ::"n"(kTrainThreads * PAIRS) : "memory");
+            float best = use_min ? __int_as_float(0x7f800000) : 0.0f;
+            if (!use_min) sv = 253;
+#pragma unroll
+            for (int q = 0; q < PAIRS; ++q) {
+                const float4 q0 = xchg[KB][q][0][lane], q1 = xchg[KB][q][1][lane], q2 = xchg[KB][q][2][lane];
+                // channel means and the weighted sum, both views at once (same operations, same order as the scalar form)
+                const float2 ssum = add2(add2(make_float2(q0.x, q0.y), make_float2(q1.x, q1.y)), make_float2(q2.x, q2.y));
+                const float2 lsum = add2(add2(make_float2(q0.z, q0.w), make_float2(q1.z, q1.w)), make_float2(q2.z, q2.w));
+                const float2 pm = add2(mul2(bc2(opts.ssim_w), third2(ssum)), mul2(bc2(l1_w), third2(lsum)));
+                if (use_min) {
+                    if (pm.x < best) { best = pm.x; sv = 2 * q; }
+                    if (pm.y < best) { best = pm.y; sv = 2 * q + 1; }
+                } else {
+                    best += pm.x;
+                    best += pm.y;
+                }
             }
+            if (use_min && am < best) { best = am; sv = 255; }
             const bool centre_in = col_in && (INNER || (gc >= 0 && gc < H));
             if (!centre_in) sv = 254;
-            if (c == 0 && out_lane && j >= 3 && j < kTrainBandH + 3 && (INNER || gc < H)) {
+            if (c == 0 && pr == 0 && out_lane && j >= 3 && j < kTrainBandH + 3 && (INNER || gc < H)) {
                 local += best;
                 if (spl != nullptr) {
                     if constexpr (INNER) *srow = static_cast<uint8_t>(use_min ? sv : 254);
@@ -1848,7 +1855,7 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
             // coefficients of the windows that carry a gradient
             // (branch-free: every quantity is finite -- den >= C1 * C2 -- so a window without a gradient is masked by a
             // multiplication with zero instead of a divergent branch around the block)
-            const bool on0 = sv == 0 || sv == 253, on1 = sv == 1 || sv == 253;
+            const bool on0 = sv == 2 * pr || sv == 253, on1 = sv == 2 * pr + 1 || sv == 253;
             const bool k0 = on0 && l0 >= 0.0f && l0 <= 1.0f, k1 = on1 && l1 >= 0.0f && l1 <= 1.0f;
             const float2 q = mul2(mul2(bc2(kp), rden), make_float2(k0 ? 1.0f : 0.0f, k1 ? 1.0f : 0.0f));
             const float2 neg1 = bc2(-1.0f);
@@ -1878,7 +1885,7 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
                     gc_ = fma2(wy2, p1.hc, fma2(wy0, cur.hc, p2.hc));
                 }
                 float2 gxv = fma2(gc_, bc2(p2.y), fma2(gb, p2.x, ga));
-                const bool q0 = sv_prev == 0 || sv_prev == 253, q1 = sv_prev == 1 || sv_prev == 253;
+                const bool q0 = sv_prev == 2 * pr || sv_prev == 253, q1 = sv_prev == 2 * pr + 1 || sv_prev == 253;
                 if (q0) {
                     const float df = p2.x.x - p2.y;
                     gxv.x += df == 0.0f ? 0.0f : __int_as_float(__float_as_int(kl1) ^ (__float_as_int(df) & 0x80000000));
@@ -1935,13 +1942,13 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
 #endif
         walk(std::false_type{});
     // loss: channel 0's lanes hold the per-pixel values of the band
-    if (c == 0) {
+    if (c == 0 && pr == 0) {
         const double part = warp_sum(static_cast<double>(local));
         if (lane == 0 && part != 0.0) atomicAdd(spread_acc(slot_at(ws, ip)), part);
     }
     Slot* ticket = slot_at(ws, n_preds);
     if (last_block(ticket, gridDim.x * gridDim.y, &flag) && threadIdx.x < 32)
-        finish_weighted_means(ws, n_preds, pp.weight, static_cast<double>(B) * P * (use_min ? 1.0 : 2.0), ticket, loss);
+        finish_weighted_means(ws, n_preds, pp.weight, static_cast<double>(B) * P * (use_min ? 1.0 : static_cast<double>(V)), ticket, loss);
 }
 
 static int check_photo(const float* image, const float* const* context, int n_views, const drosfm_photo_opts_t* opts,
@@ -2080,9 +2087,9 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
     DROSFM_REQUIRE(opts->ssim_w > 0.0f || warped_save == nullptr, DROSFM_ENOTSUP,
                    "photometric_fwd: ssim_loss_weight == 0 runs on the fused path (warped_save == NULL)");
     DROSFM_REQUIRE(!(flags & DROSFM_PHOTO_FUSE_BWD) ||
-                       (warped_save != nullptr && g_warped != nullptr && n_views == 2 && !(opts->clip_loss > 0.0f) &&
+                       (warped_save != nullptr && g_warped != nullptr && n_views % 2 == 0 && !(opts->clip_loss > 0.0f) &&
                         static_cast<long long>(B) * 3 * H * W < (1ll << 31) && static_cast<long long>(B) * n_preds <= 65535),
-                   DROSFM_ENOTSUP, "photometric_fwd: DROSFM_PHOTO_FUSE_BWD needs the staged path (warped_save, g_warped), two views, no clip");
+                   DROSFM_ENOTSUP, "photometric_fwd: DROSFM_PHOTO_FUSE_BWD needs the staged path (warped_save, g_warped), an even number of views, no clip");
     DROSFM_REQUIRE(!(opts->automask && opts->reduce_op != DROSFM_REDUCE_MIN), DROSFM_EINVAL,
                    "photometric_fwd: auto-masking needs the min reduce op");
     DROSFM_REQUIRE(!opts->automask || automask != nullptr, DROSFM_EINVAL, "photometric_fwd: automask map is NULL");
@@ -2103,9 +2110,14 @@ int drosfm_photometric_fwd(const float* image, const float* const* context, int 
             // training forward: loss, selection AND d loss / d warped (unscaled) in one pass over the warped copy
             const int nstrips = (W + kBwdStripW - 1) / kBwdStripW, nbands = (H + kTrainBandH - 1) / kTrainBandH;
             dim3 tgrid(nstrips * nbands, B * n_preds);
-            ssim_train_stream2_kernel<<<tgrid, kTrainThreads, 0, cs>>>(image, warped_save, pp, n_preds, opts->automask ? automask : nullptr,
-                                                                      *opts, l1_weight(opts), sel, loss, static_cast<Slot*>(ws), g_warped,
-                                                                      B, H, W, nstrips, nbands);
+#define TRAIN(PAIRS_) ssim_train_stream2_kernel<PAIRS_><<<tgrid, kTrainThreads * PAIRS_, 0, cs>>>(                                     \
+        image, warped_save, pp, n_preds, opts->automask ? automask : nullptr, *opts, l1_weight(opts), sel, loss, static_cast<Slot*>(ws), \
+        g_warped, B, H, W, nstrips, nbands)
+            if (n_views == 2) TRAIN(1);
+            else if (n_views == 4) TRAIN(2);
+            else if (n_views == 6) TRAIN(3);
+            else TRAIN(4);
+#undef TRAIN
         } else if (n_views <= 2 && static_cast<long long>(n_views) * B * 3 * H * W < (1ll << 31)) {
             const int nstrips = (W + kFwdStripW - 1) / kFwdStripW, nbands = (H + kFwdBandH - 1) / kFwdBandH;
             dim3 sgrid((nstrips * nbands + kSsimWarps - 1) / kSsimWarps, B * n_preds);

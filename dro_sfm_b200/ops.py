@@ -785,7 +785,7 @@ class _PhotoLoss(torch.autograd.Function):
         two_streams = staged and OVERLAP is True            # OVERLAP == "serial": split calls, one stream
         # two views in training: the forward's SSIM pass also produces d loss / d warped (unscaled); the backward of the
         # loss is then the warp adjoint alone, and the warped copy is not kept
-        fused_bwd = staged and FUSE_BWD and V == 2 and B * 3 * H * W < 2 ** 31 and B * n <= 65535
+        fused_bwd = staged and FUSE_BWD and V in (2, 4, 6, 8) and B * 3 * H * W < 2 ** 31 and B * n <= 65535
         g_warped = torch.empty_like(wsave) if fused_bwd else None
         with torch.cuda.device(dev):
             ws = L.workspace(dev, max(n * B + 1, V * n * B))
