@@ -785,7 +785,9 @@ class _PhotoLoss(torch.autograd.Function):
         two_streams = staged and OVERLAP is True            # OVERLAP == "serial": split calls, one stream
         # two views in training: the forward's SSIM pass also produces d loss / d warped (unscaled); the backward of the
         # loss is then the warp adjoint alone, and the warped copy is not kept
-        fused_bwd = staged and FUSE_BWD and V in (2, 4, 6, 8) and B * 3 * H * W < 2 ** 31 and B * n <= 65535
+        # (the library takes any even V; at 6-8 views its one-block-per-SM instantiation is slower than the separate
+        # backward stage -- sweep at 384x1280, V = 8: 3.33 vs 3.10 ms per loss fwd + bwd -- so those stay unfused)
+        fused_bwd = staged and FUSE_BWD and V in (2, 4) and B * 3 * H * W < 2 ** 31 and B * n <= 65535
         g_warped = torch.empty_like(wsave) if fused_bwd else None
         with torch.cuda.device(dev):
             ws = L.workspace(dev, max(n * B + 1, V * n * B))
