@@ -737,6 +737,7 @@ OVERLAP = os.environ.get("DROSFM_PHOTO_OVERLAP", "1") != "0"
 # DROSFM_PHOTO_FUSE_BWD=0: the window gradients of the photometric loss are computed in the backward pass (their own
 # kernel) instead of by the training forward (two-view losses on the staged path)
 FUSE_BWD = os.environ.get("DROSFM_PHOTO_FUSE_BWD", "1") != "0"
+FUSE_BWD_VIEWS = (2, 4)      # view counts that take the fused training forward (the library supports every even V)
 # DROSFM_PHOTO_RGBX=0 keeps the flat warp on the caller's planar pictures (no RGBx texel copy of the sources)
 RGBX = os.environ.get("DROSFM_PHOTO_RGBX", "1") != "0"
 
@@ -787,7 +788,7 @@ class _PhotoLoss(torch.autograd.Function):
         # loss is then the warp adjoint alone, and the warped copy is not kept
         # (the library takes any even V; at 6-8 views its one-block-per-SM instantiation is slower than the separate
         # backward stage -- sweep at 384x1280, V = 8: 3.33 vs 3.10 ms per loss fwd + bwd -- so those stay unfused)
-        fused_bwd = staged and FUSE_BWD and V in (2, 4) and B * 3 * H * W < 2 ** 31 and B * n <= 65535
+        fused_bwd = staged and FUSE_BWD and V in FUSE_BWD_VIEWS and B * 3 * H * W < 2 ** 31 and B * n <= 65535
         g_warped = torch.empty_like(wsave) if fused_bwd else None
         with torch.cuda.device(dev):
             ws = L.workspace(dev, max(n * B + 1, V * n * B))

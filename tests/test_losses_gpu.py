@@ -563,3 +563,49 @@ def test_photometric_loss_second_stream_matches_single_stream(monkeypatch):
     assert_close(m1.cpu(), m0.cpu(), rtol=1e-6, atol=0, what="terms")
     for a, b in zip(g1, g0):
         assert_close(a.cpu(), b.cpu(), rtol=1e-4, atol=1e-5 * float(b.abs().max()), what="gradient")
+
+
+@pytest.mark.parametrize("V,reduce_op,automask", [(2, "min", True), (4, "min", True), (6, "min", False), (8, "min", True), (4, "mean", False)])
+def test_fused_training_forward_matches_separate_backward_stage(monkeypatch, V, reduce_op, automask):
+    """Training forward that also produces d loss / d warped (ssim_train_stream2_kernel<V/2>, DROSFM_PHOTO_FUSE_BWD) against
+    the schedule with its own window-gradient kernel: same loss, same selection, gradients within the self-consistency
+    tolerance -- for every even view count the library instantiates (6 and 8 are off by default in ops.FUSE_BWD_VIEWS)."""
+    from dro_sfm_b200 import ops, synthetic as syn
+    g = syn.gen(40 + V)
+    B, H, W, n = 1, 70, 90, 2
+    K = syn.intrinsics("kitti", B, H, W).to(DEV)
+    image = syn.images(g, B, H, W).to(DEV)
+    context = [(0.8 * torch.roll(image.cpu(), v + 1, 3) + 0.2 * syn.images(g, B, H, W)).to(DEV) for v in range(V)]
+    invs0 = [syn.inv_depth(g, B, H, W, 0.5, 80.0).to(DEV) for _ in range(n)]
+    vecs0 = [[(syn.pose_vec(g, B, "kitti") * 0.3).to(DEV) for _ in range(n)] for _ in range(V)]
+
+    def run():
+        invs = [x.clone().requires_grad_(True) for x in invs0]
+        vecs = [[x.clone().requires_grad_(True) for x in tv] for tv in vecs0]
+        before = ops.L.lib().drosfm_launch_count()
+        out = ops.photometric_loss(image, context, invs, K, K, vecs, reduce_op=reduce_op, automask=automask, smooth_w=0.01,
+                                   want_selection=(reduce_op == "min"))
+        total = out[0]
+        grads = torch.autograd.grad(total, invs + [x for tv in vecs for x in tv])
+        torch.cuda.synchronize()
+        return total.detach(), (out[2] if reduce_op == "min" else None), grads, int(ops.L.lib().drosfm_launch_count() - before)
+
+    monkeypatch.setattr(ops, "FUSE_BWD_VIEWS", (2, 4, 6, 8))
+    monkeypatch.setattr(ops, "FUSE_BWD", True)
+    t1, s1, g1, l1 = run()
+    monkeypatch.setattr(ops, "FUSE_BWD", False)
+    t0, s0, g0, l0 = run()
+    assert l1 == l0 - 1, (l1, l0)                       # the window-gradient stage is gone
+    assert_close(t1.cpu(), t0.cpu(), rtol=RTOL_SELF, atol=0, what="loss")
+    flips = int((s1 != s0).sum()) if s1 is not None else 0
+    assert flips <= 2, flips                            # same arithmetic up to the last bit of a reciprocal: near-ties only
+    for k, (a, b) in enumerate(zip(g1, g0)):
+        a, b = a.cpu().double(), b.cpu().double()
+        bound = 1e-4 * b.abs() + 2e-5 * float(b.abs().max())
+        bad = int(((a - b).abs() > bound).sum())
+        if k < n:
+            # a flipped arg-min moves the gradient of the 3x3 windows around it (both views involved): nothing else may differ
+            assert bad <= 18 * flips, (k, bad, flips)
+        else:
+            # pose gradients are sums over all pixels: a flip is a 1 / (H W)-sized change of the sum
+            assert float((a - b).norm()) <= (1e-4 + 5e-3 * flips) * float(b.norm()) + 1e-12, (k, flips)
