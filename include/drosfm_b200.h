@@ -197,7 +197,7 @@ typedef struct {
 /* flags of drosfm_photometric_fwd / _bwd (staged path only) */
 #define DROSFM_PHOTO_WARPED_READY 1 /* fwd: warped_save already holds drosfm_warp_sources_fwd's output */
 #define DROSFM_PHOTO_NO_ADJOINT 2   /* bwd: stop after g_warped; the caller runs drosfm_warp_sources_bwd itself */
-#define DROSFM_PHOTO_FUSE_BWD 4     /* fwd (training, two views): also write g_warped = d loss / d warped, UNSCALED by the
+#define DROSFM_PHOTO_FUSE_BWD 4     /* fwd (training, 2/4/6/8 views): also write g_warped = d loss / d warped, UNSCALED by the
                                      * loss's upstream gradient -- the backward of the loss is then drosfm_warp_sources_bwd alone
                                      * (with g_scale = that upstream gradient); drosfm_photometric_bwd is not called */
 
