@@ -9,7 +9,7 @@ for line in out.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
     if m:
         kern = m.group(1); hist[kern] = collections.Counter(); order.append(kern); continue
-    m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+    m = re.match(r"\s*/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
     if m and kern:
         hist[kern][m.group(1).split(".")[0] + ("." + ".".join(m.group(1).split(".")[1:3]) if m.group(1).startswith(("LDG", "STG", "RED", "ATOM", "MUFU", "LDS", "STS", "BAR", "SHFL")) else "")] += 1
 names = subprocess.run(["c++filt"] + order, capture_output=True, text=True).stdout.splitlines()
