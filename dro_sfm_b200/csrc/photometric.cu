@@ -1686,6 +1686,12 @@ constexpr int kTrainThreads = 96;      // per view PAIR: three channel warps
 #ifndef DROSFM_SSIMT_INNER
 #define DROSFM_SSIMT_INNER 1      // bands away from the top / bottom edge run a copy of the walk without the row tests
 #endif
+#ifndef DROSFM_SSIMT_PFD
+#define DROSFM_SSIMT_PFD 3      // rows between a load and its use
+#endif
+#ifndef DROSFM_SSIMT_HSMEM
+#define DROSFM_SSIMT_HSMEM 1
+#endif
 #ifndef DROSFM_SSIMT_BAND
 #define DROSFM_SSIMT_BAND 32
 #endif
@@ -1715,6 +1721,14 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
                           int B, int H, int W, int nstrips, int nbands) {
     __shared__ float4 xchg[3][PAIRS][3][32];      // [row step within the unrolled triple][pair][channel][lane]: static offsets
     __shared__ int flag;
+#if DROSFM_SSIMT_HSMEM
+    // the horizontal coefficient sums of the three rows in flight live in shared memory (private per thread: no barrier),
+    // 18 registers less per thread
+    __shared__ float2 hrow[3][3][kTrainThreads * PAIRS];
+    hrow[0][0][threadIdx.x] = hrow[0][1][threadIdx.x] = hrow[0][2][threadIdx.x] = make_float2(0.0f, 0.0f);
+    hrow[1][0][threadIdx.x] = hrow[1][1][threadIdx.x] = hrow[1][2][threadIdx.x] = make_float2(0.0f, 0.0f);
+    hrow[2][0][threadIdx.x] = hrow[2][1][threadIdx.x] = hrow[2][2][threadIdx.x] = make_float2(0.0f, 0.0f);
+#endif
     constexpr int V = 2 * PAIRS;
     const int pr = PAIRS == 1 ? 0 : static_cast<int>(threadIdx.x) / kTrainThreads;
     const int lane = threadIdx.x & 31, c = (static_cast<int>(threadIdx.x) - pr * kTrainThreads) >> 5;
@@ -1786,7 +1800,7 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
         cur.y = mine.y;
         const float am = am_row;
         am_row = mine.am;
-        fetch(inner, gy + 2, refill);
+        fetch(inner, gy + DROSFM_SSIMT_PFD, refill);
         const float2 xl = shfl2(cur.x, nb.l), xr = shfl2(cur.x, nb.r);
         float yl, yr;
         neighbours(cur.y, nb, yl, yr);
@@ -1797,6 +1811,9 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
         cur.sxx = fma2(xr, xr, fma2(cur.x, cur.x, mul2(xl, xl)));
         cur.sxy = fma2(xr, yr2, fma2(cur.x, yc2, mul2(xl, yl2)));
         int sv = 254;
+#if DROSFM_SSIMT_HSMEM
+        float2 h1a = bc2(0.0f), h1b = h1a, h1c = h1a;
+#endif
         if (j >= 2) {
             // statistics of the window centred on (gc, gx), this channel, both views
             const float2 wsx = add2(add2(p2.sx, p1.sx), cur.sx);
@@ -1865,19 +1882,47 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
             const float2 bb = mul2(mul2(mul2(q, neg1), sm), B1);
             const float2 cq = mul2(q, A1);
             const int ll = (lane - 1) & 31, lr = (lane + 1) & 31;      // the outermost lanes' sums are never used
+#if DROSFM_SSIMT_HSMEM
+            h1a = fma2(wx2, shfl2(a, lr), fma2(wx0, shfl2(a, ll), a));
+            h1b = fma2(wx2, shfl2(bb, lr), fma2(wx0, shfl2(bb, ll), bb));
+            h1c = fma2(wx2, shfl2(cq, lr), fma2(wx0, shfl2(cq, ll), cq));
+            hrow[(KB + 2) % 3][0][threadIdx.x] = h1a;       // p1 of step KB is struct (KB + 2) % 3
+            hrow[(KB + 2) % 3][1][threadIdx.x] = h1b;
+            hrow[(KB + 2) % 3][2][threadIdx.x] = h1c;
+#else
             p1.ha = fma2(wx2, shfl2(a, lr), fma2(wx0, shfl2(a, ll), a));
             p1.hb = fma2(wx2, shfl2(bb, lr), fma2(wx0, shfl2(bb, ll), bb));
             p1.hc = fma2(wx2, shfl2(cq, lr), fma2(wx0, shfl2(cq, ll), cq));
+#endif
         }
         if (j >= 4) {
             const int gq = gy - 2;
             if (out_lane && j < kTrainBandH + 4 && (INNER || gq < H)) {
                 float2 ga, gb, gc_;
+#if DROSFM_SSIMT_HSMEM
+                // cur of step KB is struct KB, p2 is struct (KB + 1) % 3
+                const float2 cha = hrow[KB][0][threadIdx.x], chb = hrow[KB][1][threadIdx.x], chc = hrow[KB][2][threadIdx.x];
+                const float2 p2a = hrow[(KB + 1) % 3][0][threadIdx.x], p2b = hrow[(KB + 1) % 3][1][threadIdx.x],
+                             p2c = hrow[(KB + 1) % 3][2][threadIdx.x];
+                if constexpr (INNER) {
+                    ga = add2(h1a, add2(cha, p2a));
+                    gb = add2(h1b, add2(chb, p2b));
+                    gc_ = add2(h1c, add2(chc, p2c));
+                } else {
+                    const float2 wy0 = bc2(gq <= 0 ? 0.0f : (gq == 1 ? 2.0f : 1.0f));
+                    const float2 wy2 = bc2(gq >= H - 1 ? 0.0f : (gq == H - 2 ? 2.0f : 1.0f));
+                    ga = fma2(wy2, h1a, fma2(wy0, cha, p2a));
+                    gb = fma2(wy2, h1b, fma2(wy0, chb, p2b));
+                    gc_ = fma2(wy2, h1c, fma2(wy0, chc, p2c));
+                }
+                if constexpr (false) {
+#else
                 if constexpr (INNER) {      // unit weights: the same sums, bit for bit
                     ga = add2(p1.ha, add2(cur.ha, p2.ha));
                     gb = add2(p1.hb, add2(cur.hb, p2.hb));
                     gc_ = add2(p1.hc, add2(cur.hc, p2.hc));
                 } else {
+#endif
                     const float2 wy0 = bc2(gq <= 0 ? 0.0f : (gq == 1 ? 2.0f : 1.0f));
                     const float2 wy2 = bc2(gq >= H - 1 ? 0.0f : (gq == H - 2 ? 2.0f : 1.0f));
                     ga = fma2(wy2, p1.ha, fma2(wy0, cur.ha, p2.ha));
@@ -1928,16 +1973,26 @@ ssim_train_stream2_kernel(const float* __restrict__ image, const float* __restri
         }
         fetch(inner, gy0 - 2, f0);
         fetch(inner, gy0 - 1, f1);
+#if DROSFM_SSIMT_PFD == 3
+        fetch(inner, gy0, f2);
+#endif
 #pragma unroll 1
         for (int j = 0; j < kTrainBandH + 4; j += 3) {
+#if DROSFM_SSIMT_PFD == 3
+            // the row loaded for step j + 3 goes into the buffer step j has just emptied
+            step(inner, std::integral_constant<int, 0>{}, r1, r2, r0, f0, f0, j);
+            step(inner, std::integral_constant<int, 1>{}, r2, r0, r1, f1, f1, j + 1);
+            step(inner, std::integral_constant<int, 2>{}, r0, r1, r2, f2, f2, j + 2);
+#else
             step(inner, std::integral_constant<int, 0>{}, r1, r2, r0, f0, f2, j);
             step(inner, std::integral_constant<int, 1>{}, r2, r0, r1, f1, f0, j + 1);
             step(inner, std::integral_constant<int, 2>{}, r0, r1, r2, f2, f1, j + 2);
+#endif
         }
     };
     constexpr int kSteps = (kTrainBandH + 4 + 2) / 3 * 3;      // the last row fetched is gy0 + kSteps - 1
 #if DROSFM_SSIMT_INNER
-    if (gy0 >= 2 && gy0 + kSteps - 1 <= H - 1) walk(std::true_type{});
+    if (gy0 >= 2 && gy0 + kSteps - 1 + (DROSFM_SSIMT_PFD - 2) <= H - 1) walk(std::true_type{});
     else
 #endif
         walk(std::false_type{});
