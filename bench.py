@@ -45,7 +45,7 @@ NCU_NAMES = {"photometric_bwd": ["ssim_bwd_stream"], "photometric_fwd": ["ssim_t
              "warp_sources_fwd": ["pack_rgbx_kernel", "warp_sources_kernel<1>"], "warp_sources_bwd": ["warp_sources_adjoint_kernel<1, 1>"],
              "feat_cost_fwd_v1": ["feat_cost_fwd_nhwc<1>"], "feat_cost_bwd_v1": ["feat_cost_bwd_nhwc<1>"],
              "feat_cost_fwd_vN": ["feat_cost_fwd_nhwc<2>"], "feat_cost_bwd_vN": ["feat_cost_bwd_nhwc<2>"],
-             "automask_fwd": ["ssim_fwd_stream2_kernel<1>"], "smoothness_fwd": ["smooth_mean_kernel", "smooth_fwd_kernel"],
+             "automask_fwd": ["ssim_fwd_stream2_kernel<1>"], "smoothness_fwd": ["smooth_fwd_kernel"],
              "smoothness_bwd": ["smooth_bwd_kernel"]}
 
 

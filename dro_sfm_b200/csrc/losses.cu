@@ -29,46 +29,6 @@ struct DepthGrads {
 // ------------------------------------------------------------------------------------------
 // smoothness
 // ------------------------------------------------------------------------------------------
-// pass 1: per (prediction, sample) mean of the inverse depth -> stats[(i*B+b)*4 + 0]
-__global__ void __launch_bounds__(kLossThreads)
-smooth_mean_kernel(const __grid_constant__ DepthList dl, float* __restrict__ stats, Slot* ws, int B, int P) {
-    __shared__ double red[kLossThreads / 32];
-    __shared__ int flag;
-    const int ib = blockIdx.y;                 // i * B + b
-    const int i = ib / B, b = ib - i * B;
-    const float* d = dl.d[i] + static_cast<size_t>(b) * P;
-    double s = 0.0;
-    if ((P & 3) == 0 && (reinterpret_cast<size_t>(d) & 15) == 0) {
-        // 128-bit loads, two in flight per thread and iteration
-        const float4* d4 = reinterpret_cast<const float4*>(d);
-        const int P4 = P >> 2, stride = gridDim.x * kLossThreads;
-        int p = blockIdx.x * kLossThreads + threadIdx.x;
-        for (; p + stride < P4; p += 2 * stride) {
-            const float4 a = __ldg(d4 + p), c = __ldg(d4 + p + stride);
-            s += static_cast<double>((a.x + a.y) + (a.z + a.w)) + static_cast<double>((c.x + c.y) + (c.z + c.w));
-        }
-        if (p < P4) {
-            const float4 a = __ldg(d4 + p);
-            s += static_cast<double>((a.x + a.y) + (a.z + a.w));
-        }
-    } else {
-        for (int p = blockIdx.x * kLossThreads + threadIdx.x; p < P; p += gridDim.x * kLossThreads) s += __ldg(d + p);
-    }
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    Slot* slot = slot_at(ws, ib);
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int k = 0; k < kLossThreads / 32; ++k) t += red[k];
-        atomicAdd(spread_acc(slot), t);
-    }
-    if (last_block(slot, gridDim.x, &flag) && threadIdx.x == 0) {
-        stats[ib * 4 + 0] = static_cast<float>(take_acc(slot, 0) / static_cast<double>(P));
-        slot->ticket = 0ull;
-    }
-}
-
 __device__ __forceinline__ float edge_weight(const float* __restrict__ img, int P, int p, int q) {
     const float a = fabsf(__ldg(img + p) - __ldg(img + q)) + fabsf(__ldg(img + P + p) - __ldg(img + P + q)) +
                     fabsf(__ldg(img + 2 * P + p) - __ldg(img + 2 * P + q));
@@ -77,29 +37,23 @@ __device__ __forceinline__ float edge_weight(const float* __restrict__ img, int 
     return expf(-__fmaf_rn(__fmaf_rn(-3.0f, t, a), r, t));
 }
 
-// pass 2: sums of |dx|*wx and |dy|*wy per (prediction, sample); the last block folds them into the loss.
-// One thread per pixel (grid-stride), the normalisation d / mean is a multiplication by the reciprocal mean
-// (computed once per thread; 1 ulp from the reference's division, far inside the loss tolerance).
+// sums of |dx|*wx and |dy|*wy per (prediction, sample); the last block folds them into the loss.
 // NP: n_preds rounded up to a multiple of four (the per-prediction code is unrolled NP times; slots beyond n_preds are
-// predicated off but still issue)
+// predicated off but still issue).
+// ONE pass: the loss is homogeneous of degree one in the mean-normalised inverse depth, |d_p/m - d_q/m| = |d_p - d_q| / m, so
+// the per-(prediction, sample) mean m is accumulated NEXT TO the un-normalised edge-weighted sums and divides them in the
+// finisher -- no separate mean pass over the n maps (the products differ from the reference's by one rounding per term).
 template <int NP>
 __global__ void __launch_bounds__(kLossThreads)
 smooth_fwd_kernel(const float* __restrict__ image, const __grid_constant__ DepthList dl, int n_preds, float weight,
                   float* __restrict__ stats, float* __restrict__ loss, Slot* ws, int B, int H, int W) {
-    __shared__ float red[2 * NP][kLossThreads / 32];
-    __shared__ float rm_s[NP];
+    __shared__ float red[3 * NP][kLossThreads / 32];
     __shared__ int flag;
     const int b = blockIdx.y, P = H * W;
     const float* img = image + static_cast<size_t>(b) * 3 * P;
-    // reciprocal means: one division per prediction and BLOCK
-    if (threadIdx.x < NP) rm_s[threadIdx.x] = threadIdx.x < n_preds ? 1.0f / fmaxf(stats[(threadIdx.x * B + b) * 4], 1e-6f) : 0.0f;
-    __syncthreads();
-    float sx[NP], sy[NP], rm[NP];
+    float sx[NP], sy[NP], sd[NP];
 #pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        sx[i] = sy[i] = 0.0f;
-        rm[i] = rm_s[i];
-    }
+    for (int i = 0; i < NP; ++i) sx[i] = sy[i] = sd[i] = 0.0f;
     const int p0 = blockIdx.x * kLossThreads + threadIdx.x;
     int y = p0 / W, x = p0 - y * W;
     const int stride = gridDim.x * kLossThreads, sy_ = stride / W, sx_ = stride - sy_ * W;
@@ -122,9 +76,9 @@ smooth_fwd_kernel(const float* __restrict__ image, const __grid_constant__ Depth
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
             if (i < n_preds) {
-                const float c = dc[i] * rm[i];
-                sx[i] += fabsf((c - dx[i] * rm[i]) * wx);
-                sy[i] += fabsf((c - dy[i] * rm[i]) * wy);
+                sd[i] += dc[i];
+                sx[i] += fabsf((dc[i] - dx[i]) * wx);
+                sy[i] += fabsf((dc[i] - dy[i]) * wy);
             }
         }
         // next pixel of this thread: (x, y) advance without a division
@@ -136,28 +90,32 @@ smooth_fwd_kernel(const float* __restrict__ image, const __grid_constant__ Depth
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
         if (i < n_preds) {
-            const float a = warp_sum(sx[i]), c = warp_sum(sy[i]);
-            if (lane == 0) { red[2 * i][wid] = a; red[2 * i + 1][wid] = c; }
+            const float a = warp_sum(sx[i]), c = warp_sum(sy[i]), m = warp_sum(sd[i]);
+            if (lane == 0) { red[3 * i][wid] = a; red[3 * i + 1][wid] = c; red[3 * i + 2][wid] = m; }
         }
     }
     __syncthreads();
-    if (threadIdx.x < 2 * n_preds) {
+    if (threadIdx.x < 3 * n_preds) {
         double t = 0.0;
 #pragma unroll
         for (int k = 0; k < kLossThreads / 32; ++k) t += red[threadIdx.x][k];
-        const int i = threadIdx.x >> 1;
-        if (t != 0.0) atomicAdd(spread_acc(slot_at(ws, i * B + b)) + (threadIdx.x & 1), t);
+        const int i = threadIdx.x / 3;
+        if (t != 0.0) atomicAdd(spread_acc(slot_at(ws, i * B + b)) + (threadIdx.x - 3 * i), t);
     }
     Slot* ticket = slot_at(ws, n_preds * B);
     if (last_block(ticket, gridDim.x * gridDim.y, &flag)) {
-        // every thread of the last block collects (prediction, sample) pairs, so the 2 n B accumulators are read with
+        // every thread of the last block collects (prediction, sample) pairs, so the 3 n B accumulators are read with
         // one round trip; the per-prediction totals meet in shared memory (fp64), thread 0 folds them into the loss
         __shared__ double tot[2 * DROSFM_MAX_PREDS];
         if (threadIdx.x < 2 * DROSFM_MAX_PREDS) tot[threadIdx.x] = 0.0;
         __syncthreads();
         for (int k = threadIdx.x; k < n_preds * B; k += kLossThreads) {
             Slot* s = slot_at(ws, k);                          // k = i * B + bb
-            const double ax = take_acc(s, 0), ay = take_acc(s, 1);
+            const double axr = take_acc(s, 0), ayr = take_acc(s, 1);
+            const float mean = static_cast<float>(take_acc(s, 2) / static_cast<double>(P));
+            const double rm = static_cast<double>(1.0f / fmaxf(mean, 1e-6f));         // inv_depths_normalize (utils/depth.py:147-166)
+            const double ax = axr * rm, ay = ayr * rm;
+            stats[k * 4 + 0] = mean;
             stats[k * 4 + 1] = static_cast<float>(ax);
             stats[k * 4 + 2] = static_cast<float>(ay);
             atomicAdd(&tot[2 * (k / B)], ax);
@@ -575,10 +533,6 @@ int drosfm_smoothness_fwd(const float* image, const float* const* inv_depths, in
     }
     const int P = H * W;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int mb = (P + kLossThreads * 8 - 1) / (kLossThreads * 8);
-    if (mb > 64) mb = 64;
-    smooth_mean_kernel<<<dim3(mb, n_preds * B), kLossThreads, 0, s>>>(dl, stats, static_cast<Slot*>(ws), B, P);
-    if (int e = launch_status("smoothness_fwd (mean)")) return e;
     int fb = (P + kLossThreads * 4 - 1) / (kLossThreads * 4);     // four pixels per thread: the 2 n shuffle reductions + atomics of the epilogue are per thread
     if (fb < 1) fb = 1;
 #define SMOOTH_FWD(NP_) smooth_fwd_kernel<NP_><<<dim3(fb, B), kLossThreads, 0, s>>>(image, dl, n_preds, weight, stats, loss, \
