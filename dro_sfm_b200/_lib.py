@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("DROSFM_SO") or os.path.join(_HERE, "libdrosfm_b200.so")     # DROSFM_SO: alternative build (experiments)
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_VIEWS = 8
 MAX_PREDS = 16
 MAX_COST_JOBS = 9
@@ -97,8 +97,8 @@ SIGNATURES = {
     "drosfm_warp_sources_fwd": ([_pp, _int, _pp, _int, _int, _cp, _pp, _int, _vp, _vp, _int, _int, _int, _vp], _int),
     "drosfm_warp_sources_bwd": ([_vp, _pp, _int, _pp, _int, _int, _cp, _pp, _int, _vp, _vp, _pp, _pp, _vp, _int,
                                  _int, _int, _int, _vp], _int),
-    "drosfm_smoothness_fwd": ([_vp, _pp, _int, _f32, _vp, _vp, _vp, _int, _int, _int, _vp], _int),
-    "drosfm_smoothness_bwd": ([_vp, _vp, _pp, _int, _f32, _vp, _pp, _int, _int, _int, _int, _vp], _int),
+    "drosfm_smoothness_fwd": ([_vp, _pp, _int, _f32, _vp, _vp, _vp, _vp, _int, _int, _int, _vp], _int),
+    "drosfm_smoothness_bwd": ([_vp, _vp, _pp, _int, _f32, _vp, _pp, _int, _vp, _int, _int, _int, _vp], _int),
     "drosfm_sup_depth_loss_fwd": ([_vp, _pp, _int, _f32, _f32, _f32, _vp, _vp, _int, _int, _int, _vp], _int),
     "drosfm_sup_depth_loss_bwd": ([_vp, _vp, _pp, _int, _f32, _f32, _f32, _pp, _int, _int, _int, _vp], _int),
     "drosfm_relayout": ([_vp, _vp, _int, _int, _int, _int, _int, _vp], _int),

@@ -46,7 +46,7 @@ __device__ __forceinline__ float edge_weight(const float* __restrict__ img, int 
 template <int NP>
 __global__ void __launch_bounds__(kLossThreads)
 smooth_fwd_kernel(const float* __restrict__ image, const __grid_constant__ DepthList dl, int n_preds, float weight,
-                  float* __restrict__ stats, float* __restrict__ loss, Slot* ws, int B, int H, int W) {
+                  float* __restrict__ stats, float* __restrict__ loss, Slot* ws, float* __restrict__ edge_w, int B, int H, int W) {
     __shared__ float red[3 * NP][kLossThreads / 32];
     __shared__ int flag;
     const int b = blockIdx.y, P = H * W;
@@ -73,6 +73,10 @@ smooth_fwd_kernel(const float* __restrict__ image, const __grid_constant__ Depth
         }
         const float wx = hx ? edge_weight(img, P, p, px) : 0.0f;
         const float wy = hy ? edge_weight(img, P, p, py) : 0.0f;
+        if (edge_w != nullptr) {      // kept for the backward pass: the weights towards the right / lower neighbour
+            edge_w[static_cast<size_t>(2 * b) * P + p] = wx;
+            edge_w[static_cast<size_t>(2 * b + 1) * P + p] = wy;
+        }
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
             if (i < n_preds) {
@@ -140,7 +144,7 @@ __device__ __forceinline__ float sgn(float v) { return v > 0.0f ? 1.0f : (v < 0.
 __global__ void __launch_bounds__(kLossThreads)
 smooth_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict__ image, const __grid_constant__ DepthList dl,
                   int n_preds, float weight, const float* __restrict__ stats, const __grid_constant__ DepthGrads dg,
-                  int accumulate, int B, int H, int W) {
+                  int accumulate, const float* __restrict__ edge_w, int B, int H, int W) {
     // per (prediction, sample) constants, computed once per BLOCK (they hold all the divisions of the formula):
     // 1/mean, kx/mean, ky/mean and the gradient through the mean
     __shared__ float4 cst[DROSFM_MAX_PREDS];
@@ -180,10 +184,20 @@ smooth_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict__ im
         }
     };
     fetch(0);
-    const float w_r = xr ? edge_weight(img, P, p, pr) : 0.0f;
-    const float w_l = xl ? edge_weight(img, P, pl, p) : 0.0f;
-    const float w_d = yd ? edge_weight(img, P, p, pd) : 0.0f;
-    const float w_u = yu ? edge_weight(img, P, pu, p) : 0.0f;
+    float w_r, w_l, w_d, w_u;
+    if (edge_w != nullptr) {          // the forward pass left the weights behind: 4 loads instead of 24 loads + 4 exponentials
+        const float* ex = edge_w + static_cast<size_t>(2 * b) * P;
+        const float* ey = ex + P;
+        w_r = xr ? __ldg(ex + p) : 0.0f;
+        w_l = xl ? __ldg(ex + pl) : 0.0f;
+        w_d = yd ? __ldg(ey + p) : 0.0f;
+        w_u = yu ? __ldg(ey + pu) : 0.0f;
+    } else {
+        w_r = xr ? edge_weight(img, P, p, pr) : 0.0f;
+        w_l = xl ? edge_weight(img, P, pl, p) : 0.0f;
+        w_d = yd ? edge_weight(img, P, p, pd) : 0.0f;
+        w_u = yu ? edge_weight(img, P, pu, p) : 0.0f;
+    }
     for (int i0 = 0; i0 < n_preds; i0 += kGroup) {
 #pragma unroll
         for (int k = 0; k < kGroup; ++k) {
@@ -520,7 +534,7 @@ using namespace drosfm;
 extern "C" {
 
 int drosfm_smoothness_fwd(const float* image, const float* const* inv_depths, int n_preds, float weight, float* stats,
-                          float* loss, void* ws, int B, int H, int W, drosfm_stream_t stream) {
+                          float* loss, void* ws, float* edge_w, int B, int H, int W, drosfm_stream_t stream) {
     DROSFM_REQUIRE(n_preds >= 1 && n_preds <= DROSFM_MAX_PREDS, DROSFM_ERANGE, "smoothness_fwd: n_preds=%d outside [1,%d]",
                    n_preds, DROSFM_MAX_PREDS);
     DROSFM_REQUIRE(B > 0 && H > 0 && W > 0, DROSFM_EINVAL, "smoothness_fwd: empty input");
@@ -536,7 +550,7 @@ int drosfm_smoothness_fwd(const float* image, const float* const* inv_depths, in
     int fb = (P + kLossThreads * 4 - 1) / (kLossThreads * 4);     // four pixels per thread: the 2 n shuffle reductions + atomics of the epilogue are per thread
     if (fb < 1) fb = 1;
 #define SMOOTH_FWD(NP_) smooth_fwd_kernel<NP_><<<dim3(fb, B), kLossThreads, 0, s>>>(image, dl, n_preds, weight, stats, loss, \
-                                                                                  static_cast<Slot*>(ws), B, H, W)
+                                                                                  static_cast<Slot*>(ws), edge_w, B, H, W)
     if (n_preds <= 4) SMOOTH_FWD(4);
     else if (n_preds <= 8) SMOOTH_FWD(8);
     else if (n_preds <= 12) SMOOTH_FWD(12);
@@ -546,8 +560,8 @@ int drosfm_smoothness_fwd(const float* image, const float* const* inv_depths, in
 }
 
 int drosfm_smoothness_bwd(const float* g_loss, const float* image, const float* const* inv_depths, int n_preds, float weight,
-                          const float* stats, float* const* g_inv_depths, int accumulate, int B, int H, int W,
-                          drosfm_stream_t stream) {
+                          const float* stats, float* const* g_inv_depths, int accumulate, const float* edge_w, int B, int H,
+                          int W, drosfm_stream_t stream) {
     DROSFM_REQUIRE(n_preds >= 1 && n_preds <= DROSFM_MAX_PREDS, DROSFM_ERANGE, "smoothness_bwd: n_preds=%d outside [1,%d]",
                    n_preds, DROSFM_MAX_PREDS);
     DROSFM_REQUIRE(B > 0 && H > 0 && W > 0, DROSFM_EINVAL, "smoothness_bwd: empty input");
@@ -561,7 +575,7 @@ int drosfm_smoothness_bwd(const float* g_loss, const float* image, const float* 
     }
     const int P = H * W;
     smooth_bwd_kernel<<<dim3((P + kLossThreads - 1) / kLossThreads, B), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        g_loss, image, dl, n_preds, weight, stats, dg, accumulate, B, H, W);
+        g_loss, image, dl, n_preds, weight, stats, dg, accumulate, edge_w, B, H, W);
     return launch_status("smoothness_bwd");
 }
 

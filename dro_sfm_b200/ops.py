@@ -779,6 +779,8 @@ class _PhotoLoss(torch.autograd.Function):
         keep_warp = SAVE_WARP and any(ctx.needs_input_grad[6 + V:]) and not clip > 0.0 and ssim_w > 0.0
         wsave = torch.empty(n, V, B, 3, H, W, device=dev, dtype=torch.float32) if keep_warp else None
         stats = torch.empty(n, B, 4, device=dev, dtype=torch.float32) if smooth_w > 0.0 else None
+        # edge weights of the smoothness term, kept for its backward pass (8 bytes per pixel)
+        edge_w = torch.empty(B, 2, H, W, device=dev, dtype=torch.float32) if smooth_w > 0.0 and any(ctx.needs_input_grad[6 + V:6 + V + n]) else None
         # source pictures as RGBx texels for the flat warp and its adjoint (one 128-bit gather per tap)
         rgbx = torch.empty(V, B, H, W, 4, device=dev, dtype=torch.float32) if keep_warp and RGBX else None
         lib = L.lib()
@@ -806,7 +808,7 @@ class _PhotoLoss(torch.autograd.Function):
                     ev.record()
                 if smooth_w > 0.0:
                     L.check(lib.drosfm_smoothness_fwd(pc, pi, n, smooth_w, L.ptr(stats), L.ptr(losses[1:]),
-                                                      L.ptr(L.workspace(dev, n * B + 1)), B, H, W, L.stream()), "smoothness_fwd")
+                                                      L.ptr(L.workspace(dev, n * B + 1)), L.ptr(edge_w), B, H, W, L.stream()), "smoothness_fwd")
                 return ev
 
             if staged:
@@ -834,7 +836,7 @@ class _PhotoLoss(torch.autograd.Function):
                 main.wait_stream(side)
         total = losses.sum().reshape(1)
         ctx.save_for_backward(image, keep[0], keep[1], sel, stats, None if fused_bwd else wsave, rgbx if staged else None, g_warped,
-                              *context, *invs, *poses)
+                              edge_w, *context, *invs, *poses)
         ctx.cfg, ctx.V, ctx.n, ctx.kind = cfg, V, n, kind
         ctx.mark_non_differentiable(losses)
         if sel is None:
@@ -846,8 +848,8 @@ class _PhotoLoss(torch.autograd.Function):
     def backward(ctx, g_total, *unused):
         ssim_w, C1, C2, padding, reduce_op, automask, gamma, smooth_w, depth_kind, clip = ctx.cfg
         V, n, kind = ctx.V, ctx.n, ctx.kind
-        image, K, Kref, sel, stats, wsave, rgbx, g_fused = ctx.saved_tensors[:8]
-        rest = ctx.saved_tensors[8:]
+        image, K, Kref, sel, stats, wsave, rgbx, g_fused, edge_w = ctx.saved_tensors[:9]
+        rest = ctx.saved_tensors[9:]
         context, invs, poses = rest[:V], rest[V:V + n], rest[V + n:]
         B, _, H, W = image.shape
         dev = image.device
@@ -883,7 +885,7 @@ class _PhotoLoss(torch.autograd.Function):
                         side.wait_stream(main)
                     with torch.cuda.stream(side):
                         L.check(lib.drosfm_smoothness_bwd(L.ptr(g), L.ptr(image), pi, n, smooth_w, L.ptr(stats), L.ptr_array(g_invs),
-                                                          2 if concurrent else 0, B, H, W, L.stream()), "smoothness_bwd")
+                                                          2 if concurrent else 0, L.ptr(edge_w), B, H, W, L.stream()), "smoothness_bwd")
                 L.check(lib.drosfm_warp_sources_bwd(L.ptr(g_fused), pa, V, pi, depth_kind, n, cams, pp_, padding, L.ptr(rgbx), L.ptr(g),
                                                     L.ptr_array(g_invs), L.ptr_array(g_poses), L.ptr(ws), 1 if smooth else 0, B, H, W, st),
                         "warp_sources_bwd")
@@ -902,7 +904,7 @@ class _PhotoLoss(torch.autograd.Function):
                 if two_streams:
                     side.wait_stream(main)
                 with torch.cuda.stream(side):
-                    L.check(lib.drosfm_smoothness_bwd(L.ptr(g), pc, pi, n, smooth_w, L.ptr(stats), L.ptr_array(g_invs), 0, B, H, W,
+                    L.check(lib.drosfm_smoothness_bwd(L.ptr(g), pc, pi, n, smooth_w, L.ptr(stats), L.ptr_array(g_invs), 0, L.ptr(edge_w), B, H, W,
                                                       L.stream()), "smoothness_bwd")
                 L.check(lib.drosfm_photometric_bwd(L.ptr(g), pc, pa, V, pi, depth_kind, n, cams, pp_, L.ptr(sel), opts, None, None,
                                                    L.ptr(ws), L.ptr(wsave), L.ptr(g_warped), L.PHOTO_NO_ADJOINT, B, H, W, st),
@@ -917,7 +919,7 @@ class _PhotoLoss(torch.autograd.Function):
                                                    L.ptr_array(g_invs), L.ptr_array(g_poses), L.ptr(ws), L.ptr(wsave),
                                                    L.ptr(g_warped), 0, B, H, W, st), "photometric_bwd")
                 if smooth:
-                    L.check(lib.drosfm_smoothness_bwd(L.ptr(g), pc, pi, n, smooth_w, L.ptr(stats), L.ptr_array(g_invs), 1, B, H, W,
+                    L.check(lib.drosfm_smoothness_bwd(L.ptr(g), pc, pi, n, smooth_w, L.ptr(stats), L.ptr_array(g_invs), 1, L.ptr(edge_w), B, H, W,
                                                       st), "smoothness_bwd")
         return (None, None, None, None, None, None, *([None] * V), *g_invs, *g_poses)
 

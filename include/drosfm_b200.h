@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DROSFM_ABI_VERSION 3
+#define DROSFM_ABI_VERSION 4
 #define DROSFM_MAX_VIEWS 8      /* source views per call (forward_context + back_context) */
 #define DROSFM_MAX_PREDS 16     /* depth predictions per loss call (GRU iterations seen by the loss) */
 #define DROSFM_MAX_COST_JOBS 9  /* cost evaluations per batched launch: one depth cost + one pose cost per view */
@@ -256,11 +256,13 @@ int drosfm_warp_sources_bwd(const float* g_warped, const float* const* context, 
  * stats [n_preds,B,4] float scratch written by fwd and read by bwd (per-sample mean inverse depth
  * and the two per-sample edge sums); ws of drosfm_ws_bytes(n_preds*B + 1).
  * bwd: g_inv_depths[i] [B,1,H,W] written (accumulate 0), added to (1), or added to with atomic reductions (2: another kernel
- * -- the warp adjoint of the photometric term -- may add into the same maps concurrently on a second stream); entries may be NULL. */
+ * -- the warp adjoint of the photometric term -- may add into the same maps concurrently on a second stream); entries may be NULL.
+ * edge_w (optional, [B,2,H,W] floats): fwd leaves the edge weights exp(-mean_c |dI|) towards the right / lower neighbour
+ * there and bwd reads them instead of re-deriving them from the image (4 loads instead of 24 loads + 4 exponentials per pixel). */
 int drosfm_smoothness_fwd(const float* image, const float* const* inv_depths, int n_preds, float weight,
-                          float* stats, float* loss, void* ws, int B, int H, int W, drosfm_stream_t stream);
+                          float* stats, float* loss, void* ws, float* edge_w, int B, int H, int W, drosfm_stream_t stream);
 int drosfm_smoothness_bwd(const float* g_loss, const float* image, const float* const* inv_depths, int n_preds,
-                          float weight, const float* stats, float* const* g_inv_depths, int accumulate,
+                          float weight, const float* stats, float* const* g_inv_depths, int accumulate, const float* edge_w,
                           int B, int H, int W, drosfm_stream_t stream);
 
 /* ---- reprojection pose loss (supervised_loss.py:279-325) ------------------------------------
