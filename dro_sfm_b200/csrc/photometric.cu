@@ -1672,16 +1672,17 @@ ssim_bwd_stream2_kernel(const float* __restrict__ g_loss, const float* __restric
     }
 }
 
-// ---- training forward, two views: SSIM forward AND the window gradients in one pass -----------------------------
+// ---- training forward, 2 / 4 / 6 / 8 views: SSIM forward AND the window gradients in one pass -------------------
 // The backward SSIM stage recomputes every window statistic the forward stage had: with the upstream gradient being
 // a scalar factor, d loss / d warped can be produced by the forward itself (unscaled: the warp adjoint multiplies by the
 // upstream gradient of the loss), and the backward pass of the loss shrinks to the warp adjoint.
 //
 // Block = 3 warps: the three colour channels of one 28-column strip x 32-row band of one (prediction, sample), both views
 // packed as float2 (the walk of ssim_bwd_stream2_kernel).  Per row step each channel warp computes its SSIM / L1 terms of
-// the window just completed; the three warps exchange them through shared memory (double-buffered, ONE named barrier per
-// step), every warp forms the photometric values of both views, the min / auto-mask selection and from it the
-// coefficients of its own channel.  Channel 0 accumulates the loss and writes the selection.
+// the window just completed; the three warps exchange them through shared memory (three buffers at static offsets, ONE
+// named barrier per step), every warp forms the photometric values of all views, the min / auto-mask selection and from it
+// the coefficients of its own channel.  Channel 0 accumulates the loss and writes the selection.  More than two views: one
+// such warp triple per view PAIR in the block (template PAIRS), all behind the same barrier.
 constexpr int kTrainThreads = 96;      // per view PAIR: three channel warps
 #ifndef DROSFM_SSIMT_INNER
 #define DROSFM_SSIMT_INNER 1      // bands away from the top / bottom edge run a copy of the walk without the row tests
@@ -1690,7 +1691,7 @@ constexpr int kTrainThreads = 96;      // per view PAIR: three channel warps
 #define DROSFM_SSIMT_PFD 3      // rows between a load and its use
 #endif
 #ifndef DROSFM_SSIMT_HSMEM
-#define DROSFM_SSIMT_HSMEM 1
+#define DROSFM_SSIMT_HSMEM 1    // the horizontal coefficient sums of the three rows in flight in shared memory (18 registers less)
 #endif
 #ifndef DROSFM_SSIMT_BAND
 #define DROSFM_SSIMT_BAND 32
