@@ -684,13 +684,12 @@ constexpr int kFlatTileH = (kFlatThreads / 32) * kFlatRows;       // one tile: 3
 // Tuning (B200, 320x960, B=2, n=9, V=2; loss graph replay, scratch/loss_bench.py):
 //   forward : 4 blocks/SM (64 registers) 130 us, 3 blocks 142 us, 2 blocks 152 us; tiles per block 1 / 2 / 5: 136 / 142 / 130 us
 //   adjoint : 2 blocks/SM (128 registers, no spills) 202 us, 3 blocks (80 registers, 120 B spilled) 219 us;
-//             tiles per block 1 / 2 / 5: 229 / 219 / 236 us; row loop unrolled: 317 us (instruction cache)
+//             tiles per block 1 / 2 / 3 / 5 (final build, one barrier set-up): 215 / 201 / 191 / 189 us;
+//             row loop unrolled: 317 us (instruction cache)
 #ifndef DROSFM_FWD_TILES
 #define DROSFM_FWD_TILES 1
 #endif
-#ifndef DROSFM_ADJ_TILES
-#define DROSFM_ADJ_TILES 2
-#endif
+// (DROSFM_ADJ_TILES, when defined, pins the adjoint's tiles per block; by default launch_adjoint chooses per launch)
 #ifndef DROSFM_FWD_MINBLOCKS
 #define DROSFM_FWD_MINBLOCKS 4
 #endif
@@ -703,7 +702,8 @@ constexpr int kFlatTileH = (kFlatThreads / 32) * kFlatRows;       // one tile: 3
 #ifndef DROSFM_ADJ_ILP
 #define DROSFM_ADJ_ILP 1      // rows interleaved per iteration: 1 -> 203 us, 2 -> 205 us, 4 -> 323 us (registers)
 #endif
-constexpr int kFwdTiles = DROSFM_FWD_TILES, kAdjTiles = DROSFM_ADJ_TILES;   // tiles a block walks down (amortises its camera set-up)
+constexpr int kFwdTiles = DROSFM_FWD_TILES;   // tiles a block walks down (amortises its camera set-up)
+constexpr int kAdjTilesMax = 8;               // the adjoint picks its tile count per launch (launch_adjoint)
 
 // Source pictures as RGBx texels ([V][B][H][W][4] floats, x = 0): every bilinear tap of the flat warp and of its adjoint
 // is ONE 128-bit gather instead of three 32-bit ones from three planes (a third of the load instructions and address
@@ -845,7 +845,8 @@ template <bool PACKED, bool ADD>
 __global__ void __launch_bounds__(kFlatThreads, DROSFM_ADJ_MINBLOCKS)
 warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int depth_kind, int n_preds, drosfm_cams_t cams,
                             int padding, const float* __restrict__ rgbx, const float* __restrict__ g_warped,
-                            const float* __restrict__ g_scale, const __grid_constant__ PhotoGrads pg, Slot* ws, int B, int H, int W) {
+                            const float* __restrict__ g_scale, const __grid_constant__ PhotoGrads pg, Slot* ws, int tiles, int B,
+                            int H, int W) {
     __shared__ Cam cam_s;
     __shared__ int flag;
     const int tid = threadIdx.x;
@@ -864,10 +865,10 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
         return v;
     };
     const int x = blockIdx.x * 32 + (tid & 31);
-    const int row0 = blockIdx.y * kAdjTiles * kFlatTileH + (tid >> 5);       // first row of this thread; then every 8th
+    const int row0 = blockIdx.y * tiles * kFlatTileH + (tid >> 5);           // first row of this thread; then every 8th
     const bool col_ok = x < W;
     constexpr int kStride = kFlatThreads / 32;
-    constexpr int kRows = kAdjTiles * kFlatRows;
+    const int kRows = tiles * kFlatRows;       // `tiles` tiles of 64 rows per block (host: as many as keep the grid a few waves deep)
     const float* __restrict__ invd = pp.inv_depth[ip] + static_cast<size_t>(b) * P;
     float* __restrict__ gout = pg.g_inv_depth[ip] != nullptr ? pg.g_inv_depth[ip] + static_cast<size_t>(b) * P : nullptr;
     const float* __restrict__ gw = g_warped + static_cast<size_t>(slot) * 3 * P;
@@ -880,7 +881,7 @@ warp_sources_adjoint_kernel(const __grid_constant__ PhotoPtrs pp, int V, int dep
     // row loop is NOT unrolled beyond that (the body is ~400 instructions per row: eight copies thrash the instruction
     // cache).  kIlp rows are processed side by side in one basic block so that their chains and gathers overlap.
     constexpr int kIlp = DROSFM_ADJ_ILP;
-    static_assert(kRows % kIlp == 0, "rows per block must be a multiple of the interleave");
+    static_assert(kFlatRows % kIlp == 0, "rows per tile must be a multiple of the interleave");
     float gn[kIlp][3], dn[kIlp];
     auto fetch = [&](int k0) {
 #pragma unroll
@@ -993,7 +994,19 @@ __global__ void __launch_bounds__(256) zero_inv_grads_kernel(const __grid_consta
 static int launch_adjoint(const PhotoPtrs& pp, const PhotoGrads& pg, int n_views, int depth_kind, int n_preds, const drosfm_cams_t* cams,
                           int padding, const float* rgbx, const float* g_warped, const float* g_scale, Slot* ws, int accumulate,
                           int B, int H, int W, cudaStream_t cs) {
-    dim3 flat((W + 31) / 32, (H + kAdjTiles * kFlatTileH - 1) / (kAdjTiles * kFlatTileH), B * n_preds * n_views);
+    // tiles of 64 rows per block: the pose-gradient reduction, its atomics and the camera set-up are paid once per block, so
+    // as many as the picture has (KITTI 320 rows: 5 -> 189 us, 3 -> 191, 2 -> 201, 1 -> 215) while the grid stays >= 3 waves
+    const int slots = B * n_preds * n_views, cols = (W + 31) / 32;
+    int tiles = (H + kFlatTileH - 1) / kFlatTileH;
+    if (tiles > kAdjTilesMax) tiles = kAdjTilesMax;
+#ifdef DROSFM_ADJ_TILES
+    tiles = DROSFM_ADJ_TILES;
+#else
+    while (tiles > 1 && static_cast<long long>(cols) * ((H + tiles * kFlatTileH - 1) / (tiles * kFlatTileH)) * slots <
+                            3ll * kNumSMs * DROSFM_ADJ_MINBLOCKS)
+        --tiles;
+#endif
+    dim3 flat(cols, (H + tiles * kFlatTileH - 1) / (tiles * kFlatTileH), slots);
     const bool add = accumulate != 0 || n_views > 1;
     if (add && accumulate == 0) {
         const size_t n = static_cast<size_t>(B) * H * W;
@@ -1002,7 +1015,7 @@ static int launch_adjoint(const PhotoPtrs& pp, const PhotoGrads& pg, int n_views
         if (int e = launch_status("warp adjoint (zero fill)")) return e;
     }
 #define ADJ(PK, AD) warp_sources_adjoint_kernel<PK, AD><<<flat, kFlatThreads, 0, cs>>>(pp, n_views, depth_kind, n_preds, *cams, padding, rgbx, \
-                                                                                     g_warped, g_scale, pg, ws, B, H, W)
+                                                                                     g_warped, g_scale, pg, ws, tiles, B, H, W)
     if (rgbx != nullptr) { if (add) ADJ(true, true); else ADJ(true, false); }
     else { if (add) ADJ(false, true); else ADJ(false, false); }
 #undef ADJ
